@@ -1,0 +1,802 @@
+// Stage A -- Mie AOP on B200 (sm_100a).  float32 throughout, compiled with -fmad=false and written with
+// explicit round-to-nearest intrinsics so that every multiply/add rounds exactly like the reference
+// Fortran (no FMA contraction): tau/ssa/g/pmom are bit-exact.
+//
+// Reference behaviour (paths relative to AeroApps src/Shared/GMAO_Shared/Chem_Base/):
+//   Chem_MieTableMod.F90:238-719  table read / polint / RH hash      -> k_polint, k_derived, k_rhhash
+//   Chem_MieMod.F90:789-965       Chem_MieQueryByInt                 -> snap_index(), make_snap(), lerp2()
+//   MieObs_py.F90:87-214          getAOPscalar                       -> k_aop_scalar
+//   MieObs_py.F90:218-456         getAOPvector                       -> k_aop_vector
+//   MieObs_py.F90:460-770         getExt / getInt                    -> k_ext_accum, k_ext_atten, k_int
+//   MieObs_py.F90:27-83           getEdgeVars                        -> k_edge_vars
+//
+// HBM layout: one float pool per species table holding the channel-interpolated tables in the reference's
+// own order (irh fastest): bext,bsca,bbck,g,refr,refi (nrh,nch,nbin); pback (nrh,nch,nbin,npol);
+// pmom (nrh,nch,nbin,nmom,npol); reff,gf,rhop,rhod,vol,area (nrh,nbin); rh(nrh); rha(991); rhi(991, int).
+// Column state qm(km,nq,nobs), rh(km,nobs) and outputs (km,nch,nobs[,nmom,npol]) keep the f2py layouts,
+// so consecutive threads <-> consecutive (k,n,i) voxels give fully coalesced 128-B accesses.
+#include "../../include/aeroapps_b200.h"
+#include "common.h"
+#include <map>
+#include <algorithm>
+#include <cctype>
+
+#define NRHHASH 991
+#define MAXQ 40          // max tracers per call (reference uses 15-22)
+#define MAXCH 16         // max channels per call
+
+// ------------------------------------------------------------------------------------------------
+struct TableDev {
+  float *pool = nullptr;   // everything below lives in this allocation
+  int nch = 0, nrh = 0, nbin = 0, nmom = 0, npol = 0;
+  long o_rh, o_bext, o_bsca, o_bbck, o_g, o_refr, o_refi, o_pback, o_pmom, o_reff, o_gf, o_rhop, o_rhod,
+      o_vol, o_area, o_rha, o_rhi, total;
+  bool loaded = false;
+};
+
+struct ab200_mie {
+  int nch = 0, nmom = 0;
+  std::vector<float> channels;                    // [m]
+  float *d_channels = nullptr;
+  TableDev tab[AB200_NSPECIES];
+  std::map<std::string, std::pair<int, int>> reg; // UPPERCASE name -> (species, bin)
+  DevBuf ws_in, ws_out, ws_tmp;
+};
+
+static thread_local std::string g_err;
+void ab200_set_error(const std::string &msg) { g_err = msg; }
+extern "C" const char *ab200_last_error(void) { return g_err.c_str(); }
+extern "C" int ab200_version(void) { return 100; }
+extern "C" int ab200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+static std::string upper(std::string s) {
+  for (auto &c : s) c = (char)toupper((unsigned char)c);
+  return s;
+}
+static std::string trim(const std::string &s) {
+  size_t a = 0, b = s.size();
+  while (a < b && (s[a] == ' ' || s[a] == '\0')) a++;
+  while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\0')) b--;
+  return s.substr(a, b - a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// table preparation kernels
+
+// polint of Chem_MieTableMod.F90:671-717: x,y real*8; xWant, slope, dx, yWant real*4.
+__device__ __forceinline__ float polint_dev(const double *__restrict__ x, const double *__restrict__ y, int n,
+                                            float xWant, bool take_abs) {
+  int i = 0;
+  const double xw = (double)xWant;
+  if (xw < x[0]) i = 1;
+  if (xw > x[n - 1]) i = n;
+  if (i == 0)
+    for (int j = 1; j <= n; j++)
+      if (xw >= x[j - 1]) i = j;
+  double y0 = y[i - 1];
+  if (take_abs) y0 = fabs(y0);
+  float slope;
+  if (i == n) slope = 0.f;
+  else {
+    double y1 = y[i];
+    if (take_abs) y1 = fabs(y1);
+    slope = (float)__ddiv_rn(__dsub_rn(y1, y0), __dsub_rn(x[i], x[i - 1]));
+  }
+  float dx = (float)__dsub_rn(xw, x[i - 1]);
+  float sd = __fmul_rn(slope, dx);
+  return (float)__dadd_rn(y0, (double)sd);
+}
+
+// src (nlam, nrh, nbin, [nmoms, npol]) double -> dst (nrh, nch, nbin, [nmomd, npol]) float
+__global__ void k_polint(const double *__restrict__ lam, const double *__restrict__ src, float *__restrict__ dst,
+                         const float *__restrict__ chan, int nlam, int nrh, int nbin, int nch, int nmomd,
+                         int nmoms, int npol, int take_abs) {
+  long total = (long)nrh * nch * nbin * nmomd * npol;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    long r = t;
+    int i = r % nrh; r /= nrh;
+    int n = r % nch; r /= nch;
+    int j = r % nbin; r /= nbin;
+    int m = r % nmomd; r /= nmomd;
+    int p = (int)r;
+    const double *y = src + (long)nlam * (i + (long)nrh * (j + (long)nbin * (m + (long)nmoms * p)));
+    dst[t] = polint_dev(lam, y, nlam, chan[n], take_abs != 0);
+  }
+}
+
+__global__ void k_fill(float *dst, float v, long n) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) dst[t] = v;
+}
+
+// reff,gf,rhop,rhod,vol,area (nrh,nbin): Chem_MieTableMod.F90:433-491,595-610
+__global__ void k_derived(const double *__restrict__ reff, const double *__restrict__ gf,
+                          const double *__restrict__ rhop, int nrh, int nbin, float *o_reff, float *o_gf,
+                          float *o_rhop, float *o_rhod, float *o_vol, float *o_area) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrh * nbin) return;
+  int j = t / nrh;
+  double gfv = gf ? gf[t] : (double)-999.f;
+  double rhopv = rhop ? rhop[t] : (double)-999.f;
+  double rhodv = rhop ? rhop[(long)nrh * j] : (double)-999.f;
+  double reffv = reff[t];
+  double vol = __ddiv_rn(__dmul_rn(__dmul_rn(gfv, gfv), gfv), rhodv);
+  double area = __ddiv_rn(vol, __dmul_rn((double)(4.f / 3.f), reffv));
+  o_reff[t] = (float)reffv; o_gf[t] = (float)gfv; o_rhop[t] = (float)rhopv; o_rhod[t] = (float)rhodv;
+  o_vol[t] = (float)vol; o_area[t] = (float)area;
+}
+
+// RH hash, Chem_MieTableMod.F90:612-627
+__global__ void k_rhhash(const double *__restrict__ rh_raw, int nrh, float *o_rh, float *o_rha, int *o_rhi) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (j <= nrh) o_rh[j - 1] = (float)rh_raw[j - 1];
+  if (j > NRHHASH) return;
+  int rhi = 1; float rha = 0.f;
+  for (int i = nrh; i >= 1; i--) {
+    float rhi_f = (float)rh_raw[i - 1];
+    if ((j - 1) >= (int)__fmul_rn(rhi_f, 1000.f)) {
+      rhi = i;
+      if (i + 1 > nrh) rha = 0.f;
+      else {
+        float a = __fsub_rn(__fdiv_rn((float)(j - 1), 1000.f), rhi_f);
+        float b = __fsub_rn((float)rh_raw[i], rhi_f);
+        rha = __fdiv_rn(a, b);
+      }
+      break;
+    }
+  }
+  o_rha[j - 1] = rha; o_rhi[j - 1] = rhi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// query helpers (Chem_MieMod.F90:860-945)
+struct Snap { int irh, irhp1; float arh, oma; };
+
+__device__ __forceinline__ int snap_index(float rh) {
+  float rhUse = fminf(rh, 0.99f);                        // the max(rh,0.) line is dead code in the reference
+  int isnap = (int)__fmul_rn(__fadd_rn(rhUse, 0.001f), 1000.f);
+  if (isnap < 1) isnap = 1;
+  if (isnap > NRHHASH) isnap = NRHHASH;                  // never taken for finite rh; guards garbage input
+  return isnap;
+}
+__device__ __forceinline__ float lerp2(const float *__restrict__ a, const Snap &s) {
+  return __fadd_rn(__fmul_rn(__ldg(a + s.irh), s.oma), __fmul_rn(__ldg(a + s.irhp1), s.arh));
+}
+
+// per active tracer, per call.  3-D pointers are pre-offset to the tracer's bin; 2-D ones (vol,area) too.
+struct TracerDesc {
+  const float *bext, *bsca, *g, *bbck, *refr, *refi, *pback, *pmom, *vol, *area;
+  const float *rha; const int *rhi;
+  int nrh, n3, nmomt, npol_, sph, qidx;     // n3 = nrh*nch*nbin (stride of m); qidx = tracer slot in qm
+  int p22off, pad;                          // offset of pback(...,5); 0 (P22:=P11) when the table has nPol<5
+};
+struct AopParams {
+  int km, nobs, nch, nq, nqa;        // nqa = number of active tracers
+  int nmom, npol;
+  int chidx0[MAXCH];                 // 0-based table channel per requested channel
+  TracerDesc d[MAXQ];
+};
+
+__device__ __forceinline__ Snap make_snap(const TracerDesc &d, int isnap) {
+  Snap s;
+  s.arh = __ldg(d.rha + isnap - 1);
+  s.irh = __ldg(d.rhi + isnap - 1) - 1;
+  s.irhp1 = min(s.irh + 1, d.nrh - 1);
+  s.oma = __fsub_rn(1.f, s.arh);
+  return s;
+}
+
+// ---- getAOPscalar: one thread per (k,n,i) voxel-channel, k fastest (MieObs_py.F90:173-205)
+// HBM-bound: 4*(nq+1) B in + 12 B out per voxel-channel; tables (a few KB) stay in L1/L2.
+__global__ void __launch_bounds__(256) k_aop_scalar(const __grid_constant__ AopParams P,
+                                                    const float *__restrict__ qm, const float *__restrict__ rh,
+                                                    float *__restrict__ tau, float *__restrict__ ssa,
+                                                    float *__restrict__ g) {
+  const long nout = (long)P.km * P.nch * P.nobs;
+  for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < nout; o += (long)gridDim.x * blockDim.x) {
+    int k = (int)(o % P.km);
+    long r = o / P.km;
+    int n = (int)(r % P.nch);
+    long i = r / P.nch;
+    const int isnap = snap_index(__ldg(rh + k + (long)P.km * i));
+    const float *qcol = qm + k + (long)P.km * P.nq * i;
+    const int ch = P.chidx0[n];
+    float t = 0.f, s = 0.f, gg = 0.f;
+#pragma unroll 4
+    for (int a = 0; a < P.nqa; a++) {
+      const TracerDesc &d = P.d[a];
+      Snap sn = make_snap(d, isnap);
+      const int co = d.nrh * ch;
+      float bext = lerp2(d.bext + co, sn);
+      float bsca = lerp2(d.bsca + co, sn);
+      float gas = lerp2(d.g + co, sn);
+      float q = __ldcs(qcol + (long)P.km * d.qidx);
+      float tau_ = __fmul_rn(bext, q);
+      float ssa_ = __fdiv_rn(bsca, bext);
+      t = __fadd_rn(t, tau_);
+      s = __fadd_rn(s, __fmul_rn(ssa_, tau_));
+      gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(gas, ssa_), tau_));
+    }
+    if (t > 0.f) s = __fdiv_rn(s, t);
+    float dd = __fmul_rn(s, t);
+    if (dd > 0.f) gg = __fdiv_rn(gg, dd);
+    __stcs(tau + o, t); __stcs(ssa + o, s); __stcs(g + o, gg);
+  }
+}
+
+// ---- getAOPvector (MieObs_py.F90:391-446).  Block = 32 consecutive voxel-channels (lanes) x NW warps.
+// Phase 1: per-(voxel,tracer) query parameters -> shared memory; warp 0 forms tau/ssa/g.
+// Phase 2: warps split the moment axis in chunks of MCH moments x 6 matrix elements kept in registers;
+// tracer loop outermost (the reference's accumulation order), P22:=P11 / P44:=P33 overwrite after each
+// spherical tracer.  Output writes are 128-B coalesced (lanes = consecutive k).
+#define VEC_NW 8
+#define VEC_MCH 4
+__global__ void __launch_bounds__(32 * VEC_NW) k_aop_vector(const __grid_constant__ AopParams P,
+                                                            const float *__restrict__ qm,
+                                                            const float *__restrict__ rh, float *__restrict__ tau,
+                                                            float *__restrict__ ssa, float *__restrict__ g,
+                                                            float *__restrict__ pmom) {
+  __shared__ float s_tau[MAXQ][32], s_ssa[MAXQ][32], s_gas[MAXQ][32], s_arh[MAXQ][32];
+  __shared__ int s_irh[MAXQ][32];
+  __shared__ float s_den[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long nout = (long)P.km * P.nch * P.nobs;
+  const long o = (long)blockIdx.x * 32 + lane;
+  const bool valid = o < nout;
+  int k = 0, n = 0; long i = 0;
+  if (valid) { k = (int)(o % P.km); long r = o / P.km; n = (int)(r % P.nch); i = r / P.nch; }
+  const int ch = P.chidx0[n];
+
+  {
+    const int isnap = valid ? snap_index(__ldg(rh + k + (long)P.km * i)) : 1;
+    const float *qcol = qm + k + (long)P.km * P.nq * i;
+    for (int a = warp; a < P.nqa; a += VEC_NW) {
+      const TracerDesc &d = P.d[a];
+      Snap sn = make_snap(d, isnap);
+      const int co = d.nrh * ch;
+      float bext = lerp2(d.bext + co, sn);
+      float bsca = lerp2(d.bsca + co, sn);
+      float gas = lerp2(d.g + co, sn);
+      float q = valid ? __ldcs(qcol + (long)P.km * d.qidx) : 0.f;
+      s_tau[a][lane] = __fmul_rn(bext, q);
+      s_ssa[a][lane] = __fdiv_rn(bsca, bext);
+      s_gas[a][lane] = gas;
+      s_arh[a][lane] = sn.arh;
+      s_irh[a][lane] = sn.irh | (sn.irhp1 << 16);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f, s = 0.f, gg = 0.f;
+    for (int a = 0; a < P.nqa; a++) {
+      float tau_ = s_tau[a][lane], ssa_ = s_ssa[a][lane];
+      t = __fadd_rn(t, tau_);
+      s = __fadd_rn(s, __fmul_rn(ssa_, tau_));
+      gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(s_gas[a][lane], ssa_), tau_));
+    }
+    if (t > 0.f) s = __fdiv_rn(s, t);
+    float dd = __fmul_rn(s, t);
+    if (dd > 0.f) gg = __fdiv_rn(gg, dd);
+    s_den[lane] = dd;
+    if (valid) { tau[o] = t; ssa[o] = s; g[o] = gg; }
+  }
+  __syncthreads();
+  const float den = s_den[lane];
+  const int nchunk = (P.nmom + VEC_MCH - 1) / VEC_MCH;
+  for (int mc = warp; mc < nchunk; mc += VEC_NW) {
+    const int m0 = mc * VEC_MCH;
+    float acc[VEC_MCH][6];
+#pragma unroll
+    for (int mm = 0; mm < VEC_MCH; mm++)
+#pragma unroll
+      for (int p = 0; p < 6; p++) acc[mm][p] = 0.f;
+    for (int a = 0; a < P.nqa; a++) {
+      const TracerDesc &d = P.d[a];
+      const float tau_ = s_tau[a][lane], ssa_ = s_ssa[a][lane], arh = s_arh[a][lane];
+      const float oma = __fsub_rn(1.f, arh);
+      const int pk = s_irh[a][lane];
+      const float *b0 = d.pmom + d.nrh * ch + (pk & 0xffff);
+      const float *b1 = d.pmom + d.nrh * ch + (pk >> 16);
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+        if (p < d.npol_) {
+#pragma unroll
+          for (int mm = 0; mm < VEC_MCH; mm++) {
+            const int m = min(m0 + mm, P.nmom - 1);
+            const long off = (long)d.n3 * (m + (long)d.nmomt * p);
+            float v = __fadd_rn(__fmul_rn(__ldg(b0 + off), oma), __fmul_rn(__ldg(b1 + off), arh));
+            acc[mm][p] = __fadd_rn(acc[mm][p], __fmul_rn(__fmul_rn(v, ssa_), tau_));
+          }
+        }
+      }
+      if (d.sph) {
+#pragma unroll
+        for (int mm = 0; mm < VEC_MCH; mm++) { acc[mm][4] = acc[mm][0]; acc[mm][5] = acc[mm][2]; }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+        if (p < P.npol) {
+#pragma unroll
+          for (int mm = 0; mm < VEC_MCH; mm++) {
+            const int m = m0 + mm;
+            if (m < P.nmom) {
+              float v = acc[mm][p];
+              if (den > 0.f) v = __fdiv_rn(v, den);
+              __stcs(pmom + o + nout * (m + (long)P.nmom * p), v);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- getExt accumulation (MieObs_py.F90:560-590): thread per voxel-channel
+__global__ void __launch_bounds__(256) k_ext_accum(const __grid_constant__ AopParams P,
+                                                   const float *__restrict__ qc, const float *__restrict__ qm,
+                                                   const float *__restrict__ rh, float *__restrict__ ext,
+                                                   float *__restrict__ sca, float *__restrict__ bsc,
+                                                   float *__restrict__ tau, float *__restrict__ depol) {
+  const long nout = (long)P.km * P.nch * P.nobs;
+  for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < nout; o += (long)gridDim.x * blockDim.x) {
+    int k = (int)(o % P.km);
+    long r = o / P.km;
+    int n = (int)(r % P.nch);
+    long i = r / P.nch;
+    const int isnap = snap_index(__ldg(rh + k + (long)P.km * i));
+    const long qo = k + (long)P.km * P.nq * i;
+    const int ch = P.chidx0[n];
+    float e = 0.f, s = 0.f, b = 0.f, t = 0.f, dn = 0.f, dd = 0.f;
+    for (int a = 0; a < P.nqa; a++) {
+      const TracerDesc &d = P.d[a];
+      Snap sn = make_snap(d, isnap);
+      const int co = d.nrh * ch;
+      float bext = lerp2(d.bext + co, sn);
+      float bsca = lerp2(d.bsca + co, sn);
+      float bbck = lerp2(d.bbck + co, sn);
+      float qcv = __ldg(qc + qo + (long)P.km * d.qidx);
+      float qmv = __ldg(qm + qo + (long)P.km * d.qidx);
+      float ext_ = __fmul_rn(bext, qcv);
+      float ssa_ = __fdiv_rn(bsca, bext);
+      e = __fadd_rn(e, ext_);
+      s = __fadd_rn(s, __fmul_rn(ssa_, ext_));
+      b = __fadd_rn(b, __fmul_rn(bbck, qcv));
+      float tau_ = __fmul_rn(bext, qmv);
+      float p11 = lerp2(d.pback + co, sn);
+      float p22 = lerp2(d.pback + co + d.p22off, sn);
+      t = __fadd_rn(t, tau_);
+      dn = __fadd_rn(dn, __fmul_rn(__fmul_rn(__fsub_rn(p11, p22), ssa_), tau_));
+      dd = __fadd_rn(dd, __fmul_rn(__fmul_rn(__fadd_rn(p11, p22), ssa_), tau_));
+    }
+    depol[o] = dd > 0.f ? __fdiv_rn(dn, dd) : 0.f;
+    bsc[o] = __fmul_rn(b, 1e03f); ext[o] = __fmul_rn(e, 1e03f); sca[o] = __fmul_rn(s, 1e03f);
+    tau[o] = t;
+  }
+}
+// exp() of the reference is libm expf; evaluate in double and round (<=1 ulp of float vs glibc)
+__device__ __forceinline__ float expf_ref(float x) { return (float)exp((double)x); }
+
+// attenuated backscatter (MieObs_py.F90:604-636): the reference's O(km^2) re-summation order is kept
+__global__ void k_ext_atten(int km, long ncol, const float *__restrict__ tau, const float *__restrict__ bsc,
+                            float *__restrict__ absc_sfc, float *__restrict__ absc_toa) {
+  const long nout = (long)km * ncol;
+  for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < nout; o += (long)gridDim.x * blockDim.x) {
+    int k = (int)(o % km) + 1;
+    const float *tc = tau + (o - (k - 1));
+    float bv = bsc[o];
+    if (k == 1) absc_toa[o] = __fmul_rn(bv, expf_ref(-tc[0]));
+    else {
+      float taulev = 0.f;
+      for (int l = 1; l <= k - 1; l++) taulev = __fadd_rn(taulev, tc[l - 1]);
+      taulev = __fadd_rn(taulev, __fmul_rn(0.5f, tc[k - 1]));
+      absc_toa[o] = __fmul_rn(bv, expf_ref(__fmul_rn(-2.f, taulev)));
+    }
+    if (k == km) absc_sfc[o] = __fmul_rn(bv, expf_ref(-tc[km - 1]));
+    else {
+      float taulev = 0.f;
+      for (int l = km; l >= k + 1; l--) taulev = __fadd_rn(taulev, tc[l - 1]);
+      taulev = __fadd_rn(taulev, __fmul_rn(0.5f, tc[k - 1]));
+      absc_sfc[o] = __fmul_rn(bv, expf_ref(__fmul_rn(-2.f, taulev)));
+    }
+  }
+}
+
+// ---- getInt (MieObs_py.F90:737-768)
+__global__ void __launch_bounds__(256) k_int(const __grid_constant__ AopParams P, const float *__restrict__ qc,
+                                             const float *__restrict__ rh, float *__restrict__ vol,
+                                             float *__restrict__ area, float *__restrict__ refr,
+                                             float *__restrict__ refi, float *__restrict__ reff) {
+  const long nout = (long)P.km * P.nch * P.nobs;
+  for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < nout; o += (long)gridDim.x * blockDim.x) {
+    int k = (int)(o % P.km);
+    long r = o / P.km;
+    int n = (int)(r % P.nch);
+    long i = r / P.nch;
+    const int isnap = snap_index(__ldg(rh + k + (long)P.km * i));
+    const long qo = k + (long)P.km * P.nq * i;
+    const int ch = P.chidx0[n];
+    float v = 0.f, ar = 0.f, rr = 0.f, ri = 0.f;
+    for (int a = 0; a < P.nqa; a++) {
+      const TracerDesc &d = P.d[a];
+      Snap sn = make_snap(d, isnap);
+      const int co = d.nrh * ch;
+      float vol_ = lerp2(d.vol, sn);
+      float area_ = lerp2(d.area, sn);
+      float refr_ = lerp2(d.refr + co, sn);
+      float refi_ = lerp2(d.refi + co, sn);
+      float qcv = __ldg(qc + qo + (long)P.km * d.qidx);
+      v = __fadd_rn(v, __fmul_rn(vol_, qcv));
+      ar = __fadd_rn(ar, __fmul_rn(area_, qcv));
+      rr = __fadd_rn(rr, __fmul_rn(__fmul_rn(refr_, vol_), qcv));
+      ri = __fadd_rn(ri, __fmul_rn(__fmul_rn(refi_, vol_), qcv));
+    }
+    reff[o] = __fdiv_rn(__fmul_rn(0.75f, v), ar);
+    if (v > 0.f) { rr = __fdiv_rn(rr, v); ri = __fdiv_rn(ri, v); }
+    vol[o] = v; area[o] = ar; refr[o] = rr; refi[o] = ri;
+  }
+}
+
+// ---- getEdgeVars (MieObs_py.F90:27-83): one thread per column (sequential prefix sums keep the
+// reference's float32 summation order); log/pow evaluated in double then rounded (<=1 ulp vs libm)
+__global__ void k_edge_vars(int km, int nobs, const float *__restrict__ airdens, const float *__restrict__ delp,
+                            float ptop, float *__restrict__ pe, float *__restrict__ ze, float *__restrict__ te) {
+  const float grav = 9.80616f, Rgas = 287.f, kappa = 2.0f / 7.0f;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nobs) return;
+  float *pen = pe + (long)(km + 1) * n, *zen = ze + (long)(km + 1) * n, *ten = te + (long)(km + 1) * n;
+  const float *ad = airdens + (long)km * n, *dp = delp + (long)km * n;
+  float p = ptop;
+  pen[0] = p;
+  for (int k = 0; k < km; k++) { p = __fadd_rn(p, dp[k]); pen[k + 1] = p; }
+  float z = 0.f;
+  zen[km] = z;
+  for (int k = km - 1; k >= 0; k--) { z = __fadd_rn(z, __fdiv_rn(dp[k], __fmul_rn(ad[k], grav))); zen[k] = z; }
+  float pm_prev = 0.f, tm_prev = 0.f;
+  for (int k = 0; k < km; k++) {
+    float pm = __fdiv_rn(__fadd_rn(pen[k], pen[k + 1]), 2.0f);
+    float tm = __fdiv_rn(pm, __fmul_rn(ad[k], Rgas));
+    if (k == 0) ten[0] = tm;
+    else {
+      float l1 = (float)log((double)__fdiv_rn(pen[k], pm_prev));
+      float l2 = (float)log((double)__fdiv_rn(pm, pm_prev));
+      float alpha = __fdiv_rn(l1, l2);
+      ten[k] = __fadd_rn(tm_prev, __fmul_rn(alpha, __fsub_rn(tm, tm_prev)));
+    }
+    if (k == km - 1) ten[km] = __fmul_rn(tm, (float)pow((double)__fdiv_rn(pen[km], pm), (double)kappa));
+    pm_prev = pm; tm_prev = tm;
+  }
+}
+
+// ================================================================================================
+// host side
+static inline int grid_for(long n, int block, int maxblocks = 148 * 16) {
+  long b = (n + block - 1) / block;
+  return (int)std::max<long>(1, std::min<long>(b, maxblocks));
+}
+
+extern "C" int ab200_mie_create(int nch, const float *channels_m, int nmom, ab200_mie **out) {
+  if (!out || nch < 1 || nch > MAXCH || !channels_m || nmom < 0) { ab200_set_error("ab200_mie_create: bad argument"); return AB200_ERR_ARG; }
+  ab200_mie *h = new ab200_mie();
+  h->nch = nch; h->nmom = nmom;
+  h->channels.assign(channels_m, channels_m + nch);
+  cudaError_t e = cudaMalloc(&h->d_channels, sizeof(float) * nch);
+  if (e != cudaSuccess) { ab200_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); delete h; return AB200_ERR_CUDA; }
+  cudaMemcpy(h->d_channels, channels_m, sizeof(float) * nch, cudaMemcpyHostToDevice);
+  // default registry == the variable tables of Chem_MieRegistry.rc + the SU/NI name filter of
+  // Chem_MieMod.F90:376-400
+  char buf[32];
+  for (int b = 1; b <= 5; b++) { snprintf(buf, sizeof buf, "DU%03d", b); h->reg[buf] = {AB200_DU, b}; }
+  for (int b = 1; b <= 5; b++) { snprintf(buf, sizeof buf, "SS%03d", b); h->reg[buf] = {AB200_SS, b}; }
+  h->reg["BCPHOBIC"] = {AB200_BC, 1}; h->reg["BCPHILIC"] = {AB200_BC, 2};
+  h->reg["OCPHOBIC"] = {AB200_OC, 1}; h->reg["OCPHILIC"] = {AB200_OC, 2};
+  h->reg["BRCPHOBIC"] = {AB200_BRC, 1}; h->reg["BRCPHILIC"] = {AB200_BRC, 2};
+  h->reg["SO4"] = {AB200_SU, 1};
+  h->reg["NO3AN1"] = {AB200_NI, 1}; h->reg["NO3AN2"] = {AB200_NI, 2}; h->reg["NO3AN3"] = {AB200_NI, 3};
+  *out = h;
+  return 0;
+}
+
+extern "C" int ab200_mie_destroy(ab200_mie *h) {
+  if (!h) return 0;
+  for (auto &t : h->tab) if (t.pool) cudaFree(t.pool);
+  if (h->d_channels) cudaFree(h->d_channels);
+  h->ws_in.release(); h->ws_out.release(); h->ws_tmp.release();
+  delete h;
+  return 0;
+}
+
+extern "C" int ab200_mie_register_tracer(ab200_mie *h, const char *name, int species, int bin) {
+  if (!h || !name || species < 0 || species >= AB200_NSPECIES || bin < 1) { ab200_set_error("register_tracer: bad argument"); return AB200_ERR_ARG; }
+  h->reg[upper(trim(name))] = {species, bin};
+  return 0;
+}
+
+extern "C" int ab200_mie_query_idx(ab200_mie *h, const char *qname, int *species) {
+  std::string name = trim(qname ? qname : "");
+  size_t q = name.find("::");
+  if (q != std::string::npos) name = name.substr(q + 2);      // GOCART::du001 -> du001
+  auto it = h->reg.find(upper(trim(name)));
+  if (it == h->reg.end()) return -1;
+  if (species) *species = it->second.first;
+  return it->second.second;
+}
+
+extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh, int nbin, int nmom_file, int npol,
+                                    const double *lambda, const double *rh, const double *reff,
+                                    const double *bext, const double *bsca, const double *bbck, const double *g,
+                                    const double *refr, const double *refi, const double *pback,
+                                    const double *pmom, const double *gf, const double *rhop) {
+  if (!h || species < 0 || species >= AB200_NSPECIES || nlam < 1 || nrh < 1 || nbin < 1 || !lambda || !rh ||
+      !reff || !bext || !bsca || !bbck || !g) { ab200_set_error("load_table: bad argument"); return AB200_ERR_ARG; }
+  if (nrh > 0xffff) { ab200_set_error("load_table: nrh too large"); return AB200_ERR_ARG; }
+  const int nmom = h->nmom;
+  if (nmom > 0 && (!pmom || nmom > nmom_file)) return 99;     // Chem_MieTableMod.F90:300-304
+  if (nmom == 0) npol = 6;                                    // nPol_table default, :270
+  TableDev &T = h->tab[species];
+  if (T.pool) { cudaFree(T.pool); T.pool = nullptr; }
+  T.nch = h->nch; T.nrh = nrh; T.nbin = nbin; T.nmom = nmom; T.npol = npol;
+  const long n3 = (long)nrh * T.nch * nbin, n2 = (long)nrh * nbin;
+  long o = 0;
+  auto take = [&](long n) { long r = o; o += (n + 31) / 32 * 32; return r; };   // 128-B aligned sub-arrays
+  T.o_rh = take(nrh); T.o_bext = take(n3); T.o_bsca = take(n3); T.o_bbck = take(n3); T.o_g = take(n3);
+  T.o_refr = take(n3); T.o_refi = take(n3); T.o_pback = take(n3 * npol); T.o_pmom = take(n3 * nmom * npol);
+  T.o_reff = take(n2); T.o_gf = take(n2); T.o_rhop = take(n2); T.o_rhod = take(n2); T.o_vol = take(n2);
+  T.o_area = take(n2); T.o_rha = take(NRHHASH); T.o_rhi = take(NRHHASH);
+  T.total = o;
+  AB_CUDA_OK(cudaMalloc(&T.pool, sizeof(float) * T.total));
+  // stage raw doubles
+  const long r3 = (long)nlam * nrh * nbin;
+  size_t raw_bytes = sizeof(double) * (nlam + nrh + 3 * n2 + 6 * r3 + r3 * npol + (nmom > 0 ? r3 * (long)nmom_file * npol : 0));
+  AB_CUDA_OK(h->ws_tmp.reserve(raw_bytes));
+  double *d = h->ws_tmp.as<double>();
+  auto up = [&](const double *src, long n) -> double * {
+    if (!src) return nullptr;
+    double *dst = d; d += n;
+    cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice);
+    return dst;
+  };
+  double *d_lam = up(lambda, nlam), *d_rh = up(rh, nrh), *d_reff = up(reff, n2), *d_gf = up(gf, n2), *d_rhop = up(rhop, n2);
+  double *d_bext = up(bext, r3), *d_bsca = up(bsca, r3), *d_bbck = up(bbck, r3), *d_g = up(g, r3);
+  double *d_refr = up(refr, r3), *d_refi = up(refi, r3), *d_pback = up(pback, r3 * npol);
+  double *d_pmom = nmom > 0 ? up(pmom, r3 * (long)nmom_file * npol) : nullptr;
+  float *P = T.pool;
+  auto interp = [&](double *src, long off, int nmomd, int nmoms, int np, int take_abs, float fillv) {
+    long n = n3 * nmomd * np;
+    if (n == 0) return;
+    if (src) k_polint<<<grid_for(n, 256), 256>>>(d_lam, src, P + off, h->d_channels, nlam, nrh, nbin, T.nch, nmomd, nmoms, np, take_abs);
+    else k_fill<<<grid_for(n, 256), 256>>>(P + off, fillv, n);
+  };
+  interp(d_bext, T.o_bext, 1, 1, 1, 0, 0.f); interp(d_bsca, T.o_bsca, 1, 1, 1, 0, 0.f);
+  interp(d_bbck, T.o_bbck, 1, 1, 1, 0, 0.f); interp(d_g, T.o_g, 1, 1, 1, 0, 0.f);
+  interp(d_refr, T.o_refr, 1, 1, 1, 0, -999.f); interp(d_refi, T.o_refi, 1, 1, 1, 1, -999.f);
+  interp(d_pback, T.o_pback, 1, 1, npol, 0, 1.f);
+  if (nmom > 0) interp(d_pmom, T.o_pmom, nmom, nmom_file, npol, 0, 0.f);
+  k_derived<<<(int)((n2 + 127) / 128), 128>>>(d_reff, d_gf, d_rhop, nrh, nbin, P + T.o_reff, P + T.o_gf, P + T.o_rhop,
+                                              P + T.o_rhod, P + T.o_vol, P + T.o_area);
+  k_rhhash<<<(std::max(NRHHASH, nrh) + 127) / 128, 128>>>(d_rh, nrh, P + T.o_rh, P + T.o_rha, (int *)(P + T.o_rhi));
+  AB_CUDA_OK(cudaGetLastError());
+  AB_CUDA_OK(cudaDeviceSynchronize());
+  T.loaded = true;
+  return 0;
+}
+
+extern "C" long ab200_mie_get_table(ab200_mie *h, int species, const char *var, void *dst, long cap) {
+  if (!h || species < 0 || species >= AB200_NSPECIES || !h->tab[species].loaded) return -1;
+  TableDev &T = h->tab[species];
+  const long n3 = (long)T.nrh * T.nch * T.nbin, n2 = (long)T.nrh * T.nbin;
+  std::string v(var);
+  long off, n;
+  if (v == "rh") { off = T.o_rh; n = T.nrh; } else if (v == "bext") { off = T.o_bext; n = n3; }
+  else if (v == "bsca") { off = T.o_bsca; n = n3; } else if (v == "bbck") { off = T.o_bbck; n = n3; }
+  else if (v == "g") { off = T.o_g; n = n3; } else if (v == "refr") { off = T.o_refr; n = n3; }
+  else if (v == "refi") { off = T.o_refi; n = n3; } else if (v == "pback") { off = T.o_pback; n = n3 * T.npol; }
+  else if (v == "pmom") { off = T.o_pmom; n = n3 * T.nmom * T.npol; } else if (v == "reff") { off = T.o_reff; n = n2; }
+  else if (v == "gf") { off = T.o_gf; n = n2; } else if (v == "rhop") { off = T.o_rhop; n = n2; }
+  else if (v == "rhod") { off = T.o_rhod; n = n2; } else if (v == "vol") { off = T.o_vol; n = n2; }
+  else if (v == "area") { off = T.o_area; n = n2; } else if (v == "rha") { off = T.o_rha; n = NRHHASH; }
+  else if (v == "rhi") { off = T.o_rhi; n = NRHHASH; } else return -1;
+  if (dst && cap > 0) cudaMemcpy(dst, T.pool + off, 4 * std::min(n, cap), cudaMemcpyDeviceToHost);
+  return n;
+}
+
+// Build the per-call parameter block: channel match (MieObs_py.F90:146-163), tracer lookup
+// (Chem_MieQueryIdx), moment / nPol checks (:369-388).  vector==true applies the latter.
+static int build_params(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels, const char *vname,
+                        bool vector, int nmom, int npol, AopParams &P, int *rc) {
+  *rc = 0;
+  if (!h || km < 1 || nobs < 0 || nch < 1 || nch > MAXCH || nq < 1 || !channels || !vname) {
+    ab200_set_error("getAOP*: bad argument"); return AB200_ERR_ARG;
+  }
+  memset(&P, 0, sizeof P);
+  P.km = km; P.nobs = nobs; P.nch = nch; P.nq = nq; P.nmom = nmom; P.npol = npol;
+  if (vector && nmom > h->nmom) { *rc = 99; return 0; }                       // MieObs_py.F90:313-317
+  for (int n = 0; n < nch; n++) {
+    int idx = -1;
+    for (int m = 0; m < h->nch; m++)
+      if (fabsf(channels[n] - 1.e9f * h->channels[m]) < 1.f) { idx = m; break; }
+    if (idx < 0) { *rc = 99; return 0; }
+    P.chidx0[n] = idx;
+  }
+  int na = 0;
+  for (int iq = 0; iq < nq; iq++) {
+    char nm[17];
+    for (int c = 0; c < 16; c++) nm[c] = vname[iq + (size_t)nq * c];          // character vname(nq,16)
+    nm[16] = 0;
+    int sp = -1;
+    int bin = ab200_mie_query_idx(h, nm, &sp);
+    if (bin < 0) continue;                                                    // idxTable == -1 -> cycle
+    TableDev &T = h->tab[sp];
+    if (!T.loaded) { ab200_set_error(std::string("tracer ") + nm + " maps to a table that was not loaded"); return AB200_ERR_ARG; }
+    if (bin > T.nbin) { ab200_set_error(std::string("tracer ") + nm + ": bin beyond table"); return AB200_ERR_ARG; }
+    if (na >= MAXQ) { ab200_set_error("too many active tracers"); return AB200_ERR_ARG; }
+    TracerDesc &d = P.d[na];
+    const long n3 = (long)T.nrh * T.nch * T.nbin;
+    const long b3 = (long)T.nrh * T.nch * (bin - 1), b2 = (long)T.nrh * (bin - 1);
+    float *B = T.pool;
+    d.bext = B + T.o_bext + b3; d.bsca = B + T.o_bsca + b3; d.g = B + T.o_g + b3; d.bbck = B + T.o_bbck + b3;
+    d.refr = B + T.o_refr + b3; d.refi = B + T.o_refi + b3; d.pback = B + T.o_pback + b3;
+    d.pmom = B + T.o_pmom + b3; d.vol = B + T.o_vol + b2; d.area = B + T.o_area + b2;
+    d.rha = B + T.o_rha; d.rhi = (const int *)(B + T.o_rhi);
+    d.nrh = T.nrh; d.n3 = (int)n3; d.nmomt = T.nmom; d.qidx = iq;
+    d.p22off = T.npol >= 5 ? (int)(4 * n3) : 0;
+    if (vector) {
+      if (nmom > T.nmom) { *rc = 666; return 0; }
+      if (npol <= T.npol) { d.npol_ = npol; d.sph = 0; }
+      else if (npol == 6 && T.npol == 4) { d.npol_ = 4; d.sph = 1; }
+      else { *rc = 777; return 0; }
+    }
+    na++;
+  }
+  P.nqa = na;
+  return 0;
+}
+
+extern "C" int ab200_get_aop_scalar_dev(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
+                                        const char *vname, const float *qm, const float *rh, float *tau,
+                                        float *ssa, float *g, void *stream, int *rc) {
+  AopParams P; int rc_;
+  int e = build_params(h, km, nobs, nch, nq, channels, vname, false, 0, 0, P, &rc_);
+  if (rc) *rc = rc_;
+  if (e || rc_) return e ? e : rc_;
+  long nout = (long)km * nch * nobs;
+  if (nout == 0) return 0;
+  k_aop_scalar<<<grid_for(nout, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(P, qm, rh, tau, ssa, g);
+  AB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ab200_get_aop_vector_dev(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
+                                        const char *vname, const float *qm, const float *rh, int nmom, int npol,
+                                        float *tau, float *ssa, float *g, float *pmom, void *stream, int *rc) {
+  AopParams P; int rc_;
+  if (npol < 1 || npol > 6 || nmom < 1) { ab200_set_error("getAOPvector: nMom>=1 and 1<=nPol<=6 required"); return AB200_ERR_ARG; }
+  int e = build_params(h, km, nobs, nch, nq, channels, vname, true, nmom, npol, P, &rc_);
+  if (rc) *rc = rc_;
+  if (e || rc_) return e ? e : rc_;
+  long nout = (long)km * nch * nobs;
+  if (nout == 0) return 0;
+  k_aop_vector<<<(unsigned)((nout + 31) / 32), 32 * VEC_NW, 0, (cudaStream_t)stream>>>(P, qm, rh, tau, ssa, g, pmom);
+  AB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// host-pointer drop-ins ---------------------------------------------------------------------------
+extern "C" int ab200_get_aop_scalar(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
+                                    const char *vname, int verbose, const float *qm, const float *rh, float *tau,
+                                    float *ssa, float *g, int *rc) {
+  (void)verbose;
+  if (!h) { ab200_set_error("null handle"); return AB200_ERR_ARG; }
+  size_t nin_q = (size_t)km * nq * nobs, nin_r = (size_t)km * nobs, nout = (size_t)km * nch * nobs;
+  AB_CUDA_OK(h->ws_in.reserve(4 * (nin_q + nin_r) + 256));
+  AB_CUDA_OK(h->ws_out.reserve(4 * 3 * nout + 256));
+  float *d_qm = h->ws_in.as<float>(), *d_rh = d_qm + nin_q;
+  float *d_tau = h->ws_out.as<float>(), *d_ssa = d_tau + nout, *d_g = d_ssa + nout;
+  AB_CUDA_OK(cudaMemcpyAsync(d_qm, qm, 4 * nin_q, cudaMemcpyHostToDevice, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(d_rh, rh, 4 * nin_r, cudaMemcpyHostToDevice, 0));
+  int e = ab200_get_aop_scalar_dev(h, km, nobs, nch, nq, channels, vname, d_qm, d_rh, d_tau, d_ssa, d_g, 0, rc);
+  if (e) return e;
+  AB_CUDA_OK(cudaMemcpyAsync(tau, d_tau, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(ssa, d_ssa, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(g, d_g, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+extern "C" int ab200_get_aop_vector(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
+                                    const char *vname, int verbose, const float *qm, const float *rh, int nmom,
+                                    int npol, float *tau, float *ssa, float *g, float *pmom, int *rc) {
+  (void)verbose;
+  if (!h) { ab200_set_error("null handle"); return AB200_ERR_ARG; }
+  size_t nin_q = (size_t)km * nq * nobs, nin_r = (size_t)km * nobs, nout = (size_t)km * nch * nobs;
+  size_t npm = nout * (size_t)std::max(nmom, 0) * (size_t)std::max(npol, 0);
+  AB_CUDA_OK(h->ws_in.reserve(4 * (nin_q + nin_r) + 256));
+  AB_CUDA_OK(h->ws_out.reserve(4 * (3 * nout + npm) + 256));
+  float *d_qm = h->ws_in.as<float>(), *d_rh = d_qm + nin_q;
+  float *d_tau = h->ws_out.as<float>(), *d_ssa = d_tau + nout, *d_g = d_ssa + nout, *d_pm = d_g + nout;
+  AB_CUDA_OK(cudaMemcpyAsync(d_qm, qm, 4 * nin_q, cudaMemcpyHostToDevice, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(d_rh, rh, 4 * nin_r, cudaMemcpyHostToDevice, 0));
+  int e = ab200_get_aop_vector_dev(h, km, nobs, nch, nq, channels, vname, d_qm, d_rh, nmom, npol, d_tau, d_ssa, d_g,
+                                   d_pm, 0, rc);
+  if (e) return e;
+  AB_CUDA_OK(cudaMemcpyAsync(tau, d_tau, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(ssa, d_ssa, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(g, d_g, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(pmom, d_pm, 4 * npm, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+extern "C" int ab200_get_ext(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
+                             const char *vname, int verbose, const float *qc, const float *qm, const float *rh,
+                             float *ext, float *sca, float *bsc, float *absc_sfc, float *absc_toa, float *depol,
+                             int *rc) {
+  (void)verbose;
+  AopParams P; int rc_;
+  int e = build_params(h, km, nobs, nch, nq, channels, vname, false, 0, 0, P, &rc_);
+  if (rc) *rc = rc_;
+  if (e || rc_) return e ? e : rc_;
+  size_t nin_q = (size_t)km * nq * nobs, nin_r = (size_t)km * nobs, nout = (size_t)km * nch * nobs;
+  if (nout == 0) return 0;
+  AB_CUDA_OK(h->ws_in.reserve(4 * (2 * nin_q + nin_r) + 256));
+  AB_CUDA_OK(h->ws_out.reserve(4 * 7 * nout + 256));
+  float *d_qc = h->ws_in.as<float>(), *d_qm = d_qc + nin_q, *d_rh = d_qm + nin_q;
+  float *o = h->ws_out.as<float>();
+  float *d_ext = o, *d_sca = o + nout, *d_bsc = o + 2 * nout, *d_tau = o + 3 * nout, *d_dep = o + 4 * nout,
+        *d_sfc = o + 5 * nout, *d_toa = o + 6 * nout;
+  AB_CUDA_OK(cudaMemcpyAsync(d_qc, qc, 4 * nin_q, cudaMemcpyHostToDevice, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(d_qm, qm, 4 * nin_q, cudaMemcpyHostToDevice, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(d_rh, rh, 4 * nin_r, cudaMemcpyHostToDevice, 0));
+  k_ext_accum<<<grid_for(nout, 256), 256>>>(P, d_qc, d_qm, d_rh, d_ext, d_sca, d_bsc, d_tau, d_dep);
+  k_ext_atten<<<grid_for(nout, 256), 256>>>(km, (long)nch * nobs, d_tau, d_bsc, d_sfc, d_toa);
+  AB_CUDA_OK(cudaGetLastError());
+  float *dsts[6] = {ext, sca, bsc, depol, absc_sfc, absc_toa};
+  float *srcs[6] = {d_ext, d_sca, d_bsc, d_dep, d_sfc, d_toa};
+  for (int i = 0; i < 6; i++) AB_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+extern "C" int ab200_get_int(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
+                             const char *vname, int verbose, const float *qc, const float *qm, const float *rh,
+                             float *vol, float *area, float *refr, float *refi, float *reff, int *rc) {
+  (void)verbose; (void)qm;
+  AopParams P; int rc_;
+  int e = build_params(h, km, nobs, nch, nq, channels, vname, false, 0, 0, P, &rc_);
+  if (rc) *rc = rc_;
+  if (e || rc_) return e ? e : rc_;
+  size_t nin_q = (size_t)km * nq * nobs, nin_r = (size_t)km * nobs, nout = (size_t)km * nch * nobs;
+  if (nout == 0) return 0;
+  AB_CUDA_OK(h->ws_in.reserve(4 * (nin_q + nin_r) + 256));
+  AB_CUDA_OK(h->ws_out.reserve(4 * 5 * nout + 256));
+  float *d_qc = h->ws_in.as<float>(), *d_rh = d_qc + nin_q;
+  float *o = h->ws_out.as<float>();
+  AB_CUDA_OK(cudaMemcpyAsync(d_qc, qc, 4 * nin_q, cudaMemcpyHostToDevice, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(d_rh, rh, 4 * nin_r, cudaMemcpyHostToDevice, 0));
+  k_int<<<grid_for(nout, 256), 256>>>(P, d_qc, d_rh, o, o + nout, o + 2 * nout, o + 3 * nout, o + 4 * nout);
+  AB_CUDA_OK(cudaGetLastError());
+  float *dsts[5] = {vol, area, refr, refi, reff};
+  for (int i = 0; i < 5; i++) AB_CUDA_OK(cudaMemcpyAsync(dsts[i], o + i * nout, 4 * nout, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+extern "C" int ab200_get_edge_vars(int km, int nobs, const float *airdens, const float *delp, float ptop,
+                                   float *pe, float *ze, float *te) {
+  if (km < 1 || nobs < 0) { ab200_set_error("getEdgeVars: bad argument"); return AB200_ERR_ARG; }
+  if (nobs == 0) return 0;
+  size_t nin = (size_t)km * nobs, nout = (size_t)(km + 1) * nobs;
+  float *d = nullptr;
+  AB_CUDA_OK(cudaMalloc(&d, 4 * (2 * nin + 3 * nout)));
+  float *d_ad = d, *d_dp = d + nin, *d_pe = d + 2 * nin, *d_ze = d_pe + nout, *d_te = d_ze + nout;
+  cudaMemcpyAsync(d_ad, airdens, 4 * nin, cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(d_dp, delp, 4 * nin, cudaMemcpyHostToDevice, 0);
+  k_edge_vars<<<(nobs + 127) / 128, 128>>>(km, nobs, d_ad, d_dp, ptop, d_pe, d_ze, d_te);
+  cudaMemcpyAsync(pe, d_pe, 4 * nout, cudaMemcpyDeviceToHost, 0);
+  cudaMemcpyAsync(ze, d_ze, 4 * nout, cudaMemcpyDeviceToHost, 0);
+  cudaMemcpyAsync(te, d_te, 4 * nout, cudaMemcpyDeviceToHost, 0);
+  cudaError_t e = cudaStreamSynchronize(0);
+  cudaFree(d);
+  if (e != cudaSuccess) { ab200_set_error(cudaGetErrorString(e)); return AB200_ERR_CUDA; }
+  return 0;
+}

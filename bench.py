@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- measures the AeroApps hot path on B200 (contract: one JSON line on rank 0).
+
+  python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.
+`value` is whole-job throughput with inputs resident in HBM; `e2e` is the same metric through the
+host-pointer C-ABI entry (pinned host buffers, H2D + D2H inside the timed region).  `roofline`
+describes the dominant kernel; `cpu_baseline` is the CPU oracle timed on a bounded sample.
+`--impl reference` times the reference algorithm's CPU restatement (oracle/) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "_source": "fallback"}
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# =================================================================================================
+# workload: Stage A scalar AOP, BASELINE config 1 (c90: 48 600 columns x 72 levels, 20 tracers, 550 nm)
+class AopScalarWorkload:
+    name = "mie_aop_scalar_c90"
+    metric = "Mie AOP voxels/sec (tau, ssa, g at 550 nm; 72 levels, 20 GOCART tracers, 7 species tables)"
+    unit = "voxels/s"
+    dtype = "f32"
+    km, nobs, nch = 72, 48600, 1
+
+    def __init__(self, nobs=None):
+        from aeroapps_b200 import mietables as mt
+        self.mt = mt
+        if nobs:
+            self.nobs = nobs
+        self.tables = mt.synthetic_tables(nmom=0)
+        self.chan_m = [550e-9]
+        self.channels = np.array([550.0], np.float32)
+        self.state = mt.synthetic_state(self.nobs, self.km, seed=20260101 + 1)
+        self.vnames = self.state["vnames"]
+        self.nq = len(self.vnames)
+        self.units_per_step = self.km * self.nobs * self.nch
+        # algorithmic bytes per voxel: 4*(nq+1) in + 12*nch out
+        self.bytes_per_unit = 4 * (self.nq + 1) + 12 * self.nch
+
+    def config(self):
+        return {"workload": self.name, "km": self.km, "nobs_per_gpu": self.nobs, "nq": self.nq, "nch": self.nch,
+                "l2": "inputs (%.0f MB/step) larger than the 126 MB L2" % (self.units_per_step * 4 * (self.nq + 1) / 1e6)}
+
+    # ---- GPU arm
+    def setup_gpu(self, torch, dev):
+        import ctypes as C
+        from aeroapps_b200 import MieObs_
+        from aeroapps_b200._lib import lib, check
+        self.C, self.lib, self.check = C, lib(), check
+        self.mie = MieObs_.ChemMie(self.chan_m, 0, self.tables)
+        self.vn = self.mt.pad_names(self.vnames)
+        st = self.state
+        self.d_qm = torch.from_numpy(np.ascontiguousarray(st["qm"].T)).to(dev)      # memory == Fortran (km,nq,nobs)
+        self.d_rh = torch.from_numpy(np.ascontiguousarray(st["rh"].T)).to(dev)
+        nout = self.units_per_step
+        self.d_out = [torch.empty(nout, dtype=torch.float32, device=dev) for _ in range(3)]
+        # pinned host buffers for the e2e leg
+        self.h_qm = torch.from_numpy(np.ascontiguousarray(st["qm"].T)).pin_memory()
+        self.h_rh = torch.from_numpy(np.ascontiguousarray(st["rh"].T)).pin_memory()
+        self.h_out = [torch.empty(nout, dtype=torch.float32).pin_memory() for _ in range(3)]
+        self.h2d = self.h_qm.numel() * 4 + self.h_rh.numel() * 4
+        self.d2h = 3 * nout * 4
+        self.launches_per_step = 1
+
+    def step_gpu(self, stream):
+        C = self.C
+        p = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_float))
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_get_aop_scalar_dev(
+            self.mie.handle, self.km, self.nobs, self.nch, self.nq, self.channels.ctypes.data_as(C.POINTER(C.c_float)),
+            self.vn.ctypes.data_as(C.c_char_p), p(self.d_qm), p(self.d_rh), p(self.d_out[0]), p(self.d_out[1]),
+            p(self.d_out[2]), C.c_void_p(stream), C.byref(rc)), "aop_scalar_dev")
+        assert rc.value == 0
+
+    def step_e2e(self):
+        C = self.C
+        p = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_float))
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_get_aop_scalar(
+            self.mie.handle, self.km, self.nobs, self.nch, self.nq, self.channels.ctypes.data_as(C.POINTER(C.c_float)),
+            self.vn.ctypes.data_as(C.c_char_p), 0, p(self.h_qm), p(self.h_rh), p(self.h_out[0]), p(self.h_out[1]),
+            p(self.h_out[2]), C.byref(rc)), "aop_scalar")
+        assert rc.value == 0
+
+    # ---- CPU arm (oracle = restatement of the reference Fortran; test infrastructure used as checker/baseline)
+    def setup_cpu(self, sample_cols):
+        from oracle import mie_oracle as orc
+        self.orc = orc.OracleMie(self.chan_m, 0, self.tables)
+        self.sample_cols = min(sample_cols, self.nobs)
+        st = self.state
+        self.c_qm = np.asfortranarray(st["qm"][:, :, :self.sample_cols])
+        self.c_rh = np.asfortranarray(st["rh"][:, :self.sample_cols])
+
+    def step_cpu(self, nthreads):
+        from concurrent.futures import ThreadPoolExecutor
+        n = self.sample_cols
+        edges = np.linspace(0, n, nthreads + 1).astype(int)
+        chunks = [(np.asfortranarray(self.c_qm[:, :, a:b]), np.asfortranarray(self.c_rh[:, a:b]))
+                  for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(lambda c: self.orc.getaopscalar(self.channels, self.vnames, c[0], c[1]), chunks))
+        dt = time.perf_counter() - t0
+        return self.km * n * self.nch, dt
+
+    def roofline(self, kernel_ms):
+        pk = peaks()
+        achieved = self.units_per_step * self.bytes_per_unit / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "k_aop_scalar", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["_source"],
+                "bytes_per_unit": self.bytes_per_unit}
+
+
+WORKLOADS = {"aop_scalar": AopScalarWorkload}
+DEFAULT_WORKLOAD = "aop_scalar"
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference algorithm's CPU implementation (oracle restatement; the Fortran
+    itself cannot be built here: no Fortran compiler, MAPL/ESMF un-vendored) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wl.setup_cpu(sample_cols=args.cpu_sample)
+    for _ in range(args.warmup):
+        wl.step_cpu(cores)
+    units = 0; secs = 0.0
+    for _ in range(args.steps):
+        u, dt = wl.step_cpu(cores)
+        units += u; secs += dt
+    v = units / secs
+    sample = f"{wl.sample_cols} of {wl.nobs} columns per step"
+    print(json.dumps({
+        "impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
+        "cpu_baseline": {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--nobs", type=int, default=0, help="override columns/pixels per GPU (debug)")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="columns/pixels in the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    wl = WORKLOADS[args.workload](nobs=args.nobs or None)
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import __graft_entry__ as g
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        g.build()
+    if dist:
+        dist.barrier()
+    wl.setup_gpu(torch, dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        wl.step_gpu(stream)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local) as cs:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            wl.step_gpu(stream)
+            ev[i + 1].record()
+        barrier()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        # keep the sampler alive long enough for at least a few samples on very short runs
+        if total_ms < 1500:
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                wl.step_gpu(stream)
+            torch.cuda.synchronize()
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = wl.units_per_step * world * args.steps / (total_ms * 1e-3)
+
+    # e2e leg: host (pinned) buffers through the host-pointer C-ABI call, copies inside the timed region
+    for _ in range(2):
+        wl.step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        wl.step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = wl.units_per_step * world * e2e_steps / (float(t.item()) * 1e-3)
+
+    out = None
+    if rank == 0:
+        kernel_ms = float(np.mean(per_step)) / wl.launches_per_step if wl.launches_per_step == 1 else None
+        out = {
+            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
+            "roofline": wl.roofline(float(np.mean(per_step))),
+            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
+            "gpu_launches": wl.launches_per_step * args.steps, "clocks": cs.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            wl.setup_cpu(sample_cols=args.cpu_sample)
+            wl.step_cpu(cores)
+            u, dt = wl.step_cpu(cores)
+            out["cpu_baseline"] = {"value": u / dt, "unit": wl.unit, "cores": cores, "kind": "port",
+                                   "sample": f"{wl.sample_cols} of {wl.nobs} columns, 1 pass"}
+        print(json.dumps(out))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
