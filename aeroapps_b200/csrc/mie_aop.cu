@@ -20,10 +20,12 @@
 #include <map>
 #include <algorithm>
 #include <cctype>
+#include <cstdint>
 
 #define NRHHASH 991
 #define MAXQ 40          // max tracers per call (reference uses 15-22)
 #define MAXCH 16         // max channels per call
+#define MAXH 2           // RH-hash classes handled by the tiled kernel (more -> generic kernel)
 
 // ------------------------------------------------------------------------------------------------
 struct TableDev {
@@ -32,6 +34,8 @@ struct TableDev {
   long o_rh, o_bext, o_bsca, o_bbck, o_g, o_refr, o_refi, o_pback, o_pmom, o_reff, o_gf, o_rhop, o_rhod,
       o_vol, o_area, o_rha, o_rhi, total;
   bool loaded = false;
+  std::vector<int> h_rhi;      // host copies of the RH hash (to find tables that hash identically)
+  std::vector<float> h_rha;
 };
 
 struct ab200_mie {
@@ -174,6 +178,11 @@ struct AopParams {
   int nmom, npol;
   int chidx0[MAXCH];                 // 0-based table channel per requested channel
   TracerDesc d[MAXQ];
+  // RH-hash classes (tables whose rh grids hash identically share one snap per voxel)
+  int nh, nrh_max;
+  int hcls[MAXQ];
+  int qoff[MAXQ];                    // km*qidx: offset of the tracer inside a column of qm
+  const float *hrha[MAXH]; const int *hrhi[MAXH]; int hnrh[MAXH];
 };
 
 __device__ __forceinline__ Snap make_snap(const TracerDesc &d, int isnap) {
@@ -220,6 +229,141 @@ __global__ void __launch_bounds__(256) k_aop_scalar(const __grid_constant__ AopP
     float dd = __fmul_rn(s, t);
     if (dd > 0.f) gg = __fdiv_rn(gg, dd);
     __stcs(tau + o, t); __stcs(ssa + o, s); __stcs(g + o, gg);
+  }
+}
+
+// ---- getAOPscalar, tiled + TMA-pipelined variant (the one bench.py times).
+// A tile = C whole columns: qm(:,:,i0:i0+C) and rh(:,i0:i0+C) are CONTIGUOUS in HBM, so each tile is two
+// 1-D bulk copies (cp.async.bulk -> UBLKCP) into shared memory, completion tracked by an mbarrier, double
+// buffered; a persistent CTA walks tiles blockIdx.x, +gridDim.x, ...  Table values are pre-paired in shared
+// memory as (T[irh],T[irh+1]) so a lerp costs one LDS.128/LDS.64 instead of six LDG with 64-bit addressing.
+// Arithmetic (and its order) is identical to k_aop_scalar -> still bit-exact.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct TileCfg { int C, ntiles, nrhp, stage_floats, off_pairB, off_ssaT, off_stage; };
+
+// SNAP: ssa_ = bsca/bext depends on the voxel only through isnap (the RH is snapped to a 991-entry grid),
+// so each CTA tabulates it once per (tracer, channel, isnap) with the reference's own operations and the
+// hot loop replaces a lerp + IEEE division by one LDS.  ONEH: all active tables share one RH hash.
+template <bool SNAP, bool ONEH>
+__global__ void __launch_bounds__(640) k_aop_scalar_tiled(const __grid_constant__ AopParams P, const TileCfg T,
+                                                          const float *__restrict__ qm, const float *__restrict__ rh,
+                                                          float *__restrict__ tau, float *__restrict__ ssa,
+                                                          float *__restrict__ g) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smraw);
+  float4 *pairA = reinterpret_cast<float4 *>(smraw + 128);            // (b0,b1,g0,g1)[a][n][irh]
+  float2 *pairB = reinterpret_cast<float2 *>(smraw + T.off_pairB);    // (s0,s1)
+  float *ssaT = reinterpret_cast<float *>(smraw + T.off_ssaT);        // [a][n][isnap-1]  (SNAP only)
+  float *stages = reinterpret_cast<float *>(smraw + T.off_stage);
+  const int tid = threadIdx.x;
+  const int tile_vox = T.C * P.km;                       // voxels per tile
+  const unsigned qm_bytes = (unsigned)tile_vox * P.nq * 4u, rh_bytes = (unsigned)tile_vox * 4u;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int idx = tid; idx < P.nqa * P.nch * T.nrhp; idx += blockDim.x) {
+    int irh = idx % T.nrhp, an = idx / T.nrhp, n = an % P.nch, a = an / P.nch;
+    const TracerDesc &d = P.d[a];
+    int i0 = min(irh, d.nrh - 1), i1 = min(irh + 1, d.nrh - 1), co = d.nrh * P.chidx0[n];
+    pairA[idx] = make_float4(d.bext[co + i0], d.bext[co + i1], d.g[co + i0], d.g[co + i1]);
+    pairB[idx] = make_float2(d.bsca[co + i0], d.bsca[co + i1]);
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int st) {
+    float *sq = stages + st * T.stage_floats;
+    mbar_expect_tx(&bars[st], qm_bytes + rh_bytes);
+    bulk_g2s(sq, qm + (size_t)tile * tile_vox * P.nq, qm_bytes, &bars[st]);
+    bulk_g2s(sq + tile_vox * P.nq, rh + (size_t)tile * tile_vox, rh_bytes, &bars[st]);
+  };
+  if (tid == 0 && (int)blockIdx.x < T.ntiles) issue(blockIdx.x, 0);
+  if (SNAP) {
+    for (int idx = tid; idx < P.nqa * P.nch * NRHHASH; idx += blockDim.x) {
+      int is = idx % NRHHASH, an = idx / NRHHASH;
+      const int h = ONEH ? 0 : P.hcls[an / P.nch];
+      const float arh = __ldg(P.hrha[h] + is), oma = __fsub_rn(1.f, arh);
+      const int pi = an * T.nrhp + __ldg(P.hrhi[h] + is) - 1;
+      const float4 A = pairA[pi];
+      const float2 B = pairB[pi];
+      const float bext = __fadd_rn(__fmul_rn(A.x, oma), __fmul_rn(A.y, arh));
+      const float bsca = __fadd_rn(__fmul_rn(B.x, oma), __fmul_rn(B.y, arh));
+      ssaT[idx] = __fdiv_rn(bsca, bext);
+    }
+    __syncthreads();
+  }
+
+  const int col = tid / P.km, k = tid - col * P.km;
+  const int qbase = k + P.km * P.nq * col;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x, it++) {
+    const int st = it & 1;
+    if (tid == 0 && tile + (int)gridDim.x < T.ntiles) issue(tile + gridDim.x, st ^ 1);
+    mbar_wait(&bars[st], (it >> 1) & 1);
+    if (tid < tile_vox) {
+      const float *sq = stages + st * T.stage_floats;
+      const int isnap = snap_index(sq[tile_vox * P.nq + tid]);
+      int irh0, irh1 = 0; float arh0, oma0, arh1 = 0.f, oma1 = 0.f;
+      arh0 = __ldg(P.hrha[0] + isnap - 1); irh0 = __ldg(P.hrhi[0] + isnap - 1) - 1; oma0 = __fsub_rn(1.f, arh0);
+      if (!ONEH) { arh1 = __ldg(P.hrha[1] + isnap - 1); irh1 = __ldg(P.hrhi[1] + isnap - 1) - 1; oma1 = __fsub_rn(1.f, arh1); }
+      const float *qv = sq + qbase;
+      for (int n = 0; n < P.nch; n++) {
+        float t = 0.f, s = 0.f, gg = 0.f;
+#pragma unroll 4
+        for (int a = 0; a < P.nqa; a++) {
+          const bool h1 = ONEH ? false : (P.hcls[a] != 0);
+          const int irh = h1 ? irh1 : irh0;
+          const float arh = h1 ? arh1 : arh0, oma = h1 ? oma1 : oma0;
+          const int an = a * P.nch + n;
+          const float4 A = pairA[an * T.nrhp + irh];
+          const float q = qv[P.qoff[a]];
+          const float bext = __fadd_rn(__fmul_rn(A.x, oma), __fmul_rn(A.y, arh));
+          const float gas = __fadd_rn(__fmul_rn(A.z, oma), __fmul_rn(A.w, arh));
+          float ssa_;
+          if (SNAP) ssa_ = ssaT[an * NRHHASH + isnap - 1];
+          else {
+            const float2 B = pairB[an * T.nrhp + irh];
+            ssa_ = __fdiv_rn(__fadd_rn(__fmul_rn(B.x, oma), __fmul_rn(B.y, arh)), bext);
+          }
+          const float tau_ = __fmul_rn(bext, q);
+          t = __fadd_rn(t, tau_);
+          s = __fadd_rn(s, __fmul_rn(ssa_, tau_));
+          gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(gas, ssa_), tau_));
+        }
+        if (t > 0.f) s = __fdiv_rn(s, t);
+        float dd = __fmul_rn(s, t);
+        if (dd > 0.f) gg = __fdiv_rn(gg, dd);
+        const size_t o = k + (size_t)P.km * (n + (size_t)P.nch * ((size_t)tile * T.C + col));
+        __stcs(tau + o, t); __stcs(ssa + o, s); __stcs(g + o, gg);
+      }
+    }
+    __syncthreads();          // everyone is done with stage st before it is refilled next iteration
   }
 }
 
@@ -577,6 +721,9 @@ extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh
   k_rhhash<<<(std::max(NRHHASH, nrh) + 127) / 128, 128>>>(d_rh, nrh, P + T.o_rh, P + T.o_rha, (int *)(P + T.o_rhi));
   AB_CUDA_OK(cudaGetLastError());
   AB_CUDA_OK(cudaDeviceSynchronize());
+  T.h_rhi.resize(NRHHASH); T.h_rha.resize(NRHHASH);
+  AB_CUDA_OK(cudaMemcpy(T.h_rhi.data(), P + T.o_rhi, 4 * NRHHASH, cudaMemcpyDeviceToHost));
+  AB_CUDA_OK(cudaMemcpy(T.h_rha.data(), P + T.o_rha, 4 * NRHHASH, cudaMemcpyDeviceToHost));
   T.loaded = true;
   return 0;
 }
@@ -619,6 +766,7 @@ static int build_params(ab200_mie *h, int km, int nobs, int nch, int nq, const f
     P.chidx0[n] = idx;
   }
   int na = 0;
+  std::vector<const TableDev *> classes;
   for (int iq = 0; iq < nq; iq++) {
     char nm[17];
     for (int c = 0; c < 16; c++) nm[c] = vname[iq + (size_t)nq * c];          // character vname(nq,16)
@@ -640,6 +788,19 @@ static int build_params(ab200_mie *h, int km, int nobs, int nch, int nq, const f
     d.rha = B + T.o_rha; d.rhi = (const int *)(B + T.o_rhi);
     d.nrh = T.nrh; d.n3 = (int)n3; d.nmomt = T.nmom; d.qidx = iq;
     d.p22off = T.npol >= 5 ? (int)(4 * n3) : 0;
+    {
+      int c = -1;
+      for (size_t j = 0; j < classes.size(); j++)
+        if (classes[j] == &T || (classes[j]->nrh == T.nrh && classes[j]->h_rhi == T.h_rhi &&
+                                 memcmp(classes[j]->h_rha.data(), T.h_rha.data(), 4 * NRHHASH) == 0)) { c = (int)j; break; }
+      if (c < 0) {
+        c = (int)classes.size(); classes.push_back(&T);
+        if (c < MAXH) { P.hrha[c] = d.rha; P.hrhi[c] = d.rhi; P.hnrh[c] = T.nrh; }
+      }
+      P.hcls[na] = c;
+      P.qoff[na] = km * iq;
+      P.nrh_max = std::max(P.nrh_max, T.nrh);
+    }
     if (vector) {
       if (nmom > T.nmom) { *rc = 666; return 0; }
       if (npol <= T.npol) { d.npol_ = npol; d.sph = 0; }
@@ -649,8 +810,11 @@ static int build_params(ab200_mie *h, int km, int nobs, int nch, int nq, const f
     na++;
   }
   P.nqa = na;
+  P.nh = (int)classes.size();
   return 0;
 }
+
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 extern "C" int ab200_get_aop_scalar_dev(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels,
                                         const char *vname, const float *qm, const float *rh, float *tau,
@@ -661,8 +825,52 @@ extern "C" int ab200_get_aop_scalar_dev(ab200_mie *h, int km, int nobs, int nch,
   if (e || rc_) return e ? e : rc_;
   long nout = (long)km * nch * nobs;
   if (nout == 0) return 0;
-  k_aop_scalar<<<grid_for(nout, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(P, qm, rh, tau, ssa, g);
-  AB_CUDA_OK(cudaGetLastError());
+  // tiled/TMA kernel whenever its layout preconditions hold; the generic kernel takes the rest (and the
+  // tail columns that do not fill a tile)
+  int done_cols = 0;
+  if (P.nqa > 0 && P.nh <= MAXH && km <= 256 && ((uintptr_t)qm % 16 == 0) && ((uintptr_t)rh % 16 == 0)) {
+    TileCfg T;
+    int c0 = 4 / gcd_i(km, 4);
+    auto cfg = [&](int target, bool snap, size_t &smem, int &threads) {
+      T.C = c0 * std::max(1, (target + km * c0 - 1) / (km * c0));
+      T.ntiles = nobs / T.C;
+      T.nrhp = P.nrh_max;
+      T.stage_floats = (T.C * km * (nq + 1) + 31) / 32 * 32;
+      threads = (T.C * km + 31) / 32 * 32;
+      size_t o = 128 + (size_t)P.nqa * nch * T.nrhp * 16;
+      T.off_pairB = (int)o; o += (size_t)P.nqa * nch * T.nrhp * 8;
+      o = (o + 15) / 16 * 16;
+      T.off_ssaT = (int)o; if (snap) o += (size_t)P.nqa * nch * NRHHASH * 4;
+      o = (o + 127) / 128 * 128;
+      T.off_stage = (int)o; o += 2 * (size_t)T.stage_floats * 4;
+      smem = o;
+    };
+    size_t smem; int threads;
+    bool snap = true;
+    cfg(512, true, smem, threads);                        // ssa table + 2 stages of ~8 columns: 1 CTA/SM
+    if (smem > 220 * 1024 || threads > 640 || T.ntiles < 148) { snap = false; cfg(256, false, smem, threads); }
+    if (T.ntiles > 0 && threads <= 640 && smem <= 220 * 1024) {
+      auto kern = snap ? (P.nh == 1 ? k_aop_scalar_tiled<true, true> : k_aop_scalar_tiled<true, false>)
+                       : (P.nh == 1 ? k_aop_scalar_tiled<false, true> : k_aop_scalar_tiled<false, false>);
+      AB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int bps = 1;
+      AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem));
+      int nsm = 148;
+      int grid = std::min(T.ntiles, nsm * std::max(1, bps));
+      kern<<<grid, threads, smem, (cudaStream_t)stream>>>(P, T, qm, rh, tau, ssa, g);
+      AB_CUDA_OK(cudaGetLastError());
+      done_cols = T.ntiles * T.C;
+    }
+  }
+  if (done_cols < nobs) {
+    AopParams Q = P;
+    Q.nobs = nobs - done_cols;
+    long nrest = (long)km * nch * Q.nobs;
+    k_aop_scalar<<<grid_for(nrest, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        Q, qm + (size_t)km * nq * done_cols, rh + (size_t)km * done_cols, tau + (size_t)km * nch * done_cols,
+        ssa + (size_t)km * nch * done_cols, g + (size_t)km * nch * done_cols);
+    AB_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 

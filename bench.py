@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--nobs", type=int, default=0, help="override columns/pixels per GPU (debug)")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="columns/pixels in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=48600, help="columns/pixels in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
