@@ -1,0 +1,657 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU oracle for Stage B: a C++ restatement of the part of VLIDORT 2.8.3 that the
+ * AeroApps wrappers exercise (observation geometry, one geometry, upwelling TOA radiance, Green's-function
+ * particular integral, delta-M, FO correction, Lambertian or supplied BRDF Fourier components).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+ *
+ * Follows (paths relative to /root/reference/src/Components/rtms/RTSI/VLIDORT2p8p3/vlidort_main/regular/):
+ *   vlidort_masters_V2p8p3.f90:1139-2760,3107-5085   VLIDORT_MASTER / VLIDORT_FOURIER
+ *   vlidort_inputs.f90:3396-3460,3692-3821,3825-4603 checks + VLIDORT_DERIVE_INPUT
+ *   vlidort_geometry.f90:119-700                     VLIDORT_CHAPMAN
+ *   vlidort_miscsetups.f90:370-1295,1296-1617,2273-2935,3187-3424
+ *   vlidort_solutions.f90:150-1650,2649-3073         QHOM/UHOM/HMULT/GBEAM/GUSER
+ *   vlidort_bvproblem.f90:147-2314                   BVP set-up and solution (banded LU)
+ *   vlidort_intensity.f90:145-646,1096-1499          UPUSER_INTENSITY / GET_BOA_SOURCE
+ *   vlidort_PostProcessing.f90:139-454               WHOLELAYER_STERM_UP
+ *   vlidort_converge.f90:825-1231                    VLIDORT_CONVERGE_OBSGEO
+ *   vlidort_vfo_interface.f90:128-728                VFO_MASTER_INTERFACE
+ * Pinned against VLIDORT's own saved results (tests/test_vlidort_oracle_golden.py).
+ */
+#include "vl_fo.h"
+#include "vlidort_oracle.h"
+#include <cstdio>
+
+using namespace vl;
+
+namespace {
+
+struct Ctx {
+  int S, N, L, NM, n, N2;   /* nstokes, nstreams, nlayers, nmoments, nstokes*nstreams, 2*nstreams */
+};
+
+inline int MI(int o1, int o2) { return 4 * o1 + o2; }   /* MUELLER_INDEX - 1, 0-based o1,o2 */
+
+}  // namespace
+
+extern "C" int vl_master(const vl_input *in, vl_output *out) {
+  memset(out, 0, sizeof(*out));
+  const int S = in->nstokes, N = in->nstreams, L = in->nlayers, n = S * N, N2 = 2 * N, NMI = in->nmoments_input;
+  const int TAYLOR_ORDER = 3;
+  const double FLUX_FACTOR = in->flux_factor;
+  /* ---------------- input checks that lead to STATUS_INPUTCHECK != 0 (-> rc=3 in the AeroApps glue) */
+  if (!(in->sza >= 0.0 && in->sza < 90.0) || !(in->raa >= 0.0 && in->raa <= 360.0) || !(in->vza >= 0.0 && in->vza <= 90.0)) { out->status = 3; return 3; }
+  if (in->do_lambertian && (in->albedo < 0.0 || in->albedo > 1.0)) { out->status = 3; return 3; }
+  for (int k = 0; k < L; k++) {
+    if (in->deltau[k] <= 0.0 || in->omega[k] > 1.0 - OMEGA_SMALLNUM || in->omega[k] < OMEGA_SMALLNUM ||
+        in->greekmat[((size_t)0 * L + k) * 16 + 0] != 1.0) { out->status = 3; return 3; }
+  }
+  const bool do_focorr = in->do_focorr != 0, do_deltam = in->do_deltam != 0, lamb = in->do_lambertian != 0;
+  const bool planpar = in->do_plane_parallel != 0;
+  const bool msmode = do_focorr;                 /* DO_MSMODE_VLIDORT: FULLRAD + FOCORR */
+  const bool dbcorrection = do_focorr;
+  /* ---------------- DERIVE_INPUT */
+  const int NM = std::min(2 * N - 1, NMI);       /* NMOMENTS */
+  std::vector<double> qx(N), qw(N), qsw(N), qhw(N);
+  if (N == 1) { qx[0] = std::sqrt(1.0 / 3.0); qw[0] = 1.0; } else getquad2(0.0, 1.0, N, qx.data(), qw.data());
+  for (int i = 0; i < N; i++) { qsw[i] = qx[i] * qw[i]; qhw[i] = 0.5 * qw[i]; }
+  const double cos_sza = std::cos(in->sza * DEG_TO_RAD);
+  const double ustream = std::cos(DEG_TO_RAD * in->vza), usec = 1.0 / ustream;
+  const double DMAT[4] = {1.0, 1.0, -1.0, -1.0};
+  const double *GIN = in->greekmat;
+#define GIN_(l, k, q) GIN[((size_t)(l) * L + (k)) * 16 + (q)]
+  std::vector<char> layscat((size_t)(NM + 1) * L, 1);          /* DO_LAYER_SCATTERING(m,n) */
+  for (int M = 3; M <= NM; M++) {
+    int QC = NM - M + 1;
+    for (int k = 0; k < L; k++) {
+      int Q = 0;
+      for (int l = M; l <= NM; l++) if (GIN_(l, k, 0) == 0.0) Q++;
+      layscat[(size_t)M * L + k] = (Q < QC);
+    }
+  }
+  /* ---------------- CHAPMAN */
+  std::vector<double> chap((size_t)L * L, 0.0);                /* chap[n][k], k<=n */
+  {
+    const double *H = in->height_grid;
+    std::vector<double> radii(L + 1), delz(L + 1, 0.0);
+    for (int k = 0; k <= L; k++) radii[k] = H[k] + in->earth_radius;
+    for (int k = 1; k <= L; k++) delz[k] = H[k - 1] - H[k];
+    double mu_toa = std::cos(in->sza * DEG_TO_RAD), sn_toa = std::sqrt(1.0 - mu_toa * mu_toa);
+    if (planpar) { for (int nn = 1; nn <= L; nn++) for (int k = 1; k <= nn; k++) chap[(size_t)(nn - 1) * L + k - 1] = 1.0 / mu_toa; }
+    else if (sn_toa == 0.0) { for (int nn = 1; nn <= L; nn++) for (int k = 1; k <= nn; k++) chap[(size_t)(nn - 1) * L + k - 1] = 1.0; }
+    else {
+      for (int nn = 1; nn <= L; nn++) {
+        double sinth1 = sn_toa * radii[nn] / radii[0], sth1 = std::asin(sinth1), re_upper = radii[0];
+        for (int k = 1; k <= nn; k++) {
+          double re_lower = re_upper - delz[k];
+          double sinth2 = re_upper * sinth1 / re_lower, sth2 = std::asin(sinth2);
+          double phi = sth2 - sth1, dist = re_upper * std::sin(phi) / sinth2;
+          chap[(size_t)(nn - 1) * L + k - 1] = dist / delz[k];
+          re_upper = re_lower; sinth1 = sinth2; sth1 = sth2;
+        }
+      }
+    }
+  }
+  /* ---------------- DELTAMSCALE + SSALBINIT */
+  std::vector<double> deltau(L), omega(L), fac1(L, 1.0), truncf(L, 0.0), gtot((size_t)(NM + 1) * L * 16, 0.0);
+#define GT_(l, k, q) gtot[((size_t)(l) * L + (k)) * 16 + (q)]
+  static const int KT1[4] = {0, 5, 10, 15}, KT2[4] = {1, 4, 11, 14};
+  for (int k = 0; k < L; k++) {
+    if (do_deltam) {
+      int nm1 = NM + 1; double dnm1 = (double)(2 * nm1 + 1);
+      double fdel = (nm1 <= NMI ? GIN_(nm1, k, 0) : 0.0) / dnm1, fac2 = 1.0 - fdel;
+      fac1[k] = 1.0 - fdel * in->omega[k]; truncf[k] = fdel;
+      for (int l = 0; l <= NM; l++) {
+        double fdnl1 = fdel * (double)(2 * l + 1);
+        if (S > 1) for (int q = 0; q < 4; q++) { GT_(l, k, KT1[q]) = (GIN_(l, k, KT1[q]) - fdnl1) / fac2; GT_(l, k, KT2[q]) = GIN_(l, k, KT2[q]) / fac2; }
+        else GT_(l, k, 0) = (GIN_(l, k, 0) - fdnl1) / fac2;
+      }
+      GT_(0, k, 0) = 1.0;
+      deltau[k] = in->deltau[k] * fac1[k];
+      omega[k] = in->omega[k] * fac2 / fac1[k];
+    } else {
+      omega[k] = in->omega[k]; deltau[k] = in->deltau[k];
+      for (int l = 0; l <= NM; l++) {
+        if (S > 1) for (int q = 0; q < 4; q++) { GT_(l, k, KT1[q]) = GIN_(l, k, KT1[q]); GT_(l, k, KT2[q]) = GIN_(l, k, KT2[q]); }
+        else GT_(l, k, 0) = GIN_(l, k, 0);
+      }
+    }
+  }
+  for (int k = 0; k < L; k++) {                               /* singularity busters, vlidort_miscsetups.f90:624-656 */
+    if (omega[k] > 0.999999999) omega[k] = 0.999999999; else if (omega[k] < 1.0e-9) omega[k] = 1.0e-9;
+    if (NM >= 1) {
+      double g = GT_(1, k, 0) / 3.0;
+      if (g > 0.999999999) g = 0.999999999; else if (g < -0.999999999) g = -0.999999999;
+      else if (g >= 0.0 && g < 1.0e-9) g = 1.0e-9; else if (g < 0.0 && g > -1.0e-9) g = -1.0e-9;
+      GT_(1, k, 0) = 3.0 * g;
+    }
+  }
+  std::vector<double> og((size_t)(NM + 1) * L * 16, 0.0);     /* OMEGA_GREEK(l,n,o1,o2) */
+#define OG_(l, k, o1, o2) og[((size_t)(l) * L + (k)) * 16 + MI(o1, o2)]
+  for (int k = 0; k < L; k++) for (int l = 0; l <= NM; l++) for (int o1 = 0; o1 < S; o1++) for (int o2 = 0; o2 < S; o2++)
+    OG_(l, k, o1, o2) = omega[k] * GT_(l, k, MI(o1, o2));
+  /* slant optical depths */
+  std::vector<double> dslant((size_t)L * L, 0.0), taugrid(L + 1, 0.0);
+  for (int k = 0; k < L; k++) taugrid[k + 1] = taugrid[k] + deltau[k];
+  for (int nn = 0; nn < L; nn++) for (int k = 0; k <= nn; k++) dslant[(size_t)nn * L + k] = in->deltau[k] * chap[(size_t)nn * L + k] * (do_deltam ? fac1[k] : 1.0);
+  /* ---------------- QSPREP */
+  std::vector<double> avsec(L, 0.0), itrans(L, 0.0), tdmubar(L, 0.0), tauslant(L + 1, 0.0);
+  int beam_cutoff = L;                                          /* 1-based layer index */
+  double tau_solar;
+  if (planpar) {
+    double sec0 = 1.0 / cos_sza;
+    for (int nn = 1; nn <= L; nn++) {
+      tauslant[nn] = taugrid[nn] * sec0;
+      if (nn <= beam_cutoff) {
+        if (tauslant[nn] > MAX_TAU_SPATH) beam_cutoff = nn;
+        avsec[nn - 1] = sec0; itrans[nn - 1] = std::exp(-taugrid[nn - 1] * sec0);
+      }
+    }
+    tau_solar = tauslant[L];
+  } else {
+    for (int nn = 1; nn <= L; nn++) { double t = 0.0; for (int k = 0; k < nn; k++) t += dslant[(size_t)(nn - 1) * L + k]; tauslant[nn] = t; }
+    tau_solar = tauslant[L];
+    double s_t_1 = 0.0, s_t_0 = 1.0;
+    for (int nn = 1; nn <= L; nn++) {
+      if (nn <= beam_cutoff) {
+        if (tauslant[nn] > MAX_TAU_SPATH) beam_cutoff = nn; else s_t_1 = std::exp(-tauslant[nn]);
+        avsec[nn - 1] = (tauslant[nn] - tauslant[nn - 1]) / deltau[nn - 1];
+        itrans[nn - 1] = s_t_0; s_t_0 = s_t_1;
+      }
+    }
+  }
+  double trans_solar_beam = 0.0; bool do_reflected_directbeam = false;
+  if (tau_solar < MAX_TAU_SPATH) { trans_solar_beam = std::exp(-tau_solar); do_reflected_directbeam = true; }
+  /* ---------------- PREPTRANS + EMULT */
+  std::vector<double> tduserm(L, 0.0), itrans_userm(L, 0.0), emult_up(L, 0.0), sigma_p(L, 0.0);
+  for (int k = 0; k < L; k++) {
+    if (k + 1 <= beam_cutoff) { double sp = deltau[k] * avsec[k]; tdmubar[k] = sp > MAX_TAU_SPATH ? 0.0 : std::exp(-sp); }
+    itrans_userm[k] = itrans[k] * usec;
+    double sp = deltau[k] * usec; tduserm[k] = sp > MAX_TAU_UPATH ? 0.0 : std::exp(-sp);
+    sigma_p[k] = avsec[k] + usec;
+    if (k + 1 <= beam_cutoff) { double wudel = tdmubar[k] * tduserm[k]; emult_up[k] = itrans_userm[k] * (1.0 - wudel) / sigma_p[k]; }
+  }
+  /* ---------------- FO (VFO_MASTER_INTERFACE) */
+  double fo_ss[4] = {0, 0, 0, 0}, fo_db[4] = {0, 0, 0, 0};
+  if (do_focorr) {
+    int mode = planpar ? 0 : (in->do_focorr_nadir ? 1 : 2);
+    FOGeom G;
+    fo_geometry(mode, L, in->nfine, in->earth_radius, in->height_grid, in->sza, in->vza, in->raa, G);
+    std::vector<double> gs1, gs2; double rot[4];
+    fo_spherfuncs(NMI, S, in->sza, in->vza, in->raa, G.cosscat, gs1, gs2, rot);
+    std::vector<double> ext(L), dus(L);
+    for (int k = 0; k < L; k++) {
+      dus[k] = do_deltam ? deltau[k] : in->deltau[k];
+      ext[k] = dus[k] / (in->height_grid[k] - in->height_grid[k + 1]);
+    }
+    FOOptical O;
+    O.L = L; O.nstokes = S; O.nmoms_in = NMI; O.do_deltam = do_deltam; O.lambertian = lamb; O.flux = FLUX_FACTOR / PI4;
+    O.extinction = ext.data(); O.deltaus = dus.data(); O.omega = in->omega; O.truncfac = truncf.data(); O.greek = GIN;
+    O.albedo = in->albedo; O.reflec16 = in->exactdb;
+    fo_ssv_integral_up(mode, G, O, gs1, gs2, rot, fo_ss, fo_db);
+  }
+  for (int o = 0; o < S; o++) { out->stokes_ss[o] = fo_ss[o]; out->stokes_db[o] = fo_db[o]; }
+
+  /* ---------------- Fourier loop */
+  const int NSA = N + 2;                                        /* quadrature, 1 user stream, 1 beam */
+  std::vector<double> XM(NSA);
+  for (int i = 0; i < N; i++) XM[i] = qx[i];
+  XM[N] = ustream; XM[N + 1] = cos_sza;
+  /* saved Pi-matrix helper arrays (computed at m=0, reused) */
+  std::vector<double> DF_L(NM + 2), DF_LP1(NM + 2), DF_2LP1(NM + 2), DF_LSQM4(NM + 2, 0.0), DF_RT(NM + 2, 0.0), ZHELP(NM + 2, 0.0);
+  std::vector<double> PLEG20(NSA), UMXSQ(NSA), RT_UMXSQ(NSA), X_RT_UMXSQ(NSA), UPXSQ_D(NSA), M2X_D(NSA), PIMM_11(NSA, 0.0), PIMM_KM(NSA, 0.0);
+  std::vector<double> PISIGN((size_t)(NM + 1) * (NM + 1), 1.0);
+  /* PI(l,i,4,4) */
+  std::vector<double> PIv((size_t)(NM + 2) * NSA * 16);
+#define PI_(l, i, a, b) PIv[(((size_t)(l) * NSA + (i)) * 4 + (a)) * 4 + (b)]
+  std::vector<double> XQP((size_t)(NM + 1) * N * 16), XQM(XQP.size()), XQM_PRE(XQP.size()), XQM_POST(XQP.size()), XQP_PRE(XQP.size());
+#define Q_(A, l, i, a, b) A[(((size_t)(l) * N + (i)) * 4 + (a)) * 4 + (b)]
+  std::vector<double> XUP((size_t)(NM + 1) * 16), XUM(XUP.size()), XUP_PRE(XUP.size()), XUM_POST(XUP.size()), X0P(XUP.size());
+#define U_(A, l, a, b) A[((size_t)(l) * 4 + (a)) * 4 + (b)]
+  /* per-layer homogeneous solutions */
+  std::vector<double> XPOS((size_t)L * n * N2 * S), XNEG(XPOS.size()), KEIG((size_t)L * n), TDE((size_t)L * n), NORMS((size_t)L * n);
+#define XP_(k, e, i, o) XPOS[(((size_t)(k) * n + (e)) * N2 + (i)) * S + (o)]
+#define XN_(k, e, i, o) XNEG[(((size_t)(k) * n + (e)) * N2 + (i)) * S + (o)]
+  std::vector<double> UHOM_UPDN((size_t)L * n * S), UHOM_UPUP(UHOM_UPDN.size()), HMULT1((size_t)L * n), HMULT2((size_t)L * n), ZETA_M((size_t)L * n), ZETA_P((size_t)L * n);
+  std::vector<char> HSINGO((size_t)L * n);
+  std::vector<double> WUPPER((size_t)L * N2 * S), WLOWER(WUPPER.size()), ATERM((size_t)L * n), BTERM((size_t)L * n), GAMMA_M((size_t)L * n), GAMMA_P((size_t)L * n);
+  std::vector<double> UPAR_UP_1((size_t)L * S, 0.0);
+  std::vector<double> LCON((size_t)L * n), MCON((size_t)L * n);
+  std::vector<double> SAB((size_t)n * n), DABm((size_t)n * n), EIG((size_t)n * n), EVEC((size_t)n * n), EVAL(n);
+  BandLU blu;
+  double total[4] = {0, 0, 0, 0};
+  int testconv = 0, fourier_saved = 0;
+  bool local_iteration = true;
+  const int N_FOURIERS = NM;
+  int FOURIER = -1;
+  const int kl = (L == 1) ? 2 * n - 1 : 3 * n - 1;
+  const int NTOTAL = N2 * S * L;
+
+  while (local_iteration && FOURIER < N_FOURIERS) {
+    FOURIER++;
+    const int M = FOURIER;
+    if (in->max_fourier_override >= 0 && M > in->max_fourier_override) { FOURIER--; break; }
+    bool include_surface = true;
+    if (lamb) { if (M != 0) include_surface = false; else if (in->albedo == 0.0) include_surface = false; }
+    const double SURFACE_FACTOR = (M == 0) ? 2.0 : 1.0, DELTA_FACTOR = (M == 0) ? 1.0 : 2.0, FLUX_MULTIPLIER = DELTA_FACTOR;
+    const bool do_localbeam = include_surface && do_reflected_directbeam;
+    /* BRDF Fourier component slices */
+    const double *BRDF_F = nullptr, *BRDF_F_0 = nullptr, *UBRDF_F = nullptr, *UBRDF_F_0 = nullptr;
+    if (!lamb) {
+      BRDF_F = in->brdf_f + (size_t)M * 16 * N * N; BRDF_F_0 = in->brdf_f_0 + (size_t)M * 16 * N;
+      UBRDF_F = in->user_brdf_f + (size_t)M * 16 * N; UBRDF_F_0 = in->user_brdf_f_0 + (size_t)M * 16;
+    }
+#define BF_(q, i, j) BRDF_F[((size_t)(q) * N + (i)) * N + (j)]
+    /* ---- DIRECTRADIANCE */
+    std::vector<double> direct_beam((size_t)N * S, 0.0), user_direct_beam(S, 0.0);
+    if (include_surface && do_localbeam) {
+      double x0_flux = 4.0 * cos_sza / DELTA_FACTOR; x0_flux = FLUX_FACTOR * x0_flux / PI4;
+      double attn = x0_flux * trans_solar_beam;
+      if (lamb) { if (M == 0) { for (int i = 0; i < N; i++) direct_beam[(size_t)i * S] = attn * in->albedo; user_direct_beam[0] = attn * in->albedo; } }
+      else {
+        for (int i = 0; i < N; i++) for (int o1 = 0; o1 < S; o1++) direct_beam[(size_t)i * S + o1] = attn * BRDF_F_0[(size_t)MI(o1, 0) * N + i];
+        for (int o1 = 0; o1 < S; o1++) user_direct_beam[o1] = attn * UBRDF_F_0[MI(o1, 0)];
+      }
+    }
+    /* ---- PIMATRIX_SETUP */
+    {
+      const double RCONST_20 = 0.25 * std::sqrt(6.0), RCONST_21 = 2.0 * RCONST_20;
+      std::vector<double> PHI(NM + 2, 0.0), PINORM(NM + 2, 0.0);
+      double fac = 1.0; for (int l = 1; l <= 2 * M; l++) fac *= (double)l;
+      PHI[M] = 1.0 / fac;
+      for (int l = M + 1; l <= NM; l++) PHI[l] = PHI[l - 1] * ((double)(l - M) / (double)(l + M));
+      for (int l = M; l <= NM; l++) PINORM[l] = std::sqrt(PHI[l]);
+      if (M == 0) {
+        for (int m1 = 0; m1 <= NM; m1++) for (int l = m1; l <= NM; l++) PISIGN[(size_t)l * (NM + 1) + m1] = ((l - m1) % 2 == 0) ? 1.0 : -1.0;
+        for (int l = 0; l <= NM; l++) { DF_L[l] = l; DF_LP1[l] = l + 1; DF_2LP1[l] = 2 * l + 1; }
+        for (int l = 3; l <= NM; l++) DF_LSQM4[l] = std::sqrt((double)(l * l - 4));
+        for (int l = 2; l <= NM; l++) { DF_RT[l] = std::sqrt((double)((l + 3) * (l - 1))); ZHELP[l] = 2.0 * DF_2LP1[l] / DF_LP1[l] / DF_L[l]; }
+        for (int i = 0; i < NSA; i++) {
+          double xsq = XM[i] * XM[i];
+          PLEG20[i] = 0.5 * (3.0 * xsq - 1.0); UMXSQ[i] = 1.0 - xsq;
+          if (XM[i] == 1.0) { RT_UMXSQ[i] = 0; X_RT_UMXSQ[i] = 0; UPXSQ_D[i] = 0; M2X_D[i] = 0; }
+          else { RT_UMXSQ[i] = std::sqrt(UMXSQ[i]); X_RT_UMXSQ[i] = RT_UMXSQ[i] * XM[i]; UPXSQ_D[i] = (1.0 + xsq) / UMXSQ[i]; M2X_D[i] = -2.0 * XM[i] / UMXSQ[i]; }
+        }
+      }
+      std::vector<double> XLM((size_t)(NM + 2) * 4, 0.0), YLM((size_t)(NM + 2) * 4, 0.0), ZLM23(NM + 2, 0.0);
+      if (M == 0) {
+        for (int l = 2; l <= NM; l++) {
+          XLM[l * 4 + 0] = DF_LP1[l]; XLM[l * 4 + 1] = DF_RT[l]; XLM[l * 4 + 2] = XLM[l * 4 + 1]; XLM[l * 4 + 3] = XLM[l * 4 + 0];
+          for (int s = 0; s < S; s++) XLM[l * 4 + s] = 1.0 / XLM[l * 4 + s];
+          YLM[l * 4 + 0] = DF_L[l]; YLM[l * 4 + 1] = DF_LSQM4[l]; YLM[l * 4 + 2] = YLM[l * 4 + 1]; YLM[l * 4 + 3] = YLM[l * 4 + 0];
+        }
+      } else {
+        for (int l = M; l <= NM; l++) {
+          double lp1mm = (double)(l + 1 - M);
+          XLM[l * 4 + 0] = 1.0 / lp1mm;
+          if (l == 1) XLM[l * 4 + 1] = 0.0; else XLM[l * 4 + 1] = 1.0 / (DF_RT[l] * lp1mm / DF_LP1[l]);
+          XLM[l * 4 + 2] = XLM[l * 4 + 1]; XLM[l * 4 + 3] = XLM[l * 4 + 0];
+        }
+        for (int l = M + 1; l <= NM; l++) {
+          double lpm = (double)(l + M);
+          YLM[l * 4 + 0] = lpm; YLM[l * 4 + 1] = lpm * DF_LSQM4[l] / DF_L[l]; YLM[l * 4 + 2] = YLM[l * 4 + 1]; YLM[l * 4 + 3] = YLM[l * 4 + 0];
+        }
+        for (int l = 2; l <= NM; l++) ZLM23[l] = (double)M * ZHELP[l];
+      }
+      std::fill(PIv.begin(), PIv.end(), 0.0);
+      auto zlm = [&](int l, int a, int b) { return ((a == 1 && b == 2) || (a == 2 && b == 1)) ? ZLM23[l] : 0.0; };
+      if (M == 0) {
+        for (int i = 0; i < NSA; i++) {
+          PI_(0, i, 0, 0) += 1.0; PI_(0, i, 3, 3) += 1.0;
+          if (NM >= 1) { PI_(1, i, 0, 0) += XM[i]; PI_(1, i, 3, 3) += XM[i]; }
+          if (NM >= 2) {
+            PI_(2, i, 0, 0) += PLEG20[i]; PI_(2, i, 1, 1) += RCONST_20 * UMXSQ[i];
+            PI_(2, i, 2, 2) = PI_(2, i, 1, 1); PI_(2, i, 3, 3) = PI_(2, i, 0, 0);
+          }
+        }
+        for (int l = 2; l <= NM - 1; l++) for (int i = 0; i < NSA; i++) for (int a = 0; a < S; a++) for (int b = 0; b < S; b++) {
+          double HX = XM[i] * DF_2LP1[l] * PI_(l, i, a, b), HY = YLM[l * 4 + a] * PI_(l - 1, i, a, b);
+          PI_(l + 1, i, a, b) = (HX - HY) * XLM[l * 4 + a];
+        }
+      } else if (M == 1) {
+        for (int i = 0; i < NSA; i++) {
+          PI_(1, i, 0, 0) += RT_UMXSQ[i]; PI_(1, i, 3, 3) += RT_UMXSQ[i];
+          if (NM >= 2) {
+            double PL21 = 3.0 * X_RT_UMXSQ[i], RL21 = -RCONST_21 * X_RT_UMXSQ[i], TL21 = RCONST_21 * RT_UMXSQ[i];
+            PI_(2, i, 0, 0) += PL21; PI_(2, i, 1, 1) += RL21; PI_(2, i, 1, 2) += TL21;
+            PI_(2, i, 2, 2) = PI_(2, i, 1, 1); PI_(2, i, 3, 3) = PI_(2, i, 0, 0); PI_(2, i, 2, 1) = PI_(2, i, 1, 2);
+          }
+        }
+        for (int l = 2; l <= NM - 1; l++) for (int i = 0; i < NSA; i++) for (int a = 0; a < S; a++) for (int b = 0; b < S; b++) {
+          double HX = XM[i] * DF_2LP1[l] * PI_(l, i, a, b), HY = YLM[l * 4 + a] * PI_(l - 1, i, a, b), HZ = 0.0;
+          for (int c = 0; c < S; c++) HZ += zlm(l, a, c) * PI_(l, i, c, b);
+          PI_(l + 1, i, a, b) = (HX - HY + HZ) * XLM[l * 4 + a];
+        }
+      } else {
+        if (M == 2) {
+          for (int i = 0; i < NSA; i++) { PIMM_11[i] = 3.0 * UMXSQ[i]; PIMM_KM[i] = (XM[i] == 1.0) ? RCONST_21 : RCONST_21 * UMXSQ[i]; }
+        } else {
+          double H1 = DF_2LP1[M - 1], H2 = DF_LP1[M - 1] * H1 / DF_RT[M - 1];
+          for (int i = 0; i < NSA; i++) {
+            PIMM_11[i] = H1 * RT_UMXSQ[i] * PIMM_11[i];
+            PIMM_KM[i] = (XM[i] == 1.0) ? 0.0 : H2 * RT_UMXSQ[i] * PIMM_KM[i];
+          }
+        }
+        for (int i = 0; i < NSA; i++) {
+          PI_(M, i, 0, 0) += PIMM_11[i];
+          if (XM[i] == 1.0) { PI_(M, i, 1, 1) += PIMM_KM[i] * 2.0; PI_(M, i, 1, 2) -= PIMM_KM[i] * 2.0; }
+          else { PI_(M, i, 1, 1) += PIMM_KM[i] * UPXSQ_D[i]; PI_(M, i, 1, 2) += PIMM_KM[i] * M2X_D[i]; }
+          PI_(M, i, 2, 2) = PI_(M, i, 1, 1); PI_(M, i, 3, 3) = PI_(M, i, 0, 0); PI_(M, i, 2, 1) = PI_(M, i, 1, 2);
+        }
+        if (M < NM) for (int i = 0; i < NSA; i++) for (int a = 0; a < S; a++) for (int b = 0; b < S; b++) {
+          double HX = XM[i] * DF_2LP1[M] * PI_(M, i, a, b), HZ = 0.0;
+          for (int c = 0; c < S; c++) HZ += zlm(M, a, c) * PI_(M, i, c, b);
+          PI_(M + 1, i, a, b) = (HX + HZ) * XLM[M * 4 + a];
+        }
+        for (int l = M + 1; l <= NM - 1; l++) for (int i = 0; i < NSA; i++) for (int a = 0; a < S; a++) for (int b = 0; b < S; b++) {
+          double HX = XM[i] * DF_2LP1[l] * PI_(l, i, a, b), HY = YLM[l * 4 + a] * PI_(l - 1, i, a, b), HZ = 0.0;
+          for (int c = 0; c < S; c++) HZ += zlm(l, a, c) * PI_(l, i, c, b);
+          PI_(l + 1, i, a, b) = (HX - HY + HZ) * XLM[l * 4 + a];
+        }
+      }
+      for (int l = M; l <= NM; l++) {
+        double ps = PISIGN[(size_t)l * (NM + 1) + M];
+        for (int i = 0; i < N; i++) for (int a = 0; a < S; a++) for (int b = 0; b < S; b++) {
+          double v = PI_(l, i, a, b) * PINORM[l];
+          Q_(XQP, l, i, a, b) = v;
+          Q_(XQP_PRE, l, i, a, b) = DMAT[a] * v;
+          Q_(XQM_PRE, l, i, a, b) = DMAT[a] * v * ps;
+          Q_(XQM_POST, l, i, a, b) = v * DMAT[b] * ps;
+          Q_(XQM, l, i, a, b) = DMAT[a] * v * DMAT[b] * ps;
+        }
+        for (int a = 0; a < S; a++) for (int b = 0; b < S; b++) {
+          double v = PI_(l, N, a, b) * PINORM[l];
+          U_(XUP, l, a, b) = v; U_(XUP_PRE, l, a, b) = DMAT[a] * v; U_(XUM_POST, l, a, b) = v * DMAT[b] * ps;
+          U_(XUM, l, a, b) = DMAT[a] * v * DMAT[b] * ps;
+          U_(X0P, l, a, b) = PI_(l, N + 1, a, b) * PINORM[l];
+        }
+      }
+    }
+    /* ---- homogeneous solutions layer by layer */
+    for (int k = 0; k < L; k++) {
+      /* SAB, DAB: vlidort_solutions.f90:425-475 */
+      std::vector<double> H2P((size_t)(NM + 1) * N * 16, 0.0), H2M(H2P.size(), 0.0);
+      for (int j = 0; j < N; j++) for (int o2 = 0; o2 < S; o2++) for (int l = M; l <= NM; l++) for (int o3 = 0; o3 < S; o3++) {
+        double sp = 0.0, sm = 0.0;
+        for (int o = 0; o < S; o++) { sp += OG_(l, k, o3, o) * Q_(XQP, l, j, o, o2); sm += OG_(l, k, o3, o) * Q_(XQM_PRE, l, j, o, o2); }
+        Q_(H2P, l, j, o3, o2) = sp; Q_(H2M, l, j, o3, o2) = sm;
+      }
+      for (int i = 0; i < N; i++) {
+        double xinv = -1.0 / qx[i];
+        for (int j = 0; j < N; j++) {
+          double facj = xinv * qhw[j];
+          for (int o1 = 0; o1 < S; o1++) for (int o2 = 0; o2 < S; o2++) {
+            double DP = 0.0, DM = 0.0;
+            for (int l = M; l <= NM; l++) for (int o = 0; o < S; o++) { DP += Q_(XQP, l, i, o1, o) * Q_(H2P, l, j, o, o2); DM += Q_(XQP, l, i, o1, o) * Q_(H2M, l, j, o, o2); }
+            SAB[(size_t)(S * i + o1) + (size_t)(S * j + o2) * n] = facj * (DP + DM);
+            DABm[(size_t)(S * i + o1) + (size_t)(S * j + o2) * n] = facj * (DP - DM);
+          }
+        }
+        for (int o1 = 0; o1 < S; o1++) { SAB[(size_t)(S * i + o1) * (n + 1)] -= xinv; DABm[(size_t)(S * i + o1) * (n + 1)] -= xinv; }
+      }
+      for (int r = 0; r < n; r++) for (int c = 0; c < n; c++) {
+        double s = 0.0;
+        for (int t = 0; t < n; t++) s += DABm[r + (size_t)t * n] * SAB[t + (size_t)c * n];
+        EIG[r + (size_t)c * n] = s;
+      }
+      std::vector<double> EIGsave(EIG);
+      bool bad = false;
+      int ier = asymtx(in->asymtx_tolerance > 0 ? in->asymtx_tolerance : 1.0e-12, EIG.data(), n, EVEC.data(), EVAL.data(), &bad);
+      if (bad) { out->status = 4; return 4; }
+      if (ier > 0) { EIG = EIGsave; ier = asymtx(1.0e-10, EIG.data(), n, EVEC.data(), EVAL.data(), &bad);
+        if (ier > 0) { EIG = EIGsave; ier = asymtx(1.0e-8, EIG.data(), n, EVEC.data(), EVAL.data(), &bad); if (ier > 0) { out->status = 4; return 4; } } }
+      for (int e = 0; e < n; e++) {
+        double nr = 0.0; for (int r = 0; r < n; r++) nr += EVEC[r + (size_t)e * n] * EVEC[r + (size_t)e * n];
+        nr = std::sqrt(nr); for (int r = 0; r < n; r++) EVEC[r + (size_t)e * n] /= nr;
+      }
+      for (int e = 0; e < n; e++) {
+        double keig = std::sqrt(EVAL[e]);
+        if (!(keig == keig)) { out->status = 4; return 4; }
+        KEIG[(size_t)k * n + e] = keig;
+        double sc = 1.0 / keig, nr = 0.0;
+        for (int r = 0; r < n; r++) nr += EVEC[r + (size_t)e * n] * EVEC[r + (size_t)e * n];
+        nr = std::sqrt(nr);
+        std::vector<double> sumv(n), difv(n);
+        for (int r = 0; r < n; r++) sumv[r] = EVEC[r + (size_t)e * n] / nr;
+        for (int r = 0; r < n; r++) { double h = 0.0; for (int t = 0; t < n; t++) h += SAB[r + (size_t)t * n] * sumv[t]; difv[r] = h * sc; }
+        for (int i = 0; i < N; i++) for (int o = 0; o < S; o++) {
+          double fpd = 0.5 * (sumv[S * i + o] + difv[S * i + o]), fnd = 0.5 * (sumv[S * i + o] - difv[S * i + o]);
+          XP_(k, e, i, o) = fpd; XN_(k, e, i, o) = fnd;
+          if (o < 2) { XP_(k, e, i + N, o) = fnd; XN_(k, e, i + N, o) = fpd; } else { XP_(k, e, i + N, o) = -fnd; XN_(k, e, i + N, o) = -fpd; }
+        }
+        double help = keig * deltau[k];
+        TDE[(size_t)k * n + e] = help > MAX_TAU_QPATH ? 0.0 : std::exp(-help);
+      }
+      /* UHOM: vlidort_solutions.f90:1290-1420 */
+      for (int e = 0; e < n; e++) {
+        double rho_p = usec + KEIG[(size_t)k * n + e], rho_m = usec - KEIG[(size_t)k * n + e];
+        ZETA_P[(size_t)k * n + e] = 1.0 / rho_p;
+        HSINGO[(size_t)k * n + e] = std::fabs(rho_m) < TAYLOR_SMALL;
+        ZETA_M[(size_t)k * n + e] = HSINGO[(size_t)k * n + e] ? rho_m : 1.0 / rho_m;
+      }
+      if (!layscat[(size_t)M * L + k]) {
+        for (int e = 0; e < n; e++) for (int o = 0; o < S; o++) { UHOM_UPDN[((size_t)k * n + e) * S + o] = 0.0; UHOM_UPUP[((size_t)k * n + e) * S + o] = 0.0; }
+      } else {
+        for (int e = 0; e < n; e++) {
+          std::vector<double> gaux((size_t)(NM + 1) * 4, 0.0);
+          for (int l = M; l <= NM; l++) {
+            double hs[4] = {0, 0, 0, 0};
+            for (int o1 = 0; o1 < S; o1++) {
+              double sps = 0.0;
+              for (int j = 0; j < N; j++) {
+                double sp = 0.0, sm = 0.0;
+                for (int o = 0; o < S; o++) { sp += Q_(XQP, l, j, o1, o) * qhw[j] * XP_(k, e, j, o); sm += Q_(XQM_PRE, l, j, o1, o) * qhw[j] * XN_(k, e, j, o); }
+                sps += sp + sm;
+              }
+              hs[o1] = sps;
+            }
+            for (int o1 = 0; o1 < S; o1++) { double g = 0.0; for (int o = 0; o < S; o++) g += OG_(l, k, o1, o) * hs[o]; gaux[l * 4 + o1] = g; }
+          }
+          for (int o1 = 0; o1 < S; o1++) {
+            double a = 0.0, b = 0.0;
+            for (int l = M; l <= NM; l++) for (int o = 0; o < S; o++) { a += U_(XUM, l, o1, o) * gaux[l * 4 + o]; b += U_(XUP_PRE, l, o1, o) * gaux[l * 4 + o]; }
+            UHOM_UPDN[((size_t)k * n + e) * S + o1] = a; UHOM_UPUP[((size_t)k * n + e) * S + o1] = b;
+          }
+        }
+      }
+    }
+    /* ---- QHOM_NORMS, HMULT */
+    for (int k = 0; k < L; k++) for (int e = 0; e < n; e++) {
+      double norm = 0.0;
+      for (int j = 0; j < N; j++) { double t1 = 0.0, t2 = 0.0; for (int o = 0; o < S; o++) { t1 += XP_(k, e, j, o) * XP_(k, e, j, o); t2 += XN_(k, e, j, o) * XN_(k, e, j, o); } norm += qsw[j] * (t1 - t2); }
+      NORMS[(size_t)k * n + e] = norm;
+      double udel = tduserm[k], zdel = TDE[(size_t)k * n + e];
+      if (HSINGO[(size_t)k * n + e]) HMULT1[(size_t)k * n + e] = taylor_series_1(TAYLOR_ORDER, ZETA_M[(size_t)k * n + e], deltau[k], udel, usec);
+      else HMULT1[(size_t)k * n + e] = usec * (zdel - udel) * ZETA_M[(size_t)k * n + e];
+      HMULT2[(size_t)k * n + e] = usec * (1.0 - zdel * udel) * ZETA_P[(size_t)k * n + e];
+    }
+    /* ---- BVP matrix */
+    std::vector<double> R2_HOMP((size_t)n * N * S, 0.0), R2_HOMM(R2_HOMP.size(), 0.0);   /* [e][i][o] */
+    if (include_surface) {
+      const int NL = L - 1;
+      if (lamb) {
+        double kmult = SURFACE_FACTOR * in->albedo;
+        for (int e = 0; e < n; e++) {
+          double sp = 0.0, sm = 0.0;
+          for (int j = 0; j < N; j++) { sp += qsw[j] * XP_(NL, e, j, 0); sm += qsw[j] * XN_(NL, e, j, 0); }
+          for (int i = 0; i < N; i++) { R2_HOMP[((size_t)e * N + i) * S] = sp * kmult; R2_HOMM[((size_t)e * N + i) * S] = sm * kmult; }
+        }
+      } else {
+        for (int e = 0; e < n; e++) for (int i = 0; i < N; i++) for (int o1 = 0; o1 < S; o1++) {
+          double sp = 0.0, sm = 0.0;
+          for (int j = 0; j < N; j++) for (int o2 = 0; o2 < S; o2++) { double ax = qsw[j] * BF_(MI(o1, o2), i, j); sp += ax * XP_(NL, e, j, o2); sm += ax * XN_(NL, e, j, o2); }
+          R2_HOMP[((size_t)e * N + i) * S + o1] = SURFACE_FACTOR * sp; R2_HOMM[((size_t)e * N + i) * S + o1] = SURFACE_FACTOR * sm;
+        }
+      }
+    }
+    blu.init(NTOTAL, kl, kl);
+    {
+      const int n2 = 2 * n;
+      for (int i = 0; i < N; i++) for (int o = 0; o < S; o++) {       /* TOA: no downwelling diffuse */
+        int row = S * i + o;
+        for (int e = 0; e < n; e++) { blu.at(row, e) = XP_(0, e, i, o); blu.at(row, e + n) = XN_(0, e, i, o) * TDE[e]; }
+      }
+      for (int k = 1; k < L; k++) {                                    /* continuity at the top of layer k (0-based) */
+        int c0 = k * n2 - n;
+        for (int i = 0; i < N2; i++) for (int o = 0; o < S; o++) {
+          int row = c0 + S * i + o;
+          for (int e = 0; e < n; e++) {
+            blu.at(row, (k - 1) * n2 + e) = TDE[(size_t)(k - 1) * n + e] * XP_(k - 1, e, i, o);
+            blu.at(row, (k - 1) * n2 + n + e) = XN_(k - 1, e, i, o);
+            blu.at(row, k * n2 + e) = -XP_(k, e, i, o);
+            blu.at(row, k * n2 + n + e) = -TDE[(size_t)k * n + e] * XN_(k, e, i, o);
+          }
+        }
+      }
+      int c0 = (L - 1) * n2 + n, NL = L - 1;
+      for (int i = 0; i < N; i++) for (int o = 0; o < S; o++) {       /* surface */
+        int row = c0 + S * i + o;
+        for (int e = 0; e < n; e++) {
+          double xpnet = XP_(NL, e, i + N, o) - R2_HOMP[((size_t)e * N + i) * S + o];
+          double xmnet = XN_(NL, e, i + N, o) - R2_HOMM[((size_t)e * N + i) * S + o];
+          blu.at(row, NL * n2 + e) = TDE[(size_t)NL * n + e] * xpnet;
+          blu.at(row, NL * n2 + n + e) = xmnet;
+        }
+      }
+    }
+    if (blu.factor() != 0) { out->status = 4; return 4; }
+    /* ---- beam particular integral (Green's function): vlidort_solutions.f90:2649-2935 */
+    const double F1 = FLUX_FACTOR / PI4;
+    for (int k = 0; k < L; k++) {
+      double *WU = &WUPPER[(size_t)k * N2 * S], *WL = &WLOWER[(size_t)k * N2 * S];
+      for (int o = 0; o < S; o++) UPAR_UP_1[(size_t)k * S + o] = 0.0;
+      if (k + 1 > beam_cutoff || !layscat[(size_t)M * L + k]) { for (int t = 0; t < N2 * S; t++) { WU[t] = 0.0; WL[t] = 0.0; } continue; }
+      double secbar = avsec[k], cst = itrans[k], wdel = tdmubar[k];
+      std::vector<double> CF(n), DF(n);
+      for (int e = 0; e < n; e++) {
+        double zdel = TDE[(size_t)k * n + e], zwdel = zdel * wdel;
+        GAMMA_P[(size_t)k * n + e] = secbar + KEIG[(size_t)k * n + e];
+        double eps = secbar - KEIG[(size_t)k * n + e]; GAMMA_M[(size_t)k * n + e] = eps;
+        if (std::fabs(eps) < TAYLOR_SMALL) CF[e] = taylor_series_1(TAYLOR_ORDER, eps, deltau[k], wdel, cst);
+        else CF[e] = cst * (zdel - wdel) / eps;
+        DF[e] = cst * (1.0 - zwdel) / GAMMA_P[(size_t)k * n + e];
+      }
+      std::vector<double> HQ((size_t)(NM + 1) * 4, 0.0);
+      for (int o1 = 0; o1 < S; o1++) for (int l = M; l <= NM; l++) {
+        double g = 0.0; for (int o2 = 0; o2 < S; o2++) g += OG_(l, k, o1, o2) * U_(X0P, l, o2, 0);   /* DFLUX = (1,0,0,0) */
+        HQ[l * 4 + o1] = g;
+      }
+      std::vector<double> DPI((size_t)N * S), DMI((size_t)N * S);
+      for (int o1 = 0; o1 < S; o1++) for (int i = 0; i < N; i++) {
+        double a = 0.0, b = 0.0;
+        for (int l = M; l <= NM; l++) for (int o = 0; o < S; o++) { a += Q_(XQP, l, i, o1, o) * HQ[l * 4 + o]; b += Q_(XQM_POST, l, i, o1, o) * HQ[l * 4 + o]; }
+        DPI[(size_t)i * S + o1] = F1 * a; DMI[(size_t)i * S + o1] = F1 * b;
+      }
+      std::vector<double> GUP(n), GDN(n);
+      for (int e = 0; e < n; e++) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < N; i++) {
+          double h1 = 0.0, h2 = 0.0;
+          for (int o = 0; o < S; o++) { h1 += DPI[(size_t)i * S + o] * XP_(k, e, i, o) + DMI[(size_t)i * S + o] * XN_(k, e, i, o); h2 += DMI[(size_t)i * S + o] * XP_(k, e, i, o) + DPI[(size_t)i * S + o] * XN_(k, e, i, o); }
+          s1 += qw[i] * h1; s2 += qw[i] * h2;
+        }
+        ATERM[(size_t)k * n + e] = s1 / NORMS[(size_t)k * n + e]; BTERM[(size_t)k * n + e] = s2 / NORMS[(size_t)k * n + e];
+        GDN[e] = CF[e] * ATERM[(size_t)k * n + e]; GUP[e] = DF[e] * BTERM[(size_t)k * n + e];
+      }
+      for (int o = 0; o < S; o++) for (int i = 0; i < N; i++) {
+        double a = 0, b = 0, c = 0, d = 0;
+        for (int e = 0; e < n; e++) { a += GUP[e] * XN_(k, e, i, o); b += GUP[e] * XP_(k, e, i, o); c += GDN[e] * XN_(k, e, i, o); d += GDN[e] * XP_(k, e, i, o); }
+        double sg = o > 1 ? -1.0 : 1.0;
+        WU[(size_t)i * S + o] = a; WU[(size_t)(i + N) * S + o] = sg * b; WL[(size_t)(i + N) * S + o] = sg * c; WL[(size_t)i * S + o] = d;
+      }
+      if (!msmode) {                                           /* GUSER_SOLUTION: truncated single scatter */
+        for (int o1 = 0; o1 < S; o1++) {
+          double s = 0.0;
+          for (int l = M; l <= NM; l++) for (int o = 0; o < S; o++) s += F1 * HQ[l * 4 + o] * U_(XUM, l, o1, o);
+          UPAR_UP_1[(size_t)k * S + o1] = s;
+        }
+      }
+    }
+    /* ---- BVP right-hand side and solution */
+    std::vector<double> R2_BEAM((size_t)N * S, 0.0), COL(NTOTAL, 0.0);
+    if (include_surface) {
+      const double *WL = &WLOWER[(size_t)(L - 1) * N2 * S];
+      if (lamb) { double r = 0.0; for (int j = 0; j < N; j++) r += qsw[j] * WL[(size_t)j * S]; r *= SURFACE_FACTOR * in->albedo; for (int i = 0; i < N; i++) R2_BEAM[(size_t)i * S] = r; }
+      else for (int i = 0; i < N; i++) for (int o1 = 0; o1 < S; o1++) {
+        double r = 0.0; for (int j = 0; j < N; j++) for (int o2 = 0; o2 < S; o2++) r += qsw[j] * BF_(MI(o1, o2), i, j) * WL[(size_t)j * S + o2];
+        R2_BEAM[(size_t)i * S + o1] = SURFACE_FACTOR * r;
+      }
+    }
+    {
+      const int n2 = 2 * n;
+      for (int i = 0; i < N; i++) for (int o = 0; o < S; o++) COL[S * i + o] = -WUPPER[(size_t)i * S + o];
+      for (int k = 1; k < L; k++) { int c0 = k * n2 - n; for (int i = 0; i < N2; i++) for (int o = 0; o < S; o++) COL[c0 + S * i + o] = WUPPER[((size_t)k * N2 + i) * S + o] - WLOWER[((size_t)(k - 1) * N2 + i) * S + o]; }
+      int c0 = (L - 1) * n2 + n;
+      for (int i = 0; i < N; i++) for (int o = 0; o < S; o++) {
+        double v = -WLOWER[((size_t)(L - 1) * N2 + i + N) * S + o];
+        if (include_surface) { v += R2_BEAM[(size_t)i * S + o]; if (do_localbeam) v += direct_beam[(size_t)i * S + o]; }
+        COL[c0 + S * i + o] = v;
+      }
+      blu.solve(COL.data());
+      for (int k = 0; k < L; k++) for (int e = 0; e < n; e++) { LCON[(size_t)k * n + e] = COL[k * n2 + e]; MCON[(size_t)k * n + e] = COL[k * n2 + n + e]; }
+    }
+    /* ---- post-processing: upwelling at TOA */
+    double cumsrc[4] = {0, 0, 0, 0};
+    if (include_surface) {
+      const int NL = L - 1;
+      std::vector<double> sdown((size_t)N * S);
+      for (int i = 0; i < N; i++) for (int o = 0; o < S; o++) {
+        double sh = 0.0;
+        for (int e = 0; e < n; e++) sh += LCON[(size_t)NL * n + e] * XP_(NL, e, i, o) * TDE[(size_t)NL * n + e] + MCON[(size_t)NL * n + e] * XN_(NL, e, i, o);
+        sdown[(size_t)i * S + o] = qsw[i] * (WLOWER[((size_t)NL * N2 + i) * S + o] + sh);
+      }
+      if (lamb) { if (M == 0) { double r = 0.0; for (int i = 0; i < N; i++) r += sdown[(size_t)i * S]; cumsrc[0] = SURFACE_FACTOR * in->albedo * r; } }
+      else for (int o1 = 0; o1 < S; o1++) {
+        double r = 0.0; for (int j = 0; j < N; j++) for (int o2 = 0; o2 < S; o2++) r += sdown[(size_t)j * S + o2] * UBRDF_F[(size_t)MI(o1, o2) * N + j];
+        cumsrc[o1] = SURFACE_FACTOR * r;
+      }
+      const bool include_directrf = do_localbeam && !dbcorrection && !msmode;
+      if (include_directrf) for (int o = 0; o < S; o++) cumsrc[o] += user_direct_beam[o];
+    }
+    for (int k = L - 1; k >= 0; k--) {
+      double src[4] = {0, 0, 0, 0};
+      if (layscat[(size_t)M * L + k]) {
+        for (int o = 0; o < S; o++) {
+          double h = 0.0;
+          for (int e = 0; e < n; e++) h += LCON[(size_t)k * n + e] * UHOM_UPDN[((size_t)k * n + e) * S + o] * HMULT2[(size_t)k * n + e] + MCON[(size_t)k * n + e] * UHOM_UPUP[((size_t)k * n + e) * S + o] * HMULT1[(size_t)k * n + e];
+          src[o] = h;
+        }
+        if (k + 1 <= beam_cutoff) {
+          double wdel = tdmubar[k], itr = itrans[k], itw = -itr * wdel;
+          for (int e = 0; e < n; e++) {
+            double SD, SU;
+            if (std::fabs(GAMMA_M[(size_t)k * n + e]) < TAYLOR_SMALL) {
+              double mult = taylor_series_2(TAYLOR_ORDER, GAMMA_M[(size_t)k * n + e], sigma_p[k], deltau[k], 1.0, wdel * tduserm[k], 1.0);
+              SD = itrans_userm[k] * mult;
+            } else SD = (itr * HMULT2[(size_t)k * n + e] - emult_up[k]) / GAMMA_M[(size_t)k * n + e];
+            SU = (itw * HMULT1[(size_t)k * n + e] + emult_up[k]) / GAMMA_P[(size_t)k * n + e];
+            for (int o = 0; o < S; o++)
+              src[o] += UHOM_UPDN[((size_t)k * n + e) * S + o] * SD * ATERM[(size_t)k * n + e] + UHOM_UPUP[((size_t)k * n + e) * S + o] * SU * BTERM[(size_t)k * n + e];
+          }
+          if (!msmode) for (int o = 0; o < S; o++) src[o] += UPAR_UP_1[(size_t)k * S + o] * emult_up[k];
+        }
+      }
+      for (int o = 0; o < S; o++) cumsrc[o] = src[o] + tduserm[k] * cumsrc[o];
+    }
+    double stokes_f[4] = {0, 0, 0, 0};
+    for (int o = 0; o < S; o++) stokes_f[o] = FLUX_MULTIPLIER * cumsrc[o];
+    /* ---- CONVERGE_OBSGEO */
+    if (M == 0) {
+      for (int o = 0; o < S; o++) { total[o] = stokes_f[o]; if (do_focorr) total[o] += fo_ss[o] + fo_db[o]; }
+      fourier_saved = 0;
+    } else {
+      double arg = in->raa * (double)M * DEG_TO_RAD, cf = std::cos(arg), sf = std::sin(arg);
+      double azm[4] = {cf, cf, sf, sf}, tazm[4], tnew[4];
+      for (int o = 0; o < S; o++) { tazm[o] = azm[o] * stokes_f[o]; tnew[o] = total[o] + tazm[o]; }
+      int count = 0;
+      if (tazm[0] != 0.0) { if (std::fabs(tazm[0] / tnew[0]) < in->accuracy) count++; } else count++;
+      for (int o = 0; o < S; o++) total[o] = tnew[o];
+      if (in->max_fourier_override < 0) {
+        if (count == 1) { testconv++; if (testconv == 2) local_iteration = false; if (!local_iteration) fourier_saved = M; }
+        else { testconv = 0; fourier_saved = 2 * N - 1; }
+      } else fourier_saved = M;
+    }
+  }
+  for (int o = 0; o < S; o++) out->stokes[o] = total[o];
+  out->nfourier = fourier_saved;
+  out->status = 0;
+  return 0;
+}
