@@ -1,0 +1,92 @@
+"""Host-side mirror of the reference's f2py module ``VLIDORT_POLAR_`` (LV/VLIDORT_POLAR_py.F90, built by
+LV/CMakeLists.txt:13-19): same lower-case function names, positional argument order (dimension integers are
+inferred from the array shapes, as f2py does) and returned tuples.  Everything is computed by the CUDA library
+through the C ABI of include/aeroapps_b200_rt.h; there is no CPU fallback.
+
+    ROT, depol, rc                      = rot_calc(channels, pe, he, te, MISSING, verbose)
+    I, reflectance, rc                  = scalar_lambert(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g,
+                                                         pmom, pe, he, te, albedo, sza, raa, vza, MISSING, verbose)
+    I, reflectance, Q, U, rc            = vector_lambert(channels, nstreams, plane_parallel, ROT, depol, alpha, tau,
+                                                         ssa, pmom, pe, he, te, albedo, sza, raa, vza, flux_factor,
+                                                         MISSING, verbose)
+"""
+import ctypes as C
+import numpy as np
+
+from ._lib import lib, check
+
+_dp = C.POINTER(C.c_double)
+
+
+def _F(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _v(a):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _dims(tau, pmom):
+    km, nch, nobs = tau.shape
+    assert pmom.shape[:3] == (km, nch, nobs), "pmom must be (km,nch,nobs,nMom,nPol)"
+    return km, nch, nobs, pmom.shape[3], pmom.shape[4]
+
+
+def rot_calc(channels, pe, he, te, MISSING, verbose):
+    pe, he, te = _F(pe), _F(he), _F(te)
+    ch = _v(channels)
+    km, nobs, nch = pe.shape[0] - 1, pe.shape[1], len(ch)
+    ROT = np.zeros((km, nobs, nch), order="F"); depol = np.zeros(nch)
+    rc = C.c_int(0)
+    check(lib().ab200_rot_calc(km, nch, nobs, _p(ch), _p(pe), _p(he), _p(te), C.c_double(MISSING), int(verbose), _p(ROT),
+                               _p(depol), C.byref(rc)), "ab200_rot_calc")
+    return ROT, depol, rc.value
+
+
+def scalar_lambert(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, pe, he, te, albedo,
+                   solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    ROT, tau, ssa, g, pmom, pe, he, te, albedo = (_F(x) for x in (ROT, tau, ssa, g, pmom, pe, he, te, albedo))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    rad = np.zeros((nobs, nch), order="F"); refl = np.zeros((nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_lambert(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                             _p(ROT), _p(dp), _p(tau), _p(ssa), _p(g), _p(pmom), _p(pe), _p(he), _p(te),
+                                             _p(albedo), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                             _p(rad), _p(refl), C.byref(rc)), "ab200_vlidort_scalar_lambert")
+    return rad, refl, rc.value
+
+
+def vector_lambert(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, albedo,
+                   solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor = (_F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te,
+                                                                                  albedo, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(4)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_lambert(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                             _p(ROT), _p(dp), _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te),
+                                             _p(albedo), _p(sza), _p(raa), _p(vza), _p(flux_factor), C.c_double(MISSING),
+                                             int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_lambert")
+    return outs[0], outs[1], outs[2], outs[3], rc.value
+
+
+def last_diag():
+    """(nfourier, status) per pixel (nobs, nch) of the most recent VLIDORT call -- diagnostics, not in the reference."""
+    lib().ab200_vlidort_last_diag.restype = C.c_long
+    n = lib().ab200_vlidort_last_diag(None, None, C.c_long(0))
+    nf = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+    lib().ab200_vlidort_last_diag(nf.ctypes.data_as(C.POINTER(C.c_int)), st.ctypes.data_as(C.POINTER(C.c_int)), C.c_long(n))
+    return nf, st
+
+
+def stats(reset=False):
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    d, e, f = C.c_long(), C.c_long(), C.c_long()
+    lib().ab200_vlidort_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), C.byref(f), int(reset))
+    return dict(ms_setup=a.value, ms_eigen=b.value, ms_bvp=c.value, n_eigen=d.value, n_bvp=e.value, npix=f.value)

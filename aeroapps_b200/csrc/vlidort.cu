@@ -1,0 +1,442 @@
+// Stage B -- VLIDORT drop-in entry points on B200: kernel wrappers, chunked host driver, C ABI.
+// Kernels: k_vl_setup (K1, CTA per pixel), k_vl_eigen (K2, warp per pixel-layer), k_vl_bvp (K3, persistent CTAs,
+// one pixel at a time), k_vl_finish.  The Fourier loop runs on the host; pixels that have converged drop out
+// of the device-side active list, so later components only launch work for the pixels that still need it.
+#include "../../include/aeroapps_b200.h"
+#include "common.h"
+#include "vl_bvp.cuh"
+#include <algorithm>
+#include <vector>
+#include <cmath>
+
+using namespace vlk;
+
+struct VLStats { double ms_setup, ms_eigen, ms_bvp; long n_eigen_problems, n_bvp_problems; int nfourier_hist[64]; long npix; };
+static VLStats g_stats;
+static std::vector<int> g_last_nfourier, g_last_status;
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) k_vl_setup(VLIn in, VLPix X, int p0) {
+  extern __shared__ double smem_d[];
+  __shared__ double sd[64];
+  __shared__ int si[64];
+  BlockTeam T(sd, si);
+  const int pl = blockIdx.x;                 // pixel index inside the chunk
+  // the inputs are indexed by the global pixel, the per-pixel state by the chunk-local pixel
+  VLPix Xl = X;
+  VLIn inl = in;
+  // shift input pixel numbering: setup_pixel derives (j,i) from p, outputs are addressed with the same p
+  // -> give it a state view whose arrays start p0 pixels "before" the chunk
+  const int L = X.L, NM = X.NM;
+  Xl.deltau -= (size_t)p0 * L; Xl.og -= (size_t)p0 * (NM + 1) * L * 4; Xl.avsec -= (size_t)p0 * L; Xl.itrans -= (size_t)p0 * L;
+  Xl.tdmubar -= (size_t)p0 * L; Xl.tduserm -= (size_t)p0 * L; Xl.emult_up -= (size_t)p0 * L; Xl.sigma_p -= (size_t)p0 * L;
+  Xl.itrans_userm -= (size_t)p0 * L; Xl.scal -= (size_t)p0 * 16; Xl.ibuf -= (size_t)p0 * 4; Xl.layscat -= (size_t)p0 * (NM + 1) * L;
+  setup_pixel(T, inl, Xl, p0 + pl, smem_d);
+}
+
+template <int S>
+__global__ void k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m, const int *__restrict__ active,
+                           int nactive, int scr_doubles) {
+  extern __shared__ double smem_d[];
+  const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const long prob = (long)blockIdx.x * wpc + warp;
+  if (prob >= (long)nactive * X.L) return;
+  const int p = active[prob / X.L], k = (int)(prob % X.L);
+  WarpTeam T;
+  eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)warp * scr_doubles);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
+                                                int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
+                                                int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta) {
+  extern __shared__ double smem_d[];
+  __shared__ double sd[64];
+  __shared__ int si[64];
+  const int n = S * QD.N;
+  int *iscr = reinterpret_cast<int *>(smem_d + bvp_smem_doubles(n));
+  BlockTeam T(sd, si);
+  double *Ug = work + (size_t)blockIdx.x * work_per_cta;
+  for (int a = blockIdx.x; a < nactive; a += gridDim.x) {
+    const int p = active[a];
+    if (Z.fail[p]) {
+      if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
+    } else {
+      bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
+    __syncthreads();
+  }
+}
+
+// outputs in the drop-in layout (nobs,nch); reflectance uses the single-precision pi of the glue
+// (VLIDORT_ScatMod.F90:344,596)
+__global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int npix_chunk, int nch, int nobs, const double *__restrict__ sza,
+                            double MISSING, int S, double *radiance, double *reflectance, double *Q, double *U,
+                            int *nfourier, int *status) {
+  const int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= npix_chunk) return;
+  const int p = p0 + pl, j = p / nch, i = p % nch;
+  const size_t o = j + (size_t)nobs * i;
+  const int st0 = X.ibuf[(size_t)pl * 4 + 1];
+  const int fail = CV.state[(size_t)pl * 4 + 3];
+  const int st = st0 != 0 ? st0 : fail;
+  if (status) status[p] = st;
+  if (nfourier) nfourier[p] = CV.state[(size_t)pl * 4 + 2];
+  if (st != 0) {
+    radiance[o] = MISSING; reflectance[o] = MISSING;
+    if (Q) Q[o] = MISSING;
+    if (U) U[o] = MISSING;
+    return;
+  }
+  const double pi_f = (double)3.14159274101257324f;      // 4.*atan(1.0) in real*4
+  const double I = CV.total[(size_t)pl * 4];
+  radiance[o] = I;
+  reflectance[o] = (pi_f * I) / (cos(sza[j] * pi_f / 180.0) * X.scal[(size_t)pl * 16 + 5]);
+  if (Q) Q[o] = S > 1 ? CV.total[(size_t)pl * 4 + 1] : 0.0;
+  if (U) U[o] = S > 1 ? CV.total[(size_t)pl * 4 + 2] : 0.0;
+}
+
+__global__ void k_vl_init_active(VLPix X, VLConv CV, VLSol Z, int npix_chunk, int *list, int *count) {
+  const int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= npix_chunk) return;
+  const bool ok = X.ibuf[(size_t)pl * 4 + 1] == 0;
+  CV.state[(size_t)pl * 4] = ok ? 1 : 0; CV.state[(size_t)pl * 4 + 1] = 0; CV.state[(size_t)pl * 4 + 2] = 0; CV.state[(size_t)pl * 4 + 3] = 0;
+  for (int o = 0; o < 4; o++) CV.total[(size_t)pl * 4 + o] = 0.0;
+  Z.fail[pl] = 0;
+  if (ok) { const int idx = atomicAdd(count, 1); list[idx] = pl; }
+}
+
+// Rayleigh optical thickness (VLIDORT_ROT_CALC): one thread per (layer, obs, channel)
+__device__ double f_air_dev(double XX2, double C) {
+  const double depol1 = (double)1.034f + (double)3.17e-4f * XX2;
+  const double depol2 = (double)1.096f + (double)1.385e-3f * XX2 + (double)1.448e-4f * XX2 * XX2;
+  const float s3 = (78.084f + 20.946f) + 0.934f;
+  return ((double)78.084f * depol1 + (double)20.946f * depol2 + (double)0.934f * 1.0 + C * (double)100.0f * (double)1.15f) /
+         ((double)s3 + C * (double)100.0f);
+}
+__global__ void k_rot_calc(int km, int nch, int nobs, const double *__restrict__ channels, const double *__restrict__ pe,
+                           const double *__restrict__ he, const double *__restrict__ te, double *__restrict__ ROT,
+                           double *__restrict__ depol) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= (long)km * nobs * nch) return;
+  const int k = (int)(t % km); const long r = t / km; const int j = (int)(r % nobs), i = (int)(r / nobs);
+  const double Av = (double)6.0221367e23f, Ts = (double)288.15f, Ps = (double)1013.25f;
+  const double pi = (double)3.14159274101257324f;
+  const double Ns = (Av / (double)22.4141f) * ((double)273.15f / Ts) * (double)(1.0f / 1000.f);
+  const double C = (double)(360.0f * 1e-6f);
+  const double wmicron = channels[i] * (double)1.e-3f;
+  const double XX = 1.0 / wmicron, XX2 = XX * XX, CM = wmicron / (double)10000.0f, pi3 = pi * pi * pi;
+  double RI = (double)8060.51f + (double)2480990.0f / ((double)132.274f - XX2) + (double)17455.7f / ((double)39.32957f - XX2);
+  RI = RI * (double)1e-8f + 1.0;
+  RI = (RI - 1) * (1.0 + (double)0.54f * (C - (double)0.0003f)) + 1;
+  const double RI2 = RI * RI, fa = f_air_dev(XX2, C);
+  const double A = 24.0 * pi3 * fa * ((RI2 - 1) * (RI2 - 1)) / (Ns * Ns * CM * CM * CM * CM * (RI2 + 2) * (RI2 + 2));
+  if (k == 0 && j == 0) depol[i] = 6.0 * (fa - 1.0) / (7.0 * fa + 3.0);
+  const size_t e0 = k + (size_t)(km + 1) * j;
+  double v0 = A * Ns * ((pe[e0] * (double)1.e-2f) / Ps) * (Ts / te[e0]); v0 = v0 * (double)1.e5f;
+  double v1 = A * Ns * ((pe[e0 + 1] * (double)1.e-2f) / Ps) * (Ts / te[e0 + 1]); v1 = v1 * (double)1.e5f;
+  const double difz = he[e0] * (double)1.e-3f - he[e0 + 1] * (double)1.e-3f;
+  ROT[k + (size_t)km * (j + (size_t)nobs * i)] = difz * (v0 + v1) / 2.0;
+}
+
+// ------------------------------------------------------------------------------------------------ host driver
+namespace {
+
+struct DevArena {                      // one allocation carved into aligned pieces
+  char *base = nullptr; size_t cap = 0, off = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) { off = 0; return cudaSuccess; }
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0; off = 0;
+    cudaError_t e = cudaMalloc((void **)&base, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  template <class T> T *take(size_t n) { off = (off + 255) / 256 * 256; T *p = reinterpret_cast<T *>(base + off); off += n * sizeof(T); return p; }
+};
+DevArena g_arena;          // grow-only; released by ab200_vlidort_release()
+
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct RunDesc {
+  int S, N, km, nch, nobs, nMom, nPol, planpar, lambertian, scalar_glue;
+  double MISSING;
+  // device inputs (Fortran layouts)
+  const double *ROT, *depol, *alpha, *tau, *ssa, *pmom, *he, *albedo, *sza, *raa, *vza, *flux_factor;
+  // BRDF (device, per pixel) when !lambertian
+  VLSurf surf; const double *exactdb;
+  // host copies of the per-obs angles and the per-pixel skip mask (host decides MISSING / state quirk)
+  const std::vector<double> *h_sza; const std::vector<unsigned char> *h_skip;
+  // device outputs (nobs,nch)
+  double *radiance, *reflectance, *Q, *U; int *nfourier, *status;
+  cudaStream_t stream;
+};
+
+int run_vlidort(const RunDesc &R) {
+  const int S = R.S, N = R.N, L = R.km, n = S * N, NM = std::min(2 * N - 1, R.nMom), npix = R.nobs * R.nch;
+  if (npix == 0) return 0;
+  if (N < 1 || N > 32 || L < 1 || L > MAXLAY || (S != 1 && S != 3) || 2 * N > MAXMOM) { ab200_set_error("vlidort: unsupported nstreams/nlayers/nstokes"); return AB200_ERR_ARG; }
+  cudaStream_t st = R.stream;
+  // ---- sizes
+  const size_t per_pix_state = (size_t)L * 8 * 8 + (size_t)(NM + 1) * L * 4 * 8 + 16 * 8 + 4 * 4 + (size_t)(NM + 1) * L;
+  const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + (6 + 2 * S) * n + 2 * n + 2 * 2 * n) * 8;
+  const size_t per_pix = per_pix_state + per_pix_sol + 4 * 8 + 4 * 4 + 4 * 3;
+  double ws_gb = 24.0;
+  if (const char *e = getenv("AB200_VL_WORKSPACE_GB")) ws_gb = atof(e);
+  size_t freeb = 0, totalb = 0;
+  cudaMemGetInfo(&freeb, &totalb);
+  size_t budget = (size_t)(ws_gb * 1e9);
+  budget = std::min(budget, (size_t)(0.6 * (double)(freeb + g_arena.cap)));
+  // K3 geometry
+  const int bvp_threads = 256;
+  const size_t bvp_smem = bvp_smem_doubles(n) * 8 + (size_t)(7 * n + 16) * 4;
+  int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  int bvp_per_sm = 1;
+  auto kb = (S == 1) ? (const void *)k_vl_bvp<1> : (const void *)k_vl_bvp<3>;
+  auto ke = (S == 1) ? (const void *)k_vl_eigen<1> : (const void *)k_vl_eigen<3>;
+  if (bvp_smem > 227 * 1024) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory BVP window"); return AB200_ERR_ARG; }
+  AB_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvp_smem));
+  AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bvp_per_sm, kb, bvp_threads, bvp_smem));
+  bvp_per_sm = std::max(1, std::min(bvp_per_sm, 8));
+  const int bvp_grid_max = nsm * bvp_per_sm;
+  const size_t work_per_cta = bvp_work_doubles(n, L);
+  const size_t bvp_work_bytes = (size_t)bvp_grid_max * work_per_cta * 8;
+  // K2 geometry
+  const int scr_d = eigen_scratch_doubles(n, NM);
+  int wpc = (int)std::min<size_t>(8, (200 * 1024) / ((size_t)scr_d * 8));
+  if (wpc < 1) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory eigen scratch"); return AB200_ERR_ARG; }
+  const size_t eig_smem = (size_t)wpc * scr_d * 8;
+  AB_CUDA_OK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
+  const size_t setup_smem = (size_t)(12 * (L + 1) + 2 * (R.nMom + 1) + 2 * 4 + 16) * 8;
+
+  size_t chunk = npix;
+  if (budget > bvp_work_bytes + (64 << 20)) chunk = std::min<size_t>(npix, (budget - bvp_work_bytes - (64 << 20)) / per_pix);
+  else chunk = 1;
+  chunk = std::max<size_t>(1, chunk);
+  const size_t total_bytes = chunk * per_pix + chunk * 64 + bvp_work_bytes + (size_t)(NM + 1) * (NM + 1) * N * 3 * 8 + (size_t)npix + (64 << 20);
+  AB_CUDA_OK(g_arena.reserve(total_bytes));
+  DevArena &A = g_arena;
+  VLPix X; X.L = L; X.NM = NM; X.S = S; X.npix = (int)chunk;
+  X.deltau = A.take<double>(chunk * L); X.og = A.take<double>(chunk * (NM + 1) * L * 4);
+  X.avsec = A.take<double>(chunk * L); X.itrans = A.take<double>(chunk * L); X.tdmubar = A.take<double>(chunk * L);
+  X.tduserm = A.take<double>(chunk * L); X.emult_up = A.take<double>(chunk * L); X.sigma_p = A.take<double>(chunk * L);
+  X.itrans_userm = A.take<double>(chunk * L); X.scal = A.take<double>(chunk * 16); X.ibuf = A.take<int>(chunk * 4);
+  X.layscat = A.take<unsigned char>(chunk * (NM + 1) * L);
+  VLSol Z; Z.n = n; Z.S = S; Z.N = N;
+  const size_t nq = chunk * L;
+  Z.keig = A.take<double>(nq * n); Z.tde = A.take<double>(nq * n); Z.xp = A.take<double>(nq * n * n); Z.xn = A.take<double>(nq * n * n);
+  Z.uh_dn = A.take<double>(nq * n * S); Z.uh_up = A.take<double>(nq * n * S); Z.hm1 = A.take<double>(nq * n); Z.hm2 = A.take<double>(nq * n);
+  Z.aterm = A.take<double>(nq * n); Z.bterm = A.take<double>(nq * n); Z.gam_m = A.take<double>(nq * n); Z.gam_p = A.take<double>(nq * n);
+  Z.wupper = A.take<double>(nq * 2 * n); Z.wlower = A.take<double>(nq * 2 * n); Z.fail = A.take<int>(chunk);
+  VLConv CV; CV.total = A.take<double>(chunk * 4); CV.state = A.take<int>(chunk * 4);
+  int *listA = A.take<int>(chunk), *listB = A.take<int>(chunk), *counts = A.take<int>(2 * (NM + 4));
+  double *d_pq = A.take<double>((size_t)(NM + 1) * N * 3 * (NM + 1));
+  double *work = A.take<double>((size_t)bvp_grid_max * work_per_cta);
+  unsigned char *d_skip = A.take<unsigned char>(npix);
+  if (A.off > A.cap) { ab200_set_error("vlidort: internal workspace accounting error"); return AB200_ERR_ARG; }
+
+  // ---- quadrature and the Pi tables at the quadrature cosines for every Fourier component (pixel independent)
+  VLQuad QD; memset(&QD, 0, sizeof QD); QD.N = N;
+  if (N == 1) { QD.x[0] = std::sqrt(1.0 / 3.0); QD.w[0] = 1.0; } else gauss01(N, QD.x, QD.w);
+  {
+    std::vector<double> h_pq((size_t)(NM + 1) * N * 3 * (NM + 1), 0.0), tmp(3 * (NM + 2));
+    for (int m = 0; m <= NM; m++)
+      for (int i = 0; i < N; i++) {
+        pi_prt(m, NM, QD.x[i], tmp.data());
+        for (int l = m; l <= NM; l++) for (int c = 0; c < 3; c++) h_pq[(size_t)m * (NM + 1) * N * 3 + ((size_t)l * N + i) * 3 + c] = tmp[3 * l + c];
+      }
+    AB_CUDA_OK(cudaMemcpyAsync(d_pq, h_pq.data(), h_pq.size() * 8, cudaMemcpyHostToDevice, st));
+    AB_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  // ---- skip mask and the FOCORR_NADIR state quirk (first obs with solar_zenith == 0.0 that is actually run)
+  int nadir_from = R.nobs;
+  {
+    const std::vector<unsigned char> &sk = *R.h_skip;
+    for (int j = 0; j < R.nobs && nadir_from == R.nobs; j++)
+      if ((*R.h_sza)[j] == 0.0) for (int i = 0; i < R.nch; i++) if (!sk[(size_t)j * R.nch + i]) { nadir_from = j; break; }
+    AB_CUDA_OK(cudaMemcpyAsync(d_skip, sk.data(), npix, cudaMemcpyHostToDevice, st));
+  }
+  VLIn in; memset(&in, 0, sizeof in);
+  in.km = L; in.nch = R.nch; in.nobs = R.nobs; in.nMom = R.nMom; in.nPol = R.nPol; in.S = S; in.N = N; in.nfine = 3;
+  in.planpar = R.planpar; in.lambertian = R.lambertian; in.scalar_glue = R.scalar_glue; in.nadir_from_obs = nadir_from;
+  in.MISSING = R.MISSING; in.earth_radius = 6371.0;
+  in.ROT = R.ROT; in.depol = R.depol; in.alpha = R.alpha; in.tau = R.tau; in.ssa = R.ssa; in.pmom = R.pmom; in.ze = R.he;
+  in.albedo = R.albedo; in.sza = R.sza; in.raa = R.raa; in.vza = R.vza; in.flux_factor = R.flux_factor; in.exactdb = R.exactdb;
+  in.skip = d_skip;
+  const double accuracy = (double)0.0001f;
+  cudaEvent_t ev[4];
+  for (auto &e : ev) cudaEventCreate(&e);
+
+  for (size_t p0 = 0; p0 < (size_t)npix; p0 += chunk) {
+    const int nc = (int)std::min<size_t>(chunk, npix - p0);
+    AB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * (NM + 4), st));
+    cudaEventRecord(ev[0], st);
+    k_vl_setup<<<nc, 128, setup_smem, st>>>(in, X, (int)p0);
+    k_vl_init_active<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, Z, nc, listA, counts);
+    cudaEventRecord(ev[1], st);
+    AB_CUDA_OK(cudaGetLastError());
+    int nactive = 0;
+    AB_CUDA_OK(cudaMemcpyAsync(&nactive, counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); g_stats.ms_setup += ms;
+    // BRDF pointers are indexed with the global pixel inside bvp_pixel via SF; shift them to the chunk
+    VLSurf SFc = R.surf;
+    if (!R.lambertian) {
+      SFc.brdf_f += (size_t)p0 * SFc.nmfour * 16 * N * N; SFc.brdf_f_0 += (size_t)p0 * SFc.nmfour * 16 * N;
+      SFc.user_brdf_f += (size_t)p0 * SFc.nmfour * 16 * N; SFc.user_brdf_f_0 += (size_t)p0 * SFc.nmfour * 16;
+    }
+    int *cur = listA, *nxt = listB;
+    for (int m = 0; m <= NM && nactive > 0; m++) {
+      const long nprob = (long)nactive * L;
+      const int egrid = (int)((nprob + wpc - 1) / wpc);
+      const double *pqm = d_pq + (size_t)m * (NM + 1) * N * 3;
+      cudaEventRecord(ev[0], st);
+      if (S == 1) k_vl_eigen<1><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+      else k_vl_eigen<3><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+      cudaEventRecord(ev[1], st);
+      const int bgrid = std::min(nactive, bvp_grid_max);
+      int *cnt = counts + 1 + m;
+      if (S == 1) k_vl_bvp<1><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
+      else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
+      cudaEventRecord(ev[2], st);
+      AB_CUDA_OK(cudaGetLastError());
+      g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive;
+      AB_CUDA_OK(cudaMemcpyAsync(&nactive, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+      AB_CUDA_OK(cudaStreamSynchronize(st));
+      float m1 = 0, m2 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);
+      g_stats.ms_eigen += m1; g_stats.ms_bvp += m2;
+      std::swap(cur, nxt);
+    }
+    k_vl_finish<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, (int)p0, nc, R.nch, R.nobs, R.sza, R.MISSING, S, R.radiance, R.reflectance, R.Q, R.U,
+                                                  R.nfourier, R.status);
+    AB_CUDA_OK(cudaGetLastError());
+    AB_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  g_stats.npix += npix;
+  return 0;
+}
+
+bool is_missing_h(double x, double MISSING) { return std::fabs(x / MISSING - 1.0) < (double)0.001f; }
+
+// host-pointer front end shared by the Lambertian entry points
+int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+                 const double *ROT, const double *depol, const double *alpha, const double *tau, const double *ssa,
+                 const double *pmom, const double *he, const double *albedo, const double *sza, const double *raa,
+                 const double *vza, const double *flux_factor, double MISSING, double *radiance, double *reflectance,
+                 double *Q, double *U, int *rc) {
+  *rc = 0;
+  // VLIDORT_Init dimension checks (V283/VLIDORT_Mod.F90:366-374; GEOS-sized maxima of vlidort_pars.f90:136-199)
+  if (nstreams > 25) { *rc = 2; return 2; }
+  if (km > 72) { *rc = 3; return 3; }
+  if (nMom > 1000) { *rc = 5; return 5; }
+  const size_t npix = (size_t)nobs * nch;
+  if (npix == 0) return 0;
+  const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
+  size_t bytes = 8 * (n_rot * (alpha ? 4 : 3) + n_pm + n_he + npix * (1 + (flux_factor ? 1 : 0)) + 3 * (size_t)nobs + nch + 4 * npix) + 8 * npix + 4096 * 16;
+  static DevBuf io;
+  AB_CUDA_OK(io.reserve(bytes));
+  char *b = io.as<char>(); size_t off = 0;
+  auto put = [&](const double *src, size_t n) -> double * { off = align256(off); double *d = (double *)(b + off); off += n * 8; if (src) cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, 0); return d; };
+  RunDesc R; memset(&R, 0, sizeof R);
+  R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
+  R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING;
+  R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.alpha = alpha ? put(alpha, n_rot) : nullptr; R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
+  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.albedo = put(albedo, npix); R.sza = put(sza, nobs); R.raa = put(raa, nobs); R.vza = put(vza, nobs);
+  R.flux_factor = flux_factor ? put(flux_factor, npix) : nullptr;
+  R.radiance = put(nullptr, npix); R.reflectance = put(nullptr, npix); R.Q = put(nullptr, npix); R.U = put(nullptr, npix);
+  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * npix; off = align256(off); R.status = (int *)(b + off); off += 4 * npix;
+  std::vector<double> h_sza(sza, sza + nobs);
+  std::vector<unsigned char> skip(npix, 0);
+  for (int j = 0; j < nobs; j++) {
+    const bool ma = is_missing_h(sza[j], MISSING) || is_missing_h(vza[j], MISSING) || is_missing_h(raa[j], MISSING);
+    for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || is_missing_h(albedo[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
+  }
+  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = 0;
+  int e = run_vlidort(R);
+  if (e) return e;
+  AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * npix, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * npix, cudaMemcpyDeviceToHost, 0));
+  if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * npix, cudaMemcpyDeviceToHost, 0));
+  if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * npix, cudaMemcpyDeviceToHost, 0));
+  g_last_nfourier.resize(npix); g_last_status.resize(npix);
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * npix, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * npix, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int ab200_vlidort_scalar_lambert(int km, int nch, int nobs, const double *channels, int nstreams,
+                                            int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                            const double *tau, const double *ssa, const double *g, const double *pmom,
+                                            const double *pe, const double *he, const double *te, const double *albedo,
+                                            const double *solar_zenith, const double *relat_azymuth,
+                                            const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL,
+                                            double *reflectance_VL, int *rc) {
+  (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
+  return lambert_host(1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, nullptr, tau, ssa, pmom, he, albedo,
+                      solar_zenith, relat_azymuth, sensor_zenith, nullptr, MISSING, radiance_VL, reflectance_VL, nullptr, nullptr, rc);
+}
+
+extern "C" int ab200_vlidort_vector_lambert(int km, int nch, int nobs, const double *channels, int nstreams,
+                                            int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                            const double *alpha, const double *tau, const double *ssa, const double *pmom,
+                                            const double *pe, const double *he, const double *te, const double *albedo,
+                                            const double *solar_zenith, const double *relat_azymuth,
+                                            const double *sensor_zenith, const double *flux_factor, double MISSING,
+                                            int verbose, double *radiance_VL, double *reflectance_VL, double *Q, double *U,
+                                            int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  return lambert_host(3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, he, albedo,
+                      solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, radiance_VL, reflectance_VL, Q, U, rc);
+}
+
+extern "C" int ab200_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
+                              const double *te, double MISSING, int verbose, double *ROT, double *depol, int *rc) {
+  (void)MISSING; (void)verbose;
+  *rc = 0;
+  if (km > 72) { *rc = 3; return 3; }
+  const size_t ne = (size_t)(km + 1) * nobs, nr = (size_t)km * nobs * nch;
+  if (nr == 0) return 0;
+  static DevBuf io;
+  AB_CUDA_OK(io.reserve(8 * (3 * ne + nr + 2 * nch) + 4096));
+  double *d = io.as<double>();
+  double *d_pe = d, *d_he = d + ne, *d_te = d + 2 * ne, *d_ch = d + 3 * ne, *d_dp = d_ch + nch, *d_rot = d_dp + nch;
+  cudaMemcpyAsync(d_pe, pe, 8 * ne, cudaMemcpyHostToDevice, 0); cudaMemcpyAsync(d_he, he, 8 * ne, cudaMemcpyHostToDevice, 0);
+  cudaMemcpyAsync(d_te, te, 8 * ne, cudaMemcpyHostToDevice, 0); cudaMemcpyAsync(d_ch, channels, 8 * nch, cudaMemcpyHostToDevice, 0);
+  k_rot_calc<<<(unsigned)((nr + 255) / 256), 256>>>(km, nch, nobs, d_ch, d_pe, d_he, d_te, d_rot, d_dp);
+  AB_CUDA_OK(cudaGetLastError());
+  cudaMemcpyAsync(ROT, d_rot, 8 * nr, cudaMemcpyDeviceToHost, 0); cudaMemcpyAsync(depol, d_dp, 8 * nch, cudaMemcpyDeviceToHost, 0);
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+// diagnostics of the most recent call: per-pixel Fourier count (FOURIER_SAVED) and status, p = j*nch + i
+extern "C" long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap) {
+  const long n = (long)g_last_nfourier.size();
+  for (long k = 0; k < n && k < cap; k++) { if (nfourier_out) nfourier_out[k] = g_last_nfourier[k]; if (status_out) status_out[k] = g_last_status[k]; }
+  return n;
+}
+
+extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,
+                                   int reset) {
+  if (ms_setup) *ms_setup = g_stats.ms_setup;
+  if (ms_eigen) *ms_eigen = g_stats.ms_eigen;
+  if (ms_bvp) *ms_bvp = g_stats.ms_bvp;
+  if (n_eigen) *n_eigen = g_stats.n_eigen_problems;
+  if (n_bvp) *n_bvp = g_stats.n_bvp_problems;
+  if (npix) *npix = g_stats.npix;
+  if (reset) memset(&g_stats, 0, sizeof g_stats);
+  return 0;
+}
+
+extern "C" int ab200_vlidort_release(void) {
+  if (g_arena.base) cudaFree(g_arena.base);
+  g_arena.base = nullptr; g_arena.cap = 0; g_arena.off = 0;
+  return 0;
+}

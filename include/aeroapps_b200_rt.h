@@ -1,4 +1,38 @@
-/* Stage B (VLIDORT) part of the C ABI -- included by aeroapps_b200.h */
+/* Stage B (VLIDORT) part of the C ABI -- included by aeroapps_b200.h.
+ * Every entry point keeps the argument list of the Fortran module procedure / f2py subroutine it replaces
+ * (scalars by value, arrays by pointer in the Fortran layout, `logical` as int, rc through a pointer).
+ * Per-pixel failures do not set rc: the outputs of that (obs, channel) become MISSING, as in the reference.
+ */
 #ifndef AEROAPPS_B200_RT_H
 #define AEROAPPS_B200_RT_H
+
+/* VLIDORT_ROT_CALC (Components/rtms/geo_vlidort/VLIDORT_ROT.F90:19-86; f2py ROT_CALC,
+ * Components/rtms/leo_vlidort/VLIDORT_POLAR_py.F90:9): pe,he,te (km+1,nobs) -> ROT (km,nobs,nch), depol (nch) */
+int ab200_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
+                   const double *te, double MISSING, int verbose, double *ROT, double *depol, int *rc);
+
+/* VLIDORT_Scalar_Lambert (geo_vlidort/VLIDORT_LAMBERT.F90:34-168; f2py SCALAR_LAMBERT, VLIDORT_POLAR_py.F90:371) */
+int ab200_vlidort_scalar_lambert(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                 int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                 const double *ssa, const double *g, const double *pmom, const double *pe,
+                                 const double *he, const double *te, const double *albedo, const double *solar_zenith,
+                                 const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                 double *radiance_VL, double *reflectance_VL, int *rc);
+
+/* VLIDORT_Vector_Lambert_SingleGeom (VLIDORT_LAMBERT.F90:172-342; f2py VECTOR_LAMBERT, VLIDORT_POLAR_py.F90:457) */
+int ab200_vlidort_vector_lambert(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                 int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                 const double *tau, const double *ssa, const double *pmom, const double *pe,
+                                 const double *he, const double *te, const double *albedo, const double *solar_zenith,
+                                 const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                 double MISSING, int verbose, double *radiance_VL, double *reflectance_VL, double *Q,
+                                 double *U, int *rc);
+
+/* diagnostics of the most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i; returns npix */
+long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap);
+/* accumulated device timings (CUDA events) of the three kernels and problem counts; reset != 0 clears them */
+int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,
+                        int reset);
+/* frees the grow-only device workspace */
+int ab200_vlidort_release(void);
 #endif

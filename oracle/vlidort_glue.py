@@ -1,0 +1,79 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the wrapper-level oracle entry points (orc_vlidort_run,
+orc_rot_calc) and a synthetic scene builder used by tests, smoke() and the bench CPU arms."""
+import ctypes as C
+import numpy as np
+
+from . import vlidort_oracle as vo
+from . import mie_oracle as mo
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def F(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def rot_calc(channels, pe, he, te):
+    pe, he, te = F(pe), F(he), F(te)
+    km = pe.shape[0] - 1; nobs = pe.shape[1]
+    ch = np.ascontiguousarray(channels, dtype=np.float64); nch = len(ch)
+    ROT = np.zeros((km, nobs, nch), order="F"); depol = np.zeros(nch)
+    vo.lib().orc_rot_calc(km, nch, nobs, _p(ch), _p(pe), _p(he), _p(te), _p(ROT), _p(depol))
+    return ROT, depol
+
+
+def vlidort_run(nstokes, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, he, sza, raa, vza, albedo=None,
+                alpha=None, flux_factor=None, MISSING=1e15, scalar_glue=False, brdf=None, skip=None, obs_range=None):
+    """Wrapper-level oracle: returns dict(radiance, reflectance, Q, U (nobs,nch), nfourier, status (nobs,nch))."""
+    ROT, tau, ssa, pmom, he = F(ROT), F(tau), F(ssa), F(pmom), F(he)
+    km, nch, nobs = tau.shape
+    nMom, nPol = pmom.shape[3], pmom.shape[4]
+    depol = np.ascontiguousarray(depol, dtype=np.float64)
+    sza, raa, vza = (np.ascontiguousarray(x, dtype=np.float64) for x in (sza, raa, vza))
+    alb = F(albedo) if albedo is not None else None
+    al = F(alpha) if alpha is not None else None
+    ff = F(flux_factor) if flux_factor is not None else None
+    out = {k: np.zeros((nobs, nch), order="F") for k in ("radiance", "reflectance", "Q", "U")}
+    nf = np.zeros((nobs, nch), np.int32); st = np.zeros((nobs, nch), np.int32)
+    b = {k: None for k in ("brdf_f", "brdf_f_0", "user_brdf_f", "user_brdf_f_0", "exactdb")}
+    if brdf is not None:
+        b = {k: np.ascontiguousarray(brdf[k], dtype=np.float64) for k in b}
+    sk = None if skip is None else np.ascontiguousarray(skip, dtype=np.uint8)
+    o0, o1 = obs_range if obs_range else (0, nobs)
+    vo.lib().orc_vlidort_run(int(nstokes), int(scalar_glue), km, nch, nobs, int(nstreams), int(plane_parallel), nMom, nPol,
+                             _p(ROT), _p(depol), _p(al), _p(tau), _p(ssa), _p(pmom), _p(he), _p(alb), _p(sza), _p(raa),
+                             _p(vza), _p(ff), C.c_double(MISSING), 0 if brdf is None else 1, _p(b["brdf_f"]),
+                             _p(b["brdf_f_0"]), _p(b["user_brdf_f"]), _p(b["user_brdf_f_0"]), _p(b["exactdb"]),
+                             None if sk is None else sk.ctypes.data_as(C.POINTER(C.c_ubyte)), o0, o1,
+                             _p(out["radiance"]), _p(out["reflectance"]), _p(out["Q"]), _p(out["U"]),
+                             nf.ctypes.data_as(C.POINTER(C.c_int)), st.ctypes.data_as(C.POINTER(C.c_int)))
+    out["nfourier"] = nf; out["status"] = st
+    return out
+
+
+def synthetic_scene(nobs, nch_nm=(550.0,), nmom=64, km=72, seed=7, tables=None, mt=None, sza_max=75.0, vza_max=65.0):
+    """SURVEY.md section 8(d) synthetic pixels: GOCART-like columns -> Mie oracle (vector AOPs) -> edge variables ->
+    Rayleigh; returns float64 Fortran arrays in the drop-in layouts."""
+    if mt is None:
+        from aeroapps_b200 import mietables as mt
+    tables = tables or mt.synthetic_tables(nmom=nmom)
+    st = mt.synthetic_state(nobs, km, seed=seed)
+    chan_m = [c * 1e-9 for c in nch_nm]
+    om = mo.OracleMie(chan_m, nmom, tables)
+    tau, ssa, g, pmom, rc = om.getaopvector(list(nch_nm), st["vnames"], st["qm"], st["rh"], nmom, 6)
+    assert rc == 0
+    pe, ze, te = mo.getedgevars(st["airdens"], st["delp"], 1.0)
+    pmom = pmom.astype(np.float64)
+    pmom[..., 1] *= -1.0; pmom[..., 3] *= -1.0           # caller-side sign flip of P12, P34 (LV/py_leo_vlidort/vlidort.py:438-440)
+    ROT, depol = rot_calc(nch_nm, pe, ze, te)
+    rng = np.random.default_rng(seed + 1000)
+    scene = dict(km=km, nobs=nobs, nch=len(nch_nm), channels=np.array(nch_nm, dtype=np.float64), nMom=nmom, nPol=6,
+                 tau=F(tau), ssa=F(ssa), g=F(g), pmom=F(pmom), pe=F(pe), he=F(ze), te=F(te), ROT=F(ROT), depol=depol,
+                 sza=rng.uniform(0.0, sza_max, nobs), vza=rng.uniform(0.0, vza_max, nobs), raa=rng.uniform(0.0, 180.0, nobs),
+                 albedo=F(rng.uniform(0.02, 0.4, (nobs, len(nch_nm)))),
+                 u10m=rng.normal(0, 5, nobs), v10m=rng.normal(0, 5, nobs), mr=np.full(len(nch_nm), 1.334))
+    return scene

@@ -655,3 +655,133 @@ extern "C" int vl_master(const vl_input *in, vl_output *out) {
   out->status = 0;
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * AeroApps glue (V283/VLIDORT_ScatMod.F90:143-281, 284-617, 975-1247) and the per-pixel loop of the drop-in
+ * wrappers (GV/VLIDORT_LAMBERT.F90:34-168,172-342; GV/VLIDORT_BRDF_CX.F90:587-762).  Single-precision
+ * literals of the Fortran are kept as (double)(float) values.
+ */
+static inline bool is_missing(double x, double MISSING) { return std::fabs(x / MISSING - 1.0) < (double)0.001f; }
+
+extern "C" int orc_vlidort_run(int nstokes, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel,
+                    int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                    const double *tau, const double *ssa, const double *pmom, const double *he,
+                    const double *albedo, const double *sza, const double *raa, const double *vza,
+                    const double *flux_factor, double MISSING, int surface, const double *brdf_f,
+                    const double *brdf_f_0, const double *user_brdf_f, const double *user_brdf_f_0,
+                    const double *exactdb, const unsigned char *skip, int obs_begin, int obs_end,
+                    double *radiance, double *reflectance, double *Q, double *U, int *nfourier, int *status) {
+  (void)nPol;
+  const int L = km, N = nstreams;
+  const double pi_f = (double)(4.f * atanf(1.0f));             /* real*8 parameter pi = 4.*atan(1.0) */
+  const double f1em3 = (double)1.e-3f, wclamp = (double)0.99999f, sqrt6f = (double)sqrtf(6.f);
+  std::vector<double> greek((size_t)(nMom + 1) * L * 16), dtau(L), omg(L), hgrid(L + 1);
+  /* reference state quirk: once a pixel with solar_zenith == 0.0 has been run, FOCORR_NADIR stays on */
+  bool nadir_state = false;
+  for (int j = 0; j < obs_begin; j++) if (sza[j] == 0.0 && !is_missing(sza[j], MISSING) && !is_missing(vza[j], MISSING) && !is_missing(raa[j], MISSING)) nadir_state = true;
+  for (int j = obs_begin; j < obs_end; j++) {
+    const bool miss_ang = is_missing(sza[j], MISSING) || is_missing(vza[j], MISSING) || is_missing(raa[j], MISSING);
+    for (int i = 0; i < nch; i++) {
+      const size_t o = j + (size_t)nobs * i, p = (size_t)j * nch + i;
+      auto set_missing = [&]() { radiance[o] = MISSING; reflectance[o] = MISSING; if (Q) Q[o] = MISSING; if (U) U[o] = MISSING; if (status) status[p] = 99; if (nfourier) nfourier[p] = 0; };
+      if (miss_ang) { set_missing(); continue; }
+      if (surface == 0 && is_missing(albedo[o], MISSING)) { set_missing(); continue; }
+      if (skip && skip[p]) { set_missing(); continue; }
+      if (sza[j] == 0.0) nadir_state = true;
+      const double dep = depol[i];
+      const double gammamom2 = -sqrt6f * (1.0 - dep) / (2.0 + dep), alphamom2 = 6.0 * (1.0 - dep) / (2.0 + dep);
+      const double raysmom2 = (1.0 - dep) / (2.0 + dep);
+      std::fill(greek.begin(), greek.end(), 0.0);
+      for (int k = 0; k <= L; k++) hgrid[k] = he[k + (size_t)(L + 1) * j] * f1em3;
+      for (int k = 0; k < L; k++) {
+        const double ray = ROT[k + (size_t)L * (j + (size_t)nobs * i)], alp = alpha ? alpha[k + (size_t)L * (j + (size_t)nobs * i)] : 0.0;
+        const double t = tau[k + (size_t)L * (i + (size_t)nch * j)], w = ssa[k + (size_t)L * (i + (size_t)nch * j)];
+        const double tau_ext = alp + ray + t, tau_scat = ray + w * t;
+        double ssa_tot = tau_scat / tau_ext;
+        if (ssa_tot > wclamp) ssa_tot = wclamp;
+        dtau[k] = tau_ext; omg[k] = ssa_tot;
+        const double aerswt = w * t / tau_scat, rayswt = ray / tau_scat;
+        auto PM = [&](int l, int pol) { return pmom[k + (size_t)L * (i + (size_t)nch * (j + (size_t)nobs * (l + (size_t)nMom * pol)))]; };
+#define GK_(l, q) greek[((size_t)(l) * L + k) * 16 + (q)]
+        if (scalar_glue) {
+          GK_(0, 0) = 1.0;
+          if (nMom >= 1) GK_(1, 0) = (1 <= nMom - 1 ? PM(1, 0) : 0.0) * aerswt;
+          if (nMom >= 2) GK_(2, 0) = raysmom2 * rayswt + (2 <= nMom - 1 ? PM(2, 0) : 0.0) * aerswt;
+          for (int l = 3; l <= nMom; l++) GK_(l, 0) = (l <= nMom - 1 ? PM(l, 0) : 0.0) * aerswt;
+        } else {
+          for (int l = 0; l <= nMom; l++) {
+            double a[16]; for (int q = 0; q < 16; q++) a[q] = 0.0;
+            if (l <= nMom - 1) { a[0] = PM(l, 0); a[1] = PM(l, 1); a[4] = PM(l, 1); a[10] = PM(l, 2); a[11] = PM(l, 3); a[14] = -PM(l, 3); a[5] = PM(l, 4); a[15] = PM(l, 5); }
+            double r[16]; for (int q = 0; q < 16; q++) r[q] = 0.0;
+            if (l == 0) r[0] = 1.0;
+            if (l == 1) r[15] = 3.0 * (1.0 - 2.0 * dep) / (2.0 + dep);
+            if (l == 2) { r[0] = raysmom2; r[1] = gammamom2; r[4] = gammamom2; r[5] = alphamom2; }
+            for (int q = 0; q < 16; q++) GK_(l, q) = (l <= 2 ? r[q] * rayswt : 0.0) + a[q] * aerswt;
+          }
+          GK_(0, 0) = 1.0;
+        }
+#undef GK_
+      }
+      vl_input in; memset(&in, 0, sizeof in);
+      in.nstokes = nstokes; in.nstreams = N; in.nlayers = L; in.nmoments_input = nMom; in.nfine = 3;
+      in.do_plane_parallel = plane_parallel; in.do_focorr = 1; in.do_focorr_nadir = nadir_state ? 1 : 0; in.do_focorr_outgoing = nadir_state ? 0 : 1;
+      in.do_deltam = 1; in.do_lambertian = (surface == 0); in.max_fourier_override = -1;
+      in.accuracy = (double)0.0001f; in.asymtx_tolerance = 1.0e-12; in.flux_factor = flux_factor ? flux_factor[i + (size_t)nch * j] : 1.0;
+      in.earth_radius = 6371.0; in.albedo = (surface == 0) ? albedo[o] : 0.0; in.sza = sza[j]; in.vza = vza[j]; in.raa = raa[j];
+      in.height_grid = hgrid.data(); in.deltau = dtau.data(); in.omega = omg.data(); in.greekmat = greek.data();
+      if (surface != 0) {
+        in.brdf_f = brdf_f + p * (size_t)2 * N * 16 * N * N; in.brdf_f_0 = brdf_f_0 + p * (size_t)2 * N * 16 * N;
+        in.user_brdf_f = user_brdf_f + p * (size_t)2 * N * 16 * N; in.user_brdf_f_0 = user_brdf_f_0 + p * (size_t)2 * N * 16; in.exactdb = exactdb + p * 16;
+      }
+      vl_output out;
+      int rc = vl_master(&in, &out);
+      if (status) status[p] = rc;
+      if (nfourier) nfourier[p] = out.nfourier;
+      if (rc != 0) { radiance[o] = MISSING; reflectance[o] = MISSING; if (Q) Q[o] = MISSING; if (U) U[o] = MISSING; continue; }
+      radiance[o] = out.stokes[0];
+      if (Q) Q[o] = out.stokes[1];
+      if (U) U[o] = out.stokes[2];
+      reflectance[o] = (pi_f * out.stokes[0]) / (std::cos(sza[j] * pi_f / 180.0) * in.flux_factor);
+    }
+  }
+  return 0;
+}
+
+/* VLIDORT_Rayleigh: Bodhaine et al. / Tomasi et al. -- single-precision literals kept */
+static double f_air(double XX2, double C) {
+  const double depol1 = (double)1.034f + (double)3.17e-4f * XX2;
+  const double depol2 = (double)1.096f + (double)1.385e-3f * XX2 + (double)1.448e-4f * XX2 * XX2;
+  const double depol3 = 1.0, depol4 = (double)1.15f;
+  const float s3 = (78.084f + 20.946f) + 0.934f;                        /* real*4 constant sum */
+  return ((double)78.084f * depol1 + (double)20.946f * depol2 + (double)0.934f * depol3 + C * (double)100.0f * depol4) /
+         ((double)s3 + C * (double)100.0f);
+}
+extern "C" void orc_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
+                             const double *te, double *ROT, double *depol) {
+  const double Av = (double)6.0221367e23f, Ts = (double)288.15f, Ps = (double)1013.25f;
+  const double pi = (double)(4.f * atanf(1.0f));
+  const double Ns = (Av / (double)22.4141f) * ((double)273.15f / Ts) * (double)(1.0f / 1000.f);
+  const double C = (double)(360.0f * 1e-6f);
+  for (int i = 0; i < nch; i++) {
+    const double wmicron = channels[i] * (double)1.e-3f;
+    const double XX = 1.0 / wmicron, XX2 = XX * XX, CM = wmicron / (double)10000.0f, pi3 = pi * pi * pi;
+    double RI = (double)8060.51f + (double)2480990.0f / ((double)132.274f - XX2) + (double)17455.7f / ((double)39.32957f - XX2);
+    RI = RI * (double)1e-8f + 1.0;
+    RI = (RI - 1) * (1.0 + (double)0.54f * (C - (double)0.0003f)) + 1;
+    const double RI2 = RI * RI;
+    const double A = 24.0 * pi3 * f_air(XX2, C) * ((RI2 - 1) * (RI2 - 1)) / (Ns * Ns * CM * CM * CM * CM * (RI2 + 2) * (RI2 + 2));
+    depol[i] = 6.0 * (f_air(XX2, C) - 1.0) / (7.0 * f_air(XX2, C) + 3.0);
+    for (int j = 0; j < nobs; j++) {
+      std::vector<double> vol(km + 1);
+      for (int k = 0; k <= km; k++) {
+        const double hp = pe[k + (size_t)(km + 1) * j] * (double)1.e-2f, T = te[k + (size_t)(km + 1) * j];
+        vol[k] = A * Ns * (hp / Ps) * (Ts / T);
+        vol[k] = vol[k] * (double)1.e5f;
+      }
+      for (int k = 0; k < km; k++) {
+        const double difz = he[k + (size_t)(km + 1) * j] * (double)1.e-3f - he[k + 1 + (size_t)(km + 1) * j] * (double)1.e-3f;
+        ROT[k + (size_t)km * (j + (size_t)nobs * i)] = difz * (vol[k] + vol[k + 1]) / 2.0;
+      }
+    }
+  }
+}

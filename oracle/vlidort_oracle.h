@@ -27,3 +27,26 @@ int vl_master(const vl_input *in, vl_output *out);
 }
 #endif
 #endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* AeroApps glue + drop-in wrapper level (V283/VLIDORT_ScatMod.F90, GV/VLIDORT_LAMBERT.F90 ...), Fortran layouts.
+ * surface: 0 Lambertian (albedo(nobs,nch)); 1 BRDF Fourier components supplied per pixel p = j*nch+i
+ *          (brdf_f [p][2N][16][N][N], brdf_f_0 [p][2N][16][N], user_brdf_f [p][2N][16][N], user_brdf_f_0 [p][2N][16],
+ *           exactdb [p][16]); skip[p] != 0 marks pixels whose surface set-up failed.
+ * outputs (nobs,nch): radiance, reflectance, Q, U (Q,U may be NULL for scalar); nfourier/status (npix) optional. */
+int orc_vlidort_run(int nstokes, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel,
+                    int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                    const double *tau, const double *ssa, const double *pmom, const double *he,
+                    const double *albedo, const double *sza, const double *raa, const double *vza,
+                    const double *flux_factor, double MISSING, int surface, const double *brdf_f,
+                    const double *brdf_f_0, const double *user_brdf_f, const double *user_brdf_f_0,
+                    const double *exactdb, const unsigned char *skip, int obs_begin, int obs_end,
+                    double *radiance, double *reflectance, double *Q, double *U, int *nfourier, int *status);
+/* VLIDORT_ROT_CALC (GV/VLIDORT_ROT.F90:19-86 -> V283/VLIDORT_ScatMod.F90:143-281) */
+void orc_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
+                  const double *te, double *ROT, double *depol);
+#ifdef __cplusplus
+}
+#endif

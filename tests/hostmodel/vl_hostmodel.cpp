@@ -1,0 +1,74 @@
+// TEST-ONLY build of the product's Stage-B kernel bodies (aeroapps_b200/csrc/vl_*.cuh) with a one-lane
+// SerialTeam, so that their mathematics can be compared with the CPU oracle in the GPU-less build container.
+// Not part of the shipped library; the product has no CPU path.
+#define AB_HOST_MODEL 1
+#include "../../aeroapps_b200/csrc/vl_bvp.cuh"
+#include <vector>
+#include <cstring>
+#include <cstdio>
+using namespace vlk;
+
+extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int nPol, int planpar, int lambertian,
+                          int scalar_glue, int nfine, int nadir_from_obs, double earth_radius, double accuracy,
+                          const double *ROT, const double *depol, const double *alpha, const double *tau,
+                          const double *ssa, const double *pmom, const double *ze, const double *albedo,
+                          const double *sza, const double *raa, const double *vza, const double *flux_factor,
+                          const double *brdf_f, const double *brdf_f_0, const double *user_brdf_f,
+                          const double *user_brdf_f_0, const double *exactdb, int max_fourier_override,
+                          double *stokes /*[npix][4]*/, int *nfourier /*[npix]*/, int *status /*[npix]*/) {
+  const int npix = nobs * nch, L = km, n = S * N, NM = std::min(2 * N - 1, nMom);
+  VLIn in; memset(&in, 0, sizeof in);
+  in.km = km; in.nch = nch; in.nobs = nobs; in.nMom = nMom; in.nPol = nPol; in.S = S; in.N = N; in.nfine = nfine;
+  in.planpar = planpar; in.lambertian = lambertian; in.scalar_glue = scalar_glue; in.nadir_from_obs = nadir_from_obs;
+  in.earth_radius = earth_radius; in.ROT = ROT; in.depol = depol; in.alpha = alpha; in.tau = tau; in.ssa = ssa; in.pmom = pmom;
+  in.ze = ze; in.albedo = albedo; in.sza = sza; in.raa = raa; in.vza = vza; in.flux_factor = flux_factor; in.exactdb = exactdb;
+  VLPix X; X.L = L; X.NM = NM; X.S = S; X.npix = npix;
+  std::vector<double> deltau((size_t)npix * L), og((size_t)npix * (NM + 1) * L * 4), a1((size_t)npix * L), a2(a1), a3(a1), a4(a1), a5(a1), a6(a1), a7(a1), scal((size_t)npix * 16, 0.0);
+  std::vector<int> ibuf((size_t)npix * 4, 0);
+  std::vector<unsigned char> layscat((size_t)npix * (NM + 1) * L, 1);
+  X.deltau = deltau.data(); X.og = og.data(); X.avsec = a1.data(); X.itrans = a2.data(); X.tdmubar = a3.data(); X.tduserm = a4.data();
+  X.emult_up = a5.data(); X.sigma_p = a6.data(); X.itrans_userm = a7.data(); X.scal = scal.data(); X.ibuf = ibuf.data(); X.layscat = layscat.data();
+  SerialTeam T;
+  std::vector<double> scr(12 * (L + 1) + 2 * (nMom + 1) + 2 * std::max(nfine, 1) + 16);
+  for (int p = 0; p < npix; p++) setup_pixel(T, in, X, p, scr.data());
+  VLQuad QD; QD.N = N;
+  if (N == 1) { QD.x[0] = std::sqrt(1.0 / 3.0); QD.w[0] = 1.0; } else gauss01(N, QD.x, QD.w);
+  // one pixel at a time to keep the workspace small
+  VLSol Z; Z.n = n; Z.S = S; Z.N = N;
+  std::vector<double> keig((size_t)L * n), tde(keig), xp((size_t)L * n * n), xn(xp), uhd((size_t)L * n * S), uhu(uhd), hm1(keig), hm2(keig), at(keig), bt(keig), gm(keig), gp(keig), wu((size_t)L * 2 * n), wl(wu);
+  std::vector<int> fail(npix, 0);
+  std::vector<double> total((size_t)npix * 4, 0.0); std::vector<int> cstate((size_t)npix * 4, 0);
+  VLConv CV; CV.total = total.data(); CV.state = cstate.data();
+  VLSurf SFc; SFc.brdf_f = brdf_f; SFc.brdf_f_0 = brdf_f_0; SFc.user_brdf_f = user_brdf_f; SFc.user_brdf_f_0 = user_brdf_f_0; SFc.nmfour = 2 * N;
+  std::vector<double> pq((size_t)(NM + 1) * N * 3), tmp(3 * (NM + 2));
+  std::vector<double> escr(eigen_scratch_doubles(n, NM) + 64), bscr(bvp_smem_doubles(n) + 64), Ug(bvp_work_doubles(n, L));
+  std::vector<int> iscr(3 * n + 4 * n + 16);
+  for (int p = 0; p < npix; p++) {
+    status[p] = ibuf[(size_t)p * 4 + 1]; nfourier[p] = 0;
+    for (int o = 0; o < 4; o++) stokes[(size_t)p * 4 + o] = 0.0;
+    if (status[p] != 0) continue;
+    // solution arrays are indexed with q = p*L + k inside the bodies: shift the base pointers for this pixel
+    const size_t q0 = (size_t)p * L;
+    Z.keig = keig.data() - q0 * n; Z.tde = tde.data() - q0 * n; Z.xp = xp.data() - q0 * n * n; Z.xn = xn.data() - q0 * n * n;
+    Z.uh_dn = uhd.data() - q0 * n * S; Z.uh_up = uhu.data() - q0 * n * S; Z.hm1 = hm1.data() - q0 * n; Z.hm2 = hm2.data() - q0 * n;
+    Z.aterm = at.data() - q0 * n; Z.bterm = bt.data() - q0 * n; Z.gam_m = gm.data() - q0 * n; Z.gam_p = gp.data() - q0 * n;
+    Z.wupper = wu.data() - q0 * 2 * n; Z.wlower = wl.data() - q0 * 2 * n; Z.fail = fail.data();
+    cstate[(size_t)p * 4] = 1;
+    for (int m = 0; m <= NM && cstate[(size_t)p * 4] == 1; m++) {
+      if (max_fourier_override >= 0 && m > max_fourier_override) break;
+      for (int i = 0; i < N; i++) { pi_prt(m, NM, QD.x[i], tmp.data()); for (int l = m; l <= NM; l++) for (int c = 0; c < 3; c++) pq[((size_t)l * N + i) * 3 + c] = tmp[3 * l + c]; }
+      for (int k = 0; k < L; k++) {
+        if (S == 1) eigen_problem<1>(T, X, Z, QD, pq.data(), m, p, k, escr.data());
+        else eigen_problem<3>(T, X, Z, QD, pq.data(), m, p, k, escr.data());
+      }
+      if (fail[p]) { status[p] = 4; break; }
+      const double acc = (max_fourier_override >= 0) ? -1.0 : accuracy;
+      if (S == 1) bvp_pixel<1>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
+      else bvp_pixel<3>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
+      if (cstate[(size_t)p * 4 + 3]) { status[p] = 4; break; }
+      nfourier[p] = m;
+    }
+    for (int o = 0; o < S; o++) stokes[(size_t)p * 4 + o] = total[(size_t)p * 4 + o];
+  }
+  return 0;
+}
