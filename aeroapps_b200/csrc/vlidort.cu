@@ -11,7 +11,7 @@
 
 using namespace vlk;
 
-struct VLStats { double ms_setup, ms_eigen, ms_bvp; long n_eigen_problems, n_bvp_problems; int nfourier_hist[64]; long npix; };
+struct VLStats { double ms_setup, ms_eigen, ms_bvp, flops_eigen, flops_bvp; long n_eigen_problems, n_bvp_problems, n_launches; long npix; };
 static VLStats g_stats;
 static std::vector<int> g_last_nfourier, g_last_status;
 
@@ -302,7 +302,12 @@ int run_vlidort(const RunDesc &R) {
       else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());
-      g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive;
+      g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive; g_stats.n_launches += 2;
+      {  // algorithmic flops of SURVEY.md 8(d): eigen part (2+25+2) n^3 + 4 S^3 N^2 (2N-m); BVP part (14/3)(2n)^3 + 12 (2n)^2
+        const double n3 = (double)n * n * n;
+        g_stats.flops_eigen += (double)nprob * (29.0 * n3 + 4.0 * S * S * S * (double)N * N * (2 * N - m));
+        g_stats.flops_bvp += (double)nprob * ((14.0 / 3.0) * 8.0 * n3 + 12.0 * 4.0 * n * n);
+      }
       AB_CUDA_OK(cudaMemcpyAsync(&nactive, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
       AB_CUDA_OK(cudaStreamSynchronize(st));
       float m1 = 0, m2 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);
@@ -315,7 +320,7 @@ int run_vlidort(const RunDesc &R) {
     AB_CUDA_OK(cudaStreamSynchronize(st));
   }
   for (auto &e : ev) cudaEventDestroy(e);
-  g_stats.npix += npix;
+  g_stats.npix += npix; g_stats.n_launches += 3 * ((npix + chunk - 1) / chunk);
   return 0;
 }
 
@@ -421,6 +426,51 @@ extern "C" long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long
   const long n = (long)g_last_nfourier.size();
   for (long k = 0; k < n && k < cap; k++) { if (nfourier_out) nfourier_out[k] = g_last_nfourier[k]; if (status_out) status_out[k] = g_last_status[k]; }
   return n;
+}
+
+extern "C" int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long *n_launches) {
+  if (flops_eigen) *flops_eigen = g_stats.flops_eigen;
+  if (flops_bvp) *flops_bvp = g_stats.flops_bvp;
+  if (n_launches) *n_launches = g_stats.n_launches;
+  return 0;
+}
+
+// device-pointer variant of ab200_vlidort_vector_lambert: every array already resident in HBM (same layouts)
+extern "C" int ab200_vlidort_vector_lambert_dev(int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+                                                const double *ROT, const double *depol, const double *alpha,
+                                                const double *tau, const double *ssa, const double *pmom, const double *he,
+                                                const double *albedo, const double *sza, const double *raa, const double *vza,
+                                                const double *flux_factor, double MISSING, double *radiance,
+                                                double *reflectance, double *Q, double *U, void *stream, int *rc) {
+  *rc = 0;
+  if (nstreams > 25) { *rc = 2; return 2; }
+  if (km > 72) { *rc = 3; return 3; }
+  if (nMom > 1000) { *rc = 5; return 5; }
+  const size_t npix = (size_t)nobs * nch;
+  if (npix == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<double> h_sza(nobs), h_vza(nobs), h_raa(nobs), h_alb(npix);
+  AB_CUDA_OK(cudaMemcpyAsync(h_sza.data(), sza, 8 * (size_t)nobs, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(h_vza.data(), vza, 8 * (size_t)nobs, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(h_raa.data(), raa, 8 * (size_t)nobs, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(h_alb.data(), albedo, 8 * npix, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<unsigned char> skip(npix, 0);
+  for (int j = 0; j < nobs; j++) {
+    const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
+    for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || is_missing_h(h_alb[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
+  }
+  static DevBuf diag;
+  AB_CUDA_OK(diag.reserve(8 * npix + 512));
+  RunDesc R; memset(&R, 0, sizeof R);
+  R.S = 3; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
+  R.lambertian = 1; R.scalar_glue = 0; R.MISSING = MISSING;
+  R.ROT = ROT; R.depol = depol; R.alpha = alpha; R.tau = tau; R.ssa = ssa; R.pmom = pmom; R.he = he; R.albedo = albedo;
+  R.sza = sza; R.raa = raa; R.vza = vza; R.flux_factor = flux_factor;
+  R.radiance = radiance; R.reflectance = reflectance; R.Q = Q; R.U = U;
+  R.nfourier = diag.as<int>(); R.status = diag.as<int>() + npix;
+  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
+  return run_vlidort(R);
 }
 
 extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,

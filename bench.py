@@ -172,8 +172,144 @@ class AopScalarWorkload:
                 "bytes_per_unit": self.bytes_per_unit}
 
 
-WORKLOADS = {"aop_scalar": AopScalarWorkload}
-DEFAULT_WORKLOAD = "aop_scalar"
+# =================================================================================================
+# workload: Stage B vector VLIDORT (BASELINE configs[2]: nstokes=3, 12 streams, 72 layers, Greek moments from the
+# Mie tables, nMom=300), processed in batches; the Mie-AOP stage that feeds it is timed as `aop` extra info.
+class RtVectorWorkload:
+    name = "vlidort_vector_n12_l72_lambert"
+    metric = "VLIDORT pixels/sec (vector nstokes=3, 12 streams, 72 layers, nMom=300, FO + delta-M, Lambertian surface)"
+    unit = "pixels/s"
+    dtype = "f64"
+    km, nobs, nch, N, S, nmom = 72, 2048, 1, 12, 3, 300
+
+    def __init__(self, nobs=None):
+        from aeroapps_b200 import mietables as mt
+        self.mt = mt
+        if nobs:
+            self.nobs = nobs
+        self.units_per_step = self.nobs * self.nch
+        self.plane_parallel = False
+
+    def config(self):
+        n = self.S * self.N
+        return {"workload": self.name, "km": self.km, "pixels_per_step_per_gpu": self.nobs, "nstokes": self.S, "nstreams": self.N,
+                "nMom": self.nmom, "plane_parallel": self.plane_parallel,
+                "l2": "per-step working set (%.1f GB of layer solutions and BVP factors) far larger than the 126 MB L2"
+                      % (self.nobs * self.km * (2 * n * n + 20 * n) * 8 / 1e9)}
+
+    def _scene_gpu(self):
+        """synthetic pixels built with the PRODUCT's own Stage A (CUDA): Mie AOP vector -> edge vars -> Rayleigh"""
+        from aeroapps_b200 import MieObs_, VLIDORT_POLAR_ as VP
+        mt = self.mt
+        tables = mt.synthetic_tables(nmom=self.nmom)
+        st = mt.synthetic_state(self.nobs, self.km, seed=20260101 + 3)
+        mie = MieObs_.ChemMie([550e-9], self.nmom, tables)
+        t0 = time.perf_counter()
+        tau, ssa, g, pmom, rc = mie.getaopvector([550.0], st["vnames"], 0, st["qm"], st["rh"], self.nmom, 6)
+        self.aop_e2e_voxels_per_s = self.km * self.nobs / (time.perf_counter() - t0)
+        assert rc == 0
+        pe, ze, te = MieObs_.getedgevars(st["airdens"], st["delp"], 1.0)
+        pmom = pmom.astype(np.float64); pmom[..., 1] *= -1.0; pmom[..., 3] *= -1.0
+        F = lambda a: np.asfortranarray(a, dtype=np.float64)
+        ch = np.array([550.0])
+        ROT, depol, rc = VP.rot_calc(ch, F(pe), F(ze), F(te), 1e15, 0)
+        rng = np.random.default_rng(20260101 + 4)
+        n = self.nobs
+        return dict(channels=ch, ROT=F(ROT), depol=depol, alpha=np.zeros_like(F(ROT)), tau=F(tau), ssa=F(ssa), pmom=F(pmom),
+                    pe=F(pe), he=F(ze), te=F(te), albedo=F(rng.uniform(0.02, 0.4, (n, 1))), sza=rng.uniform(0, 75, n),
+                    raa=rng.uniform(0, 180, n), vza=rng.uniform(0, 65, n), flux=np.ones((1, n), order="F"))
+
+    def setup_gpu(self, torch, dev):
+        import ctypes as C
+        from aeroapps_b200._lib import lib, check
+        self.C, self.lib, self.check, self.torch = C, lib(), check, torch
+        sc = self.scene = self._scene_gpu()
+        keys = ["ROT", "depol", "alpha", "tau", "ssa", "pmom", "he", "albedo", "sza", "raa", "vza", "flux"]
+        flat = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F")))
+        self.h = {k: flat(sc[k]).pin_memory() for k in keys + ["pe", "te", "channels"]}
+        self.d = {k: self.h[k].to(dev) for k in keys}
+        self.d_out = [torch.empty(self.nobs * self.nch, dtype=torch.float64, device=dev) for _ in range(4)]
+        self.h_out = [torch.empty(self.nobs * self.nch, dtype=torch.float64).pin_memory() for _ in range(4)]
+        self.h2d = sum(self.h[k].numel() * 8 for k in keys + ["pe", "te"])
+        self.d2h = 4 * self.nobs * self.nch * 8
+        self.lib.ab200_vlidort_stats(None, None, None, None, None, None, 1)
+
+    def _p(self, t):
+        return self.C.cast(t.data_ptr(), self.C.POINTER(self.C.c_double))
+
+    def step_gpu(self, stream):
+        C, d, p = self.C, self.d, self._p
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_vlidort_vector_lambert_dev(
+            self.km, self.nch, self.nobs, self.N, int(self.plane_parallel), self.nmom, 6, p(d["ROT"]), p(d["depol"]), p(d["alpha"]),
+            p(d["tau"]), p(d["ssa"]), p(d["pmom"]), p(d["he"]), p(d["albedo"]), p(d["sza"]), p(d["raa"]), p(d["vza"]), p(d["flux"]),
+            C.c_double(1e15), *[p(o) for o in self.d_out], C.c_void_p(stream), C.byref(rc)), "vector_lambert_dev")
+        assert rc.value == 0
+
+    def step_e2e(self):
+        C, h, p = self.C, self.h, self._p
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_vlidort_vector_lambert(
+            self.km, self.nch, self.nobs, p(h["channels"]), self.N, int(self.plane_parallel), self.nmom, 6, p(h["ROT"]), p(h["depol"]),
+            p(h["alpha"]), p(h["tau"]), p(h["ssa"]), p(h["pmom"]), p(h["pe"]), p(h["he"]), p(h["te"]), p(h["albedo"]), p(h["sza"]),
+            p(h["raa"]), p(h["vza"]), p(h["flux"]), C.c_double(1e15), 0, *[p(o) for o in self.h_out], C.byref(rc)), "vector_lambert")
+        assert rc.value == 0
+
+    def stats(self, reset=False):
+        C = self.C
+        a, b, c = C.c_double(), C.c_double(), C.c_double(); d, e, f = C.c_long(), C.c_long(), C.c_long()
+        fe, fb, nl = C.c_double(), C.c_double(), C.c_long()
+        self.lib.ab200_vlidort_stats2(C.byref(fe), C.byref(fb), C.byref(nl))
+        self.lib.ab200_vlidort_stats(C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), C.byref(f), int(reset))
+        return dict(ms_setup=a.value, ms_eigen=b.value, ms_bvp=c.value, n_eigen=d.value, n_bvp=e.value, npix=f.value,
+                    flops_eigen=fe.value, flops_bvp=fb.value, n_launches=nl.value)
+
+    # ---- CPU arm: the oracle restatement of the reference at the wrapper level
+    def setup_cpu(self, sample_cols):
+        from oracle import vlidort_glue as vg
+        self.vg = vg
+        cores = os.cpu_count() or 1
+        self.sample_cols = max(cores, min(sample_cols, 16 * cores, self.nobs))
+        if getattr(self, "scene", None) is None:          # --impl reference: no GPU -> inputs from the CPU oracle of Stage A
+            sc = vg.synthetic_scene(self.sample_cols, nmom=self.nmom, seed=20260101 + 3)
+            sc["flux"] = np.ones((1, self.sample_cols), order="F"); sc["alpha"] = np.zeros_like(sc["ROT"])
+            self.cpu_scene = sc
+        else:
+            s = self.scene; n = self.sample_cols
+            self.cpu_scene = dict(ROT=s["ROT"][:, :n], depol=s["depol"], alpha=s["alpha"][:, :n], tau=s["tau"][:, :, :n], ssa=s["ssa"][:, :, :n],
+                                  pmom=s["pmom"][:, :, :n], he=s["he"][:, :n], albedo=s["albedo"][:n], sza=s["sza"][:n], raa=s["raa"][:n],
+                                  vza=s["vza"][:n], flux=s["flux"][:, :n])
+
+    def step_cpu(self, nthreads):
+        from concurrent.futures import ThreadPoolExecutor
+        s, n, vg = self.cpu_scene, self.sample_cols, self.vg
+        edges = np.linspace(0, n, nthreads + 1).astype(int)
+        rng = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(lambda ab: vg.vlidort_run(3, self.N, self.plane_parallel, s["ROT"], s["depol"], s["tau"], s["ssa"], s["pmom"], s["he"],
+                                                  s["sza"], s["raa"], s["vza"], albedo=s["albedo"], alpha=s["alpha"], flux_factor=s["flux"],
+                                                  obs_range=ab), rng))
+        return n * self.nch, time.perf_counter() - t0
+
+    def roofline(self, step_ms):
+        st = self.stats()
+        fp = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+        peak = json.load(open(fp))["dfma_tflops"] if os.path.exists(fp) else 37.0
+        dom = "k_vl_eigen" if st["ms_eigen"] >= st["ms_bvp"] else "k_vl_bvp"
+        ms = st["ms_eigen"] if dom == "k_vl_eigen" else st["ms_bvp"]
+        fl = st["flops_eigen"] if dom == "k_vl_eigen" else st["flops_bvp"]
+        ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        tot = (st["flops_eigen"] + st["flops_bvp"]) / ((st["ms_eigen"] + st["ms_bvp"] + st["ms_setup"]) * 1e-3) / 1e12
+        return {"bound": "fp64", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "measured DFMA microbenchmark on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak.json); "
+                               "MEASURED_PEAKS.json holds no FP64 figure",
+                "whole_rt_tflops": tot, "kernel_ms_share": {"setup": st["ms_setup"], "eigen": st["ms_eigen"], "bvp": st["ms_bvp"]},
+                "fourier_terms_per_pixel": st["n_bvp"] / max(st["npix"], 1)}
+
+
+WORKLOADS = {"aop_scalar": AopScalarWorkload, "rt_vector": RtVectorWorkload}
+DEFAULT_WORKLOAD = "rt_vector"
 
 
 def run_reference(args, wl):
@@ -201,18 +337,85 @@ def run_reference(args, wl):
         "gpu_launches": 0}))
 
 
+def run_gpu(wl, args, torch, dev, dist, rank, world, local):
+    """W warm-up + K timed steps of one workload (device-resident inputs), then the e2e leg; returns the JSON dict"""
+    wl.setup_gpu(torch, dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        wl.step_gpu(stream)
+    barrier()
+    if hasattr(wl, "stats"):
+        wl.stats(reset=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local) as cs:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            wl.step_gpu(stream)
+            ev[i + 1].record()
+        barrier()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        roof = wl.roofline(total_ms / args.steps) if rank == 0 else None
+        launches = wl.stats()["n_launches"] if hasattr(wl, "stats") else wl.launches_per_step * args.steps
+        # keep the sampler alive long enough for at least a few samples on very short runs
+        if total_ms < 1500:
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                wl.step_gpu(stream)
+            torch.cuda.synchronize()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = wl.units_per_step * world * args.steps / (total_ms * 1e-3)
+
+    # e2e leg: host (pinned) buffers through the host-pointer C-ABI call, copies inside the timed region
+    for _ in range(2):
+        wl.step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        wl.step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = wl.units_per_step * world * e2e_steps / (float(t.item()) * 1e-3)
+    if rank != 0:
+        return None
+    return {
+        "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(), "roofline": roof,
+        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
+        "gpu_launches": int(launches), "clocks": cs.summary(),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--nobs", type=int, default=0, help="override columns/pixels per GPU (debug)")
-    ap.add_argument("--cpu-sample", type=int, default=48600, help="columns/pixels in the bounded CPU sample")
+    ap.add_argument("--nobs", type=int, default=0, help="override columns/pixels per GPU per step (debug)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="columns/pixels in the bounded CPU sample (0 = workload default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-aop", action="store_true", help="skip the extra Mie-AOP measurement attached to the RT line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if not args.cpu_sample:
+        args.cpu_sample = 48600 if args.workload == "aop_scalar" else 10 ** 9
 
     wl = WORKLOADS[args.workload](nobs=args.nobs or None)
     if args.impl == "reference":
@@ -235,73 +438,23 @@ def main():
         g.build()
     if dist:
         dist.barrier()
-    wl.setup_gpu(torch, dev)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def barrier():
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        wl.step_gpu(stream)
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as cs:
-        barrier()
-        ev[0].record()
-        for i in range(args.steps):
-            wl.step_gpu(stream)
-            ev[i + 1].record()
-        barrier()
-        total_ms = ev[0].elapsed_time(ev[-1])
-        # keep the sampler alive long enough for at least a few samples on very short runs
-        if total_ms < 1500:
-            t_end = time.time() + 1.5
-            while time.time() < t_end:
-                wl.step_gpu(stream)
-            torch.cuda.synchronize()
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = wl.units_per_step * world * args.steps / (total_ms * 1e-3)
-
-    # e2e leg: host (pinned) buffers through the host-pointer C-ABI call, copies inside the timed region
-    for _ in range(2):
-        wl.step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(3, min(args.steps, 10))
-    e0.record()
-    for _ in range(e2e_steps):
-        wl.step_e2e()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = wl.units_per_step * world * e2e_steps / (float(t.item()) * 1e-3)
-
-    out = None
+    out = run_gpu(wl, args, torch, dev, dist, rank, world, local)
+    if args.workload == "rt_vector" and not args.no_aop:
+        # the second half of the BASELINE metric: Mie AOP voxels/s (BASELINE configs[0], c90 scalar AOPs)
+        import copy
+        a2 = copy.copy(args); a2.steps = 20; a2.warmup = 5
+        aop = run_gpu(AopScalarWorkload(), a2, torch, dev, dist, rank, world, local)
+        if rank == 0:
+            out["aop"] = {k: aop[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "config")}
+            out["aop"]["vector_e2e_voxels_per_s_nmom300"] = getattr(wl, "aop_e2e_voxels_per_s", None)
     if rank == 0:
-        kernel_ms = float(np.mean(per_step)) / wl.launches_per_step if wl.launches_per_step == 1 else None
-        out = {
-            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.config(),
-            "roofline": wl.roofline(float(np.mean(per_step))),
-            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
-            "gpu_launches": wl.launches_per_step * args.steps, "clocks": cs.summary(),
-        }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             wl.setup_cpu(sample_cols=args.cpu_sample)
-            wl.step_cpu(cores)
             u, dt = wl.step_cpu(cores)
             out["cpu_baseline"] = {"value": u / dt, "unit": wl.unit, "cores": cores, "kind": "port",
-                                   "sample": f"{wl.sample_cols} of {wl.nobs} columns, 1 pass"}
+                                   "sample": f"{wl.sample_cols} of {wl.nobs} {wl.unit.split('/')[0]} of the same workload, 1 pass, "
+                                             f"{cores} threads (oracle/: C/C++ restatement of the reference Fortran)"}
         print(json.dumps(out))
     if dist:
         dist.barrier()

@@ -28,6 +28,16 @@ int ab200_vlidort_vector_lambert(int km, int nch, int nobs, const double *channe
                                  double MISSING, int verbose, double *radiance_VL, double *reflectance_VL, double *Q,
                                  double *U, int *rc);
 
+/* device-pointer variant (inputs/outputs resident in HBM, launched on `stream` = cudaStream_t) */
+int ab200_vlidort_vector_lambert_dev(int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+                                     const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                     const double *ssa, const double *pmom, const double *he, const double *albedo,
+                                     const double *sza, const double *raa, const double *vza, const double *flux_factor,
+                                     double MISSING, double *radiance, double *reflectance, double *Q, double *U,
+                                     void *stream, int *rc);
+/* algorithmic FLOP counters (SURVEY.md 8(d) formula) and kernel-launch counter since the last reset */
+int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long *n_launches);
+
 /* diagnostics of the most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i; returns npix */
 long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap);
 /* accumulated device timings (CUDA events) of the three kernels and problem counts; reset != 0 clears them */

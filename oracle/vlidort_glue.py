@@ -48,7 +48,7 @@ def vlidort_run(nstokes, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, h
                              _p(ROT), _p(depol), _p(al), _p(tau), _p(ssa), _p(pmom), _p(he), _p(alb), _p(sza), _p(raa),
                              _p(vza), _p(ff), C.c_double(MISSING), 0 if brdf is None else 1, _p(b["brdf_f"]),
                              _p(b["brdf_f_0"]), _p(b["user_brdf_f"]), _p(b["user_brdf_f_0"]), _p(b["exactdb"]),
-                             None if sk is None else sk.ctypes.data_as(C.POINTER(C.c_ubyte)), o0, o1,
+                             None if sk is None else sk.ctypes.data_as(C.POINTER(C.c_ubyte)), int(o0), int(o1),
                              _p(out["radiance"]), _p(out["reflectance"]), _p(out["Q"]), _p(out["U"]),
                              nf.ctypes.data_as(C.POINTER(C.c_int)), st.ctypes.data_as(C.POINTER(C.c_int)))
     out["nfourier"] = nf; out["status"] = st
