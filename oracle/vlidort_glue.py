@@ -77,3 +77,21 @@ def synthetic_scene(nobs, nch_nm=(550.0,), nmom=64, km=72, seed=7, tables=None, 
                  albedo=F(rng.uniform(0.02, 0.4, (nobs, len(nch_nm)))),
                  u10m=rng.normal(0, 5, nobs), v10m=rng.normal(0, 5, nobs), mr=np.full(len(nch_nm), 1.334))
     return scene
+
+
+def vbrdf(nstokes, nstreams, which, factors, pars, lambertian, nstreams_brdf, do_shadow, sza, vza, raa):
+    """VBRDF supplement for one geometry (oracle/vbrdf_oracle.cpp).  Returns the Fourier arrays in the layout
+    vl_master consumes: brdf_f[m][q][i][j], brdf_f_0[m][q][i], user_brdf_f[m][q][j], user_brdf_f_0[m][q], exactdb[q]."""
+    L = vo.lib()
+    N, nk = int(nstreams), len(which)
+    w = np.asarray(which, np.int32); f = np.asarray(factors, np.float64)
+    p = np.ascontiguousarray(np.asarray(pars, np.float64).reshape(nk, 4)); lf = np.asarray(lambertian, np.int32)
+    bf = np.zeros((2 * N, 16, N, N)); bf0 = np.zeros((2 * N, 16, N)); ubf = np.zeros((2 * N, 16, N)); ubf0 = np.zeros((2 * N, 16))
+    ex = np.zeros(16); wsa = C.c_double(0.0)
+    dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
+    L.orc_vbrdf.restype = C.c_int
+    st = L.orc_vbrdf(int(nstokes), N, nk, w.ctypes.data_as(ip), f.ctypes.data_as(dp), p.ctypes.data_as(dp), lf.ctypes.data_as(ip),
+                     int(nstreams_brdf), int(bool(do_shadow)), C.c_double(sza), C.c_double(vza), C.c_double(raa),
+                     bf.ctypes.data_as(dp), bf0.ctypes.data_as(dp), ubf.ctypes.data_as(dp), ubf0.ctypes.data_as(dp),
+                     ex.ctypes.data_as(dp), C.byref(wsa))
+    return dict(status=st, brdf_f=bf, brdf_f_0=bf0, user_brdf_f=ubf, user_brdf_f_0=ubf0, exactdb=ex, wsa=wsa.value)

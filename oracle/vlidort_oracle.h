@@ -50,3 +50,15 @@ void orc_rot_calc(int km, int nch, int nobs, const double *channels, const doubl
 #ifdef __cplusplus
 }
 #endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* VBRDF supplement as the AeroApps surface glue calls it; see vbrdf_oracle.cpp */
+int orc_vbrdf(int nstokes, int nstreams, int nkernels, const int *which, const double *factors, const double *pars,
+              const int *lambertian_flag, int nstreams_brdf_in, int do_shadow, double sza, double vza, double raa,
+              double *brdf_f, double *brdf_f_0, double *user_brdf_f, double *user_brdf_f_0, double *exactdb,
+              double *wsa_out);
+#ifdef __cplusplus
+}
+#endif
