@@ -76,6 +76,85 @@ def vector_lambert(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, s
     return outs[0], outs[1], outs[2], outs[3], rc.value
 
 
+def _cx(entry, channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+        relat_azymuth, sensor_zenith, MISSING, verbose):
+    ROT, tau, ssa, pmom, pe, he, te = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    assert len(u) == nobs and len(v) == nobs and len(m) == nch
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(getattr(lib(), entry)(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp),
+                                _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sza), _p(raa),
+                                _p(vza), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)), entry)
+    return (*outs, rc.value)
+
+
+def vector_cx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+              relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_CX (VLIDORT_POLAR_py.F90:830): returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    return _cx("ab200_vlidort_vector_cx", channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m,
+               mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose)
+
+
+def vector_gisscx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+                  relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_GissCX (VLIDORT_POLAR_py.F90:673): returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    return _cx("ab200_vlidort_vector_gisscx", channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m,
+               V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose)
+
+
+def vector_brdf_modis(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, kernel_wt, param,
+                      solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_BRDF_MODIS (VLIDORT_POLAR_py.F90:137): kernel_wt (3,nch,nobs) = fiso,fgeo,fvol; param (2,nch,nobs).
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te, kernel_wt, param = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, kernel_wt, param))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert kernel_wt.shape[1:] == (nch, nobs) and param.shape[1:] == (nch, nobs)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_brdf_modis(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                kernel_wt.shape[0], param.shape[0], _p(ROT), _p(dp), _p(tau), _p(ssa), _p(pmom),
+                                                _p(pe), _p(he), _p(te), _p(kernel_wt), _p(param), _p(sza), _p(raa), _p(vza),
+                                                C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_brdf_modis")
+    return (*outs, rc.value)
+
+
+def scalar_cx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+              relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Scalar_CX (VLIDORT_BRDF_CX.F90:420): returns (radiance, reflectance, BRDF (1,nobs,nch), rc)."""
+    ROT, tau, ssa, g, pmom, pe, he, te = (_F(x) for x in (ROT, tau, ssa, g, pmom, pe, he, te))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    rad = np.zeros((nobs, nch), order="F"); refl = np.zeros((nobs, nch), order="F"); brdf = np.zeros((1, nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_cx(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT),
+                                        _p(dp), _p(tau), _p(ssa), _p(g), _p(pmom), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m),
+                                        _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose), _p(rad), _p(refl),
+                                        _p(brdf), C.byref(rc)), "ab200_vlidort_scalar_cx")
+    return rad, refl, brdf, rc.value
+
+
+def scalar_brdf_modis(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, pe, he, te, kernel_wt, param,
+                      solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Scalar_LandMODIS (VLIDORT_BRDF_MODIS.F90:35): returns (radiance, reflectance, BR, rc)."""
+    ROT, tau, ssa, g, pmom, pe, he, te, kernel_wt, param = (_F(x) for x in (ROT, tau, ssa, g, pmom, pe, he, te, kernel_wt, param))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(3)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_brdf_modis(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                _p(ROT), _p(dp), _p(tau), _p(ssa), _p(g), _p(pmom), _p(pe), _p(he), _p(te),
+                                                _p(kernel_wt), _p(param), _p(sza), _p(raa), _p(vza), C.c_double(MISSING),
+                                                int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_scalar_brdf_modis")
+    return (*outs, rc.value)
+
+
 def last_diag():
     """(nfourier, status) per pixel (nobs, nch) of the most recent VLIDORT call -- diagnostics, not in the reference."""
     lib().ab200_vlidort_last_diag.restype = C.c_long

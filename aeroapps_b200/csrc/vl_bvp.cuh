@@ -17,11 +17,12 @@
 namespace vlk {
 
 struct VLSurf {                  // BRDF Fourier components per pixel (null pointers for Lambertian)
-  const double *brdf_f;          // [p][m][q16][i][j]
-  const double *brdf_f_0;        // [p][m][q16][i]
-  const double *user_brdf_f;     // [p][m][q16][j]
-  const double *user_brdf_f_0;   // [p][m][q16]
+  const double *brdf_f;          // [p][m][q][i][j]   q = 4*o1+o2 < nq
+  const double *brdf_f_0;        // [p][m][q][i]
+  const double *user_brdf_f;     // [p][m][q][j]
+  const double *user_brdf_f_0;   // [p][m][q]         (not needed: the direct bounce comes from the FO code)
   int nmfour;                    // number of Fourier components stored (2N)
+  int nq;                        // 1: only the (1,1) element is non-zero (scalar kernels), 16: Mueller layout
 };
 
 struct VLConv {                  // per pixel, persistent over the Fourier loop
@@ -57,10 +58,17 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   const double SFAC = (m == 0) ? 2.0 : 1.0, DELTA_FACTOR = (m == 0) ? 1.0 : 2.0;
   const bool localbeam = include_surface && refl_direct;
   const double *BF = nullptr, *BF0 = nullptr, *UBF = nullptr;
+  const int nq = SF.nq;
+  auto BFq = [&](int o1, int o2, int i, int jj) -> double {
+    return nq == 16 ? BF[((size_t)(4 * o1 + o2) * N + i) * N + jj] : ((o1 | o2) == 0 ? BF[(size_t)i * N + jj] : 0.0);
+  };
+  auto UBFq = [&](int o1, int o2, int jj) -> double {
+    return nq == 16 ? UBF[(size_t)(4 * o1 + o2) * N + jj] : ((o1 | o2) == 0 ? UBF[jj] : 0.0);
+  };
   if (!lambertian) {
-    BF = SF.brdf_f + ((size_t)p * SF.nmfour + m) * 16 * N * N;
-    BF0 = SF.brdf_f_0 + ((size_t)p * SF.nmfour + m) * 16 * N;
-    UBF = SF.user_brdf_f + ((size_t)p * SF.nmfour + m) * 16 * N;
+    BF = SF.brdf_f + ((size_t)p * SF.nmfour + m) * SF.nq * N * N;
+    BF0 = SF.brdf_f_0 + ((size_t)p * SF.nmfour + m) * SF.nq * N;
+    UBF = SF.user_brdf_f + ((size_t)p * SF.nmfour + m) * SF.nq * N;
   }
   double attn = 0.0;
   if (localbeam) attn = FLUXF * (4.0 * cos_sza / DELTA_FACTOR) / PI4 * sc[3];
@@ -123,7 +131,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
           } else {
             for (int jj = 0; jj < N; jj++)
               for (int o2 = 0; o2 < S; o2++) {
-                const double a = QD.x[jj] * QD.w[jj] * BF[((size_t)(4 * o1 + o2) * N + i) * N + jj];
+                const double a = QD.x[jj] * QD.w[jj] * BFq(o1, o2, i, jj);
                 rp += a * Z.xp[(qa * n + e) * n + S * jj + o2]; rm += a * Z.xn[(qa * n + e) * n + S * jj + o2];
               }
             rp *= SFAC; rm *= SFAC;
@@ -141,13 +149,13 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
           if (lambertian) {
             if (o1 == 0) { for (int jj = 0; jj < N; jj++) rb += QD.x[jj] * QD.w[jj] * Z.wlower[qa * n2 + S * jj]; rb *= SFAC * albedo; }
           } else {
-            for (int jj = 0; jj < N; jj++) for (int o2 = 0; o2 < S; o2++) rb += QD.x[jj] * QD.w[jj] * BF[((size_t)(4 * o1 + o2) * N + i) * N + jj] * Z.wlower[qa * n2 + S * jj + o2];
+            for (int jj = 0; jj < N; jj++) for (int o2 = 0; o2 < S; o2++) rb += QD.x[jj] * QD.w[jj] * BFq(o1, o2, i, jj) * Z.wlower[qa * n2 + S * jj + o2];
             rb *= SFAC;
           }
           v += rb;
           if (localbeam) {
             if (lambertian) { if (m == 0 && o1 == 0) v += attn * albedo; }
-            else v += attn * BF0[(size_t)(4 * o1) * N + i];
+            else v += attn * (nq == 16 ? BF0[(size_t)(4 * o1) * N + i] : (o1 == 0 ? BF0[i] : 0.0));
           }
         }
         W[(size_t)freeslot[r] * Cs + RH] = v;
@@ -254,7 +262,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
 #pragma unroll
           for (int o1 = 0; o1 < S; o1++) {
             double rr = 0.0;
-            for (int jj = 0; jj < N; jj++) for (int o2 = 0; o2 < S; o2++) rr += red[S * jj + o2] * UBF[(size_t)(4 * o1 + o2) * N + jj];
+            for (int jj = 0; jj < N; jj++) for (int o2 = 0; o2 < S; o2++) rr += red[S * jj + o2] * UBFq(o1, o2, jj);
             cum[o1] = SFAC * rr;
           }
         }

@@ -24,7 +24,7 @@ struct VLIn {                 // device pointers in the reference's Fortran layo
   const double *sza, *raa, *vza;   // (nobs)
   const double *flux_factor;  // (nch,nobs) or null (=1)
   const double *exactdb;      // (npix,16) exact direct-bounce BRDF (non-Lambertian) or null
-  const unsigned char *skip;  // (npix) 1 = pixel not run (MISSING inputs / surface failure), may be null
+  const unsigned char *skip;  // (npix) 1 = pixel not run (MISSING inputs), 2 = not run, outputs -500 (RTLS BR < 0); may be null
 };
 
 // per-pixel state produced by K1 and consumed by K2/K3 (structure of arrays, pixel-major)
@@ -138,7 +138,7 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
   const int j = p / in.nch, i = p % in.nch;
   int *ib = X.ibuf + (size_t)p * 4;
   double *sc = X.scal + (size_t)p * 16;
-  if (in.skip && in.skip[p]) { if (T.rank == 0) ib[1] = 99; return; }
+  if (in.skip && in.skip[p]) { if (T.rank == 0) ib[1] = (in.skip[p] == 2) ? 98 : 99; return; }
   // scratch carve-up
   double *H = scr;                    // heights [km], 0..L
   double *din = H + (L + 1);          // deltau input

@@ -5,6 +5,7 @@
 #include "../../include/aeroapps_b200.h"
 #include "common.h"
 #include "vl_bvp.cuh"
+#include "vl_brdf.cuh"
 #include <algorithm>
 #include <vector>
 #include <cmath>
@@ -70,6 +71,32 @@ __global__ void __launch_bounds__(256) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
   }
 }
 
+// K0a: exact direct-bounce BRDF of every pixel + the wrappers' BR outputs (nobs,nch)
+__global__ void k_vl_brdf_exact(VLBrdf B, int npix, const unsigned char *__restrict__ skip, double *BR, double *BR_Q, double *BR_U) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int j = p / B.nch, i = p % B.nch;
+  const size_t o = j + (size_t)B.nobs * i;
+  if (skip[p]) { for (int q = 0; q < 16; q++) B.exactdb[(size_t)p * 16 + q] = 0.0; BR[o] = 0.0; if (BR_Q) { BR_Q[o] = 0.0; BR_U[o] = 0.0; } return; }
+  brdf_exact_pixel(B, p);
+  double br = B.exactdb[(size_t)p * 16];
+  const bool neg = (B.kind == SURF_MODIS && br < 0);
+  if (neg) br = -500.0;
+  BR[o] = br;
+  if (BR_Q) { BR_Q[o] = neg ? -500.0 : 0.0; BR_U[o] = neg ? -500.0 : 0.0; }
+}
+
+// K0b: BRDF Fourier components of the pixels of one chunk, one CTA per pixel
+__global__ void __launch_bounds__(256) k_vl_brdf_fourier(VLBrdf B, int p0, const unsigned char *__restrict__ skip, int nscr) {
+  extern __shared__ double smem_d[];
+  __shared__ double sd[64];
+  __shared__ int si[64];
+  const int pc = blockIdx.x, p = p0 + pc;
+  if (skip[p]) return;
+  BlockTeam T(sd, si);
+  brdf_pixel(T, B, p, pc, smem_d, nscr);
+}
+
 // outputs in the drop-in layout (nobs,nch); reflectance uses the single-precision pi of the glue
 // (VLIDORT_ScatMod.F90:344,596)
 __global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int npix_chunk, int nch, int nobs, const double *__restrict__ sza,
@@ -85,9 +112,10 @@ __global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int npix_chunk, int nch,
   if (status) status[p] = st;
   if (nfourier) nfourier[p] = CV.state[(size_t)pl * 4 + 2];
   if (st != 0) {
-    radiance[o] = MISSING; reflectance[o] = MISSING;
-    if (Q) Q[o] = MISSING;
-    if (U) U[o] = MISSING;
+    const double fill = (st == 98) ? -500.0 : MISSING;     // 98: RTLS bidirectional reflectance < 0 (GV/VLIDORT_BRDF_MODIS.F90:368-377)
+    radiance[o] = fill; reflectance[o] = fill;
+    if (Q) Q[o] = fill;
+    if (U) U[o] = fill;
     return;
   }
   const double pi_f = (double)3.14159274101257324f;      // 4.*atan(1.0) in real*4
@@ -167,6 +195,7 @@ struct RunDesc {
   const double *ROT, *depol, *alpha, *tau, *ssa, *pmom, *he, *albedo, *sza, *raa, *vza, *flux_factor;
   // BRDF (device, per pixel) when !lambertian
   VLSurf surf; const double *exactdb;
+  const VLBrdf *brdf;              // non-null: the Fourier components are computed per chunk from the wrappers' surface inputs
   // host copies of the per-obs angles and the per-pixel skip mask (host decides MISSING / state quirk)
   const std::vector<double> *h_sza; const std::vector<unsigned char> *h_skip;
   // device outputs (nobs,nch)
@@ -182,7 +211,17 @@ int run_vlidort(const RunDesc &R) {
   // ---- sizes
   const size_t per_pix_state = (size_t)L * 8 * 8 + (size_t)(NM + 1) * L * 4 * 8 + 16 * 8 + 4 * 4 + (size_t)(NM + 1) * L;
   const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + (6 + 2 * S) * n + 2 * n + 2 * 2 * n) * 8;
-  const size_t per_pix = per_pix_state + per_pix_sol + 4 * 8 + 4 * 4 + 4 * 3;
+  size_t per_pix_brdf = 0; int brdf_nscr = 0; size_t brdf_smem = 0;
+  if (R.brdf) {
+    const VLBrdf &B0 = *R.brdf;
+    per_pix_brdf = (brdf_out_f(B0) + 2 * brdf_out_f0(B0)) * 8;
+    const int nqs = (B0.nq == 16) ? 9 : 1, NE = N * N + 2 * N;
+    const size_t want = (size_t)NE * nqs * B0.NB, cap = 20000;
+    brdf_nscr = 256 + (int)std::min(want, std::max<size_t>(cap, (size_t)nqs * B0.NB));
+    brdf_smem = (size_t)brdf_nscr * 8;
+    AB_CUDA_OK(cudaFuncSetAttribute((const void *)k_vl_brdf_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brdf_smem));
+  }
+  const size_t per_pix = per_pix_state + per_pix_sol + 4 * 8 + 4 * 4 + 4 * 3 + per_pix_brdf;
   double ws_gb = 24.0;
   if (const char *e = getenv("AB200_VL_WORKSPACE_GB")) ws_gb = atof(e);
   size_t freeb = 0, totalb = 0;
@@ -235,6 +274,12 @@ int run_vlidort(const RunDesc &R) {
   double *d_pq = A.take<double>((size_t)(NM + 1) * N * 3 * (NM + 1));
   double *work = A.take<double>((size_t)bvp_grid_max * work_per_cta);
   unsigned char *d_skip = A.take<unsigned char>(npix);
+  VLBrdf Bd; VLSurf SFb; memset(&SFb, 0, sizeof SFb);
+  if (R.brdf) {
+    Bd = *R.brdf;
+    Bd.brdf_f = A.take<double>(chunk * brdf_out_f(Bd)); Bd.brdf_f_0 = A.take<double>(chunk * brdf_out_f0(Bd)); Bd.user_brdf_f = A.take<double>(chunk * brdf_out_f0(Bd));
+    SFb.brdf_f = Bd.brdf_f; SFb.brdf_f_0 = Bd.brdf_f_0; SFb.user_brdf_f = Bd.user_brdf_f; SFb.user_brdf_f_0 = nullptr; SFb.nmfour = 2 * N; SFb.nq = Bd.nq;
+  }
   if (A.off > A.cap) { ab200_set_error("vlidort: internal workspace accounting error"); return AB200_ERR_ARG; }
 
   // ---- quadrature and the Pi tables at the quadrature cosines for every Fourier component (pixel independent)
@@ -273,6 +318,7 @@ int run_vlidort(const RunDesc &R) {
     const int nc = (int)std::min<size_t>(chunk, npix - p0);
     AB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * (NM + 4), st));
     cudaEventRecord(ev[0], st);
+    if (R.brdf) { k_vl_brdf_fourier<<<nc, 256, brdf_smem, st>>>(Bd, (int)p0, d_skip, brdf_nscr); g_stats.n_launches += 1; }
     k_vl_setup<<<nc, 128, setup_smem, st>>>(in, X, (int)p0);
     k_vl_init_active<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, Z, nc, listA, counts);
     cudaEventRecord(ev[1], st);
@@ -283,9 +329,10 @@ int run_vlidort(const RunDesc &R) {
     float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); g_stats.ms_setup += ms;
     // BRDF pointers are indexed with the global pixel inside bvp_pixel via SF; shift them to the chunk
     VLSurf SFc = R.surf;
-    if (!R.lambertian) {
-      SFc.brdf_f += (size_t)p0 * SFc.nmfour * 16 * N * N; SFc.brdf_f_0 += (size_t)p0 * SFc.nmfour * 16 * N;
-      SFc.user_brdf_f += (size_t)p0 * SFc.nmfour * 16 * N; SFc.user_brdf_f_0 += (size_t)p0 * SFc.nmfour * 16;
+    if (R.brdf) SFc = SFb;                                   // chunk-local arrays, rewritten for every chunk
+    else if (!R.lambertian) {
+      SFc.brdf_f += (size_t)p0 * SFc.nmfour * SFc.nq * N * N; SFc.brdf_f_0 += (size_t)p0 * SFc.nmfour * SFc.nq * N;
+      SFc.user_brdf_f += (size_t)p0 * SFc.nmfour * SFc.nq * N;
     }
     int *cur = listA, *nxt = listB;
     for (int m = 0; m <= NM && nactive > 0; m++) {
@@ -370,6 +417,113 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
   AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * npix, cudaMemcpyDeviceToHost, 0));
   AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * npix, cudaMemcpyDeviceToHost, 0));
   AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ BRDF wrappers
+struct SurfArgs { int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; };
+
+// pixel-independent BRDF tables -> device
+int build_brdf_tables(VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, cudaStream_t st) {
+  std::vector<double> h;
+  brdf_host_tables(B, kind, S, scalar_glue, N, NM, nch, nobs, h);
+  static DevBuf tab;
+  AB_CUDA_OK(tab.reserve(h.size() * 8));
+  AB_CUDA_OK(cudaMemcpyAsync(tab.as<double>(), h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+  AB_CUDA_OK(cudaStreamSynchronize(st));
+  brdf_rebase_tables(B, h.data(), tab.as<double>());
+  return 0;
+}
+
+// front end of the Cox-Munk / GISS Cox-Munk / MODIS RTLS wrappers; dev: every array pointer is a device pointer
+int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+               const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
+               const double *he, const double *sza, const double *raa, const double *vza, double MISSING, const SurfArgs &sa,
+               double *radiance, double *reflectance, double *Q, double *U, cudaStream_t st, int *rc) {
+  *rc = 0;
+  if (nstreams > 25) { *rc = 2; return 2; }
+  if (km > 72) { *rc = 3; return 3; }
+  if (nMom > 1000) { *rc = 5; return 5; }
+  const size_t npix = (size_t)nobs * nch;
+  if (npix == 0) return 0;
+  const bool cx = (sa.kind != SURF_MODIS);
+  const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
+  const size_t bytes = 8 * (n_rot * 3 + n_pm + n_he + 5 * (size_t)nobs + 2 * nch + 5 * npix + 7 * npix + 16 * npix) + 16 * npix + 4096 * 32;
+  static DevBuf io;
+  AB_CUDA_OK(io.reserve(dev ? 8 * (16 * npix + 7 * npix) + 16 * npix + 4096 * 8 : bytes));
+  char *b = io.as<char>(); size_t off = 0;
+  auto put = [&](const double *src, size_t n) -> double * {
+    if (dev && src) return const_cast<double *>(src);
+    off = align256(off); double *d = (double *)(b + off); off += n * 8;
+    if (src) cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st);
+    return d;
+  };
+  RunDesc R; memset(&R, 0, sizeof R);
+  R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
+  R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING;
+  R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
+  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.sza = put(sza, nobs); R.raa = put(raa, nobs); R.vza = put(vza, nobs);
+  const double *d_u = cx ? put(sa.u10m, nobs) : nullptr, *d_v = cx ? put(sa.v10m, nobs) : nullptr, *d_mr = cx ? put(sa.mr, nch) : nullptr;
+  const double *d_kw = cx ? nullptr : put(sa.kernel_wt, 3 * npix), *d_pr = cx ? nullptr : put(sa.param, 2 * npix);
+  double *d_exact = put(nullptr, 16 * npix);
+  double *d_BR, *d_BRQ, *d_BRU;
+  if (dev) {
+    R.radiance = radiance; R.reflectance = reflectance; R.Q = Q; R.U = U; d_BR = sa.BR; d_BRQ = sa.BR_Q; d_BRU = sa.BR_U;
+  } else {
+    R.radiance = put(nullptr, npix); R.reflectance = put(nullptr, npix); R.Q = put(nullptr, npix); R.U = put(nullptr, npix);
+    d_BR = put(nullptr, npix); d_BRQ = put(nullptr, npix); d_BRU = put(nullptr, npix);
+  }
+  if (!d_BR) d_BR = put(nullptr, npix);
+  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * npix; off = align256(off); R.status = (int *)(b + off); off += 4 * npix;
+  off = align256(off); unsigned char *d_skip0 = (unsigned char *)(b + off); off += npix;
+  // host copies for the MISSING screening
+  std::vector<double> h_sza(nobs), h_vza(nobs), h_raa(nobs), h_u, h_v, h_mr;
+  auto fetch = [&](std::vector<double> &hv, const double *src, size_t n) {
+    hv.resize(n);
+    if (dev) cudaMemcpyAsync(hv.data(), src, 8 * n, cudaMemcpyDeviceToHost, st); else std::copy(src, src + n, hv.begin());
+  };
+  fetch(h_sza, sza, nobs); fetch(h_vza, vza, nobs); fetch(h_raa, raa, nobs);
+  if (cx) { fetch(h_u, sa.u10m, nobs); fetch(h_v, sa.v10m, nobs); fetch(h_mr, sa.mr, nch); }
+  if (dev) AB_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<unsigned char> skip(npix, 0);
+  for (int j = 0; j < nobs; j++) {
+    const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
+    const bool mw = cx && (is_missing_h(h_u[j], MISSING) || is_missing_h(h_v[j], MISSING));
+    for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || mw || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
+  }
+  AB_CUDA_OK(cudaMemcpyAsync(d_skip0, skip.data(), npix, cudaMemcpyHostToDevice, st));
+  VLBrdf B;
+  const int NM = std::min(2 * nstreams - 1, nMom);
+  if (int e = build_brdf_tables(B, sa.kind, S, scalar_glue, nstreams, NM, nch, nobs, st)) return e;
+  B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
+  B.exactdb = d_exact;
+  off = align256(off); B.wsa_fail = (int *)(b + off); off += 4 * npix;
+  k_vl_brdf_exact<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(B, (int)npix, d_skip0, d_BR, d_BRQ, d_BRU);
+  AB_CUDA_OK(cudaGetLastError());
+  g_stats.n_launches += 1;
+  if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel not run
+    std::vector<double> h_br(npix);
+    AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * npix, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaStreamSynchronize(st));
+    for (int j = 0; j < nobs; j++) for (int i = 0; i < nch; i++) if (!skip[(size_t)j * nch + i] && h_br[j + (size_t)nobs * i] < 0) skip[(size_t)j * nch + i] = 2;
+  }
+  R.exactdb = d_exact; R.brdf = &B;
+  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
+  if (int e = run_vlidort(R)) return e;
+  g_last_nfourier.resize(npix); g_last_status.resize(npix);
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * npix, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * npix, cudaMemcpyDeviceToHost, st));
+  if (!dev) {
+    AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * npix, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * npix, cudaMemcpyDeviceToHost, st));
+    if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * npix, cudaMemcpyDeviceToHost, st));
+    if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * npix, cudaMemcpyDeviceToHost, st));
+    if (sa.BR) AB_CUDA_OK(cudaMemcpyAsync(sa.BR, d_BR, 8 * npix, cudaMemcpyDeviceToHost, st));
+    if (sa.BR_Q) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_Q, d_BRQ, 8 * npix, cudaMemcpyDeviceToHost, st));
+    if (sa.BR_U) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_U, d_BRU, 8 * npix, cudaMemcpyDeviceToHost, st));
+  }
+  AB_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -471,6 +625,75 @@ extern "C" int ab200_vlidort_vector_lambert_dev(int km, int nch, int nobs, int n
   R.nfourier = diag.as<int>(); R.status = diag.as<int>() + npix;
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
   return run_vlidort(R);
+}
+
+// ---- BRDF surfaces (argument lists follow LV/VLIDORT_POLAR_py.F90:137-213 VECTOR_BRDF_MODIS, :673-745 VECTOR_GissCX,
+//      :830-902 VECTOR_CX; scalar forms GV/VLIDORT_BRDF_CX.F90:420-584, GV/VLIDORT_BRDF_MODIS.F90:35-202)
+#define AB_CX_ARGS int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom, int nPol, \
+  const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom, const double *pe,   \
+  const double *he, const double *te, const double *U10m, const double *V10m, const double *mr,                         \
+  const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose
+extern "C" int ab200_vlidort_vector_cx(AB_CX_ARGS, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                       double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_gisscx(AB_CX_ARGS, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                           double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_scalar_cx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                       int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                       const double *g, const double *pmom, const double *pe, const double *he, const double *te,
+                                       const double *U10m, const double *V10m, const double *mr, const double *solar_zenith,
+                                       const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                       double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc) {
+  (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BRDF, nullptr, nullptr};
+  return brdf_front(false, 1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                               int nMom, int nPol, int nkernel, int nparam, const double *ROT, const double *depol,
+                                               const double *tau, const double *ssa, const double *pmom, const double *pe,
+                                               const double *he, const double *te, const double *kernel_wt, const double *param,
+                                               const double *solar_zenith, const double *relat_azymuth,
+                                               const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                               double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q,
+                                               double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (nkernel != 3 || nparam != 2) { ab200_set_error("vector_brdf_modis: nkernel must be 3 and nparam 2 (GV/VLIDORT_BRDF_MODIS.F90:224-225)"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                               int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                               const double *ssa, const double *g, const double *pmom, const double *pe,
+                                               const double *he, const double *te, const double *kernel_wt, const double *param,
+                                               const double *solar_zenith, const double *relat_azymuth,
+                                               const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                               double *reflectance_VL_SURF, double *BR, int *rc) {
+  (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, nullptr, nullptr};
+  return brdf_front(false, 1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
+}
+// device-pointer variant of ab200_vlidort_vector_cx (every array resident in HBM, outputs too)
+extern "C" int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+                                           const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                           const double *pmom, const double *he, const double *U10m, const double *V10m,
+                                           const double *mr, const double *sza, const double *raa, const double *vza,
+                                           double MISSING, double *radiance, double *reflectance, double *BR, double *Q, double *U,
+                                           void *stream, int *rc) {
+  SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BR, nullptr, nullptr};
+  return brdf_front(true, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, sza, raa, vza,
+                    MISSING, sa, radiance, reflectance, Q, U, (cudaStream_t)stream, rc);
 }
 
 extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,

@@ -308,8 +308,71 @@ class RtVectorWorkload:
                 "fourier_terms_per_pixel": st["n_bvp"] / max(st["npix"], 1)}
 
 
-WORKLOADS = {"aop_scalar": AopScalarWorkload, "rt_vector": RtVectorWorkload}
-DEFAULT_WORKLOAD = "rt_vector"
+class RtVectorCxWorkload(RtVectorWorkload):
+    """BASELINE.json configs[2]: vector VLIDORT, 12 streams, 72 layers, Greek moments from the Mie tables, Cox-Munk ocean
+    BRDF (f2py VECTOR_CX), leo_vlidort-style swath of synthetic pixels."""
+    name = "vlidort_vector_n12_l72_coxmunk"
+    metric = "VLIDORT pixels/sec (vector nstokes=3, 12 streams, 72 layers, nMom=300, FO + delta-M, Cox-Munk BRDF)"
+
+    def _scene_gpu(self):
+        sc = super()._scene_gpu()
+        rng = np.random.default_rng(20260101 + 5)
+        n = self.nobs
+        sc.update(u10m=rng.normal(0, 5, n), v10m=rng.normal(0, 5, n), mr=np.array([1.334]))
+        return sc
+
+    def setup_gpu(self, torch, dev):
+        super().setup_gpu(torch, dev)
+        flat = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F")))
+        for k in ("u10m", "v10m", "mr"):
+            self.h[k] = flat(self.scene[k]).pin_memory(); self.d[k] = self.h[k].to(dev)
+        # radiance, reflectance, BR, Q, U (+ BR_Q, BR_U on the host path)
+        self.d_out = [torch.empty(self.nobs * self.nch, dtype=torch.float64, device=dev) for _ in range(5)]
+        self.h_out = [torch.empty(self.nobs * self.nch, dtype=torch.float64).pin_memory() for _ in range(7)]
+        keys = ["ROT", "depol", "tau", "ssa", "pmom", "pe", "he", "te", "u10m", "v10m", "mr", "sza", "raa", "vza"]
+        self.h2d = sum(self.h[k].numel() * 8 for k in keys)
+        self.d2h = 7 * self.nobs * self.nch * 8
+
+    def step_gpu(self, stream):
+        C, d, p = self.C, self.d, self._p
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_vlidort_vector_cx_dev(
+            self.km, self.nch, self.nobs, self.N, int(self.plane_parallel), self.nmom, 6, p(d["ROT"]), p(d["depol"]), p(d["tau"]),
+            p(d["ssa"]), p(d["pmom"]), p(d["he"]), p(d["u10m"]), p(d["v10m"]), p(d["mr"]), p(d["sza"]), p(d["raa"]), p(d["vza"]),
+            C.c_double(1e15), *[p(o) for o in self.d_out], C.c_void_p(stream), C.byref(rc)), "vector_cx_dev")
+        assert rc.value == 0
+
+    def step_e2e(self):
+        C, h, p = self.C, self.h, self._p
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_vlidort_vector_cx(
+            self.km, self.nch, self.nobs, p(h["channels"]), self.N, int(self.plane_parallel), self.nmom, 6, p(h["ROT"]), p(h["depol"]),
+            p(h["tau"]), p(h["ssa"]), p(h["pmom"]), p(h["pe"]), p(h["he"]), p(h["te"]), p(h["u10m"]), p(h["v10m"]), p(h["mr"]),
+            p(h["sza"]), p(h["raa"]), p(h["vza"]), C.c_double(1e15), 0, *[p(o) for o in self.h_out], C.byref(rc)), "vector_cx")
+        assert rc.value == 0
+
+    def setup_cpu(self, sample_cols):
+        had_scene = getattr(self, "scene", None) is not None
+        super().setup_cpu(sample_cols)
+        n = self.sample_cols
+        if had_scene:
+            self.cpu_scene.update(u10m=self.scene["u10m"][:n], v10m=self.scene["v10m"][:n], mr=self.scene["mr"])
+
+    def step_cpu(self, nthreads):
+        from concurrent.futures import ThreadPoolExecutor
+        s, n, vg = self.cpu_scene, self.sample_cols, self.vg
+        edges = np.linspace(0, n, nthreads + 1).astype(int)
+        rng = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(lambda ab: vg.vlidort_run_surface("cx", 3, self.N, self.plane_parallel, s["ROT"], s["depol"], s["tau"], s["ssa"],
+                                                          s["pmom"], s["he"], s["sza"], s["raa"], s["vza"], s["u10m"], s["v10m"], s["mr"],
+                                                          obs_range=ab), rng))
+        return n * self.nch, time.perf_counter() - t0
+
+
+WORKLOADS = {"aop_scalar": AopScalarWorkload, "rt_vector": RtVectorWorkload, "rt_vector_cx": RtVectorCxWorkload}
+DEFAULT_WORKLOAD = "rt_vector_cx"
 
 
 def run_reference(args, wl):
@@ -439,7 +502,7 @@ def main():
     if dist:
         dist.barrier()
     out = run_gpu(wl, args, torch, dev, dist, rank, world, local)
-    if args.workload == "rt_vector" and not args.no_aop:
+    if args.workload.startswith("rt_vector") and not args.no_aop:
         # the second half of the BASELINE metric: Mie AOP voxels/s (BASELINE configs[0], c90 scalar AOPs)
         import copy
         a2 = copy.copy(args); a2.steps = 20; a2.warmup = 5

@@ -38,6 +38,60 @@ int ab200_vlidort_vector_lambert_dev(int km, int nch, int nobs, int nstreams, in
 /* algorithmic FLOP counters (SURVEY.md 8(d) formula) and kernel-launch counter since the last reset */
 int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long *n_launches);
 
+/* ---- BRDF surfaces.  Surface set-up: RTSI/VLIDORT2p8p3/VLIDORT_SurfaceMod.F90 (CoxMunk :816-1042, GissCoxMunk :586-814,
+ * LANDMODIS :1376-1596) + the VBRDF supplement (vsup/vbrdf).  Outputs (nobs,nch).  BR = exact direct-bounce BRDF
+ * element (1,1); BR_Q = BR_U = 0 as in the reference.  MODIS RTLS: BR < 0 -> every output of that pixel is -500. */
+
+/* VLIDORT_Vector_CX_SingleGeom (geo_vlidort/VLIDORT_BRDF_CX.F90:587-762; f2py VECTOR_CX, VLIDORT_POLAR_py.F90:830-902).
+ * U10m,V10m (nobs), mr (nch). */
+int ab200_vlidort_vector_cx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                            int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                            const double *pmom, const double *pe, const double *he, const double *te, const double *U10m,
+                            const double *V10m, const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                            const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                            double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U,
+                            int *rc);
+/* VLIDORT_Vector_GissCX (VLIDORT_BRDF_CX.F90:1720-1894; f2py VECTOR_GissCX, VLIDORT_POLAR_py.F90:673-745) */
+int ab200_vlidort_vector_gisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                const double *ssa, const double *pmom, const double *pe, const double *he, const double *te,
+                                const double *U10m, const double *V10m, const double *mr, const double *solar_zenith,
+                                const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Scalar_CX (VLIDORT_BRDF_CX.F90:420-584); BRDF (1,nobs,nch) */
+int ab200_vlidort_scalar_cx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                            int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                            const double *g, const double *pmom, const double *pe, const double *he, const double *te,
+                            const double *U10m, const double *V10m, const double *mr, const double *solar_zenith,
+                            const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                            double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc);
+/* VLIDORT_Vector_LandMODIS_SingleGeom (geo_vlidort/VLIDORT_BRDF_MODIS.F90:206-410; f2py VECTOR_BRDF_MODIS,
+ * VLIDORT_POLAR_py.F90:137-213).  kernel_wt (nkernel=3,nch,nobs) = fiso,fgeo,fvol; param (nparam=2,nch,nobs). */
+int ab200_vlidort_vector_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                    int nMom, int nPol, int nkernel, int nparam, const double *ROT, const double *depol,
+                                    const double *tau, const double *ssa, const double *pmom, const double *pe,
+                                    const double *he, const double *te, const double *kernel_wt, const double *param,
+                                    const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                    double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                    double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Scalar_LandMODIS (VLIDORT_BRDF_MODIS.F90:35-202) */
+int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                    int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                    const double *ssa, const double *g, const double *pmom, const double *pe,
+                                    const double *he, const double *te, const double *kernel_wt, const double *param,
+                                    const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                    double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                    double *BR, int *rc);
+/* ab200_vlidort_vector_cx with every array (inputs and outputs) resident in device memory; stream = cudaStream_t */
+int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+                                const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                const double *pmom, const double *he, const double *U10m, const double *V10m,
+                                const double *mr, const double *sza, const double *raa, const double *vza, double MISSING,
+                                double *radiance, double *reflectance, double *BR, double *Q, double *U, void *stream,
+                                int *rc);
+
+
 /* diagnostics of the most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i; returns npix */
 long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap);
 /* accumulated device timings (CUDA events) of the three kernels and problem counts; reset != 0 clears them */

@@ -55,6 +55,42 @@ def vlidort_run(nstokes, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, h
     return out
 
 
+def set_asymtx_tolerance(tol=1e-12):
+    """ASYMTX tolerance of the wrapper-level oracle runs (reference value 1e-12)."""
+    vo.lib().orc_set_asymtx_tolerance(C.c_double(tol))
+
+
+class _OrcSurface(C.Structure):
+    _fields_ = [("kind", C.c_int)] + [(n, C.POINTER(C.c_double)) for n in ("u10m", "v10m", "mr", "kernel_wt", "param", "BR", "BR_Q", "BR_U")]
+
+
+SURFACE_KINDS = {"cx": 2, "gisscx": 3, "modis": 4}
+
+
+def vlidort_run_surface(kind, nstokes, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, he, sza, raa, vza, u10m=None,
+                        v10m=None, mr=None, kernel_wt=None, param=None, MISSING=1e15, scalar_glue=False, obs_range=None):
+    """BRDF wrappers (VLIDORT_Vector_CX / _GissCX / _LandMODIS and their scalar forms): dict(radiance, reflectance, Q, U,
+    BR, BR_Q, BR_U (nobs,nch), nfourier, status)."""
+    ROT, tau, ssa, pmom, he = F(ROT), F(tau), F(ssa), F(pmom), F(he)
+    km, nch, nobs = tau.shape
+    nMom, nPol = pmom.shape[3], pmom.shape[4]
+    depol = np.ascontiguousarray(depol, dtype=np.float64)
+    sza, raa, vza = (np.ascontiguousarray(x, dtype=np.float64) for x in (sza, raa, vza))
+    out = {k: np.zeros((nobs, nch), order="F") for k in ("radiance", "reflectance", "Q", "U", "BR", "BR_Q", "BR_U")}
+    nf = np.zeros((nobs, nch), np.int32); st = np.zeros((nobs, nch), np.int32)
+    keep = [np.ascontiguousarray(x, dtype=np.float64) if x is not None else None for x in (u10m, v10m, mr)]
+    keep += [F(kernel_wt) if kernel_wt is not None else None, F(param) if param is not None else None]
+    sf = _OrcSurface(SURFACE_KINDS[kind], *[_p(k) for k in keep], _p(out["BR"]), _p(out["BR_Q"]), _p(out["BR_U"]))
+    o0, o1 = obs_range if obs_range else (0, nobs)
+    vo.lib().orc_vlidort_run_surf(int(nstokes), int(scalar_glue), km, nch, nobs, int(nstreams), int(plane_parallel), nMom, nPol,
+                                  _p(ROT), _p(depol), None, _p(tau), _p(ssa), _p(pmom), _p(he), None, _p(sza), _p(raa), _p(vza),
+                                  None, C.c_double(MISSING), 0, None, None, None, None, None, None, int(o0), int(o1),
+                                  _p(out["radiance"]), _p(out["reflectance"]), _p(out["Q"]), _p(out["U"]),
+                                  nf.ctypes.data_as(C.POINTER(C.c_int)), st.ctypes.data_as(C.POINTER(C.c_int)), C.byref(sf))
+    out["nfourier"] = nf; out["status"] = st
+    return out
+
+
 def synthetic_scene(nobs, nch_nm=(550.0,), nmom=64, km=72, seed=7, tables=None, mt=None, sza_max=75.0, vza_max=65.0):
     """SURVEY.md section 8(d) synthetic pixels: GOCART-like columns -> Mie oracle (vector AOPs) -> edge variables ->
     Rayleigh; returns float64 Fortran arrays in the drop-in layouts."""
@@ -75,7 +111,10 @@ def synthetic_scene(nobs, nch_nm=(550.0,), nmom=64, km=72, seed=7, tables=None, 
                  tau=F(tau), ssa=F(ssa), g=F(g), pmom=F(pmom), pe=F(pe), he=F(ze), te=F(te), ROT=F(ROT), depol=depol,
                  sza=rng.uniform(0.0, sza_max, nobs), vza=rng.uniform(0.0, vza_max, nobs), raa=rng.uniform(0.0, 180.0, nobs),
                  albedo=F(rng.uniform(0.02, 0.4, (nobs, len(nch_nm)))),
-                 u10m=rng.normal(0, 5, nobs), v10m=rng.normal(0, 5, nobs), mr=np.full(len(nch_nm), 1.334))
+                 u10m=rng.normal(0, 5, nobs), v10m=rng.normal(0, 5, nobs), mr=np.full(len(nch_nm), 1.334),
+                 kernel_wt=F(np.stack([rng.uniform(0.02, 0.3, (len(nch_nm), nobs)), rng.uniform(0.0, 0.05, (len(nch_nm), nobs)),
+                                       rng.uniform(0.0, 0.15, (len(nch_nm), nobs))])),
+                 param=F(np.stack([np.full((len(nch_nm), nobs), 2.0), np.full((len(nch_nm), nobs), 1.0)])))
     return scene
 
 

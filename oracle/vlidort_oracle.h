@@ -44,6 +44,24 @@ int orc_vlidort_run(int nstokes, int scalar_glue, int km, int nch, int nobs, int
                     const double *brdf_f_0, const double *user_brdf_f, const double *user_brdf_f_0,
                     const double *exactdb, const unsigned char *skip, int obs_begin, int obs_end,
                     double *radiance, double *reflectance, double *Q, double *U, int *nfourier, int *status);
+/* same, with the surface set up from the BRDF wrappers' own inputs: kind 2 Cox-Munk (u10m,v10m (nobs), mr (nch)),
+ * 3 GISS Cox-Munk (same), 4 MODIS RTLS (kernel_wt (3,nch,nobs) = fiso,fgeo,fvol; param (2,nch,nobs)).
+ * BR/BR_Q/BR_U (nobs,nch) receive the wrappers' surface outputs. */
+typedef struct {
+  int kind;
+  const double *u10m, *v10m, *mr, *kernel_wt, *param;
+  double *BR, *BR_Q, *BR_U;
+} orc_surface;
+int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel,
+                    int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                    const double *tau, const double *ssa, const double *pmom, const double *he,
+                    const double *albedo, const double *sza, const double *raa, const double *vza,
+                    const double *flux_factor, double MISSING, int surface, const double *brdf_f,
+                    const double *brdf_f_0, const double *user_brdf_f, const double *user_brdf_f_0,
+                    const double *exactdb, const unsigned char *skip, int obs_begin, int obs_end,
+                    double *radiance, double *reflectance, double *Q, double *U, int *nfourier, int *status,
+                    const orc_surface *sf);
+void orc_set_asymtx_tolerance(double tol);   /* default 1e-12 = the reference glue's value */
 /* VLIDORT_ROT_CALC (GV/VLIDORT_ROT.F90:19-86 -> V283/VLIDORT_ScatMod.F90:143-281) */
 void orc_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
                   const double *te, double *ROT, double *depol);

@@ -28,7 +28,7 @@ def _p(a):
 
 
 def run(nstokes, nstreams, plane_parallel, sc, lambertian=True, scalar_glue=False, nfine=3, nadir_from_obs=None,
-        accuracy=float(np.float32(0.0001)), brdf=None, alpha=None, flux_factor=None, max_fourier=-1):
+        accuracy=float(np.float32(0.0001)), brdf=None, alpha=None, flux_factor=None, max_fourier=-1, surface=None):
     F = lambda a: np.asfortranarray(a, dtype=np.float64)
     km, nch, nobs = sc["tau"].shape
     npix = nobs * nch
@@ -39,9 +39,20 @@ def run(nstokes, nstreams, plane_parallel, sc, lambertian=True, scalar_glue=Fals
     arrs = [F(sc["ROT"]), np.ascontiguousarray(sc["depol"], dtype=np.float64), None if alpha is None else F(alpha), F(sc["tau"]),
             F(sc["ssa"]), F(sc["pmom"]), F(sc["he"]), F(sc["albedo"])] + [np.ascontiguousarray(sc[k], dtype=np.float64) for k in ("sza", "raa", "vza")]
     ff = None if flux_factor is None else F(flux_factor)
+    kinds = {None: 0, "cx": 2, "gisscx": 3, "modis": 4}
+    sk = kinds[surface]
+    sarr = [None] * 5
+    if sk in (2, 3):
+        sarr[:3] = [np.ascontiguousarray(sc[k], dtype=np.float64) for k in ("u10m", "v10m", "mr")]
+    elif sk == 4:
+        sarr[3:] = [F(sc["kernel_wt"]), F(sc["param"])]
+    BR = np.zeros(npix); wsa = np.zeros(npix, np.int32)
     lib().hm_vlidort(int(nstokes), int(nstreams), km, nch, nobs, sc["nMom"], sc["nPol"], int(plane_parallel), int(lambertian),
                      int(scalar_glue), int(nfine), nobs if nadir_from_obs is None else int(nadir_from_obs), C.c_double(6371.0),
                      C.c_double(accuracy), *[_p(a) for a in arrs], _p(ff), _p(b["brdf_f"]), _p(b["brdf_f_0"]), _p(b["user_brdf_f"]),
-                     _p(b["user_brdf_f_0"]), _p(b["exactdb"]), int(max_fourier), _p(stokes), nf.ctypes.data_as(C.POINTER(C.c_int)),
+                     _p(b["user_brdf_f_0"]), _p(b["exactdb"]), int(max_fourier), sk, *[_p(a) for a in sarr], _p(BR),
+                     wsa.ctypes.data_as(C.POINTER(C.c_int)), _p(stokes), nf.ctypes.data_as(C.POINTER(C.c_int)),
                      st.ctypes.data_as(C.POINTER(C.c_int)))
+    if surface is not None:
+        return stokes.reshape(nobs, nch, 4), nf.reshape(nobs, nch), st.reshape(nobs, nch), BR.reshape(nobs, nch), wsa.reshape(nobs, nch)
     return stokes.reshape(nobs, nch, 4), nf.reshape(nobs, nch), st.reshape(nobs, nch)

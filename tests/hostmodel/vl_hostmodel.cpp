@@ -3,6 +3,7 @@
 // Not part of the shipped library; the product has no CPU path.
 #define AB_HOST_MODEL 1
 #include "../../aeroapps_b200/csrc/vl_bvp.cuh"
+#include "../../aeroapps_b200/csrc/vl_brdf.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdio>
@@ -15,6 +16,8 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
                           const double *sza, const double *raa, const double *vza, const double *flux_factor,
                           const double *brdf_f, const double *brdf_f_0, const double *user_brdf_f,
                           const double *user_brdf_f_0, const double *exactdb, int max_fourier_override,
+                          int surf_kind, const double *u10m, const double *v10m, const double *mr, const double *kernel_wt,
+                          const double *param, double *BR /*[npix]*/, int *wsa_fail /*[npix]*/,
                           double *stokes /*[npix][4]*/, int *nfourier /*[npix]*/, int *status /*[npix]*/) {
   const int npix = nobs * nch, L = km, n = S * N, NM = std::min(2 * N - 1, nMom);
   VLIn in; memset(&in, 0, sizeof in);
@@ -22,6 +25,20 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
   in.planpar = planpar; in.lambertian = lambertian; in.scalar_glue = scalar_glue; in.nadir_from_obs = nadir_from_obs;
   in.earth_radius = earth_radius; in.ROT = ROT; in.depol = depol; in.alpha = alpha; in.tau = tau; in.ssa = ssa; in.pmom = pmom;
   in.ze = ze; in.albedo = albedo; in.sza = sza; in.raa = raa; in.vza = vza; in.flux_factor = flux_factor; in.exactdb = exactdb;
+  // BRDF wrappers: the same per-pixel bodies the CUDA kernels run, one pixel at a time
+  VLBrdf B; std::vector<double> btab, bex, bf, bf0, buf, bscr_b;
+  if (surf_kind != 0) {
+    brdf_host_tables(B, surf_kind, S, scalar_glue, N, NM, nch, nobs, btab);
+    B.sza = sza; B.vza = vza; B.raa = raa; B.u10m = u10m; B.v10m = v10m; B.mr = mr; B.kernel_wt = kernel_wt; B.param = param;
+    bex.assign((size_t)npix * 16, 0.0); B.exactdb = bex.data(); B.wsa_fail = wsa_fail;
+    bf.assign((size_t)npix * brdf_out_f(B), 0.0); bf0.assign((size_t)npix * brdf_out_f0(B), 0.0); buf.assign((size_t)npix * brdf_out_f0(B), 0.0);
+    B.brdf_f = bf.data(); B.brdf_f_0 = bf0.data(); B.user_brdf_f = buf.data();
+    const int nscr = 1 + 7 * ((B.nq == 16) ? 9 : 1) * B.NB;        // small batches: exercises the batching logic
+    bscr_b.assign(nscr, 0.0);
+    SerialTeam Tb;
+    for (int p = 0; p < npix; p++) { brdf_exact_pixel(B, p); BR[p] = bex[(size_t)p * 16]; brdf_pixel(Tb, B, p, p, bscr_b.data(), nscr); }
+    in.exactdb = bex.data();
+  }
   VLPix X; X.L = L; X.NM = NM; X.S = S; X.npix = npix;
   std::vector<double> deltau((size_t)npix * L), og((size_t)npix * (NM + 1) * L * 4), a1((size_t)npix * L), a2(a1), a3(a1), a4(a1), a5(a1), a6(a1), a7(a1), scal((size_t)npix * 16, 0.0);
   std::vector<int> ibuf((size_t)npix * 4, 0);
@@ -39,7 +56,8 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
   std::vector<int> fail(npix, 0);
   std::vector<double> total((size_t)npix * 4, 0.0); std::vector<int> cstate((size_t)npix * 4, 0);
   VLConv CV; CV.total = total.data(); CV.state = cstate.data();
-  VLSurf SFc; SFc.brdf_f = brdf_f; SFc.brdf_f_0 = brdf_f_0; SFc.user_brdf_f = user_brdf_f; SFc.user_brdf_f_0 = user_brdf_f_0; SFc.nmfour = 2 * N;
+  VLSurf SFc; SFc.brdf_f = brdf_f; SFc.brdf_f_0 = brdf_f_0; SFc.user_brdf_f = user_brdf_f; SFc.user_brdf_f_0 = user_brdf_f_0; SFc.nmfour = 2 * N; SFc.nq = 16;
+  if (surf_kind != 0) { SFc.brdf_f = bf.data(); SFc.brdf_f_0 = bf0.data(); SFc.user_brdf_f = buf.data(); SFc.user_brdf_f_0 = nullptr; SFc.nq = B.nq; }
   std::vector<double> pq((size_t)(NM + 1) * N * 3), tmp(3 * (NM + 2));
   std::vector<double> escr(eigen_scratch_doubles(n, NM) + 64), bscr(bvp_smem_doubles(n) + 64), Ug(bvp_work_doubles(n, L));
   std::vector<int> iscr(3 * n + 4 * n + 16);

@@ -41,3 +41,21 @@ def test_hostmodel_status_and_nadir_quirk():
     assert status[1, 0] == 3 and ref["status"][1, 0] == 3
     ok = [0, 2, 3]
     assert rel(st[ok, 0, 0], ref["radiance"][ok, 0], ref["radiance"][ok, 0]) < TOL
+
+
+@pytest.mark.parametrize("kind,S,N", [("cx", 3, 5), ("gisscx", 3, 4), ("modis", 3, 5), ("cx", 1, 6), ("gisscx", 1, 4), ("modis", 1, 4)])
+def test_hostmodel_brdf_surfaces(kind, S, N):
+    """K0 (vl_brdf.cuh: kernel evaluation, WSA check, Fourier projection) feeding the BVP's BRDF surface condition."""
+    sc = vg.synthetic_scene(4, nmom=30, seed=20 + N)
+    sc["vza"][1] = 0.0
+    ref = vg.vlidort_run_surface(kind, S, N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"],
+                                 sc["raa"], sc["vza"], sc["u10m"], sc["v10m"], sc["mr"], sc["kernel_wt"], sc["param"],
+                                 scalar_glue=(S == 1))
+    st, nf, status, BR, wsa = hm.run(S, N, False, sc, lambertian=False, scalar_glue=(S == 1), surface=kind)
+    assert (status == 0).all() and (ref["status"] == 0).all() and (wsa == 0).all()
+    assert np.array_equal(nf, ref["nfourier"])
+    assert rel(BR, ref["BR"], ref["BR"]) < 1e-12
+    I = ref["radiance"]
+    assert rel(st[..., 0], I, I) < TOL
+    if S == 3:
+        assert rel(st[..., 1], ref["Q"], I) < TOL and rel(st[..., 2], ref["U"], I) < TOL
