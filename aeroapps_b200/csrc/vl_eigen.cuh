@@ -5,8 +5,9 @@
 //   SAB = M^-1 (I - Zs W/2),  DAB = M^-1 (I - Zd W/2),   Zs,Zd = sum_l Pi_i B_l (I +- (-1)^(l-m) D) Pi_j
 // with Zs, Zd SYMMETRIC for nstokes <= 3 (B_l is block diagonal {I,Q}|{U} and commutes with D).  With the diagonal
 // similarity  E = T^-1 M^-1/2 (P Q) M^1/2 T  (T = W^1/2),  P,Q symmetric and Q positive definite, so
-//   Q = C C^T (Cholesky),   G = C^T P C symmetric,   G = V diag(k^2) V^T  (parallel cyclic Jacobi),
-//   eigenvector of EIGENMAT:  sigma = T^-1 M^-1/2 C^-T v,      SAB sigma = T^-1 M^-1/2 C v
+//   Q = C C^T,  P = Lp Lp^T (Cholesky),   G = C^T P C = A A^T with A = C^T Lp,
+//   one-sided (Hestenes) Jacobi on the columns of A:  A J = U diag(k)   ->  G = U diag(k^2) U^T
+//   eigenvector of EIGENMAT:  sigma = T^-1 M^-1/2 C^-T u,      SAB sigma = T^-1 M^-1/2 C u
 // i.e. the non-symmetric Hessenberg/QR eigensolver (ASYMTX) of the reference is replaced by a symmetric Jacobi
 // solve that is regular, branch-free and whose eigenvectors are exactly orthogonal in the metric the Green's
 // function normalisation (NORM_SAVED) assumes -- also inside degenerate clusters.
@@ -31,63 +32,136 @@ struct VLQuad {                // quadrature (pixel independent)
 };
 
 // shared/scratch size in doubles for one problem
-HDFN int eigen_scratch_doubles(int n, int NM) { return 3 * n * n + 8 * n + 6 * (NM + 1) + 8; }
+HDFN int eig_lda(int n) { return n | 1; }                                  // odd leading dimension: conflict-free column access
+HDFN int eigen_scratch_doubles(int n, int NM) { return n * (n + 1) + n * eig_lda(n) + 18 * n + 6 * (NM + 1) + 8; }
+
+// one Jacobi rotation of the column pair (a,b) of A (length n).  NR > 0: both columns live in registers (n <= NR).
+template <int NR>
+DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n) {
+  double al = 0.0, be = 0.0, ga = 0.0;
+  if (NR > 0) {
+    double ra[NR > 0 ? NR : 1], rb[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int r = 0; r < NR; r++) { ra[r] = r < n ? a[r] : 0.0; rb[r] = r < n ? b[r] : 0.0; }
+    double al2 = 0.0, be2 = 0.0, ga2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < NR; r += 2) {
+      al += ra[r] * ra[r]; be += rb[r] * rb[r]; ga += ra[r] * rb[r];
+      if (r + 1 < NR) { al2 += ra[r + 1] * ra[r + 1]; be2 += rb[r + 1] * rb[r + 1]; ga2 += ra[r + 1] * rb[r + 1]; }
+    }
+    al += al2; be += be2; ga += ga2;
+    const double rel = fabs(ga) / sqrt(al * be + 1.0e-300);
+    if (rel > 1.0e-15) {
+      const double ze = (be - al) / (2.0 * ga);
+      const double t = (ze >= 0.0 ? 1.0 : -1.0) / (fabs(ze) + sqrt(1.0 + ze * ze));
+      const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+        if (r < n) { a[r] = c * ra[r] - s * rb[r]; b[r] = s * ra[r] + c * rb[r]; }
+    }
+    return rel;
+  } else {
+    for (int r = 0; r < n; r++) { const double x = a[r], y = b[r]; al += x * x; be += y * y; ga += x * y; }
+    const double rel = fabs(ga) / sqrt(al * be + 1.0e-300);
+    if (rel > 1.0e-15) {
+      const double ze = (be - al) / (2.0 * ga);
+      const double t = (ze >= 0.0 ? 1.0 : -1.0) / (fabs(ze) + sqrt(1.0 + ze * ze));
+      const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+      for (int r = 0; r < n; r++) { const double x = a[r], y = b[r]; a[r] = c * x - s * y; b[r] = s * x + c * y; }
+    }
+    return rel;
+  }
+}
+
+// back-transformation of eigenvector column e:  y = C u (in place in the column),  x = C^-T u (returned through xg)
+template <int NR>
+DEVFN void eig_backtransform(const double *AB_RESTRICT B1, int LDB, double *AB_RESTRICT col, double isig, int n, double *AB_RESTRICT xg) {
+  if (NR > 0) {
+    double u[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int r = 0; r < NR; r++) u[r] = r < n ? col[r] * isig : 0.0;
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+      if (r < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t <= r; t++) s += B1[r * LDB + t] * u[t];
+        col[r] = s;
+      }
+#pragma unroll
+    for (int r = NR - 1; r >= 0; r--)
+      if (r < n) {
+        double s = u[r];
+#pragma unroll
+        for (int t = r + 1; t < NR; t++) if (t < n) s -= B1[t * LDB + r] * u[t];
+        u[r] = s / B1[r * LDB + r];
+      }
+#pragma unroll
+    for (int r = 0; r < NR; r++) if (r < n) xg[r] = u[r];
+  } else {
+    for (int r = 0; r < n; r++) xg[r] = col[r] * isig;
+    for (int r = n - 1; r >= 0; r--) {
+      double s = 0.0;
+      for (int t = 0; t <= r; t++) s += B1[r * LDB + t] * xg[t];
+      col[r] = s;
+    }
+    for (int r = n - 1; r >= 0; r--) {
+      double s = xg[r];
+      for (int t = r + 1; t < n; t++) s -= B1[t * LDB + r] * xg[t];
+      xg[r] = s / B1[r * LDB + r];
+    }
+  }
+}
 
 template <int S, class Team>
 DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const double *AB_RESTRICT pq, int m,
                          int p, int k, double *scr) {
-  const int N = QD.N, n = S * N, NM = X.NM, L = X.L;
+  const int N = QD.N, n = S * N, NM = X.NM, L = X.L, LDB = n + 1, LDA = eig_lda(n);
   const size_t q = (size_t)p * L + k;
-  double *Qm = scr, *Pm = Qm + n * n, *V = Pm + n * n;
-  double *lam = V + n * n, *sr = lam + n, *dpi = sr + n, *dmi = dpi + n, *gup = dmi + n, *gdn = gup + n, *cs = gdn + n;   // cs: 2*(n/2+1) <= 2n
-  double *piu = cs + 2 * n;           // 3*(NM+1)  user-stream P,R,T
+  // B1: Q / C in the lower triangle (r,c<=r) at [r*LDB+c];  P / Lp (r,c<=r) transposed above it at [c*LDB+r+1]
+  double *B1 = scr, *A = B1 + n * LDB;
+  double *sig = A + n * LDA, *sr = sig + n, *dpi = sr + n, *dmi = dpi + n, *gup = dmi + n, *gdn = gup + n;
+  double *KK = gdn + n;               // 12n: user-stream operators [(2*ud+pn)*S+o][r]
+  double *piu = KK + 12 * n;          // 3*(NM+1)  user-stream P,R,T
   double *pi0 = piu + 3 * (NM + 1);   // 3*(NM+1)  solar P,R,T
-  double *misc = pi0 + 3 * (NM + 1);
   const double *og = og_ptr(X, p);                          // [(l*L + k)*4]
   const double *sc = X.scal + (size_t)p * 16;
   const int *ib = X.ibuf + (size_t)p * 4;
   const double usec = sc[2], FLUXF = sc[5];
   const bool layscat = X.layscat[((size_t)p * (NM + 1) + m) * L + k] != 0;
   const double deltau = X.deltau[pixL(X, p) + k];
+  double *XPg = Z.xp + q * n * n, *XNg = Z.xn + q * n * n;
 
   // ---- generalized spherical functions at the user and solar cosines
   if (T.rank == 0) pi_prt(m, NM, sc[1], piu);
   if (T.rank == (T.size > 1 ? 1 : 0)) pi_prt(m, NM, sc[0], pi0);
   for (int r = T.rank; r < n; r += T.size) { const int i = r / S; sr[r] = sqrt(QD.w[i] * QD.x[i]); }
-  T.sync();
 
-  // ---- symmetric matrices P (from Zd) and Q (from Zs)
-  for (int idx = T.rank; idx < N * N; idx += T.size) {
-    const int i = idx / N, j = idx % N;
+  // ---- lower triangles of the symmetric matrices Q (from Zs) and P (from Zd); item = stream pair i >= j
+  for (int idx = T.rank; idx < N * (N + 1) / 2; idx += T.size) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= idx) i++;
+    const int j = idx - i * (i + 1) / 2;
     double zs[S * S], zd[S * S];
 #pragma unroll
     for (int t = 0; t < S * S; t++) { zs[t] = 0.0; zd[t] = 0.0; }
     for (int l = m; l <= NM; l++) {
       const double *o4 = og + ((size_t)l * L + k) * 4;
       const double *pi_ = pq + ((size_t)l * N + i) * 3, *pj_ = pq + ((size_t)l * N + j) * 3;
-      const double es = ((l - m) & 1) ? 0.0 : 2.0, ed = 2.0 - es;        // I +- ps*D on the {I,Q} block; swapped on U
+      const bool even = ((l - m) & 1) == 0;                                // I +- ps*D on the {I,Q} block; swapped on U
       if (S == 1) {
-        const double t = o4[0] * pi_[0] * pj_[0];
-        zs[0] += es * t; zd[0] += ed * t;
+        const double t = 2.0 * o4[0] * pi_[0] * pj_[0];
+        if (even) zs[0] += t; else zd[0] += t;
       } else {
         const double Pi = pi_[0], Ri = pi_[1], Ti = pi_[2], Pj = pj_[0], Rj = pj_[1], Tj = pj_[2];
-        const double b11 = o4[0], b12 = o4[1], b22 = o4[2], b33 = o4[3];
-        // Y = B * Pi_j  (3x3);  B = [[b11,b12,0],[b12,b22,0],[0,0,b33]], Pi = [[P,0,0],[0,R,T],[0,T,R]]
-        const double y00 = b11 * Pj, y01 = b12 * Rj, y02 = b12 * Tj;
-        const double y10 = b12 * Pj, y11 = b22 * Rj, y12 = b22 * Tj;
-        const double y21 = b33 * Tj, y22 = b33 * Rj;                      // y20 = 0
-        // Pi_i * E * Y with E = diag(e1,e1,e2): rows of Y scaled
-        const double e1s = es, e2s = ed, e1d = ed, e2d = es;
-        // row 0 of Pi_i: (Pi,0,0); row 1: (0,Ri,Ti); row 2: (0,Ti,Ri)
-        const double a00 = Pi * y00, a01 = Pi * y01, a02 = Pi * y02;
-        const double u10 = Ri * y10, u11 = Ri * y11, u12 = Ri * y12, v11 = Ti * y21, v12 = Ti * y22;
-        const double u20 = Ti * y10, u21 = Ti * y11, u22 = Ti * y12, w21 = Ri * y21, w22 = Ri * y22;
-        zs[0] += e1s * a00; zs[1] += e1s * a01; zs[2] += e1s * a02;
-        zs[3] += e1s * u10; zs[4] += e1s * u11 + e2s * v11; zs[5] += e1s * u12 + e2s * v12;
-        zs[6] += e1s * u20; zs[7] += e1s * u21 + e2s * w21; zs[8] += e1s * u22 + e2s * w22;
-        zd[0] += e1d * a00; zd[1] += e1d * a01; zd[2] += e1d * a02;
-        zd[3] += e1d * u10; zd[4] += e1d * u11 + e2d * v11; zd[5] += e1d * u12 + e2d * v12;
-        zd[6] += e1d * u20; zd[7] += e1d * u21 + e2d * w21; zd[8] += e1d * u22 + e2d * w22;
+        const double b11 = 2.0 * o4[0], b12 = 2.0 * o4[1], b22 = 2.0 * o4[2], b33 = 2.0 * o4[3];
+        // Pi_i E B Pi_j with B = [[b11,b12,0],[b12,b22,0],[0,0,b33]], Pi = [[P,0,0],[0,R,T],[0,T,R]], E = diag(e1,e1,e2)
+        const double a00 = Pi * b11 * Pj, a01 = Pi * b12 * Rj, a02 = Pi * b12 * Tj;
+        const double u10 = Ri * b12 * Pj, u11 = Ri * b22 * Rj, u12 = Ri * b22 * Tj, v11 = Ti * b33 * Tj, v12 = Ti * b33 * Rj;
+        const double u20 = Ti * b12 * Pj, u21 = Ti * b22 * Rj, u22 = Ti * b22 * Tj, w21 = Ri * b33 * Tj, w22 = Ri * b33 * Rj;
+        double *z1 = even ? zs : zd, *z2 = even ? zd : zs;                 // e1 part / e2 part
+        z1[0] += a00; z1[1] += a01; z1[2] += a02; z1[3] += u10; z1[4] += u11; z1[5] += u12; z1[6] += u20; z1[7] += u21; z1[8] += u22;
+        z2[4] += v11; z2[5] += v12; z2[7] += w21; z2[8] += w22;
       }
     }
     const double hw = 0.5 * sqrt(QD.w[i] * QD.w[j]), im = 1.0 / sqrt(QD.x[i] * QD.x[j]);
@@ -96,186 +170,183 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
 #pragma unroll
       for (int o2 = 0; o2 < S; o2++) {
         const int r = S * i + o1, c = S * j + o2;
-        const double dlt = (r == c) ? 1.0 : 0.0;
-        Qm[r * n + c] = (dlt - hw * zs[o1 * S + o2]) * im;
-        Pm[r * n + c] = (dlt - hw * zd[o1 * S + o2]) * im;
+        if (c <= r) {
+          const double dlt = (r == c) ? 1.0 : 0.0;
+          B1[r * LDB + c] = (dlt - hw * zs[o1 * S + o2]) * im;
+          B1[c * LDB + r + 1] = (dlt - hw * zd[o1 * S + o2]) * im;
+        }
       }
   }
   T.sync();
-  // ---- Cholesky Q = C C^T (lower triangle of Qm)
+  // ---- Cholesky Q = C C^T and P = Lp Lp^T together, left-looking, in place; item = (matrix, row)
   bool ok = true;
   for (int c = 0; c < n; c++) {
-    const double d = Qm[c * n + c];
-    if (!(d > 0.0)) { ok = false; break; }
-    const double id = 1.0 / sqrt(d);
+    const int rem = n - c;
+    for (int idx = T.rank; idx < 2 * rem; idx += T.size) {
+      const int mat = idx >= rem, r = c + idx - mat * rem;
+      double s;
+      if (!mat) {
+        const double *lr = B1 + r * LDB, *lc = B1 + c * LDB;
+        s = lr[c];
+        for (int t = 0; t < c; t++) s -= lr[t] * lc[t];
+        B1[r * LDB + c] = s;
+      } else {
+        s = B1[c * LDB + r + 1];
+        for (int t = 0; t < c; t++) s -= B1[t * LDB + r + 1] * B1[t * LDB + c + 1];
+        B1[c * LDB + r + 1] = s;
+      }
+    }
     T.sync();
-    for (int r = c + T.rank; r < n; r += T.size) Qm[r * n + c] *= id;      // includes the diagonal: sqrt(d)
+    const double dq = B1[c * LDB + c], dp = B1[c * LDB + c + 1];
+    if (!(dq > 0.0) || !(dp > 0.0)) { ok = false; break; }
+    const double iq = 1.0 / sqrt(dq), ip = 1.0 / sqrt(dp);
     T.sync();
-    const int rem = n - c - 1;
-    for (int idx = T.rank; idx < rem * rem; idx += T.size) {
-      const int r = c + 1 + idx / rem, cc = c + 1 + idx % rem;
-      if (cc <= r) Qm[r * n + cc] -= Qm[r * n + c] * Qm[cc * n + c];
+    for (int idx = T.rank; idx < 2 * rem; idx += T.size) {
+      const int mat = idx >= rem, r = c + idx - mat * rem;
+      if (!mat) B1[r * LDB + c] *= iq; else B1[c * LDB + r + 1] *= ip;       // diagonal: d/sqrt(d) = sqrt(d)
     }
     T.sync();
   }
   if (!ok) { if (T.rank == 0) Z.fail[p] = 1; return; }
-  // ---- G = C^T P C : W = P C into V, then G = C^T W into Pm
-  for (int idx = T.rank; idx < n * n; idx += T.size) {
-    const int r = idx / n, c = idx % n;
-    double s = 0.0;
-    for (int t = c; t < n; t++) s += Pm[r * n + t] * Qm[t * n + c];
-    V[idx] = s;
+  // ---- A = C^T Lp  (column-major, A[c*LDA + r])
+  {
+    int r = T.rank, c = 0;
+    while (r >= n) { r -= n; c++; }
+    while (c < n) {
+      double s = 0.0;
+      for (int t = (r > c ? r : c); t < n; t++) s += B1[t * LDB + r] * B1[c * LDB + t + 1];
+      A[c * LDA + r] = s;
+      r += T.size;
+      while (r >= n) { r -= n; c++; }
+    }
   }
   T.sync();
-  for (int idx = T.rank; idx < n * n; idx += T.size) {
-    const int r = idx / n, c = idx % n;
-    double s = 0.0;
-    for (int t = r; t < n; t++) s += Qm[t * n + r] * V[t * n + c];
-    Pm[idx] = s;
-  }
-  T.sync();
-  for (int idx = T.rank; idx < n * n; idx += T.size) V[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
-  T.sync();
-  // ---- parallel cyclic Jacobi on G (Pm), eigenvectors accumulated in V
+  // ---- one-sided Jacobi, round-robin ordering, one column pair per lane
   {
     const int np = n + (n & 1), half = np / 2;
-    for (int sweep = 0; sweep < 20; sweep++) {
+    for (int sweep = 0; sweep < 30; sweep++) {
       double offmax = 0.0;
       for (int st = 0; st < np - 1; st++) {
         for (int t = T.rank; t < half; t += T.size) {
           int a, b;
-          if (t == 0) { a = np - 1; b = st; } else { a = (st + t) % (np - 1); b = (st - t + np - 1) % (np - 1); }
-          const int pp = a < b ? a : b, qq2 = a < b ? b : a;
-          double c_ = 1.0, s_ = 0.0;
-          if (qq2 < n) {
-            const double gpq = Pm[pp * n + qq2], gpp = Pm[pp * n + pp], gqq = Pm[qq2 * n + qq2];
-            const double rel = fabs(gpq) / sqrt(fabs(gpp * gqq) + 1.0e-300);
+          if (t == 0) { a = np - 1; b = st; } else { a = st + t; if (a >= np - 1) a -= np - 1; b = st - t; if (b < 0) b += np - 1; }
+          if (a < n && b < n) {
+            double rel;
+            if (n <= 12) rel = jacobi_pair<12>(A + a * LDA, A + b * LDA, n);
+            else if (n <= 24) rel = jacobi_pair<24>(A + a * LDA, A + b * LDA, n);
+            else if (n <= 36) rel = jacobi_pair<36>(A + a * LDA, A + b * LDA, n);
+            else rel = jacobi_pair<0>(A + a * LDA, A + b * LDA, n);
             if (rel > offmax) offmax = rel;
-            if (rel > 1.0e-17) {
-              const double th = (gqq - gpp) / (2.0 * gpq);
-              const double tt = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-              c_ = 1.0 / sqrt(tt * tt + 1.0); s_ = tt * c_;
-            }
-          }
-          cs[2 * t] = c_; cs[2 * t + 1] = s_;
-        }
-        T.sync();
-        for (int idx = T.rank; idx < half * n; idx += T.size) {           // rows: G <- J^T G
-          const int t = idx / n, c = idx % n;
-          int a, b;
-          if (t == 0) { a = np - 1; b = st; } else { a = (st + t) % (np - 1); b = (st - t + np - 1) % (np - 1); }
-          const int pp = a < b ? a : b, qq2 = a < b ? b : a;
-          if (qq2 < n) {
-            const double c_ = cs[2 * t], s_ = cs[2 * t + 1];
-            const double gp = Pm[pp * n + c], gq = Pm[qq2 * n + c];
-            Pm[pp * n + c] = c_ * gp - s_ * gq; Pm[qq2 * n + c] = s_ * gp + c_ * gq;
-          }
-        }
-        T.sync();
-        for (int idx = T.rank; idx < half * n; idx += T.size) {           // columns: G <- G J, V <- V J
-          const int t = idx / n, r = idx % n;
-          int a, b;
-          if (t == 0) { a = np - 1; b = st; } else { a = (st + t) % (np - 1); b = (st - t + np - 1) % (np - 1); }
-          const int pp = a < b ? a : b, qq2 = a < b ? b : a;
-          if (qq2 < n) {
-            const double c_ = cs[2 * t], s_ = cs[2 * t + 1];
-            const double gp = Pm[r * n + pp], gq = Pm[r * n + qq2];
-            Pm[r * n + pp] = c_ * gp - s_ * gq; Pm[r * n + qq2] = s_ * gp + c_ * gq;
-            const double vp = V[r * n + pp], vq = V[r * n + qq2];
-            V[r * n + pp] = c_ * vp - s_ * vq; V[r * n + qq2] = s_ * vp + c_ * vq;
           }
         }
         T.sync();
       }
       int dummy = 0;
       offmax = T.argmax(offmax, dummy);
-      if (offmax < 1.0e-15) break;
+      if (offmax < 1.0e-14) break;
     }
   }
-  for (int e = T.rank; e < n; e += T.size) lam[e] = Pm[e * n + e];
-  T.sync();
-  // ---- back to the eigenvectors of EIGENMAT:  y = C v (into Pm), x = C^-T v (in place in V); column e per lane
-  for (int e = T.rank; e < n; e += T.size) {
-    for (int r = n - 1; r >= 0; r--) {                                   // y first (needs all of v)
-      double s = 0.0;
-      for (int t = 0; t <= r; t++) s += Qm[r * n + t] * V[t * n + e];
-      Pm[r * n + e] = s;
-    }
-    for (int r = n - 1; r >= 0; r--) {
-      double s = V[r * n + e];
-      for (int t = r + 1; t < n; t++) s -= Qm[t * n + r] * V[t * n + e];
-      V[r * n + e] = s / Qm[r * n + r];
-    }
-  }
-  T.sync();
-  // ---- X+ / X- (streams 1..N), eigenvalue k, whole-layer transmittance
+  // ---- singular values = eigenvalues k of the layer; y = C u in place in A, x = C^-T u through global memory (XNg)
   bool bad = false;
   for (int e = T.rank; e < n; e += T.size) {
-    const double l2 = lam[e];
-    if (!(l2 > 0.0)) { bad = true; continue; }
-    const double ke = sqrt(l2);
+    double *col = A + e * LDA;
+    double s2 = 0.0;
+    for (int r = 0; r < n; r++) s2 += col[r] * col[r];
+    const double ke = sqrt(s2);
+    sig[e] = ke;
+    if (!(ke > 0.0)) { bad = true; continue; }
+    double *xg = XNg + (size_t)e * n;
+    if (n <= 12) eig_backtransform<12>(B1, LDB, col, 1.0 / ke, n, xg);
+    else if (n <= 24) eig_backtransform<24>(B1, LDB, col, 1.0 / ke, n, xg);
+    else if (n <= 36) eig_backtransform<36>(B1, LDB, col, 1.0 / ke, n, xg);
+    else eig_backtransform<0>(B1, LDB, col, 1.0 / ke, n, xg);
+  }
+  if (bad) Z.fail[p] = 1;
+  T.sync();                                               // C is dead from here on: B1 becomes XNEG [e*LDB + r]
+  // ---- X+ / X- (streams 1..N), whole-layer transmittance, multipliers
+  for (int e = T.rank; e < n; e += T.size) {
+    const double ke = sig[e];
+    if (!(ke > 0.0)) continue;
+    double *col = A + e * LDA, *xn = B1 + e * LDB;
+    const double *xg = XNg + (size_t)e * n;
     double nrm = 0.0;
-    for (int r = 0; r < n; r++) { const double s = V[r * n + e] / sr[r]; nrm += s * s; }
+    for (int r = 0; r < n; r++) { const double s = xg[r] / sr[r]; nrm += s * s; }
     const double inr = 1.0 / sqrt(nrm);
     for (int r = 0; r < n; r++) {
-      const double sg = V[r * n + e] / sr[r] * inr, df = Pm[r * n + e] / (sr[r] * ke) * inr;
-      Pm[r * n + e] = 0.5 * (sg + df);       // XPOS(i,o,e)
-      V[r * n + e] = 0.5 * (sg - df);        // XNEG(i,o,e)
+      const double sg = xg[r] / sr[r] * inr, df = col[r] / (sr[r] * ke) * inr;
+      col[r] = 0.5 * (sg + df);            // XPOS(i,o,e)
+      xn[r] = 0.5 * (sg - df);             // XNEG(i,o,e)
     }
     Z.keig[q * n + e] = ke;
     const double hlp = ke * deltau, tde = hlp > MAX_TAU_PATH ? 0.0 : exp(-hlp);
     Z.tde[q * n + e] = tde;
-    lam[e] = ke;
     // HMULT (whole layer, upwelling user stream): vlidort_solutions.f90:1715-1745, zeta :1290-1305
     const double rho_p = usec + ke, rho_m = usec - ke, udel = X.tduserm[pixL(X, p) + k];
     const bool hs = fabs(rho_m) < TAYLOR_SMALL;
     Z.hm1[q * n + e] = hs ? taylor_series_1(rho_m, deltau, udel, usec) : usec * (tde - udel) / rho_m;
     Z.hm2[q * n + e] = usec * (1.0 - tde * udel) / rho_p;
   }
-  if (bad) Z.fail[p] = 1;
-  T.sync();
-  double *XPg = Z.xp + q * n * n, *XNg = Z.xn + q * n * n;
-  for (int idx = T.rank; idx < n * n; idx += T.size) {
-    const int e = idx / n, r = idx % n;
-    XPg[idx] = Pm[r * n + e]; XNg[idx] = V[r * n + e];
+  // ---- user-stream operators: UHOM_UP/DN(o,e) = sum_r KK[..][r] X+-(r,e); item = (stream j, up/down)
+  for (int idx = T.rank; idx < 2 * N; idx += T.size) {
+    const int j = idx >> 1, ud = idx & 1;                                  // ud = 0: UHOM_UPDN, 1: UHOM_UPUP
+    double kp[S * S], kn[S * S];                                           // [o][c]: coefficient of X+-(S*j+c) in component o
+#pragma unroll
+    for (int t = 0; t < S * S; t++) { kp[t] = 0.0; kn[t] = 0.0; }
+    if (layscat) {
+      const double a5 = 0.5 * QD.w[j];
+      for (int l = m; l <= NM; l++) {
+        const double ps = ((l - m) & 1) ? -1.0 : 1.0, f = ud ? 1.0 : ps;
+        const double *o4 = og + ((size_t)l * L + k) * 4;
+        const double *pj_ = pq + ((size_t)l * N + j) * 3, *pu = piu + 3 * l;
+        if (S == 1) {
+          const double g = f * pu[0] * o4[0] * a5 * pj_[0];
+          kp[0] += g; kn[0] += ps * g;
+        } else {
+          const double Pj = a5 * pj_[0], Rj = a5 * pj_[1], Tj = a5 * pj_[2];
+          const double b11 = o4[0], b12 = o4[1], b22 = o4[2], b33 = o4[3], Pu = pu[0], Ru = pu[1], Tu = pu[2];
+          // hs = H X+ + ps H' X-,  H = [[Pj,0,0],[0,Rj,Tj],[0,Tj,Rj]],  H' = diag(1,1,-1) H ;  g = B hs ;  out = Uud g
+          // rows of Uud: dn: ps*[Pu,0,0],[0,Ru,-Tu],[0,-Tu,Ru] ;  up: [Pu,0,0],[0,Ru,Tu],[0,-Tu,-Ru]
+          const double s3 = ud ? 1.0 : -1.0, s4 = ud ? -1.0 : 1.0;
+          // M = Uud * B  (3x3)
+          const double m00 = f * Pu * b11, m01 = f * Pu * b12;
+          const double m10 = f * Ru * b12, m11 = f * Ru * b22, m12 = f * s3 * Tu * b33;
+          const double m20 = -f * Tu * b12, m21 = -f * Tu * b22, m22 = f * s4 * Ru * b33;
+          // times H (for X+) and H' (for X-, third row of H negated, times ps)
+          const double h00 = m00 * Pj, h01 = m01 * Rj, h02 = m01 * Tj;
+          const double h10 = m10 * Pj, h11 = m11 * Rj, h12 = m11 * Tj, g11 = m12 * Tj, g12 = m12 * Rj;
+          const double h20 = m20 * Pj, h21 = m21 * Rj, h22 = m21 * Tj, g21 = m22 * Tj, g22 = m22 * Rj;
+          kp[0] += h00; kp[1] += h01; kp[2] += h02;
+          kp[3] += h10; kp[4] += h11 + g11; kp[5] += h12 + g12;
+          kp[6] += h20; kp[7] += h21 + g21; kp[8] += h22 + g22;
+          kn[0] += ps * h00; kn[1] += ps * h01; kn[2] += ps * h02;
+          kn[3] += ps * h10; kn[4] += ps * (h11 - g11); kn[5] += ps * (h12 - g12);
+          kn[6] += ps * h20; kn[7] += ps * (h21 - g21); kn[8] += ps * (h22 - g22);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < S; o++)
+#pragma unroll
+      for (int c = 0; c < S; c++) {
+        KK[((2 * ud + 0) * S + o) * n + S * j + c] = kp[o * S + c];
+        KK[((2 * ud + 1) * S + o) * n + S * j + c] = kn[o * S + c];
+      }
   }
-  // ---- user-angle homogeneous solutions UHOM_UPDN / UHOM_UPUP
+  T.sync();
+  for (int idx = T.rank; idx < n * n; idx += T.size) XPg[idx] = A[(idx / n) * LDA + (idx % n)];
   for (int e = T.rank; e < n; e += T.size) {
+    const double *col = A + e * LDA, *xn = B1 + e * LDB;
+    double *xg = XNg + (size_t)e * n;
     double dn[S], up[S];
 #pragma unroll
     for (int o = 0; o < S; o++) { dn[o] = 0.0; up[o] = 0.0; }
-    if (layscat) {
-      for (int l = m; l <= NM; l++) {
-        const double ps = ((l - m) & 1) ? -1.0 : 1.0;
-        const double *o4 = og + ((size_t)l * L + k) * 4;
-        double hs[S];
+    for (int r = 0; r < n; r++) {
+      const double xp_ = col[r], xn_ = xn[r];
+      xg[r] = xn_;
 #pragma unroll
-        for (int o = 0; o < S; o++) hs[o] = 0.0;
-        for (int j = 0; j < N; j++) {
-          const double *pj_ = pq + ((size_t)l * N + j) * 3;
-          const double a5 = 0.5 * QD.w[j];
-          if (S == 1) hs[0] += a5 * pj_[0] * (Pm[j * n + e] + ps * V[j * n + e]);
-          else {
-            const double Pj = pj_[0], Rj = pj_[1], Tj = pj_[2];
-            const double p0 = Pm[(3 * j) * n + e], p1 = Pm[(3 * j + 1) * n + e], p2 = Pm[(3 * j + 2) * n + e];
-            const double m0 = V[(3 * j) * n + e], m1 = V[(3 * j + 1) * n + e], m2 = V[(3 * j + 2) * n + e];
-            // XQP*X+  +  (D Pi ps)*X-
-            hs[0] += a5 * (Pj * p0 + ps * Pj * m0);
-            hs[1] += a5 * (Rj * p1 + Tj * p2 + ps * (Rj * m1 + Tj * m2));
-            hs[2] += a5 * (Tj * p1 + Rj * p2 - ps * (Tj * m1 + Rj * m2));
-          }
-        }
-        const double *pu = piu + 3 * l;
-        if (S == 1) {
-          const double g0 = o4[0] * hs[0];
-          dn[0] += ps * pu[0] * g0; up[0] += pu[0] * g0;
-        } else {
-          const double g0 = o4[0] * hs[0] + o4[1] * hs[1], g1 = o4[1] * hs[0] + o4[2] * hs[1], g2 = o4[3] * hs[2];
-          const double Pu = pu[0], Ru = pu[1], Tu = pu[2];
-          // XUM = D Pi_u D ps ;  XUP_PRE = D Pi_u
-          dn[0] += ps * Pu * g0; dn[1] += ps * (Ru * g1 - Tu * g2); dn[2] += ps * (-Tu * g1 + Ru * g2);
-          up[0] += Pu * g0; up[1] += Ru * g1 + Tu * g2; up[2] += -(Tu * g1 + Ru * g2);
-        }
+      for (int o = 0; o < S; o++) {
+        dn[o] += KK[(0 * S + o) * n + r] * xp_ + KK[(1 * S + o) * n + r] * xn_;
+        up[o] += KK[(2 * S + o) * n + r] * xp_ + KK[(3 * S + o) * n + r] * xn_;
       }
     }
 #pragma unroll
@@ -287,7 +358,6 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   if (!active) {
     for (int r = T.rank; r < 2 * n; r += T.size) { WU[r] = 0.0; WL[r] = 0.0; }
     for (int e = T.rank; e < n; e += T.size) { Z.aterm[q * n + e] = 0.0; Z.bterm[q * n + e] = 0.0; Z.gam_m[q * n + e] = 1.0; Z.gam_p[q * n + e] = 1.0; }
-    (void)misc;
     return;
   }
   const double F1 = FLUXF / PI4;
@@ -313,12 +383,13 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   {
     const double secbar = X.avsec[pixL(X, p) + k], cst = X.itrans[pixL(X, p) + k], wdel = X.tdmubar[pixL(X, p) + k];
     for (int e = T.rank; e < n; e += T.size) {
+      const double *col = A + e * LDA, *xnc = B1 + e * LDB;
       double nrm = 0.0, s1 = 0.0, s2 = 0.0;
       for (int i = 0; i < N; i++) {
         double t1 = 0.0, t2 = 0.0, h1 = 0.0, h2 = 0.0;
 #pragma unroll
         for (int o = 0; o < S; o++) {
-          const double xp = Pm[(S * i + o) * n + e], xn = V[(S * i + o) * n + e];
+          const double xp = col[S * i + o], xn = xnc[S * i + o];
           t1 += xp * xp; t2 += xn * xn;
           h1 += dpi[S * i + o] * xp + dmi[S * i + o] * xn;
           h2 += dmi[S * i + o] * xp + dpi[S * i + o] * xn;
@@ -326,7 +397,7 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
         nrm += QD.x[i] * QD.w[i] * (t1 - t2);
         s1 += QD.w[i] * h1; s2 += QD.w[i] * h2;
       }
-      const double at = s1 / nrm, bt = s2 / nrm, ke = lam[e], zdel = Z.tde[q * n + e];
+      const double at = s1 / nrm, bt = s2 / nrm, ke = sig[e], zdel = ke * deltau > MAX_TAU_PATH ? 0.0 : exp(-ke * deltau);
       const double gp = secbar + ke, gm = secbar - ke;
       const double cf = fabs(gm) < TAYLOR_SMALL ? taylor_series_1(gm, deltau, wdel, cst) : cst * (zdel - wdel) / gm;
       const double df = cst * (1.0 - zdel * wdel) / gp;
@@ -339,7 +410,7 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
     const int o = r % S;
     double a = 0, b = 0, c = 0, d = 0;
     for (int e = 0; e < n; e++) {
-      const double xp = Pm[r * n + e], xn = V[r * n + e];
+      const double xp = A[e * LDA + r], xn = B1[e * LDB + r];
       a += gup[e] * xn; b += gup[e] * xp; c += gdn[e] * xn; d += gdn[e] * xp;
     }
     const double sg = o > 1 ? -1.0 : 1.0;
