@@ -32,8 +32,119 @@ struct VLConv {                  // per pixel, persistent over the Fourier loop
 
 HDFN int bvp_cols(int n) { return 4 * n + 1; }
 HDFN int bvp_stride(int n) { return (4 * n + 1) | 1; }                         // odd row stride
-HDFN size_t bvp_smem_doubles(int n) { return (size_t)3 * n * bvp_stride(n) + 8 * n + 16; }
+constexpr int BVP_NB = 8;                                                        // panel width of the blocked elimination
+HDFN size_t bvp_smem_doubles(int n) { return (size_t)3 * n * bvp_stride(n) + 8 * n + 16 + 2 * ((size_t)3 * n * BVP_NB + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB); }
 HDFN size_t bvp_work_doubles(int n, int L) { return (size_t)L * 2 * n * bvp_cols(n); }
+
+// ---- panel factorisation of the blocked elimination, executed by the panel sub-team (ranks < Team::PW).
+// Lane `rank` owns the window rows rank + PW*u.  upd: first apply the previous panel (LpP, UbP; nbp columns) to the
+// nb columns jc0.. of this panel.  Multipliers go to LpN (R x NB, zero for rows that are not active), the
+// multipliers of the pivot rows inside the panel to LUpN, the pivot rows' own panel entries back to W.
+template <int RU, class Team>
+DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *state, int *pivrow, int jc0, int nb, bool upd, int nbp,
+                     const double *AB_RESTRICT LpP, const double *AB_RESTRICT UbP, double *AB_RESTRICT LpN, double *AB_RESTRICT LUpN, int *iflag) {
+  constexpr int PW = Team::PW;
+  double pv[RU][BVP_NB], lm[RU][BVP_NB];
+  bool act[RU];
+#pragma unroll
+  for (int u = 0; u < RU; u++) {
+    const int r = T.rank + PW * u;
+    act[u] = (r < R) && state[r] == 0;
+#pragma unroll
+    for (int j = 0; j < BVP_NB; j++) { pv[u][j] = (act[u] && j < nb) ? W[(size_t)r * Cs + jc0 + j] : 0.0; lm[u][j] = 0.0; }
+    if (upd && act[u]) {
+#pragma unroll
+      for (int jj = 0; jj < BVP_NB; jj++) {
+        const double l = jj < nbp ? LpP[r * BVP_NB + jj] : 0.0;
+#pragma unroll
+        for (int j = 0; j < BVP_NB; j++) if (j < nb) pv[u][j] -= l * UbP[jj * Cs + jc0 + j];
+      }
+    }
+  }
+  bool pfail = false;
+#pragma unroll
+  for (int j = 0; j < BVP_NB; j++) {
+    if (j < nb && !pfail) {
+      double best = -1.0; int bidx = R;
+#pragma unroll
+      for (int u = 0; u < RU; u++) { const double a = fabs(pv[u][j]); if (act[u] && a > best) { best = a; bidx = T.rank + PW * u; } }
+      best = T.pargmax(best, bidx);
+      if (!(best > 0.0)) pfail = true;
+      else {
+        const int owner = bidx % PW, ustar = bidx / PW;
+        const bool mine = (T.rank == owner);
+        double prow[BVP_NB];
+#pragma unroll
+        for (int jj = 0; jj < BVP_NB; jj++) {
+          double v = 0.0;
+#pragma unroll
+          for (int u = 0; u < RU; u++) if (u == ustar) v = pv[u][jj];
+          prow[jj] = (jj >= j) ? T.pbcast(v, owner) : 0.0;
+        }
+        const double ipiv = 1.0 / prow[j];
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+          if (mine && u == ustar) {                  // this row becomes pivot row j of the panel
+            act[u] = false;
+            state[bidx] = 1 + jc0 + j; pivrow[jc0 + j] = bidx;
+#pragma unroll
+            for (int jj = 0; jj < BVP_NB; jj++) {
+              if (jj < j) LUpN[j * BVP_NB + jj] = lm[u][jj];
+              else if (jj < nb) W[(size_t)bidx * Cs + jc0 + jj] = prow[jj];
+              lm[u][jj] = 0.0;
+            }
+          } else if (act[u]) {
+            const double l = pv[u][j] * ipiv;
+            lm[u][j] = l;
+#pragma unroll
+            for (int jj = 0; jj < BVP_NB; jj++) if (jj > j) pv[u][jj] -= l * prow[jj];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < RU; u++) {
+    const int r = T.rank + PW * u;
+    if (r < R) {
+#pragma unroll
+      for (int j = 0; j < BVP_NB; j++) LpN[r * BVP_NB + j] = lm[u][j];
+    }
+  }
+  if (pfail && T.rank == 0) iflag[0] = 1;
+}
+
+template <class Team>
+DEVFN void bvp_panel_dispatch(const Team &T, double *W, int Cs, int R, int *state, int *pivrow, int jc0, int nb, bool upd, int nbp,
+                              const double *LpP, const double *UbP, double *LpN, double *LUpN, int *iflag) {
+  if constexpr (Team::PW == 1) bvp_panel<Team::PRU>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
+  else {
+    if (R <= 2 * Team::PW) bvp_panel<2>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
+    else if (R <= 4 * Team::PW) bvp_panel<4>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
+    else bvp_panel<8>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
+  }
+}
+
+// pivot rows of a factorised panel, column-parallel: U(j, c) = W(pr_j, c) - sum_{j' < j} L(pr_j, j') U(j', c), c >= jc0 + nb
+template <class Team>
+DEVFN void bvp_urows(const Team &T, double *AB_RESTRICT W, int Cs, int Cc, const int *pivrow, int jc0, int nb, const double *AB_RESTRICT LUpN,
+                     double *AB_RESTRICT UbN) {
+  for (int c = jc0 + nb + T.rank; c < Cc; c += T.size) {
+    double uv[BVP_NB];
+#pragma unroll
+    for (int j = 0; j < BVP_NB; j++) {
+      if (j < nb) {
+        const int pr = pivrow[jc0 + j];
+        double v = W[(size_t)pr * Cs + c];
+#pragma unroll
+        for (int jj = 0; jj < BVP_NB; jj++) if (jj < j) v -= LUpN[j * BVP_NB + jj] * uv[jj];
+        uv[j] = v;
+        W[(size_t)pr * Cs + c] = v;
+        UbN[j * Cs + c] = v;
+      } else { uv[j] = 0.0; UbN[j * Cs + c] = 0.0; }
+    }
+  }
+}
 
 template <int S, class Team>
 DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
@@ -44,9 +155,13 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   double *xcur = W + (size_t)R * Cs;      // 2n
   double *xnext = xcur + n2;              // 2n
   double *red = xnext + n2;               // 4n scratch
+  double *Lp = red + 4 * n + 16;              // 2 x (R x NB) multipliers of the current / next panel
+  double *Ub = Lp + (size_t)2 * R * BVP_NB;   // 2 x (NB x Cs) finished pivot rows of the current / next panel
+  double *LUp = Ub + (size_t)2 * BVP_NB * Cs; // 2 x (NB x NB) multipliers of the pivot rows inside the panel
   int *state = iscr;                      // R : -1 unused, 0 active, 1+t pivot number t
   int *pivrow = state + R;                // 2n
   int *freeslot = pivrow + n2;            // 2n
+  int *iflag = freeslot + n2;             // failure flag of the panel factorisation
   const double *sc = X.scal + (size_t)p * 16;
   const int *ib = X.ibuf + (size_t)p * 4;
   int *cst = CV.state + (size_t)p * 4;
@@ -86,6 +201,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
     return ((r % S) > 1) ? -v : v;
   };
 
+  if (T.rank == 0) iflag[0] = 0;
   for (int r = T.rank; r < R; r += T.size) state[r] = -1;
   for (int idx = T.rank; idx < R * Cs; idx += T.size) W[idx] = 0.0;
   T.sync();
@@ -163,35 +279,72 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       }
     }
     T.sync();
-    // ---- eliminate the 2n columns of layer k (partial pivoting over the active rows of the window)
-    const int nwarp = (T.size + 31) / 32, warp = T.rank / 32, lane = T.rank % 32;
-    for (int jc = 0; jc < n2; jc++) {
-      double v = -1.0; int idx = R;
-      for (int r = T.rank; r < R; r += T.size)
-        if (state[r] == 0) { const double a = fabs(W[(size_t)r * Cs + jc]); if (a > v) { v = a; idx = r; } }
-      v = T.argmax(v, idx);
-      if (!(v > 0.0)) { failed = true; break; }
-      if (T.rank == 0) { state[idx] = 1 + jc; pivrow[jc] = idx; }
+    // ---- eliminate the 2n columns of layer k: blocked (panels of BVP_NB columns), partial pivoting over the active
+    //      rows of the window, one panel of look-ahead: while the other warps apply panel P to the trailing columns,
+    //      the panel sub-team (warp 0) applies it to the columns of panel P+1 only and factorises that panel out of
+    //      its registers (pivot search by warp-wide integer reductions).
+    {
+      const int npanel = (n2 + BVP_NB - 1) / BVP_NB;
+      const bool is_panel = T.rank < Team::PW;
+      const bool is_trail = (T.size <= Team::PW) || !is_panel;
+      const int LW = T.size < 32 ? T.size : 32;
+      const int lane = T.rank % LW, nwt = (T.size <= Team::PW) ? 1 : T.size / LW - 1, wid = (T.size <= Team::PW) ? 0 : T.rank / LW - 1;
+      if (is_panel) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), false, 0, Lp, Ub, Lp, LUp, iflag);
       T.sync();
-      const double *prow = W + (size_t)idx * Cs;
-      const double ipiv = 1.0 / prow[jc];
-      if (T.size == 1) {
-        for (int r = 0; r < R; r++) if (state[r] == 0) {
-          double *row = W + (size_t)r * Cs; const double f = row[jc] * ipiv;
-          if (f != 0.0) for (int c = jc + 1; c < Cc; c++) row[c] -= f * prow[c];
+      if (iflag[0]) { failed = true; break; }
+      bvp_urows(T, W, Cs, Cc, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), LUp, Ub);
+      T.sync();
+      for (int P = 0; P < npanel; P++) {
+        const int jc0 = P * BVP_NB, nb = (n2 - jc0 < BVP_NB) ? n2 - jc0 : BVP_NB;
+        const bool has_next = P + 1 < npanel;
+        const int jc1 = jc0 + nb, nb1 = has_next ? ((n2 - jc1 < BVP_NB) ? n2 - jc1 : BVP_NB) : 0;
+        double *LpC = Lp + (size_t)(P & 1) * R * BVP_NB, *UbC = Ub + (size_t)(P & 1) * BVP_NB * Cs;
+        double *LpN = Lp + (size_t)((P + 1) & 1) * R * BVP_NB, *UbN = Ub + (size_t)((P + 1) & 1) * BVP_NB * Cs;
+        double *LUpN = LUp + ((P + 1) & 1) * BVP_NB * BVP_NB;
+        if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, true, nb, LpC, UbC, LpN, LUpN, iflag);
+        if (is_trail) {
+          // trailing update: W(r, c) -= sum_j L(r, j) U(j, c) for c >= cbeg; a warp owns a group of RG rows
+          constexpr int RG = 4;
+          const int cbeg = jc1 + nb1;
+          for (int g = wid; g * RG < R; g += nwt) {
+            const int r0 = g * RG;
+            double l[RG][BVP_NB];
+            bool any = false;
+#pragma unroll
+            for (int rr = 0; rr < RG; rr++)
+#pragma unroll
+              for (int j = 0; j < BVP_NB; j++) {
+                l[rr][j] = (r0 + rr < R) ? LpC[(r0 + rr) * BVP_NB + j] : 0.0;
+                any = any || (l[rr][j] != 0.0);
+              }
+            if (!any) continue;
+            for (int c = cbeg + lane; c < Cc; c += 2 * LW) {
+              const int c2 = c + LW;
+              const bool two = c2 < Cc;
+              double u0[BVP_NB], u1[BVP_NB];
+#pragma unroll
+              for (int j = 0; j < BVP_NB; j++) { u0[j] = UbC[j * Cs + c]; u1[j] = two ? UbC[j * Cs + c2] : 0.0; }
+#pragma unroll
+              for (int rr = 0; rr < RG; rr++) {
+                if (r0 + rr < R) {
+                  double *row = W + (size_t)(r0 + rr) * Cs;
+                  double a0 = row[c], a1 = two ? row[c2] : 0.0;
+#pragma unroll
+                  for (int j = 0; j < BVP_NB; j++) { a0 -= l[rr][j] * u0[j]; a1 -= l[rr][j] * u1[j]; }
+                  row[c] = a0;
+                  if (two) row[c2] = a1;
+                }
+              }
+            }
+          }
         }
-      } else {
-        double pv[8];
-        const int c0 = jc + 1 + lane;
-#pragma unroll
-        for (int u = 0; u < 8; u++) { const int c = c0 + 32 * u; pv[u] = c < Cc ? prow[c] : 0.0; }
-        for (int r = warp; r < R; r += nwarp) if (state[r] == 0) {
-          double *row = W + (size_t)r * Cs; const double f = row[jc] * ipiv;
-#pragma unroll
-          for (int u = 0; u < 8; u++) { const int c = c0 + 32 * u; if (c < Cc) row[c] -= f * pv[u]; }
+        T.sync();
+        if (iflag[0]) { failed = true; break; }
+        if (has_next) {
+          bvp_urows(T, W, Cs, Cc, pivrow, jc1, nb1, LUpN, UbN);
+          T.sync();
         }
       }
-      T.sync();
     }
     if (failed) break;
     // ---- spill the pivot rows (U factor + transformed rhs), recycle their slots, shift the carry rows
@@ -224,26 +377,53 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   for (int o = 0; o < S; o++) cum[o] = 0.0;
   for (int t = T.rank; t < n2; t += T.size) xnext[t] = 0.0;
   T.sync();
-  double *Ub = W;                                         // 2n x (2n+1) block copy: U_kk | b
-  const int Ubs = n2 + 1;
+  double *Ut = W;                                         // pivot rows of layer k, [t][0..Cc) (Cs == Cc); rhs moved to column n2
+  const int Ubs = Cs;
   for (int k = L - 1; k >= 0; k--) {
     const size_t qa = q0 + k;
     const double *Uk = Ug + (size_t)k * n2 * Cc;
-    for (int idx = T.rank; idx < n2 * n2; idx += T.size) { const int t = idx / n2, c = idx % n2; Ub[(size_t)t * Ubs + c] = Uk[(size_t)t * Cc + c]; }
+    for (int idx = T.rank; idx < n2 * Cc; idx += T.size) Ut[idx] = Uk[idx];
+    T.sync();
     for (int t = T.rank; t < n2; t += T.size) {
-      double b = Uk[(size_t)t * Cc + RH];
-      const double *un = Uk + (size_t)t * Cc + n2;
+      const double *un = Ut + (size_t)t * Ubs + n2;
+      double b = Ut[(size_t)t * Ubs + RH];
       for (int c = 0; c < n2; c++) b -= un[c] * xnext[c];
-      Ub[(size_t)t * Ubs + n2] = b;
+      Ut[(size_t)t * Ubs + n2] = b;
     }
     T.sync();
-    // upper-triangular solve (row t has its pivot in column t), column oriented
-    for (int t = n2 - 1; t >= 0; t--) {
-      const double xt = Ub[(size_t)t * Ubs + n2] / Ub[(size_t)t * Ubs + t];
-      T.sync();
-      if (T.rank == 0) xcur[t] = xt;
-      for (int r = T.rank; r < t; r += T.size) Ub[(size_t)r * Ubs + n2] -= Ub[(size_t)r * Ubs + t] * xt;
-      T.sync();
+    // upper-triangular solve (row t has its pivot in column t): blocks of 8 unknowns, the small diagonal block
+    // solved by one thread out of registers, the rest of the right-hand side updated by everyone
+    {
+      constexpr int TB = 8;
+      for (int t1 = n2; t1 > 0; t1 -= TB) {
+        const int t0 = t1 - TB > 0 ? t1 - TB : 0, nt = t1 - t0;
+        if (T.rank == 0) {
+          double uu[TB][TB], bb[TB], xx[TB];
+#pragma unroll
+          for (int a = 0; a < TB; a++) {
+            bb[a] = a < nt ? Ut[(size_t)(t0 + a) * Ubs + n2] : 0.0;
+#pragma unroll
+            for (int b = 0; b < TB; b++) uu[a][b] = (a < nt && b < nt && b >= a) ? Ut[(size_t)(t0 + a) * Ubs + t0 + b] : (a == b ? 1.0 : 0.0);
+          }
+#pragma unroll
+          for (int a = 0; a < TB; a++) uu[a][a] = 1.0 / uu[a][a];
+#pragma unroll
+          for (int a = TB - 1; a >= 0; a--) {
+            xx[a] = bb[a] * uu[a][a];
+#pragma unroll
+            for (int b = 0; b < TB; b++) if (b < a) bb[b] -= uu[b][a] * xx[a];
+          }
+#pragma unroll
+          for (int a = 0; a < TB; a++) if (a < nt) xcur[t0 + a] = xx[a];
+        }
+        T.sync();
+        for (int r = T.rank; r < t0; r += T.size) {
+          double b = Ut[(size_t)r * Ubs + n2];
+          for (int a = 0; a < nt; a++) b -= Ut[(size_t)r * Ubs + t0 + a] * xcur[t0 + a];
+          Ut[(size_t)r * Ubs + n2] = b;
+        }
+        T.sync();
+      }
     }
     // xcur = [LCON(1..n), MCON(1..n)] of layer k
     if (k == L - 1) {

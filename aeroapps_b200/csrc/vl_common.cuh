@@ -41,6 +41,11 @@ struct SerialTeam {
   DEVFN double bcast0(double v) const { return v; }
   // argmax over lanes: returns max value, idx receives the owner's idx
   DEVFN double argmax(double v, int &idx) const { return v; }
+  // "panel" sub-team (first PW ranks): warp-scope collectives without a block barrier
+  static constexpr int PW = 1, PRU = 256;                  // lanes, max rows per lane
+  DEVFN double pargmax(double v, int &idx) const { return v; }
+  DEVFN double pbcast(double v, int) const { return v; }
+  DEVFN void psync() const {}
 };
 
 #ifndef AB_HOST_MODEL
@@ -103,6 +108,20 @@ struct BlockTeam {
     idx = bi;
     return bv;
   }
+  // "panel" sub-team = warp 0 of the CTA (callers restrict themselves to rank < PW)
+  static constexpr int PW = 32, PRU = 8;
+  // v >= 0 or -1 (no candidate): integer max-reductions on the IEEE bit pattern (monotonic for v >= 0)
+  DEVFN double pargmax(double v, int &idx) const {
+    const unsigned long long key = v < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(v);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const bool cand = (hi == mh) && (lo == ml);
+    idx = (int)__reduce_min_sync(0xffffffffu, cand ? (unsigned)idx : 0x7fffffffu);
+    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  }
+  DEVFN double pbcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  DEVFN void psync() const { __syncwarp(); }
 };
 #endif
 
