@@ -301,7 +301,20 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
         double *LpC = Lp + (size_t)(P & 1) * R * BVP_NB, *UbC = Ub + (size_t)(P & 1) * BVP_NB * Cs;
         double *LpN = Lp + (size_t)((P + 1) & 1) * R * BVP_NB, *UbN = Ub + (size_t)((P + 1) & 1) * BVP_NB * Cs;
         double *LUpN = LUp + ((P + 1) & 1) * BVP_NB * BVP_NB;
-        if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, true, nb, LpC, UbC, LpN, LUpN, iflag);
+        if (has_next) {
+          // everyone: apply panel P to the columns of panel P+1 first, so that warp 0 can start on it right away
+          for (int idx = T.rank; idx < R * BVP_NB; idx += T.size) {
+            const int r = idx / BVP_NB, j = idx % BVP_NB;
+            if (j < nb1) {
+              double a = W[(size_t)r * Cs + jc1 + j];
+#pragma unroll
+              for (int jj = 0; jj < BVP_NB; jj++) a -= LpC[r * BVP_NB + jj] * UbC[jj * Cs + jc1 + j];
+              W[(size_t)r * Cs + jc1 + j] = a;
+            }
+          }
+          T.sync();
+        }
+        if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, false, nb, LpC, UbC, LpN, LUpN, iflag);
         if (is_trail) {
           // trailing update: W(r, c) -= sum_j L(r, j) U(j, c) for c >= cbeg; a warp owns a group of RG rows
           constexpr int RG = 4;
@@ -348,24 +361,24 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
     }
     if (failed) break;
     // ---- spill the pivot rows (U factor + transformed rhs), recycle their slots, shift the carry rows
-    double *Uk = Ug + (size_t)k * n2 * Cc;
-    for (int idx = T.rank; idx < n2 * Cc; idx += T.size) {
-      const int t = idx / Cc, c = idx % Cc;
-      Uk[idx] = W[(size_t)pivrow[t] * Cs + c];
+    {
+      double *Uk = Ug + (size_t)k * n2 * Cc;
+      const int LW = T.size < 32 ? T.size : 32, lane = T.rank % LW, wid = T.rank / LW, nw = T.size / LW;
+      for (int t = wid; t < n2; t += nw) {
+        const double *src = W + (size_t)pivrow[t] * Cs; double *dst = Uk + (size_t)t * Cc;
+        for (int c = lane; c < Cc; c += LW) dst[c] = src[c];
+      }
+      T.sync();
+      for (int t = T.rank; t < n2; t += T.size) { freeslot[t] = pivrow[t]; state[pivrow[t]] = -1; }
+      T.sync();
+      // carry rows: the next layer's block moves to the front; everything else is cleared for the new rows
+      for (int r = wid; r < R; r += nw) {
+        double *row = W + (size_t)r * Cs;
+        if (state[r] == 0) { for (int c = lane; c < n2; c += LW) { row[c] = row[n2 + c]; row[n2 + c] = 0.0; } }
+        else { for (int c = lane; c < 2 * n2; c += LW) row[c] = 0.0; }
+      }
+      T.sync();
     }
-    T.sync();
-    for (int t = T.rank; t < n2; t += T.size) { freeslot[t] = pivrow[t]; state[pivrow[t]] = -1; }
-    for (int idx = T.rank; idx < R * n2; idx += T.size) {
-      const int r = idx / n2, c = idx % n2;
-      if (state[r] == 0) { double *row = W + (size_t)r * Cs; row[c] = row[n2 + c]; }
-    }
-    T.sync();
-    for (int idx = T.rank; idx < R * n2; idx += T.size) {
-      const int r = idx / n2, c = idx % n2;
-      W[(size_t)r * Cs + n2 + c] = 0.0;
-      if (state[r] != 0) W[(size_t)r * Cs + c] = 0.0;
-    }
-    T.sync();
   }
   if (failed) { if (T.rank == 0) { cst[0] = 0; cst[3] = 4; } return; }
 
@@ -379,11 +392,10 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   T.sync();
   double *Ut = W;                                         // pivot rows of layer k, [t][0..Cc) (Cs == Cc); rhs moved to column n2
   const int Ubs = Cs;
+  T.load_begin(Ut, Ug + (size_t)(L - 1) * n2 * Cc, (size_t)n2 * Cc);
   for (int k = L - 1; k >= 0; k--) {
     const size_t qa = q0 + k;
-    const double *Uk = Ug + (size_t)k * n2 * Cc;
-    for (int idx = T.rank; idx < n2 * Cc; idx += T.size) Ut[idx] = Uk[idx];
-    T.sync();
+    T.load_wait();
     for (int t = T.rank; t < n2; t += T.size) {
       const double *un = Ut + (size_t)t * Ubs + n2;
       double b = Ut[(size_t)t * Ubs + RH];
@@ -425,6 +437,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
         T.sync();
       }
     }
+    if (k > 0) T.load_begin(Ut, Ug + (size_t)(k - 1) * n2 * Cc, (size_t)n2 * Cc);   // overlaps with the source terms below
     // xcur = [LCON(1..n), MCON(1..n)] of layer k
     if (k == L - 1) {
       // BOA source: surface-reflected diffuse field (GET_BOA_SOURCE)

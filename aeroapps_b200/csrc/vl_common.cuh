@@ -46,9 +46,13 @@ struct SerialTeam {
   DEVFN double pargmax(double v, int &idx) const { return v; }
   DEVFN double pbcast(double v, int) const { return v; }
   DEVFN void psync() const {}
+  // bulk load of n doubles into team scratch: begin (collective) ... wait (collective)
+  DEVFN void load_begin(double *dst, const double *src, size_t n) const { for (size_t i = 0; i < n; i++) dst[i] = src[i]; }
+  DEVFN void load_wait() const {}
 };
 
 #ifndef AB_HOST_MODEL
+DEVFN unsigned vl_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 struct WarpTeam {
   int rank;
   static constexpr int size = 32;
@@ -75,7 +79,45 @@ struct WarpTeam {
 struct BlockTeam {
   int rank, size;
   double *sd; int *si;
-  DEVFN BlockTeam(double *scratch_d, int *scratch_i) : rank(threadIdx.x), size(blockDim.x), sd(scratch_d), si(scratch_i) {}
+  unsigned long long *mbar;      // optional mbarrier (shared memory) for load_begin/load_wait
+  mutable unsigned mphase;
+  DEVFN BlockTeam(double *scratch_d, int *scratch_i, unsigned long long *bar = nullptr)
+      : rank(threadIdx.x), size(blockDim.x), sd(scratch_d), si(scratch_i), mbar(bar), mphase(0) {
+    if (bar) {
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vl_smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+    }
+  }
+  // 1-D TMA bulk copy global -> shared (cp.async.bulk), n*8 bytes a multiple of 16, both sides 16-byte aligned.
+  // Collective: orders the team's earlier generic-proxy accesses to dst/src before the asynchronous copy.
+  DEVFN void load_begin(double *dst, const double *src, size_t n) const {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (rank == 0) {
+      const unsigned bytes = (unsigned)(n * 8);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vl_smem_u32(mbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vl_smem_u32(dst)),
+                   "l"(src), "r"(bytes), "r"(vl_smem_u32(mbar))
+                   : "memory");
+    }
+  }
+  DEVFN void load_wait() const {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "VL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra VL_DONE;\n"
+        "bra VL_WAIT;\n"
+        "VL_DONE:\n"
+        "}" ::"r"(vl_smem_u32(mbar)),
+        "r"(mphase)
+        : "memory");
+    mphase ^= 1u;
+  }
   DEVFN void sync() const { __syncthreads(); }
   DEVFN double sum(double v) const {
 #pragma unroll

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
   __shared__ int si[64];
   const int n = S * QD.N;
   int *iscr = reinterpret_cast<int *>(smem_d + bvp_smem_doubles(n));
-  BlockTeam T(sd, si);
+  __shared__ unsigned long long mbar;
+  BlockTeam T(sd, si, &mbar);
   double *Ug = work + (size_t)blockIdx.x * work_per_cta;
   for (int a = blockIdx.x; a < nactive; a += gridDim.x) {
     const int p = active[a];
