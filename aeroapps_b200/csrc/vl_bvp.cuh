@@ -42,7 +42,8 @@ HDFN size_t bvp_work_doubles(int n, int L) { return (size_t)L * 2 * n * bvp_cols
 // multipliers of the pivot rows inside the panel to LUpN, the pivot rows' own panel entries back to W.
 template <int RU, class Team>
 DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *state, int *pivrow, int jc0, int nb, bool upd, int nbp,
-                     const double *AB_RESTRICT LpP, const double *AB_RESTRICT UbP, double *AB_RESTRICT LpN, double *AB_RESTRICT LUpN, int *iflag) {
+                     const double *AB_RESTRICT LpP, const double *AB_RESTRICT UbP, double *AB_RESTRICT LpN, double *AB_RESTRICT LUpN, int *iflag,
+                     int *rflagN) {
   constexpr int PW = Team::PW;
   double pv[RU][BVP_NB], lm[RU][BVP_NB];
   bool act[RU];
@@ -107,8 +108,10 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
   for (int u = 0; u < RU; u++) {
     const int r = T.rank + PW * u;
     if (r < R) {
+      bool nz = false;
 #pragma unroll
-      for (int j = 0; j < BVP_NB; j++) LpN[r * BVP_NB + j] = lm[u][j];
+      for (int j = 0; j < BVP_NB; j++) { LpN[r * BVP_NB + j] = lm[u][j]; nz = nz || (lm[u][j] != 0.0); }
+      rflagN[r] = nz ? 1 : 0;
     }
   }
   if (pfail && T.rank == 0) iflag[0] = 1;
@@ -116,12 +119,12 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
 
 template <class Team>
 DEVFN void bvp_panel_dispatch(const Team &T, double *W, int Cs, int R, int *state, int *pivrow, int jc0, int nb, bool upd, int nbp,
-                              const double *LpP, const double *UbP, double *LpN, double *LUpN, int *iflag) {
-  if constexpr (Team::PW == 1) bvp_panel<Team::PRU>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
+                              const double *LpP, const double *UbP, double *LpN, double *LUpN, int *iflag, int *rflagN) {
+  if constexpr (Team::PW == 1) bvp_panel<Team::PRU>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
   else {
-    if (R <= 2 * Team::PW) bvp_panel<2>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
-    else if (R <= 4 * Team::PW) bvp_panel<4>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
-    else bvp_panel<8>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag);
+    if (R <= 2 * Team::PW) bvp_panel<2>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
+    else if (R <= 4 * Team::PW) bvp_panel<4>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
+    else bvp_panel<8>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
   }
 }
 
@@ -162,6 +165,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   int *pivrow = state + R;                // 2n
   int *freeslot = pivrow + n2;            // 2n
   int *iflag = freeslot + n2;             // failure flag of the panel factorisation
+  int *rflag = iflag + 4;                 // 2 x R: row has non-zero multipliers in the current / next panel
   const double *sc = X.scal + (size_t)p * 16;
   const int *ib = X.ibuf + (size_t)p * 4;
   int *cst = CV.state + (size_t)p * 4;
@@ -289,7 +293,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       const bool is_trail = (T.size <= Team::PW) || !is_panel;
       const int LW = T.size < 32 ? T.size : 32;
       const int lane = T.rank % LW, nwt = (T.size <= Team::PW) ? 1 : T.size / LW - 1, wid = (T.size <= Team::PW) ? 0 : T.rank / LW - 1;
-      if (is_panel) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), false, 0, Lp, Ub, Lp, LUp, iflag);
+      if (is_panel) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), false, 0, Lp, Ub, Lp, LUp, iflag, rflag);
       T.sync();
       if (iflag[0]) { failed = true; break; }
       bvp_urows(T, W, Cs, Cc, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), LUp, Ub);
@@ -301,6 +305,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
         double *LpC = Lp + (size_t)(P & 1) * R * BVP_NB, *UbC = Ub + (size_t)(P & 1) * BVP_NB * Cs;
         double *LpN = Lp + (size_t)((P + 1) & 1) * R * BVP_NB, *UbN = Ub + (size_t)((P + 1) & 1) * BVP_NB * Cs;
         double *LUpN = LUp + ((P + 1) & 1) * BVP_NB * BVP_NB;
+        const int *rflagC = rflag + (P & 1) * R;
         if (has_next) {
           // everyone: apply panel P to the columns of panel P+1 first, so that warp 0 can start on it right away
           for (int idx = T.rank; idx < R * BVP_NB; idx += T.size) {
@@ -314,23 +319,22 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
           }
           T.sync();
         }
-        if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, false, nb, LpC, UbC, LpN, LUpN, iflag);
+        if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, false, nb, LpC, UbC, LpN, LUpN, iflag, rflag + ((P + 1) & 1) * R);
         if (is_trail) {
           // trailing update: W(r, c) -= sum_j L(r, j) U(j, c) for c >= cbeg; a warp owns a group of RG rows
           constexpr int RG = 4;
           const int cbeg = jc1 + nb1;
           for (int g = wid; g * RG < R; g += nwt) {
             const int r0 = g * RG;
+            bool any = false;                          // rows that are not active carry zero multipliers
+#pragma unroll
+            for (int rr = 0; rr < RG; rr++) any = any || (r0 + rr < R && rflagC[r0 + rr] != 0);
+            if (!any) continue;
             double l[RG][BVP_NB];
-            bool any = false;
 #pragma unroll
             for (int rr = 0; rr < RG; rr++)
 #pragma unroll
-              for (int j = 0; j < BVP_NB; j++) {
-                l[rr][j] = (r0 + rr < R) ? LpC[(r0 + rr) * BVP_NB + j] : 0.0;
-                any = any || (l[rr][j] != 0.0);
-              }
-            if (!any) continue;
+              for (int j = 0; j < BVP_NB; j++) l[rr][j] = (r0 + rr < R) ? LpC[(r0 + rr) * BVP_NB + j] : 0.0;
             for (int c = cbeg + lane; c < Cc; c += 2 * LW) {
               const int c2 = c + LW;
               const bool two = c2 < Cc;

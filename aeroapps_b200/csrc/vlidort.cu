@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, c
 }
 
 template <int S>
-__global__ void __launch_bounds__(256) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
+__global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
                                                 int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
                                                 int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta) {
   extern __shared__ double smem_d[];
@@ -230,8 +230,8 @@ int run_vlidort(const RunDesc &R) {
   size_t budget = (size_t)(ws_gb * 1e9);
   budget = std::min(budget, (size_t)(0.6 * (double)(freeb + g_arena.cap)));
   // K3 geometry
-  const int bvp_threads = 256;
-  const size_t bvp_smem = bvp_smem_doubles(n) * 8 + (size_t)(7 * n + 16) * 4;
+  const int bvp_threads = 384;
+  const size_t bvp_smem = bvp_smem_doubles(n) * 8 + (size_t)(13 * n + 32) * 4;
   int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int bvp_per_sm = 1;
   auto kb = (S == 1) ? (const void *)k_vl_bvp<1> : (const void *)k_vl_bvp<3>;

@@ -60,7 +60,7 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
   if (surf_kind != 0) { SFc.brdf_f = bf.data(); SFc.brdf_f_0 = bf0.data(); SFc.user_brdf_f = buf.data(); SFc.user_brdf_f_0 = nullptr; SFc.nq = B.nq; }
   std::vector<double> pq((size_t)(NM + 1) * N * 3), tmp(3 * (NM + 2));
   std::vector<double> escr(eigen_scratch_doubles(n, NM) + 64), bscr(bvp_smem_doubles(n) + 64), Ug(bvp_work_doubles(n, L));
-  std::vector<int> iscr(3 * n + 4 * n + 16);
+  std::vector<int> iscr(13 * n + 32);
   for (int p = 0; p < npix; p++) {
     status[p] = ibuf[(size_t)p * 4 + 1]; nfourier[p] = 0;
     for (int o = 0; o < 4; o++) stokes[(size_t)p * 4 + o] = 0.0;
