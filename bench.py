@@ -21,6 +21,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# every rank owns its own contiguous slab of the (virtual) swath: different synthetic pixels per rank
+RANK_SEED = 97 * int(os.environ.get("RANK", "0"))
 
 
 def peaks():
@@ -91,7 +93,7 @@ class AopScalarWorkload:
         self.tables = mt.synthetic_tables(nmom=0)
         self.chan_m = [550e-9]
         self.channels = np.array([550.0], np.float32)
-        self.state = mt.synthetic_state(self.nobs, self.km, seed=20260101 + 1)
+        self.state = mt.synthetic_state(self.nobs, self.km, seed=20260101 + 1 + RANK_SEED)
         self.vnames = self.state["vnames"]
         self.nq = len(self.vnames)
         self.units_per_step = self.km * self.nobs * self.nch
@@ -202,7 +204,7 @@ class RtVectorWorkload:
         from aeroapps_b200 import MieObs_, VLIDORT_POLAR_ as VP
         mt = self.mt
         tables = mt.synthetic_tables(nmom=self.nmom)
-        st = mt.synthetic_state(self.nobs, self.km, seed=20260101 + 3)
+        st = mt.synthetic_state(self.nobs, self.km, seed=20260101 + 3 + RANK_SEED)
         mie = MieObs_.ChemMie([550e-9], self.nmom, tables)
         t0 = time.perf_counter()
         tau, ssa, g, pmom, rc = mie.getaopvector([550.0], st["vnames"], 0, st["qm"], st["rh"], self.nmom, 6)
@@ -213,7 +215,7 @@ class RtVectorWorkload:
         F = lambda a: np.asfortranarray(a, dtype=np.float64)
         ch = np.array([550.0])
         ROT, depol, rc = VP.rot_calc(ch, F(pe), F(ze), F(te), 1e15, 0)
-        rng = np.random.default_rng(20260101 + 4)
+        rng = np.random.default_rng(20260101 + 4 + RANK_SEED)
         n = self.nobs
         return dict(channels=ch, ROT=F(ROT), depol=depol, alpha=np.zeros_like(F(ROT)), tau=F(tau), ssa=F(ssa), pmom=F(pmom),
                     pe=F(pe), he=F(ze), te=F(te), albedo=F(rng.uniform(0.02, 0.4, (n, 1))), sza=rng.uniform(0, 75, n),
@@ -316,7 +318,7 @@ class RtVectorCxWorkload(RtVectorWorkload):
 
     def _scene_gpu(self):
         sc = super()._scene_gpu()
-        rng = np.random.default_rng(20260101 + 5)
+        rng = np.random.default_rng(20260101 + 5 + RANK_SEED)
         n = self.nobs
         sc.update(u10m=rng.normal(0, 5, n), v10m=rng.normal(0, 5, n), mr=np.array([1.334]))
         return sc
@@ -502,6 +504,14 @@ def main():
     if dist:
         dist.barrier()
     out = run_gpu(wl, args, torch, dev, dist, rank, world, local)
+    if dist and hasattr(wl, "d_out"):
+        # the path's only exchange: the final gather of the per-rank slabs (outside the timed steps)
+        from aeroapps_b200 import swath
+        loc = wl.d_out[0].detach().cpu().numpy()
+        full = swath.gather_swath(loc, loc.shape[0] * world, axis=0, dist=dist, device=dev)
+        if rank == 0:
+            out["config"]["gathered_outputs"] = int(full.shape[0])
+            out["config"]["parallelism"] = f"{world} ranks x contiguous slabs, no data-path collective, final all_gather over NCCL"
     if args.workload.startswith("rt_vector") and not args.no_aop:
         # the second half of the BASELINE metric: Mie AOP voxels/s (BASELINE configs[0], c90 scalar AOPs)
         import copy
