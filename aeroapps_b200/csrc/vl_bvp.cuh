@@ -45,14 +45,15 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
                      const double *AB_RESTRICT LpP, const double *AB_RESTRICT UbP, double *AB_RESTRICT LpN, double *AB_RESTRICT LUpN, int *iflag,
                      int *rflagN) {
   constexpr int PW = Team::PW;
-  double pv[RU][BVP_NB], lm[RU][BVP_NB];
-  bool act[RU];
+  double pv[RU][BVP_NB];
+  bool act[RU], nz[RU];
 #pragma unroll
   for (int u = 0; u < RU; u++) {
     const int r = T.rank + PW * u;
     act[u] = (r < R) && state[r] == 0;
+    nz[u] = false;
 #pragma unroll
-    for (int j = 0; j < BVP_NB; j++) { pv[u][j] = (act[u] && j < nb) ? W[(size_t)r * Cs + jc0 + j] : 0.0; lm[u][j] = 0.0; }
+    for (int j = 0; j < BVP_NB; j++) pv[u][j] = (act[u] && j < nb) ? W[(size_t)r * Cs + jc0 + j] : 0.0;
     if (upd && act[u]) {
 #pragma unroll
       for (int jj = 0; jj < BVP_NB; jj++) {
@@ -72,46 +73,57 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
       best = T.pargmax(best, bidx);
       if (!(best > 0.0)) pfail = true;
       else {
-        const int owner = bidx % PW, ustar = bidx / PW;
+        const int owner = bidx % PW, ustar = bidx / PW;          // ustar is uniform over the sub-team
         const bool mine = (T.rank == owner);
         double prow[BVP_NB];
 #pragma unroll
-        for (int jj = 0; jj < BVP_NB; jj++) {
-          double v = 0.0;
+        for (int jj = 0; jj < BVP_NB; jj++) prow[jj] = 0.0;
 #pragma unroll
-          for (int u = 0; u < RU; u++) if (u == ustar) v = pv[u][jj];
-          prow[jj] = (jj >= j) ? T.pbcast(v, owner) : 0.0;
-        }
+        for (int u = 0; u < RU; u++)
+          if (u == ustar) {                                      // uniform branch: plain register copies
+#pragma unroll
+            for (int jj = 0; jj < BVP_NB; jj++) prow[jj] = pv[u][jj];
+            if (mine) act[u] = false;
+          }
+#pragma unroll
+        for (int jj = 0; jj < BVP_NB; jj++) if (jj >= j) prow[jj] = T.pbcast(prow[jj], owner);
         const double ipiv = 1.0 / prow[j];
+        if (mine) {                                              // this row becomes pivot row j of the panel
+          state[bidx] = 1 + jc0 + j; pivrow[jc0 + j] = bidx;
+#pragma unroll
+          for (int jj = 0; jj < BVP_NB; jj++) if (jj >= j && jj < nb) W[(size_t)bidx * Cs + jc0 + jj] = prow[jj];
+        }
 #pragma unroll
         for (int u = 0; u < RU; u++) {
-          if (mine && u == ustar) {                  // this row becomes pivot row j of the panel
-            act[u] = false;
-            state[bidx] = 1 + jc0 + j; pivrow[jc0 + j] = bidx;
-#pragma unroll
-            for (int jj = 0; jj < BVP_NB; jj++) {
-              if (jj < j) LUpN[j * BVP_NB + jj] = lm[u][jj];
-              else if (jj < nb) W[(size_t)bidx * Cs + jc0 + jj] = prow[jj];
-              lm[u][jj] = 0.0;
-            }
-          } else if (act[u]) {
-            const double l = pv[u][j] * ipiv;
-            lm[u][j] = l;
+          const int r = T.rank + PW * u;
+          double l = 0.0;
+          if (act[u]) {
+            l = pv[u][j] * ipiv;
+            nz[u] = nz[u] || (l != 0.0);
 #pragma unroll
             for (int jj = 0; jj < BVP_NB; jj++) if (jj > j) pv[u][jj] -= l * prow[jj];
           }
+          if (r < R) LpN[r * BVP_NB + j] = l;                    // multipliers straight to shared memory
         }
       }
+    } else {
+#pragma unroll
+      for (int u = 0; u < RU; u++) { const int r = T.rank + PW * u; if (r < R) LpN[r * BVP_NB + j] = 0.0; }
     }
   }
 #pragma unroll
-  for (int u = 0; u < RU; u++) {
-    const int r = T.rank + PW * u;
-    if (r < R) {
-      bool nz = false;
-#pragma unroll
-      for (int j = 0; j < BVP_NB; j++) { LpN[r * BVP_NB + j] = lm[u][j]; nz = nz || (lm[u][j] != 0.0); }
-      rflagN[r] = nz ? 1 : 0;
+  for (int u = 0; u < RU; u++) { const int r = T.rank + PW * u; if (r < R) rflagN[r] = nz[u] ? 1 : 0; }
+  T.psync();
+  // multipliers of the pivot rows inside the panel -> LUpN; then clear those rows so the trailing update skips them
+  if (!pfail) {
+    for (int idx = T.rank; idx < BVP_NB * BVP_NB; idx += PW) {
+      const int j = idx / BVP_NB, jj = idx % BVP_NB;
+      if (j < nb) LUpN[idx] = (jj < j) ? LpN[pivrow[jc0 + j] * BVP_NB + jj] : 0.0;
+    }
+    T.psync();
+    for (int idx = T.rank; idx < BVP_NB * BVP_NB; idx += PW) {
+      const int j = idx / BVP_NB, jj = idx % BVP_NB;
+      if (j < nb) LpN[pivrow[jc0 + j] * BVP_NB + jj] = 0.0;
     }
   }
   if (pfail && T.rank == 0) iflag[0] = 1;
