@@ -85,8 +85,7 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
             for (int jj = 0; jj < BVP_NB; jj++) prow[jj] = pv[u][jj];
             if (mine) act[u] = false;
           }
-#pragma unroll
-        for (int jj = 0; jj < BVP_NB; jj++) if (jj >= j) prow[jj] = T.pbcast(prow[jj], owner);
+        T.pbcast_n(prow, j, owner);
         const double ipiv = 1.0 / prow[j];
         if (mine) {                                              // this row becomes pivot row j of the panel
           state[bidx] = 1 + jc0 + j; pivrow[jc0 + j] = bidx;
@@ -134,9 +133,8 @@ DEVFN void bvp_panel_dispatch(const Team &T, double *W, int Cs, int R, int *stat
                               const double *LpP, const double *UbP, double *LpN, double *LUpN, int *iflag, int *rflagN) {
   if constexpr (Team::PW == 1) bvp_panel<Team::PRU>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
   else {
-    if (R <= 2 * Team::PW) bvp_panel<2>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
-    else if (R <= 4 * Team::PW) bvp_panel<4>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
-    else bvp_panel<8>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
+    if (R <= Team::PW) bvp_panel<1>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
+    else bvp_panel<2>(T, W, Cs, R, state, pivrow, jc0, nb, upd, nbp, LpP, UbP, LpN, LUpN, iflag, rflagN);
   }
 }
 
@@ -304,7 +302,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       const bool is_panel = T.rank < Team::PW;
       const bool is_trail = (T.size <= Team::PW) || !is_panel;
       const int LW = T.size < 32 ? T.size : 32;
-      const int lane = T.rank % LW, nwt = (T.size <= Team::PW) ? 1 : T.size / LW - 1, wid = (T.size <= Team::PW) ? 0 : T.rank / LW - 1;
+      const int lane = T.rank % LW, nwt = (T.size <= Team::PW) ? 1 : (T.size - Team::PW) / LW, wid = (T.size <= Team::PW) ? 0 : (T.rank - Team::PW) / LW;
       if (is_panel) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), false, 0, Lp, Ub, Lp, LUp, iflag, rflag);
       T.sync();
       if (iflag[0]) { failed = true; break; }

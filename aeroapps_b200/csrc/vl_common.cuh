@@ -44,7 +44,8 @@ struct SerialTeam {
   // "panel" sub-team (first PW ranks): warp-scope collectives without a block barrier
   static constexpr int PW = 1, PRU = 256;                  // lanes, max rows per lane
   DEVFN double pargmax(double v, int &idx) const { return v; }
-  DEVFN double pbcast(double v, int) const { return v; }
+  template <int N_>
+  DEVFN void pbcast_n(double (&)[N_], int, int) const {}
   DEVFN void psync() const {}
   // bulk load of n doubles into team scratch: begin (collective) ... wait (collective)
   DEVFN void load_begin(double *dst, const double *src, size_t n) const { for (size_t i = 0; i < n; i++) dst[i] = src[i]; }
@@ -150,8 +151,10 @@ struct BlockTeam {
     idx = bi;
     return bv;
   }
-  // "panel" sub-team = warp 0 of the CTA (callers restrict themselves to rank < PW)
-  static constexpr int PW = 32, PRU = 8;
+  // "panel" sub-team = the first 4 warps of the CTA, one per scheduler (callers restrict themselves to rank < PW).
+  // Its collectives use named barrier 1 and the upper halves of sd/si, never the CTA-wide barrier 0.
+  static constexpr int PW = 128, PRU = 2;
+  DEVFN void psync() const { asm volatile("bar.sync 1, 128;" ::: "memory"); }
   // v >= 0 or -1 (no candidate): integer max-reductions on the IEEE bit pattern (monotonic for v >= 0)
   DEVFN double pargmax(double v, int &idx) const {
     const unsigned long long key = v < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(v);
@@ -159,11 +162,26 @@ struct BlockTeam {
     const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
     const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
     const bool cand = (hi == mh) && (lo == ml);
-    idx = (int)__reduce_min_sync(0xffffffffu, cand ? (unsigned)idx : 0x7fffffffu);
-    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    const int widx = (int)__reduce_min_sync(0xffffffffu, cand ? (unsigned)idx : 0x7fffffffu);
+    if ((rank & 31) == 0) { sd[32 + (rank >> 5)] = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml)); si[32 + (rank >> 5)] = widx; }
+    psync();
+    double bv = sd[32]; int bi = si[32];
+#pragma unroll
+    for (int w = 1; w < 4; w++) { const double ov = sd[32 + w]; const int oi = si[32 + w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
+    idx = bi;
+    return bv;
   }
-  DEVFN double pbcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
-  DEVFN void psync() const { __syncwarp(); }
+  // owner's v[j0..N_) to everyone in the sub-team
+  template <int N_>
+  DEVFN void pbcast_n(double (&v)[N_], int j0, int owner) const {
+    if (rank == owner) {
+#pragma unroll
+      for (int j = 0; j < N_; j++) if (j >= j0) sd[40 + j] = v[j];
+    }
+    psync();
+#pragma unroll
+    for (int j = 0; j < N_; j++) if (j >= j0) v[j] = sd[40 + j];
+  }
 };
 #endif
 
