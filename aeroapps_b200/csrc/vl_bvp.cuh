@@ -33,7 +33,13 @@ struct VLConv {                  // per pixel, persistent over the Fourier loop
 HDFN int bvp_cols(int n) { return 4 * n + 1; }
 HDFN int bvp_stride(int n) { return (4 * n + 1) | 1; }                         // odd row stride
 constexpr int BVP_NB = 8;                                                        // panel width of the blocked elimination
-HDFN size_t bvp_smem_doubles(int n) { return (size_t)3 * n * bvp_stride(n) + 8 * n + 16 + 2 * ((size_t)3 * n * BVP_NB + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB); }
+// big region: forward phase = window + double-buffered panel arrays; backward phase = two buffers of pivot rows
+HDFN size_t bvp_big_doubles(int n) {
+  const size_t fwd = (size_t)3 * n * bvp_stride(n) + 2 * ((size_t)3 * n * BVP_NB + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB);
+  const size_t bwd = (size_t)2 * (2 * n) * bvp_cols(n);
+  return ((fwd > bwd ? fwd : bwd) + 1) & ~(size_t)1;
+}
+HDFN size_t bvp_smem_doubles(int n) { return bvp_big_doubles(n) + 8 * n + 16; }
 HDFN size_t bvp_work_doubles(int n, int L) { return (size_t)L * 2 * n * bvp_cols(n); }
 
 // ---- panel factorisation of the blocked elimination, executed by the panel sub-team (ranks < Team::PW).
@@ -165,10 +171,10 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   const int N = QD.N, n = S * N, n2 = 2 * n, L = X.L, NM = X.NM;
   const int R = 3 * n, Cc = bvp_cols(n), Cs = bvp_stride(n), RH = 4 * n;      // RH = rhs column
   double *W = scr;
-  double *xcur = W + (size_t)R * Cs;      // 2n
+  double *xcur = W + bvp_big_doubles(n);  // 2n
   double *xnext = xcur + n2;              // 2n
   double *red = xnext + n2;               // 4n scratch
-  double *Lp = red + 4 * n + 16;              // 2 x (R x NB) multipliers of the current / next panel
+  double *Lp = W + (size_t)R * Cs;            // 2 x (R x NB) multipliers of the current / next panel
   double *Ub = Lp + (size_t)2 * R * BVP_NB;   // 2 x (NB x Cs) finished pivot rows of the current / next panel
   double *LUp = Ub + (size_t)2 * BVP_NB * Cs; // 2 x (NB x NB) multipliers of the pivot rows inside the panel
   int *state = iscr;                      // R : -1 unused, 0 active, 1+t pivot number t
@@ -404,12 +410,16 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   for (int o = 0; o < S; o++) cum[o] = 0.0;
   for (int t = T.rank; t < n2; t += T.size) xnext[t] = 0.0;
   T.sync();
-  double *Ut = W;                                         // pivot rows of layer k, [t][0..Cc) (Cs == Cc); rhs moved to column n2
+  // pivot rows of layer k, [t][0..Cc) (Cs == Cc), rhs moved to column n2; two buffers: layer k-1 streams in (TMA bulk
+  // copy) while layer k is solved
   const int Ubs = Cs;
-  T.load_begin(Ut, Ug + (size_t)(L - 1) * n2 * Cc, (size_t)n2 * Cc);
+  const size_t usz = (size_t)n2 * Cc;
+  T.load_begin(W, Ug + (size_t)(L - 1) * usz, usz);
   for (int k = L - 1; k >= 0; k--) {
     const size_t qa = q0 + k;
+    double *Ut = W + (size_t)((L - 1 - k) & 1) * usz;
     T.load_wait();
+    if (k > 0) T.load_begin(W + (size_t)((L - k) & 1) * usz, Ug + (size_t)(k - 1) * usz, usz);
     for (int t = T.rank; t < n2; t += T.size) {
       const double *un = Ut + (size_t)t * Ubs + n2;
       double b = Ut[(size_t)t * Ubs + RH];
@@ -451,7 +461,6 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
         T.sync();
       }
     }
-    if (k > 0) T.load_begin(Ut, Ug + (size_t)(k - 1) * n2 * Cc, (size_t)n2 * Cc);   // overlaps with the source terms below
     // xcur = [LCON(1..n), MCON(1..n)] of layer k
     if (k == L - 1) {
       // BOA source: surface-reflected diffuse field (GET_BOA_SOURCE)
