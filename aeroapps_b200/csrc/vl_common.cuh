@@ -34,6 +34,10 @@ constexpr int TAYLOR_ORDER = 3;
 constexpr int MAXMOM = 64;                             // >= 2*nstreams
 constexpr int MAXLAY = 128;
 
+#ifdef AB_HOST_MODEL
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }     // CUDA's rsqrt on the host
+#endif
+
 struct SerialTeam {
   static constexpr int rank = 0, size = 1;
   DEVFN void sync() const {}

@@ -49,18 +49,19 @@ DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n) {
 #pragma unroll
       for (int r = 0; r < NR; r++) { ra[r] = r < n ? a[r] : 0.0; rb[r] = r < n ? b[r] : 0.0; }
     }
-    double al2 = 0.0, be2 = 0.0, ga2 = 0.0;
+    // four partial sums per dot product: 12 independent FMA chains
+    double alp[4] = {0.0, 0.0, 0.0, 0.0}, bep[4] = {0.0, 0.0, 0.0, 0.0}, gap[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int r = 0; r < NR; r += 2) {
-      al += ra[r] * ra[r]; be += rb[r] * rb[r]; ga += ra[r] * rb[r];
-      if (r + 1 < NR) { al2 += ra[r + 1] * ra[r + 1]; be2 += rb[r + 1] * rb[r + 1]; ga2 += ra[r + 1] * rb[r + 1]; }
-    }
-    al += al2; be += be2; ga += ga2;
-    const double rel = fabs(ga) / sqrt(al * be + 1.0e-300);
+    for (int r = 0; r < NR; r++) { alp[r & 3] += ra[r] * ra[r]; bep[r & 3] += rb[r] * rb[r]; gap[r & 3] += ra[r] * rb[r]; }
+    al = (alp[0] + alp[1]) + (alp[2] + alp[3]); be = (bep[0] + bep[1]) + (bep[2] + bep[3]); ga = (gap[0] + gap[1]) + (gap[2] + gap[3]);
+    // rel = |cos(a,b)|; the rotation uses  t = 2 ga / (d + sign(d) sqrt(d^2 + 4 ga^2)),  d = be - al  (one sqrt, one
+    // divide and one rsqrt on the dependent chain; rel itself is off the chain)
+    const double rel = fabs(ga) * rsqrt(al * be + 1.0e-300);
     if (rel > 1.0e-15) {
-      const double ze = (be - al) / (2.0 * ga);
-      const double t = (ze >= 0.0 ? 1.0 : -1.0) / (fabs(ze) + sqrt(1.0 + ze * ze));
-      const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+      const double d = be - al, g2 = 2.0 * ga;
+      const double rt = sqrt(d * d + g2 * g2);
+      const double t = g2 / (d >= 0.0 ? d + rt : d - rt);
+      const double c = rsqrt(1.0 + t * t), s = c * t;
       if (full) {
 #pragma unroll
         for (int r = 0; r < NR; r++) { a[r] = c * ra[r] - s * rb[r]; b[r] = s * ra[r] + c * rb[r]; }
