@@ -303,7 +303,15 @@ class RtVectorWorkload:
         fl = st["flops_eigen"] if dom == "k_vl_eigen" else st["flops_bvp"]
         ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         tot = (st["flops_eigen"] + st["flops_bvp"]) / ((st["ms_eigen"] + st["ms_bvp"] + st["ms_setup"]) * 1e-3) / 1e12
-        return {"bound": "fp64", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        traffic, tnote = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_rt_traffic.json")
+        if os.path.exists(tp) and self.nobs == 2048:
+            tj = json.load(open(tp)).get(dom)
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                tnote = "dram read+write bytes of the m=0 launch (2048 pixels) from the committed ncu --set full capture"
+        return {"bound": "fp64", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_note": tnote,
                 "peak_source": "measured DFMA microbenchmark on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak.json); "
                                "MEASURED_PEAKS.json holds no FP64 figure",
                 "whole_rt_tflops": tot, "kernel_ms_share": {"setup": st["ms_setup"], "eigen": st["ms_eigen"], "bvp": st["ms_bvp"]},
@@ -498,7 +506,19 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when the
+        # environment sets NCCL_DEBUG) goes to stderr while the communicator is created
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     if rank == 0:
         g.build()
     if dist:

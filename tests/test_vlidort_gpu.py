@@ -183,3 +183,31 @@ def test_scalar_brdf_surfaces(mods):
         assert rc == 0
         assert rel(I, ref["radiance"], ref["radiance"]) < TOL and rel(R, ref["reflectance"], ref["reflectance"]) < TOL
         assert rel(BR, ref["BR"], ref["BR"]) < 1e-12
+
+
+def test_empty_and_multichannel_brdf(mods):
+    """edge cases of the BRDF wrappers: zero observations (nothing to do, rc 0), several channels with a per-channel
+    refractive index (one MISSING -> only that channel MISSING), dimension check of VLIDORT_Init."""
+    VP, vg = mods
+    M = 1e15
+    sc = vg.synthetic_scene(4, nch_nm=(470.0, 550.0, 870.0), nmom=24, seed=17)
+    sc["mr"] = np.array([1.340, M, 1.330])
+    common = (sc["channels"], 4, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"])
+    I, R, BR, Q, U, _, _, rc = VP.vector_cx(*common, sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], M, 0)
+    assert rc == 0
+    ref = vg.vlidort_run_surface("cx", 3, 4, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"],
+                                 sc["raa"], sc["vza"], sc["u10m"], sc["v10m"], sc["mr"], MISSING=M)
+    assert (I[:, 1] == M).all() and (ref["radiance"][:, 1] == M).all()
+    for c in (0, 2):
+        assert rel(I[:, c], ref["radiance"][:, c], ref["radiance"][:, c]) < TOL
+        assert rel(Q[:, c], ref["Q"][:, c], ref["radiance"][:, c]) < TOL
+    # zero observations
+    z = lambda a, ax: np.take(a, [], axis=ax)
+    I0, R0, BR0, Q0, U0, _, _, rc = VP.vector_cx(sc["channels"], 4, False, z(sc["ROT"], 1), sc["depol"], z(sc["tau"], 2), z(sc["ssa"], 2),
+                                                z(sc["pmom"], 2), z(sc["pe"], 1), z(sc["he"], 1), z(sc["te"], 1), sc["u10m"][:0],
+                                                sc["v10m"][:0], sc["mr"], sc["sza"][:0], sc["raa"][:0], sc["vza"][:0], M, 0)
+    assert rc == 0 and I0.shape == (0, 3)
+    # too many streams for the GEOS-sized build (MAXSTREAMS 25)
+    *_, rc = VP.vector_cx(sc["channels"], 26, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"],
+                          sc["te"], sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], M, 0)
+    assert rc == 2
