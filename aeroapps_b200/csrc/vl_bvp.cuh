@@ -181,6 +181,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   int *pivrow = state + R;                // 2n
   int *freeslot = pivrow + n2;            // 2n
   int *iflag = freeslot + n2;             // failure flag of the panel factorisation
+  int *gctr = iflag + 2;                  // work counter of the trailing update
   int *rflag = iflag + 4;                 // 2 x R: row has non-zero multipliers in the current / next panel
   const double *sc = X.scal + (size_t)p * 16;
   const int *ib = X.ibuf + (size_t)p * 4;
@@ -306,9 +307,8 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
     {
       const int npanel = (n2 + BVP_NB - 1) / BVP_NB;
       const bool is_panel = T.rank < Team::PW;
-      const bool is_trail = (T.size <= Team::PW) || !is_panel;
       const int LW = T.size < 32 ? T.size : 32;
-      const int lane = T.rank % LW, nwt = (T.size <= Team::PW) ? 1 : (T.size - Team::PW) / LW, wid = (T.size <= Team::PW) ? 0 : (T.rank - Team::PW) / LW;
+      const int lane = T.rank % LW;
       if (is_panel) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), false, 0, Lp, Ub, Lp, LUp, iflag, rflag);
       T.sync();
       if (iflag[0]) { failed = true; break; }
@@ -333,14 +333,21 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
               W[(size_t)r * Cs + jc1 + j] = a;
             }
           }
+          if (T.rank == 0) gctr[0] = 0;
+          T.sync();
+        } else {
+          if (T.rank == 0) gctr[0] = 0;
           T.sync();
         }
         if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, false, nb, LpC, UbC, LpN, LUpN, iflag, rflag + ((P + 1) & 1) * R);
-        if (is_trail) {
-          // trailing update: W(r, c) -= sum_j L(r, j) U(j, c) for c >= cbeg; a warp owns a group of RG rows
+        {
+          // trailing update: W(r, c) -= sum_j L(r, j) U(j, c) for c >= cbeg; groups of RG rows are handed out to the
+          // warps through a shared counter (the panel warps join in when their panel is done)
           constexpr int RG = 4;
           const int cbeg = jc1 + nb1;
-          for (int g = wid; g * RG < R; g += nwt) {
+          for (;;) {
+            const int g = T.wfetch(gctr);
+            if (g * RG >= R) break;
             const int r0 = g * RG;
             bool any = false;                          // rows that are not active carry zero multipliers
 #pragma unroll

@@ -54,6 +54,8 @@ struct SerialTeam {
   // bulk load of n doubles into team scratch: begin (collective) ... wait (collective)
   DEVFN void load_begin(double *dst, const double *src, size_t n) const { for (size_t i = 0; i < n; i++) dst[i] = src[i]; }
   DEVFN void load_wait() const {}
+  // next item of a shared work counter, one value per 32-lane group of the team
+  DEVFN int wfetch(int *ctr) const { return (*ctr)++; }
 };
 
 #ifndef AB_HOST_MODEL
@@ -174,6 +176,11 @@ struct BlockTeam {
     for (int w = 1; w < 4; w++) { const double ov = sd[32 + w]; const int oi = si[32 + w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
     idx = bi;
     return bv;
+  }
+  DEVFN int wfetch(int *ctr) const {
+    int g = 0;
+    if ((rank & 31) == 0) g = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, g, 0);
   }
   // owner's v[j0..N_) to everyone in the sub-team
   template <int N_>
