@@ -245,7 +245,11 @@ int run_vlidort(const RunDesc &R) {
   const size_t bvp_work_bytes = (size_t)bvp_grid_max * work_per_cta * 8;
   // K2 geometry
   const int scr_d = eigen_scratch_doubles(n, NM);
-  int wpc = (int)std::min<size_t>(8, (226 * 1024) / ((size_t)scr_d * 8));   // 227 KB opt-in limit minus the static part
+  // warps (= problems) resident per SM within the 227 KB opt-in limit; two CTAs per SM when possible: problems need a
+  // different number of Jacobi sweeps and a CTA only retires when its slowest warp does (measured: 2 x 4 warps beats 1 x 8)
+  int wpc = (int)std::min<size_t>(8, (226 * 1024) / ((size_t)scr_d * 8));
+  if (wpc >= 4) wpc /= 2;
+  if (const char *e = getenv("AB200_VL_EIGEN_WARPS")) wpc = std::max(1, std::min(wpc, atoi(e)));      // tuning knob
   if (wpc < 1) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory eigen scratch"); return AB200_ERR_ARG; }
   const size_t eig_smem = (size_t)wpc * scr_d * 8;
   AB_CUDA_OK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
