@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaeroapps_b200.so")
+# AB200_LIB: developer override (instrumented builds made by tools/); the default is the in-tree library
+LIB_PATH = os.environ.get("AB200_LIB") or os.path.join(_HERE, "libaeroapps_b200.so")
 
 
 class LibraryMissing(RuntimeError):

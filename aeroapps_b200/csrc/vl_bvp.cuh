@@ -16,6 +16,16 @@
 
 namespace vlk {
 
+// optional phase timers of K3 (thread 0 of every CTA, clock64 deltas summed per phase); tools/bvp_timing.py
+#if defined(AB200_BVP_TIMING) && !defined(AB_HOST_MODEL)
+__device__ unsigned long long g_bvp_tim[16];
+#define VLT_DECL long long vlt_t = clock64(), vlt_n = 0; (void)vlt_n;
+#define VLT(i) { if (threadIdx.x == 0) { vlt_n = clock64(); atomicAdd(&g_bvp_tim[i], (unsigned long long)(vlt_n - vlt_t)); vlt_t = vlt_n; } }
+#else
+#define VLT_DECL
+#define VLT(i)
+#endif
+
 struct VLSurf {                  // BRDF Fourier components per pixel (null pointers for Lambertian)
   const double *brdf_f;          // [p][m][q][i][j]   q = 4*o1+o2 < nq
   const double *brdf_f_0;        // [p][m][q][i]
@@ -166,6 +176,10 @@ DEVFN void bvp_urows(const Team &T, double *AB_RESTRICT W, int Cs, int Cc, const
 }
 
 template <int S, class Team>
+DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
+                        int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug);
+
+template <int S, class Team>
 DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
                      int lambertian, double accuracy, int m, int p, double *scr, int *iscr, double *Ug) {
   const int N = QD.N, n = S * N, n2 = 2 * n, L = X.L, NM = X.NM;
@@ -222,6 +236,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
     return ((r % S) > 1) ? -v : v;
   };
 
+  VLT_DECL
   if (T.rank == 0) iflag[0] = 0;
   for (int r = T.rank; r < R; r += T.size) state[r] = -1;
   for (int idx = T.rank; idx < R * Cs; idx += T.size) W[idx] = 0.0;
@@ -235,6 +250,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   for (int r = T.rank; r < n; r += T.size) { W[(size_t)r * Cs + RH] = -Z.wupper[q0 * n2 + r]; state[r] = 0; }
   for (int t = T.rank; t < n2; t += T.size) freeslot[t] = n + t;
   T.sync();
+  VLT(0)
 
   bool failed = false;
   for (int k = 0; k < L; k++) {
@@ -300,6 +316,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       }
     }
     T.sync();
+    VLT(1)
     // ---- eliminate the 2n columns of layer k: blocked (panels of BVP_NB columns), partial pivoting over the active
     //      rows of the window, one panel of look-ahead: while the other warps apply panel P to the trailing columns,
     //      the panel sub-team (warp 0) applies it to the columns of panel P+1 only and factorises that panel out of
@@ -314,6 +331,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       if (iflag[0]) { failed = true; break; }
       bvp_urows(T, W, Cs, Cc, pivrow, 0, (n2 < BVP_NB ? n2 : BVP_NB), LUp, Ub);
       T.sync();
+      VLT(2)
       for (int P = 0; P < npanel; P++) {
         const int jc0 = P * BVP_NB, nb = (n2 - jc0 < BVP_NB) ? n2 - jc0 : BVP_NB;
         const bool has_next = P + 1 < npanel;
@@ -339,7 +357,9 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
           if (T.rank == 0) gctr[0] = 0;
           T.sync();
         }
+        VLT(3)
         if (is_panel && has_next) bvp_panel_dispatch(T, W, Cs, R, state, pivrow, jc1, nb1, false, nb, LpC, UbC, LpN, LUpN, iflag, rflag + ((P + 1) & 1) * R);
+        VLT(4)
         {
           // trailing update: W(r, c) -= sum_j L(r, j) U(j, c) for c >= cbeg; groups of RG rows are handed out to the
           // warps through a shared counter (the panel warps join in when their panel is done)
@@ -379,11 +399,13 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
           }
         }
         T.sync();
+        VLT(5)
         if (iflag[0]) { failed = true; break; }
         if (has_next) {
           bvp_urows(T, W, Cs, Cc, pivrow, jc1, nb1, LUpN, UbN);
           T.sync();
         }
+        VLT(6)
       }
     }
     if (failed) break;
@@ -406,12 +428,37 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       }
       T.sync();
     }
+    VLT(7)
   }
   if (failed) { if (T.rank == 0) { cst[0] = 0; cst[3] = 4; } return; }
 
-  // ---- back substitution fused with the upwelling source-function recursion
-  const double usec = sc[2];
-  (void)usec;
+  bvp_backward<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, W, xcur, xnext, red, Ug);
+}
+
+// Back substitution (pivot rows of every layer in Ug, [k][t][0..Cc) in logical column order) fused with the upwelling
+// source-function recursion, the Fourier summation and the convergence test.  big: team scratch of bvp_big_doubles(n)
+// (two buffers of pivot rows), xcur/xnext/red: 2n, 2n, 4n doubles.
+template <int S, class Team>
+DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
+                        int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug) {
+  const int N = QD.N, n = S * N, n2 = 2 * n, L = X.L, NM = X.NM;
+  const int Cc = bvp_cols(n), RH = 4 * n;
+  const double *sc = X.scal + (size_t)p * 16;
+  const int *ib = X.ibuf + (size_t)p * 4;
+  int *cst = CV.state + (size_t)p * 4;
+  const double albedo = sc[4];
+  const int cutoff = ib[0];
+  bool include_surface = true;
+  if (lambertian) { if (m != 0) include_surface = false; else if (albedo == 0.0) include_surface = false; }
+  const double SFAC = (m == 0) ? 2.0 : 1.0, DELTA_FACTOR = (m == 0) ? 1.0 : 2.0;
+  const double *UBF = nullptr;
+  const int nq = SF.nq;
+  auto UBFq = [&](int o1, int o2, int jj) -> double {
+    return nq == 16 ? UBF[(size_t)(4 * o1 + o2) * N + jj] : ((o1 | o2) == 0 ? UBF[jj] : 0.0);
+  };
+  if (!lambertian) UBF = SF.user_brdf_f + ((size_t)p * SF.nmfour + m) * SF.nq * N;
+  const size_t q0 = (size_t)p * L;
+  VLT_DECL
   double cum[S];
 #pragma unroll
   for (int o = 0; o < S; o++) cum[o] = 0.0;
@@ -419,7 +466,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   T.sync();
   // pivot rows of layer k, [t][0..Cc) (Cs == Cc), rhs moved to column n2; two buffers: layer k-1 streams in (TMA bulk
   // copy) while layer k is solved
-  const int Ubs = Cs;
+  const int Ubs = Cc;
   const size_t usz = (size_t)n2 * Cc;
   T.load_begin(W, Ug + (size_t)(L - 1) * usz, usz);
   for (int k = L - 1; k >= 0; k--) {
@@ -434,6 +481,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
       Ut[(size_t)t * Ubs + n2] = b;
     }
     T.sync();
+    VLT(8)
     // upper-triangular solve (row t has its pivot in column t): blocks of 8 unknowns, the small diagonal block
     // solved by one thread out of registers, the rest of the right-hand side updated by everyone
     {
@@ -468,6 +516,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
         T.sync();
       }
     }
+    VLT(9)
     // xcur = [LCON(1..n), MCON(1..n)] of layer k
     if (k == L - 1) {
       // BOA source: surface-reflected diffuse field (GET_BOA_SOURCE)
@@ -529,6 +578,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
     T.sync();
     for (int t = T.rank; t < n2; t += T.size) xnext[t] = xcur[t];
     T.sync();
+    VLT(10)
   }
   // ---- Fourier summation and convergence (VLIDORT_CONVERGE_OBSGEO); FLUX_MULTIPLIER = DELTA_FACTOR
   if (T.rank == 0) {

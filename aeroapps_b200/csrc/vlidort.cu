@@ -4,7 +4,7 @@
 // of the device-side active list, so later components only launch work for the pixels that still need it.
 #include "../../include/aeroapps_b200.h"
 #include "common.h"
-#include "vl_bvp.cuh"
+#include "vl_bvp3.cuh"
 #include "vl_brdf.cuh"
 #include <algorithm>
 #include <vector>
@@ -50,13 +50,15 @@ __global__ void __launch_bounds__(256) k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, c
 template <int S>
 __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
                                                 int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
-                                                int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta) {
-  extern __shared__ double smem_d[];
+                                                int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta, int v3,
+                                                int smem_doubles) {
+  extern __shared__ __align__(16) double smem_d[];
   __shared__ double sd[64];
   __shared__ int si[64];
   const int n = S * QD.N;
-  int *iscr = reinterpret_cast<int *>(smem_d + bvp_smem_doubles(n));
+  int *iscr = reinterpret_cast<int *>(smem_d + (v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n)));
   __shared__ unsigned long long mbar;
+  for (int i = threadIdx.x; i < smem_doubles; i += blockDim.x) smem_d[i] = 0.0;      // no stale NaN patterns in never-written padding
   BlockTeam T(sd, si, &mbar);
   double *Ug = work + (size_t)blockIdx.x * work_per_cta;
   for (int a = blockIdx.x; a < nactive; a += gridDim.x) {
@@ -64,7 +66,8 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
     if (Z.fail[p]) {
       if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
     } else {
-      bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      if (v3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
     }
     __syncthreads();
     if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
@@ -231,7 +234,11 @@ int run_vlidort(const RunDesc &R) {
   budget = std::min(budget, (size_t)(0.6 * (double)(freeb + g_arena.cap)));
   // K3 geometry
   const int bvp_threads = 384;
-  const size_t bvp_smem = bvp_smem_doubles(n) * 8 + (size_t)(13 * n + 32) * 4;
+  // warp-specialised forward elimination when its window (3n+16 rows) fits 128 row slots; AB200_VL_BVP_V3=0 forces the old one
+  int use_v3 = b3_supported(n) && (b3_smem_doubles(n) * 8 + b3_smem_ints(n) * 4 <= 227 * 1024) ? 1 : 0;
+  if (const char *e = getenv("AB200_VL_BVP_V3")) use_v3 = use_v3 && atoi(e) != 0;
+  const size_t bvp_smem_d = use_v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n);
+  const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
   int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int bvp_per_sm = 1;
   auto kb = (S == 1) ? (const void *)k_vl_bvp<1> : (const void *)k_vl_bvp<3>;
@@ -350,8 +357,8 @@ int run_vlidort(const RunDesc &R) {
       cudaEventRecord(ev[1], st);
       const int bgrid = std::min(nactive, bvp_grid_max);
       int *cnt = counts + 1 + m;
-      if (S == 1) k_vl_bvp<1><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
-      else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
+      if (S == 1) k_vl_bvp<1><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d);
+      else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d);
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());
       g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive; g_stats.n_launches += 2;
@@ -718,3 +725,13 @@ extern "C" int ab200_vlidort_release(void) {
   g_arena.base = nullptr; g_arena.cap = 0; g_arena.off = 0;
   return 0;
 }
+
+#ifdef AB200_BVP_TIMING
+// debug build only: summed clock64 deltas per K3 phase (thread 0 of every CTA); reading clears them
+extern "C" int ab200_vlidort_debug_timing(unsigned long long *out16) {
+  unsigned long long z[16] = {0};
+  AB_CUDA_OK(cudaMemcpyFromSymbol(out16, vlk::g_bvp_tim, sizeof z));
+  AB_CUDA_OK(cudaMemcpyToSymbol(vlk::g_bvp_tim, z, sizeof z));
+  return 0;
+}
+#endif
