@@ -234,9 +234,11 @@ int run_vlidort(const RunDesc &R) {
   budget = std::min(budget, (size_t)(0.6 * (double)(freeb + g_arena.cap)));
   // K3 geometry
   const int bvp_threads = 384;
-  // warp-specialised forward elimination when its window (3n+16 rows) fits 128 row slots; AB200_VL_BVP_V3=0 forces the old one
-  int use_v3 = b3_supported(n) && (b3_smem_doubles(n) * 8 + b3_smem_ints(n) * 4 <= 227 * 1024) ? 1 : 0;
-  if (const char *e = getenv("AB200_VL_BVP_V3")) use_v3 = use_v3 && atoi(e) != 0;
+  // warp-specialised forward elimination (vl_bvp3.cuh): opt-in with AB200_VL_BVP_V3=1 while it is slower than the blocked
+  // look-ahead one (measured 2426 vs 2893 pixels/s on configs[2]); needs its window (3n+16 rows) to fit 128 row slots
+  int use_v3 = 0;
+  if (const char *e = getenv("AB200_VL_BVP_V3"))
+    use_v3 = atoi(e) != 0 && b3_supported(n) && (b3_smem_doubles(n) * 8 + b3_smem_ints(n) * 4 <= 227 * 1024);
   const size_t bvp_smem_d = use_v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n);
   const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
   int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
