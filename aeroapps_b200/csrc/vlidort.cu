@@ -5,6 +5,7 @@
 #include "../../include/aeroapps_b200.h"
 #include "common.h"
 #include "vl_bvp3.cuh"
+#include "vl_bvp4.cuh"
 #include "vl_brdf.cuh"
 #include <algorithm>
 #include <vector>
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
   __shared__ double sd[64];
   __shared__ int si[64];
   const int n = S * QD.N;
-  int *iscr = reinterpret_cast<int *>(smem_d + (v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n)));
+  // v3: forward-elimination variant, 0 = blocked look-ahead (vl_bvp.cuh), 3 = warp-specialised (vl_bvp3.cuh), 4 = register-resident (vl_bvp4.cuh)
+  int *iscr = reinterpret_cast<int *>(smem_d + (v3 == 4 ? b4_smem_doubles(n) : (v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n))));
   __shared__ unsigned long long mbar;
   for (int i = threadIdx.x; i < smem_doubles; i += blockDim.x) smem_d[i] = 0.0;      // no stale NaN patterns in never-written padding
   BlockTeam T(sd, si, &mbar);
@@ -66,7 +68,8 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
     if (Z.fail[p]) {
       if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
     } else {
-      if (v3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      if (v3 == 4) bvp_pixel_v4<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      else if (v3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
       else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
     }
     __syncthreads();
@@ -238,9 +241,16 @@ int run_vlidort(const RunDesc &R) {
   // look-ahead one (measured 2426 vs 2893 pixels/s on configs[2]); needs its window (3n+16 rows) to fit 128 row slots
   int use_v3 = 0;
   if (const char *e = getenv("AB200_VL_BVP_V3"))
-    use_v3 = atoi(e) != 0 && b3_supported(n) && (b3_smem_doubles(n) * 8 + b3_smem_ints(n) * 4 <= 227 * 1024);
-  const size_t bvp_smem_d = use_v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n);
-  const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
+    use_v3 = (atoi(e) != 0 && b3_supported(n) && (b3_smem_doubles(n) * 8 + b3_smem_ints(n) * 4 <= 227 * 1024)) ? 3 : 0;
+  // register-resident forward elimination (vl_bvp4.cuh): opt-in with AB200_VL_BVP_V4=1 (n > 24) or =2 (every supported n).
+  // Parity green; measured 1316 ms vs 1189 ms of K3 time per 3 bench steps, so the blocked look-ahead one stays the default
+  {
+    int v4 = 0;
+    if (const char *e = getenv("AB200_VL_BVP_V4")) v4 = atoi(e);
+    if (!use_v3 && v4 && b4_supported(n) && (v4 >= 2 || n > 24)) use_v3 = 4;
+  }
+  const size_t bvp_smem_d = use_v3 == 4 ? b4_smem_doubles(n) : (use_v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n));
+  const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 == 3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
   int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int bvp_per_sm = 1;
   auto kb = (S == 1) ? (const void *)k_vl_bvp<1> : (const void *)k_vl_bvp<3>;

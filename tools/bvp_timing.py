@@ -6,7 +6,9 @@ import torch
 import bench
 
 NAMES = ["init", "load rows", "first panel+urows", "lookahead+sync", "panel", "trailing join+sync", "urows+sync", "spill/shift",
-         "bwd rhs", "tri solve", "source terms"]
+         "bwd rhs", "tri solve", "source terms", "v4 publish", "v4 barrier B", "13", "14", "15"]
+# v4 (register-resident elimination) reuses the slots: 1 new rows, 2 first pivot, 3 multiplier+spill, 4 phase 0 (rank-1 update or
+# next column + candidate), 5 barrier A, 6 select + rank-1 update of the column owners, 11 publish, 12 barrier B, 7 layer end
 wl = bench.WORKLOADS[bench.DEFAULT_WORKLOAD](int(sys.argv[1]) if len(sys.argv) > 1 else None)
 dev = torch.device("cuda:0")
 wl.setup_gpu(torch, dev)
