@@ -50,6 +50,15 @@ HDFN size_t bvp_big_doubles(int n) {
   return ((fwd > bwd ? fwd : bwd) + 1) & ~(size_t)1;
 }
 HDFN size_t bvp_smem_doubles(int n) { return bvp_big_doubles(n) + 8 * n + 16; }
+// "large n" layout (3*nstreams*nstokes rows no longer fit the 227 KB of shared memory, e.g. nstokes 3 x 16 streams): the
+// window lives in a per-CTA HBM scratch (L1/L2 resident), shared memory keeps the panel arrays and ONE buffer of pivot rows
+HDFN size_t bvp_big_doubles_g(int n) {
+  const size_t fwd = 2 * ((size_t)3 * n * BVP_NB + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB);
+  const size_t bwd = (size_t)(2 * n) * bvp_cols(n);
+  return ((fwd > bwd ? fwd : bwd) + 1) & ~(size_t)1;
+}
+HDFN size_t bvp_smem_doubles_g(int n) { return bvp_big_doubles_g(n) + 8 * n + 16; }
+HDFN size_t bvp_window_doubles(int n) { return (size_t)3 * n * bvp_stride(n); }
 HDFN size_t bvp_work_doubles(int n, int L) { return (size_t)L * 2 * n * bvp_cols(n); }
 
 // ---- panel factorisation of the blocked elimination, executed by the panel sub-team (ranks < Team::PW).
@@ -177,18 +186,20 @@ DEVFN void bvp_urows(const Team &T, double *AB_RESTRICT W, int Cs, int Cc, const
 
 template <int S, class Team>
 DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
-                        int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug);
+                        int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug,
+                        int nbuf = 2);
 
 template <int S, class Team>
 DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
-                     int lambertian, double accuracy, int m, int p, double *scr, int *iscr, double *Ug) {
+                     int lambertian, double accuracy, int m, int p, double *scr, int *iscr, double *Ug, double *wglob = nullptr) {
   const int N = QD.N, n = S * N, n2 = 2 * n, L = X.L, NM = X.NM;
   const int R = 3 * n, Cc = bvp_cols(n), Cs = bvp_stride(n), RH = 4 * n;      // RH = rhs column
-  double *W = scr;
-  double *xcur = W + bvp_big_doubles(n);  // 2n
+  // wglob != nullptr: "large n" layout, the window in HBM scratch and only the panel arrays in the team scratch
+  double *W = wglob ? wglob : scr;
+  double *xcur = scr + (wglob ? bvp_big_doubles_g(n) : bvp_big_doubles(n));  // 2n
   double *xnext = xcur + n2;              // 2n
   double *red = xnext + n2;               // 4n scratch
-  double *Lp = W + (size_t)R * Cs;            // 2 x (R x NB) multipliers of the current / next panel
+  double *Lp = wglob ? scr : W + (size_t)R * Cs;   // 2 x (R x NB) multipliers of the current / next panel
   double *Ub = Lp + (size_t)2 * R * BVP_NB;   // 2 x (NB x Cs) finished pivot rows of the current / next panel
   double *LUp = Ub + (size_t)2 * BVP_NB * Cs; // 2 x (NB x NB) multipliers of the pivot rows inside the panel
   int *state = iscr;                      // R : -1 unused, 0 active, 1+t pivot number t
@@ -432,7 +443,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   }
   if (failed) { if (T.rank == 0) { cst[0] = 0; cst[3] = 4; } return; }
 
-  bvp_backward<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, W, xcur, xnext, red, Ug);
+  bvp_backward<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, scr, xcur, xnext, red, Ug, wglob ? 1 : 2);
 }
 
 // Back substitution (pivot rows of every layer in Ug, [k][t][0..Cc) in logical column order) fused with the upwelling
@@ -440,7 +451,8 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
 // (two buffers of pivot rows), xcur/xnext/red: 2n, 2n, 4n doubles.
 template <int S, class Team>
 DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
-                        int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug) {
+                        int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug,
+                        int nbuf) {
   const int N = QD.N, n = S * N, n2 = 2 * n, L = X.L, NM = X.NM;
   const int Cc = bvp_cols(n), RH = 4 * n;
   const double *sc = X.scal + (size_t)p * 16;
@@ -471,9 +483,9 @@ DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQ
   T.load_begin(W, Ug + (size_t)(L - 1) * usz, usz);
   for (int k = L - 1; k >= 0; k--) {
     const size_t qa = q0 + k;
-    double *Ut = W + (size_t)((L - 1 - k) & 1) * usz;
+    double *Ut = W + (size_t)(nbuf == 2 ? ((L - 1 - k) & 1) : 0) * usz;
     T.load_wait();
-    if (k > 0) T.load_begin(W + (size_t)((L - k) & 1) * usz, Ug + (size_t)(k - 1) * usz, usz);
+    if (k > 0 && nbuf == 2) T.load_begin(W + (size_t)((L - k) & 1) * usz, Ug + (size_t)(k - 1) * usz, usz);
     for (int t = T.rank; t < n2; t += T.size) {
       const double *un = Ut + (size_t)t * Ubs + n2;
       double b = Ut[(size_t)t * Ubs + RH];
@@ -578,6 +590,7 @@ DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQ
     T.sync();
     for (int t = T.rank; t < n2; t += T.size) xnext[t] = xcur[t];
     T.sync();
+    if (k > 0 && nbuf == 1) T.load_begin(W, Ug + (size_t)(k - 1) * usz, usz);      // single buffer: no overlap
     VLT(10)
   }
   // ---- Fourier summation and convergence (VLIDORT_CONVERGE_OBSGEO); FLUX_MULTIPLIER = DELTA_FACTOR

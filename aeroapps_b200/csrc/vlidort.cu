@@ -52,13 +52,15 @@ template <int S>
 __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
                                                 int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
                                                 int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta, int v3,
-                                                int smem_doubles) {
+                                                int smem_doubles, double *__restrict__ wglob) {
   extern __shared__ __align__(16) double smem_d[];
   __shared__ double sd[64];
   __shared__ int si[64];
   const int n = S * QD.N;
   // v3: forward-elimination variant, 0 = blocked look-ahead (vl_bvp.cuh), 3 = warp-specialised (vl_bvp3.cuh), 4 = register-resident (vl_bvp4.cuh)
-  int *iscr = reinterpret_cast<int *>(smem_d + (v3 == 4 ? b4_smem_doubles(n) : (v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n))));
+  // wglob: "large n" layout of the default variant (window in a per-CTA HBM scratch)
+  int *iscr = reinterpret_cast<int *>(smem_d + (v3 == 4 ? b4_smem_doubles(n) : (v3 ? b3_smem_doubles(n) : (wglob ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)))));
+  double *wg = wglob ? wglob + (size_t)blockIdx.x * bvp_window_doubles(n) : nullptr;
   __shared__ unsigned long long mbar;
   for (int i = threadIdx.x; i < smem_doubles; i += blockDim.x) smem_d[i] = 0.0;      // no stale NaN patterns in never-written padding
   BlockTeam T(sd, si, &mbar);
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
     } else {
       if (v3 == 4) bvp_pixel_v4<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
       else if (v3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
-      else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug, wg);
     }
     __syncthreads();
     if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
@@ -249,7 +251,10 @@ int run_vlidort(const RunDesc &R) {
     if (const char *e = getenv("AB200_VL_BVP_V4")) v4 = atoi(e);
     if (!use_v3 && v4 && b4_supported(n) && (v4 >= 2 || n > 24)) use_v3 = 4;
   }
-  const size_t bvp_smem_d = use_v3 == 4 ? b4_smem_doubles(n) : (use_v3 ? b3_smem_doubles(n) : bvp_smem_doubles(n));
+  // default variant: when the 3n x (4n+1) window does not fit the 227 KB of shared memory (e.g. nstokes 3 x 16 streams) it moves
+  // to a per-CTA HBM scratch ("large n" layout, vl_bvp.cuh)
+  const bool big_n = !use_v3 && (bvp_smem_doubles(n) * 8 + (size_t)(13 * n + 32) * 4 > 227 * 1024);
+  const size_t bvp_smem_d = use_v3 == 4 ? b4_smem_doubles(n) : (use_v3 ? b3_smem_doubles(n) : (big_n ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)));
   const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 == 3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
   int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int bvp_per_sm = 1;
@@ -261,7 +266,7 @@ int run_vlidort(const RunDesc &R) {
   bvp_per_sm = std::max(1, std::min(bvp_per_sm, 8));
   const int bvp_grid_max = nsm * bvp_per_sm;
   const size_t work_per_cta = bvp_work_doubles(n, L);
-  const size_t bvp_work_bytes = (size_t)bvp_grid_max * work_per_cta * 8;
+  const size_t bvp_work_bytes = (size_t)bvp_grid_max * (work_per_cta + (big_n ? bvp_window_doubles(n) : 0)) * 8;
   // K2 geometry
   const int scr_d = eigen_scratch_doubles(n, NM);
   // warps (= problems) resident per SM within the 227 KB opt-in limit; two CTAs per SM when possible: problems need a
@@ -297,6 +302,7 @@ int run_vlidort(const RunDesc &R) {
   int *listA = A.take<int>(chunk), *listB = A.take<int>(chunk), *counts = A.take<int>(2 * (NM + 4));
   double *d_pq = A.take<double>((size_t)(NM + 1) * N * 3 * (NM + 1));
   double *work = A.take<double>((size_t)bvp_grid_max * work_per_cta);
+  double *wglob = big_n ? A.take<double>((size_t)bvp_grid_max * bvp_window_doubles(n)) : nullptr;
   unsigned char *d_skip = A.take<unsigned char>(npix);
   VLBrdf Bd; VLSurf SFb; memset(&SFb, 0, sizeof SFb);
   if (R.brdf) {
@@ -369,8 +375,8 @@ int run_vlidort(const RunDesc &R) {
       cudaEventRecord(ev[1], st);
       const int bgrid = std::min(nactive, bvp_grid_max);
       int *cnt = counts + 1 + m;
-      if (S == 1) k_vl_bvp<1><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d);
-      else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d);
+      if (S == 1) k_vl_bvp<1><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
+      else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());
       g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive; g_stats.n_launches += 2;

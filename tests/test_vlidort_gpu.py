@@ -165,6 +165,66 @@ def test_vector_brdf_surfaces(mods, kind, N, nobs):
     assert (BRQ[ok] == 0).all() and (BRU[ok] == 0).all()
 
 
+@pytest.mark.parametrize("kind", ["lambert", "cx"])
+def test_polar_16_streams(mods, kind):
+    """BASELINE.json configs[4] shape (polar_vlidort: nstokes 3, 16 streams, 72 layers): 48 x 48 layer eigenproblems (generic
+    shared-memory Jacobi path of K2) and a 144-row BVP window that no longer fits shared memory (K3's "large n" layout with
+    the window in HBM scratch); land = Lambertian, ocean = Cox-Munk.  Same bars as the 36 x 36 case: 5e-8 against the
+    oracle at the reference's ASYMTX tolerance, 1e-9 against the converged oracle, identical Fourier counts."""
+    VP, vg = mods
+    nobs, N, M = 4, 16, 1e15
+    sc = vg.synthetic_scene(nobs, nmom=80, seed=177)
+
+    def oracle():
+        if kind == "lambert":
+            return vg.vlidort_run(3, N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"], sc["raa"],
+                                  sc["vza"], albedo=sc["albedo"])
+        return vg.vlidort_run_surface("cx", 3, N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"],
+                                      sc["raa"], sc["vza"], sc["u10m"], sc["v10m"], sc["mr"], sc["kernel_wt"], sc["param"], MISSING=M)
+    ref = oracle()
+    if kind == "lambert":
+        alpha = np.zeros_like(sc["ROT"]); flux = np.ones((1, nobs), order="F")
+        I, R, Q, U, rc = VP.vector_lambert(sc["channels"], N, False, sc["ROT"], sc["depol"], alpha, sc["tau"], sc["ssa"], sc["pmom"],
+                                           sc["pe"], sc["he"], sc["te"], sc["albedo"], sc["sza"], sc["raa"], sc["vza"], flux, M, 0)
+    else:
+        I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_cx(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"],
+                                                    sc["pe"], sc["he"], sc["te"], sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"],
+                                                    sc["vza"], M, 0)
+    assert rc == 0
+    nf, st = VP.last_diag()
+    assert (st == 0).all() and np.array_equal(nf.reshape(nobs, 1), ref["nfourier"])
+    Iref = ref["radiance"]
+    assert rel(I, Iref, Iref) < 5 * TOL and rel(Q, ref["Q"], Iref) < 5 * TOL and rel(U, ref["U"], Iref) < 5 * TOL
+    vg.set_asymtx_tolerance(1e-16)
+    try:
+        ref2 = oracle()
+    finally:
+        vg.set_asymtx_tolerance(1e-12)
+    I2 = ref2["radiance"]
+    assert rel(I, I2, I2) < 1e-9 and rel(R, ref2["reflectance"], ref2["reflectance"]) < 1e-9
+    assert rel(Q, ref2["Q"], I2) < 1e-9 and rel(U, ref2["U"], I2) < 1e-9
+
+
+@pytest.mark.parametrize("variant", ["AB200_VL_BVP_V3=1", "AB200_VL_BVP_V4=2"])
+def test_alternative_eliminations(mods, variant, monkeypatch):
+    """the two opt-in forward eliminations of K3 (warp-specialised, register-resident) give the same answers as the default"""
+    VP, vg = mods
+    nobs, N = 5, 12
+    sc = vg.synthetic_scene(nobs, nmom=60, seed=92)
+    args = (sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"],
+            sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], 1e15, 0)
+    I0, R0, BR0, Q0, U0, _, _, rc = VP.vector_cx(*args)
+    assert rc == 0
+    nf0, _ = VP.last_diag()
+    k, v = variant.split("=")
+    monkeypatch.setenv(k, v)
+    I1, R1, BR1, Q1, U1, _, _, rc = VP.vector_cx(*args)
+    assert rc == 0
+    nf1, st1 = VP.last_diag()
+    assert (st1 == 0).all() and np.array_equal(nf0, nf1)
+    assert rel(I1, I0, I0) < 1e-11 and rel(Q1, Q0, I0) < 1e-11 and rel(U1, U0, I0) < 1e-11
+
+
 def test_scalar_brdf_surfaces(mods):
     VP, vg = mods
     nobs, N = 6, 6
