@@ -105,6 +105,33 @@ def vector_gisscx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom
                V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose)
 
 
+def vector_ocicx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+                 relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_OCICX (VLIDORT_POLAR_py.F90:903): Cox-Munk with the OCI slope variance; returns (radiance, reflectance, BR,
+    Q, U, BR_Q, BR_U, rc)."""
+    return _cx("ab200_vlidort_vector_ocicx", channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m,
+               V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose)
+
+
+def vector_ocigisscx(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, U10m, V10m, mr,
+                     solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """f2py VECTOR_OCIGissCX (VLIDORT_POLAR_py.F90:976): GISS Cox-Munk with the OCI slope variance, trace-gas absorption
+    alpha (km,nobs,nch) and flux_factor (nch,nobs); returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, flux_factor = (_F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert alpha.shape == ROT.shape and flux_factor.shape == (nch, nobs)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_ocigisscx(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                               _p(ROT), _p(dp), _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te),
+                                               _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza), _p(flux_factor),
+                                               C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_ocigisscx")
+    return (*outs, rc.value)
+
+
 def vector_brdf_modis(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, kernel_wt, param,
                       solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
     """f2py VECTOR_BRDF_MODIS (VLIDORT_POLAR_py.F90:137): kernel_wt (3,nch,nobs) = fiso,fgeo,fvol; param (2,nch,nobs).
@@ -136,6 +163,22 @@ def scalar_cx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom,
                                         _p(dp), _p(tau), _p(ssa), _p(g), _p(pmom), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m),
                                         _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose), _p(rad), _p(refl),
                                         _p(brdf), C.byref(rc)), "ab200_vlidort_scalar_cx")
+    return rad, refl, brdf, rc.value
+
+
+def scalar_gisscx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+                  relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Scalar_GissCX (VLIDORT_BRDF_CX.F90:1553): returns (radiance, reflectance, BRDF (1,nobs,nch), rc)."""
+    ROT, tau, ssa, g, pmom, pe, he, te = (_F(x) for x in (ROT, tau, ssa, g, pmom, pe, he, te))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    rad = np.zeros((nobs, nch), order="F"); refl = np.zeros((nobs, nch), order="F"); brdf = np.zeros((1, nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_gisscx(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT),
+                                            _p(dp), _p(tau), _p(ssa), _p(g), _p(pmom), _p(pe), _p(he), _p(te), _p(u), _p(v),
+                                            _p(m), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose), _p(rad),
+                                            _p(refl), _p(brdf), C.byref(rc)), "ab200_vlidort_scalar_gisscx")
     return rad, refl, brdf, rc.value
 
 

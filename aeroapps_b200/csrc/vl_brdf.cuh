@@ -18,7 +18,10 @@ namespace vlk {
 constexpr int BRDF_NSCAL = 24;       // SCALING_NSTREAMS: white-sky-albedo quadrature (vbrdf_sup_masters.f90:2238)
 constexpr int BRDF_MAXNB = 100;      // azimuth quadrature streams (MAXSTREAMS_BRDF)
 
-enum { SURF_LAMBERT = 0, SURF_CX = 2, SURF_GISSCX = 3, SURF_MODIS = 4 };
+// OCI variants (V283/VLIDORT_SurfaceMod.F90:82-538): same kernels, slope variance sigma2 = 0.00534 W instead of 0.003 + 0.00512 W
+enum { SURF_LAMBERT = 0, SURF_CX = 2, SURF_GISSCX = 3, SURF_MODIS = 4, SURF_OCICX = 5, SURF_OCIGISSCX = 6 };
+HDFN bool surf_is_giss(int kind) { return kind == SURF_GISSCX || kind == SURF_OCIGISSCX; }
+HDFN bool surf_is_oci(int kind) { return kind == SURF_OCICX || kind == SURF_OCIGISSCX; }
 
 struct VLBrdf {
   int kind, N, NM, NB, nq, half_range, nch, nobs, bns;   // bns: BRDF nstokes (1 or 3)
@@ -42,10 +45,10 @@ struct VLBrdf {
 inline void brdf_host_tables(VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, std::vector<double> &h) {
   memset(&B, 0, sizeof B);
   B.kind = kind; B.N = N; B.NM = NM; B.nch = nch; B.nobs = nobs;
-  B.half_range = (kind != SURF_GISSCX);
+  B.half_range = !surf_is_giss(kind);
   const int nsb = (kind == SURF_MODIS) ? 50 : 100;                        // NSTREAMS_BRDF of the surface glue
   B.NB = B.half_range ? nsb / 2 : nsb;
-  B.bns = (kind == SURF_GISSCX && !scalar_glue && S == 3) ? 3 : 1;
+  B.bns = (surf_is_giss(kind) && !scalar_glue && S == 3) ? 3 : 1;
   B.nq = (B.bns == 3) ? 16 : 1;
   const int NB = B.NB;
   h.assign((size_t)4 * NB + (size_t)2 * (NM + 1) * NB + 3 * BRDF_NSCAL, 0.0);
@@ -187,9 +190,9 @@ HDFN void surf_params(const VLBrdf &B, int j, int i, SurfPars &P) {
   double W = sqrt(B.u10m[j] * B.u10m[j] + B.v10m[j] * B.v10m[j]);
   if (W < 0) W = 0;
   if (W > 50) W = 50;
-  const double sigma2 = (double)0.003f + (double)0.00512f * W;                  // single-precision literals of the glue
+  const double sigma2 = surf_is_oci(B.kind) ? (double)0.00534f * W : (double)0.003f + (double)0.00512f * W;   // single-precision literals of the glue
   P.nk = 1; P.fac[0] = 1.0; P.pars[0][2] = 1.0;                                 // shadow effect on
-  if (B.kind == SURF_CX) { P.which[0] = 9; P.pars[0][0] = sigma2; P.pars[0][1] = B.mr[i] * B.mr[i]; }
+  if (!surf_is_giss(B.kind)) { P.which[0] = 9; P.pars[0][0] = sigma2; P.pars[0][1] = B.mr[i] * B.mr[i]; }
   else { P.which[0] = 10; P.pars[0][0] = 0.5 * sigma2; P.pars[0][1] = B.mr[i]; }
 }
 

@@ -92,7 +92,14 @@ __global__ void k_vl_brdf_exact(VLBrdf B, int npix, const unsigned char *__restr
   const bool neg = (B.kind == SURF_MODIS && br < 0);
   if (neg) br = -500.0;
   BR[o] = br;
-  if (BR_Q) { BR_Q[o] = neg ? -500.0 : 0.0; BR_U[o] = neg ? -500.0 : 0.0; }
+  // BRDF_Q / BRDF_U: elements (1,2) and (1,3) of the exact direct-bounce BRDF for the GISS and the OCI wrappers
+  // (BS_DBOUNCE_BRDFUNC(2,1,1,1), (3,1,1,1): VLIDORT_BRDF_CX.F90:199-201,388-389,1865-1866), 0 for Vector_CX (:733-734) and
+  // LandMODIS (VLIDORT_BRDF_MODIS.F90:365-366)
+  if (BR_Q) {
+    const bool pol = surf_is_giss(B.kind) || B.kind == SURF_OCICX;
+    BR_Q[o] = neg ? -500.0 : (pol ? B.exactdb[(size_t)p * 16 + 1] : 0.0);
+    BR_U[o] = neg ? -500.0 : (pol ? B.exactdb[(size_t)p * 16 + 2] : 0.0);
+  }
 }
 
 // K0b: BRDF Fourier components of the pixels of one chunk, one CTA per pixel
@@ -452,7 +459,7 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
 
 
 // ------------------------------------------------------------------------------------------------ BRDF wrappers
-struct SurfArgs { int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; };
+struct SurfArgs { int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; const double *alpha = nullptr, *flux_factor = nullptr; };
 
 // pixel-independent BRDF tables -> device
 int build_brdf_tables(VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, cudaStream_t st) {
@@ -479,7 +486,7 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   if (npix == 0) return 0;
   const bool cx = (sa.kind != SURF_MODIS);
   const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
-  const size_t bytes = 8 * (n_rot * 3 + n_pm + n_he + 5 * (size_t)nobs + 2 * nch + 5 * npix + 7 * npix + 16 * npix) + 16 * npix + 4096 * 32;
+  const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + 5 * (size_t)nobs + 2 * nch + 6 * npix + 7 * npix + 16 * npix) + 16 * npix + 4096 * 32;
   static DevBuf io;
   AB_CUDA_OK(io.reserve(dev ? 8 * (16 * npix + 7 * npix) + 16 * npix + 4096 * 8 : bytes));
   char *b = io.as<char>(); size_t off = 0;
@@ -494,6 +501,7 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING;
   R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
   R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.sza = put(sza, nobs); R.raa = put(raa, nobs); R.vza = put(vza, nobs);
+  R.alpha = sa.alpha ? put(sa.alpha, n_rot) : nullptr; R.flux_factor = sa.flux_factor ? put(sa.flux_factor, npix) : nullptr;
   const double *d_u = cx ? put(sa.u10m, nobs) : nullptr, *d_v = cx ? put(sa.v10m, nobs) : nullptr, *d_mr = cx ? put(sa.mr, nch) : nullptr;
   const double *d_kw = cx ? nullptr : put(sa.kernel_wt, 3 * npix), *d_pr = cx ? nullptr : put(sa.param, 2 * npix);
   double *d_exact = put(nullptr, 16 * npix);
@@ -676,6 +684,38 @@ extern "C" int ab200_vlidort_vector_gisscx(AB_CX_ARGS, double *radiance_VL_SURF,
   SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
   return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_ocicx(AB_CX_ARGS, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                          double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_OCICX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_ocigisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                              int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                              const double *tau, const double *ssa, const double *pmom, const double *pe,
+                                              const double *he, const double *te, const double *U10m, const double *V10m,
+                                              const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                              const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                              double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                              double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_OCIGISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U, alpha, flux_factor};
+  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_scalar_gisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                           int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                           const double *ssa, const double *g, const double *pmom, const double *pe,
+                                           const double *he, const double *te, const double *U10m, const double *V10m,
+                                           const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                           const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                           double *reflectance_VL_SURF, double *BRDF, int *rc) {
+  (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
+  SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BRDF, nullptr, nullptr};
+  return brdf_front(false, 1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
 }
 extern "C" int ab200_vlidort_scalar_cx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
                                        int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,

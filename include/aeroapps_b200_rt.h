@@ -40,7 +40,8 @@ int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long *n_launche
 
 /* ---- BRDF surfaces.  Surface set-up: RTSI/VLIDORT2p8p3/VLIDORT_SurfaceMod.F90 (CoxMunk :816-1042, GissCoxMunk :586-814,
  * LANDMODIS :1376-1596) + the VBRDF supplement (vsup/vbrdf).  Outputs (nobs,nch).  BR = exact direct-bounce BRDF
- * element (1,1); BR_Q = BR_U = 0 as in the reference.  MODIS RTLS: BR < 0 -> every output of that pixel is -500. */
+ * element (1,1); BR_Q, BR_U = elements (1,2), (1,3) for the GISS and OCI wrappers (BS_DBOUNCE_BRDFUNC(2..3,1,1,1)), 0 for
+ * Vector_CX and LandMODIS as in the reference.  MODIS RTLS: BR < 0 -> every output of that pixel is -500. */
 
 /* VLIDORT_Vector_CX_SingleGeom (geo_vlidort/VLIDORT_BRDF_CX.F90:587-762; f2py VECTOR_CX, VLIDORT_POLAR_py.F90:830-902).
  * U10m,V10m (nobs), mr (nch). */
@@ -59,6 +60,34 @@ int ab200_vlidort_vector_gisscx(int km, int nch, int nobs, const double *channel
                                 const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
                                 double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
                                 double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_OCICX (VLIDORT_BRDF_CX.F90:241-416; f2py VECTOR_OCICX, VLIDORT_POLAR_py.F90:903-974): Cox-Munk with the OCI
+ * slope variance sigma2 = 0.00534 W (VLIDORT_SurfaceMod.F90:82-308) */
+int ab200_vlidort_vector_ocicx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                               int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                               const double *pmom, const double *pe, const double *he, const double *te, const double *U10m,
+                               const double *V10m, const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                               const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                               double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U,
+                               int *rc);
+/* VLIDORT_Vector_OCIGissCX (VLIDORT_BRDF_CX.F90:54-236; f2py VECTOR_OCIGissCX, VLIDORT_POLAR_py.F90:976-1053): GISS Cox-Munk
+ * with the OCI slope variance (VLIDORT_SurfaceMod.F90:310-538), trace-gas absorption alpha (km,nobs,nch) and
+ * flux_factor (nch,nobs) */
+int ab200_vlidort_vector_ocigisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                   int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                   const double *tau, const double *ssa, const double *pmom, const double *pe,
+                                   const double *he, const double *te, const double *U10m, const double *V10m,
+                                   const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                   const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                   double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                   double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Scalar_GissCX (VLIDORT_BRDF_CX.F90:1553-1716); BRDF (1,nobs,nch) */
+int ab200_vlidort_scalar_gisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                const double *ssa, const double *g, const double *pmom, const double *pe, const double *he,
+                                const double *te, const double *U10m, const double *V10m, const double *mr,
+                                const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                double *BRDF, int *rc);
 /* VLIDORT_Scalar_CX (VLIDORT_BRDF_CX.F90:420-584); BRDF (1,nobs,nch) */
 int ab200_vlidort_scalar_cx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
                             int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,

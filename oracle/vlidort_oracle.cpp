@@ -699,12 +699,14 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
         /* surface set-up of the BRDF wrappers: GV/VLIDORT_BRDF_CX.F90:587-762 (Cox-Munk), :1720-1894 (GISS Cox-Munk),
          * GV/VLIDORT_BRDF_MODIS.F90:206-410 (RTLS); kernels/parameters from V283/VLIDORT_SurfaceMod.F90:586-1042,1376-1596 */
         int which[3], lam[3] = {0, 0, 0}, nk = 1, nsb = 100; double fac[3] = {1.0, 0.0, 0.0}, pars[12] = {0};
-        if (sf->kind == 2 || sf->kind == 3) {
+        /* kinds 5, 6: the OCI variants of 2, 3 (V283/VLIDORT_SurfaceMod.F90:82-538: sigma2 = 0.00534 * W10m) */
+        const bool giss = (sf->kind == 3 || sf->kind == 6), oci = (sf->kind == 5 || sf->kind == 6);
+        if (sf->kind != 4) {
           if (is_missing(sf->u10m[j], MISSING) || is_missing(sf->v10m[j], MISSING) || is_missing(sf->mr[i], MISSING)) { set_missing(); continue; }
           double W = std::sqrt(sf->u10m[j] * sf->u10m[j] + sf->v10m[j] * sf->v10m[j]);
           if (W < 0) W = 0; if (W > 50) W = 50;
-          const double sigma2 = (double)0.003f + (double)0.00512f * W;
-          if (sf->kind == 2) { which[0] = 9; pars[0] = sigma2; pars[1] = sf->mr[i] * sf->mr[i]; }
+          const double sigma2 = oci ? (double)0.00534f * W : (double)0.003f + (double)0.00512f * W;
+          if (!giss) { which[0] = 9; pars[0] = sigma2; pars[1] = sf->mr[i] * sf->mr[i]; }
           else { which[0] = 10; pars[0] = 0.5 * sigma2; pars[1] = sf->mr[i]; }
         } else {
           const double *kw = sf->kernel_wt + 3 * (i + (size_t)nch * j), *pr = sf->param + 2 * (i + (size_t)nch * j);
@@ -712,12 +714,15 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
           fac[0] = kw[0]; fac[1] = kw[2]; fac[2] = kw[1];             /* (fiso, fvol, fgeo) <- kernel_wt (fiso, fgeo, fvol) */
           pars[8] = pr[0]; pars[9] = pr[1];
         }
-        const int bns = (sf->kind == 3 && !scalar_glue) ? 3 : 1;     /* only the GISS kernel has polarised elements */
+        const int bns = (giss && !scalar_glue) ? 3 : 1;              /* only the GISS kernel has polarised elements */
         orc_vbrdf(bns, N, nk, which, fac, pars, lam, nsb, 1, sza[j], vza[j], raa[j], sb_f.data(), sb_f0.data(), sb_uf.data(),
                   sb_uf0.data(), sb_ex.data(), nullptr);
         if (sf->BR) sf->BR[o] = sb_ex[0];
-        if (sf->BR_Q) sf->BR_Q[o] = 0.0;
-        if (sf->BR_U) sf->BR_U[o] = 0.0;
+        /* BRDF_Q, BRDF_U = BS_DBOUNCE_BRDFUNC(2,1,1,1), (3,1,1,1) in Vector_GissCX / OCIGissCX / OCICX
+         * (GV/VLIDORT_BRDF_CX.F90:199-201,388-389,1865-1866); 0 in Vector_CX (:733-734) and LandMODIS */
+        const bool polout = giss || sf->kind == 5;
+        if (sf->BR_Q) sf->BR_Q[o] = polout ? sb_ex[1] : 0.0;
+        if (sf->BR_U) sf->BR_U[o] = polout ? sb_ex[2] : 0.0;
         if (sf->kind == 4 && sb_ex[0] < 0) {
           radiance[o] = reflectance[o] = -500.0; if (Q) Q[o] = -500.0; if (U) U[o] = -500.0;
           if (sf->BR) sf->BR[o] = -500.0; if (sf->BR_Q) sf->BR_Q[o] = -500.0; if (sf->BR_U) sf->BR_U[o] = -500.0;

@@ -45,7 +45,7 @@ int orc_vlidort_run(int nstokes, int scalar_glue, int km, int nch, int nobs, int
                     const double *exactdb, const unsigned char *skip, int obs_begin, int obs_end,
                     double *radiance, double *reflectance, double *Q, double *U, int *nfourier, int *status);
 /* same, with the surface set up from the BRDF wrappers' own inputs: kind 2 Cox-Munk (u10m,v10m (nobs), mr (nch)),
- * 3 GISS Cox-Munk (same), 4 MODIS RTLS (kernel_wt (3,nch,nobs) = fiso,fgeo,fvol; param (2,nch,nobs)).
+ * 3 GISS Cox-Munk (same), 5 / 6 their OCI variants, 4 MODIS RTLS (kernel_wt (3,nch,nobs) = fiso,fgeo,fvol; param (2,nch,nobs)).
  * BR/BR_Q/BR_U (nobs,nch) receive the wrappers' surface outputs. */
 typedef struct {
   int kind;

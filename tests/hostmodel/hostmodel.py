@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         src = os.path.join(_HERE, "vl_hostmodel.cpp")
-        hdrs = [os.path.join(_HERE, "..", "..", "aeroapps_b200", "csrc", f) for f in ("vl_common.cuh", "vl_setup.cuh", "vl_eigen.cuh", "vl_bvp.cuh")]
+        hdrs = [os.path.join(_HERE, "..", "..", "aeroapps_b200", "csrc", f) for f in ("vl_common.cuh", "vl_setup.cuh", "vl_eigen.cuh", "vl_bvp.cuh", "vl_brdf.cuh")]
         newest = max(os.path.getmtime(f) for f in [src] + hdrs)
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _SO, src])
@@ -39,10 +39,10 @@ def run(nstokes, nstreams, plane_parallel, sc, lambertian=True, scalar_glue=Fals
     arrs = [F(sc["ROT"]), np.ascontiguousarray(sc["depol"], dtype=np.float64), None if alpha is None else F(alpha), F(sc["tau"]),
             F(sc["ssa"]), F(sc["pmom"]), F(sc["he"]), F(sc["albedo"])] + [np.ascontiguousarray(sc[k], dtype=np.float64) for k in ("sza", "raa", "vza")]
     ff = None if flux_factor is None else F(flux_factor)
-    kinds = {None: 0, "cx": 2, "gisscx": 3, "modis": 4}
+    kinds = {None: 0, "cx": 2, "gisscx": 3, "modis": 4, "ocicx": 5, "ocigisscx": 6}
     sk = kinds[surface]
     sarr = [None] * 5
-    if sk in (2, 3):
+    if sk in (2, 3, 5, 6):
         sarr[:3] = [np.ascontiguousarray(sc[k], dtype=np.float64) for k in ("u10m", "v10m", "mr")]
     elif sk == 4:
         sarr[3:] = [F(sc["kernel_wt"]), F(sc["param"])]

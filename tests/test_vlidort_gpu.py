@@ -110,7 +110,8 @@ def test_size_independent_properties(mods):
     assert Ia[0, 0] == I1[j, 0] and Qa[0, 0] == Q1[j, 0] and Ua[0, 0] == U1[j, 0]
 
 
-@pytest.mark.parametrize("kind,N,nobs", [("cx", 6, 10), ("gisscx", 4, 6), ("modis", 6, 8), ("cx", 12, 3)])
+@pytest.mark.parametrize("kind,N,nobs", [("cx", 6, 10), ("gisscx", 4, 6), ("modis", 6, 8), ("cx", 12, 3), ("ocicx", 5, 6),
+                                         ("ocigisscx", 4, 6)])
 def test_vector_brdf_surfaces(mods, kind, N, nobs):
     """VECTOR_CX / VECTOR_GissCX / VECTOR_BRDF_MODIS: BRDF supplement (K0) + solver with a BRDF lower boundary."""
     VP, vg = mods
@@ -122,14 +123,25 @@ def test_vector_brdf_surfaces(mods, kind, N, nobs):
     else:                                        # Li-sparse only, large zenith angles -> BR < 0 -> every output -500
         sc["kernel_wt"][0, 0, 2] = 0.0; sc["kernel_wt"][1, 0, 2] = 0.4; sc["kernel_wt"][2, 0, 2] = 0.0
         sc["sza"][2] = 70.0; sc["vza"][2] = 60.0; sc["raa"][2] = 10.0
+    alpha = flux = None
+    if kind == "ocigisscx":                      # the only BRDF wrapper with trace-gas absorption and a solar flux factor
+        rng = np.random.default_rng(5)
+        alpha = np.asfortranarray(rng.uniform(0, 0.01, sc["ROT"].shape)); flux = np.asfortranarray(rng.uniform(0.5, 2.0, (1, nobs)))
     ref = vg.vlidort_run_surface(kind, 3, N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"],
-                                 sc["raa"], sc["vza"], sc["u10m"], sc["v10m"], sc["mr"], sc["kernel_wt"], sc["param"], MISSING=M)
+                                 sc["raa"], sc["vza"], sc["u10m"], sc["v10m"], sc["mr"], sc["kernel_wt"], sc["param"], MISSING=M,
+                                 alpha=alpha, flux_factor=flux)
     common = (sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"])
     geom = (sc["sza"], sc["raa"], sc["vza"], M, 0)
     if kind == "cx":
         I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_cx(*common, sc["u10m"], sc["v10m"], sc["mr"], *geom)
     elif kind == "gisscx":
         I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_gisscx(*common, sc["u10m"], sc["v10m"], sc["mr"], *geom)
+    elif kind == "ocicx":
+        I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_ocicx(*common, sc["u10m"], sc["v10m"], sc["mr"], *geom)
+    elif kind == "ocigisscx":
+        I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_ocigisscx(sc["channels"], N, False, sc["ROT"], sc["depol"], alpha, sc["tau"], sc["ssa"],
+                                                          sc["pmom"], sc["pe"], sc["he"], sc["te"], sc["u10m"], sc["v10m"], sc["mr"],
+                                                          sc["sza"], sc["raa"], sc["vza"], flux, M, 0)
     else:
         I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_brdf_modis(*common, sc["kernel_wt"], sc["param"], *geom)
     assert rc == 0
@@ -162,7 +174,12 @@ def test_vector_brdf_surfaces(mods, kind, N, nobs):
         I2 = ref2["radiance"]
         assert rel(I[ok], I2[ok], I2[ok]) < 1e-9 and rel(R[ok], ref2["reflectance"][ok], ref2["reflectance"][ok]) < 1e-9
         assert rel(Q[ok], ref2["Q"][ok], I2[ok]) < 1e-9 and rel(U[ok], ref2["U"][ok], I2[ok]) < 1e-9
-    assert (BRQ[ok] == 0).all() and (BRU[ok] == 0).all()
+    if kind in ("gisscx", "ocigisscx"):
+        # elements (1,2), (1,3) of the exact direct-bounce BRDF (BS_DBOUNCE_BRDFUNC(2..3,1,1,1), VLIDORT_BRDF_CX.F90:1865-1866)
+        scale = np.abs(ref["BR"][ok])
+        assert np.any(ref["BR_Q"][ok] != 0) and rel(BRQ[ok], ref["BR_Q"][ok], scale) < 1e-12 and rel(BRU[ok], ref["BR_U"][ok], scale) < 1e-12
+    else:
+        assert (BRQ[ok] == 0).all() and (BRU[ok] == 0).all()
 
 
 @pytest.mark.parametrize("kind", ["lambert", "cx"])
@@ -229,7 +246,7 @@ def test_scalar_brdf_surfaces(mods):
     VP, vg = mods
     nobs, N = 6, 6
     sc = vg.synthetic_scene(nobs, nch_nm=(470.0, 870.0), nmom=40, seed=91)
-    for kind in ("cx", "modis"):
+    for kind in ("cx", "gisscx", "modis"):
         ref = vg.vlidort_run_surface(kind, 1, N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"],
                                      sc["raa"], sc["vza"], sc["u10m"], sc["v10m"], sc["mr"], sc["kernel_wt"], sc["param"],
                                      scalar_glue=True)
@@ -237,6 +254,9 @@ def test_scalar_brdf_surfaces(mods):
         geom = (sc["sza"], sc["raa"], sc["vza"], 1e15, 0)
         if kind == "cx":
             I, R, BR, rc = VP.scalar_cx(*common, sc["u10m"], sc["v10m"], sc["mr"], *geom)
+            BR = BR[0]
+        elif kind == "gisscx":
+            I, R, BR, rc = VP.scalar_gisscx(*common, sc["u10m"], sc["v10m"], sc["mr"], *geom)
             BR = BR[0]
         else:
             I, R, BR, rc = VP.scalar_brdf_modis(*common, sc["kernel_wt"], sc["param"], *geom)

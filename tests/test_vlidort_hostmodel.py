@@ -43,7 +43,7 @@ def test_hostmodel_status_and_nadir_quirk():
     assert rel(st[ok, 0, 0], ref["radiance"][ok, 0], ref["radiance"][ok, 0]) < TOL
 
 
-@pytest.mark.parametrize("kind,S,N", [("cx", 3, 5), ("gisscx", 3, 4), ("modis", 3, 5), ("cx", 1, 6), ("gisscx", 1, 4), ("modis", 1, 4)])
+@pytest.mark.parametrize("kind,S,N", [("cx", 3, 5), ("gisscx", 3, 4), ("modis", 3, 5), ("cx", 1, 6), ("gisscx", 1, 4), ("modis", 1, 4), ("ocicx", 3, 4), ("ocigisscx", 3, 4)])
 def test_hostmodel_brdf_surfaces(kind, S, N):
     """K0 (vl_brdf.cuh: kernel evaluation, WSA check, Fourier projection) feeding the BVP's BRDF surface condition."""
     sc = vg.synthetic_scene(4, nmom=30, seed=20 + N)
