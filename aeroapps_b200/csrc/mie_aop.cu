@@ -989,6 +989,14 @@ extern "C" int ab200_get_int(ab200_mie *h, int km, int nobs, int nch, int nq, co
   return 0;
 }
 
+extern "C" int ab200_get_edge_vars_dev(int km, int nobs, const float *airdens, const float *delp, float ptop, float *pe, float *ze,
+                                       float *te, void *stream) {
+  if (km < 1 || nobs < 0) { ab200_set_error("getEdgeVars: bad argument"); return AB200_ERR_ARG; }
+  if (nobs == 0) return 0;
+  k_edge_vars<<<(nobs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(km, nobs, airdens, delp, ptop, pe, ze, te);
+  AB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 extern "C" int ab200_get_edge_vars(int km, int nobs, const float *airdens, const float *delp, float ptop,
                                    float *pe, float *ze, float *te) {
   if (km < 1 || nobs < 0) { ab200_set_error("getEdgeVars: bad argument"); return AB200_ERR_ARG; }

@@ -613,6 +613,17 @@ extern "C" int ab200_rot_calc(int km, int nch, int nobs, const double *channels,
   return 0;
 }
 
+// device-pointer variant of ab200_rot_calc (every array resident in HBM, kernel launched on `stream`)
+extern "C" int ab200_rot_calc_dev(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
+                                  const double *te, double *ROT, double *depol, void *stream) {
+  if (km > 72) return 3;
+  const size_t nr = (size_t)km * nobs * nch;
+  if (nr == 0) return 0;
+  k_rot_calc<<<(unsigned)((nr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(km, nch, nobs, channels, pe, he, te, ROT, depol);
+  AB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // diagnostics of the most recent call: per-pixel Fourier count (FOURIER_SAVED) and status, p = j*nch + i
 extern "C" long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap) {
   const long n = (long)g_last_nfourier.size();

@@ -211,6 +211,7 @@ class RtVectorWorkload:
         self.aop_e2e_voxels_per_s = self.km * self.nobs / (time.perf_counter() - t0)
         assert rc == 0
         pe, ze, te = MieObs_.getedgevars(st["airdens"], st["delp"], 1.0)
+        self.mie, self.state = mie, st                       # kept for the fused-pipeline leg
         pmom = pmom.astype(np.float64); pmom[..., 1] *= -1.0; pmom[..., 3] *= -1.0
         F = lambda a: np.asfortranarray(a, dtype=np.float64)
         ch = np.array([550.0])
@@ -360,6 +361,27 @@ class RtVectorCxWorkload(RtVectorWorkload):
             p(h["tau"]), p(h["ssa"]), p(h["pmom"]), p(h["pe"]), p(h["he"]), p(h["te"]), p(h["u10m"]), p(h["v10m"]), p(h["mr"]),
             p(h["sza"]), p(h["raa"]), p(h["vza"]), C.c_double(1e15), 0, *[p(o) for o in self.h_out], C.byref(rc)), "vector_cx")
         assert rc.value == 0
+
+    def pipeline_leg(self, torch, steps=3):
+        """the same pixels through ab200_pipeline_vector_cx (getEdgeVars -> ROT_CALC -> getAOPvector -> VECTOR_CX in one call):
+        host inputs are the model state, every intermediate stays in HBM.  Returns pixels/s and the bytes that cross PCIe."""
+        from aeroapps_b200 import pipeline
+        st, sc = self.state, self.scene
+        a = (self.mie, [550.0], st["vnames"], st["qm"], st["rh"], st["airdens"], st["delp"], 1.0, self.N, self.plane_parallel,
+             self.nmom, 6, sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], 1e15, 0)
+        out = pipeline.vector_cx_pipeline(*a)
+        assert out[-1] == 0
+        same = bool(np.array_equal(out[0].ravel(), self.h_out[0].numpy()) and np.array_equal(out[3].ravel(), self.h_out[3].numpy()))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pipeline.vector_cx_pipeline(*a)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        h2d = 4 * (st["qm"].size + st["rh"].size + st["airdens"].size + st["delp"].size) + 8 * 5 * self.nobs
+        return {"value": self.units_per_step / dt, "unit": self.unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 5 * 8 * self.nobs,
+                "bit_identical_to_separate_calls": same,
+                "entry": "ab200_pipeline_vector_cx (fused getEdgeVars -> ROT_CALC -> getAOPvector -> VECTOR_CX, per-rank wall clock)"}
 
     def setup_cpu(self, sample_cols):
         had_scene = getattr(self, "scene", None) is not None
@@ -532,6 +554,10 @@ def main():
         if rank == 0:
             out["config"]["gathered_outputs"] = int(full.shape[0])
             out["config"]["parallelism"] = f"{world} ranks x contiguous slabs, no data-path collective, final all_gather over NCCL"
+    if hasattr(wl, "pipeline_leg"):
+        pl = wl.pipeline_leg(torch)
+        if rank == 0:
+            out["pipeline"] = pl
     if args.workload.startswith("rt_vector") and not args.no_aop:
         # the second half of the BASELINE metric: Mie AOP voxels/s (BASELINE configs[0], c90 scalar AOPs)
         import copy

@@ -83,6 +83,9 @@ int ab200_get_aop_vector_dev(ab200_mie *h, int km, int nobs, int nch, int nq, co
                              int nmom, int npol, float *tau_dev, float *ssa_dev, float *g_dev,
                              float *pmom_dev, void *stream, int *rc);
 
+int ab200_get_edge_vars_dev(int km, int nobs, const float *airdens_dev, const float *delp_dev, float ptop, float *pe_dev,
+                            float *ze_dev, float *te_dev, void *stream);
+
 #include "aeroapps_b200_rt.h"
 
 #ifdef __cplusplus
