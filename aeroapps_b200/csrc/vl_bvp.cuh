@@ -189,9 +189,11 @@ DEVFN void bvp_backward(const Team &T, const VLPix &X, const VLSol &Z, const VLQ
                         int lambertian, double accuracy, int m, int p, double *W, double *xcur, double *xnext, double *red, const double *Ug,
                         int nbuf = 2);
 
-template <int S, class Team>
+template <int S, class Team, bool WGLOB = false>
 DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
-                     int lambertian, double accuracy, int m, int p, double *scr, int *iscr, double *Ug, double *wglob = nullptr) {
+                     int lambertian, double accuracy, int m, int p, double *scr, int *iscr, double *Ug, double *wglob_ = nullptr) {
+  // WGLOB is a compile-time switch so that, in the default layout, the compiler still sees W as a shared-memory pointer
+  double *wglob = WGLOB ? wglob_ : nullptr;
   const int N = QD.N, n = S * N, n2 = 2 * n, L = X.L, NM = X.NM;
   const int R = 3 * n, Cc = bvp_cols(n), Cs = bvp_stride(n), RH = 4 * n;      // RH = rhs column
   // wglob != nullptr: "large n" layout, the window in HBM scratch and only the panel arrays in the team scratch

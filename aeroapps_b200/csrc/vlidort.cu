@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(256) k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, c
   eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)warp * scr_doubles);
 }
 
-template <int S>
+// VAR: forward-elimination variant, one kernel each (own register allocation): 0 = blocked look-ahead (vl_bvp.cuh, the default),
+// 1 = the same with the window in a per-CTA HBM scratch ("large n"), 3 = warp-specialised (vl_bvp3.cuh), 4 = register-resident
+// window (vl_bvp4.cuh)
+template <int S, int VAR>
 __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
                                                 int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
                                                 int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta, int v3,
@@ -57,10 +60,9 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
   __shared__ double sd[64];
   __shared__ int si[64];
   const int n = S * QD.N;
-  // v3: forward-elimination variant, 0 = blocked look-ahead (vl_bvp.cuh), 3 = warp-specialised (vl_bvp3.cuh), 4 = register-resident (vl_bvp4.cuh)
-  // wglob: "large n" layout of the default variant (window in a per-CTA HBM scratch)
-  int *iscr = reinterpret_cast<int *>(smem_d + (v3 == 4 ? b4_smem_doubles(n) : (v3 ? b3_smem_doubles(n) : (wglob ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)))));
-  double *wg = wglob ? wglob + (size_t)blockIdx.x * bvp_window_doubles(n) : nullptr;
+  (void)v3;
+  int *iscr = reinterpret_cast<int *>(smem_d + (VAR == 4 ? b4_smem_doubles(n) : (VAR == 3 ? b3_smem_doubles(n) : (VAR == 1 ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)))));
+  double *wg = (VAR == 1) ? wglob + (size_t)blockIdx.x * bvp_window_doubles(n) : nullptr;
   __shared__ unsigned long long mbar;
   for (int i = threadIdx.x; i < smem_doubles; i += blockDim.x) smem_d[i] = 0.0;      // no stale NaN patterns in never-written padding
   BlockTeam T(sd, si, &mbar);
@@ -70,9 +72,10 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
     if (Z.fail[p]) {
       if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
     } else {
-      if (v3 == 4) bvp_pixel_v4<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
-      else if (v3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
-      else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug, wg);
+      if constexpr (VAR == 4) bvp_pixel_v4<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      else if constexpr (VAR == 3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
+      else if constexpr (VAR == 1) bvp_pixel<S, BlockTeam, true>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug, wg);
+      else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
     }
     __syncthreads();
     if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
@@ -265,7 +268,11 @@ int run_vlidort(const RunDesc &R) {
   const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 == 3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
   int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int bvp_per_sm = 1;
-  auto kb = (S == 1) ? (const void *)k_vl_bvp<1> : (const void *)k_vl_bvp<3>;
+  const int var = use_v3 ? use_v3 : (big_n ? 1 : 0);
+  using bvp_fn = void (*)(VLPix, VLSol, VLQuad, VLSurf, VLConv, int, double, int, const int *, int, int *, int *, double *, size_t, int, int, double *);
+  const bvp_fn kbf = (S == 1) ? (var == 4 ? k_vl_bvp<1, 4> : var == 3 ? k_vl_bvp<1, 3> : var == 1 ? k_vl_bvp<1, 1> : k_vl_bvp<1, 0>)
+                              : (var == 4 ? k_vl_bvp<3, 4> : var == 3 ? k_vl_bvp<3, 3> : var == 1 ? k_vl_bvp<3, 1> : k_vl_bvp<3, 0>);
+  auto kb = (const void *)kbf;
   auto ke = (S == 1) ? (const void *)k_vl_eigen<1> : (const void *)k_vl_eigen<3>;
   if (bvp_smem > 227 * 1024) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory BVP window"); return AB200_ERR_ARG; }
   AB_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvp_smem));
@@ -382,8 +389,7 @@ int run_vlidort(const RunDesc &R) {
       cudaEventRecord(ev[1], st);
       const int bgrid = std::min(nactive, bvp_grid_max);
       int *cnt = counts + 1 + m;
-      if (S == 1) k_vl_bvp<1><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
-      else k_vl_bvp<3><<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
+      kbf<<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());
       g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive; g_stats.n_launches += 2;
