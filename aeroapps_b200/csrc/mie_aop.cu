@@ -367,6 +367,93 @@ __global__ void __launch_bounds__(640) k_aop_scalar_tiled(const __grid_constant_
   }
 }
 
+// ---- getAOPscalar, direct variant (the one bench.py times).  The tiled kernel above is bound by shared-memory wavefronts and by
+// the latency of its 18 warps: with iid RH the 32 lanes of a warp gather 32 random table rows and every gather costs 3-8
+// wavefronts of bank conflicts (ncu: 13 per tracer and warp, l1tex 75 % busy, HBM 35 %).  Here
+//   * the pre-paired rows are REPLICATED across the banks: pairA[a][n][row][8] float4 (bext0,bext1,g0,g1), lane l reads replica
+//     l & 7, so the 8 lanes of a quarter-warp always hit 8 distinct 16-byte groups: conflict-free whatever the rows are
+//     (4 wavefronts, the minimum for 512 bytes).  36 rows x 20 tracers x 128 B = 92 KB;
+//   * ssa_ = bsca/bext comes from the snapped table of the tiled kernel (one LDS instead of a lerp and an IEEE division;
+//     79 KB, its gather keeps its conflicts but the instruction count is what binds this kernel);
+//   * qm is not staged: every thread pulls the tracer masses of its voxel straight from HBM into registers (lanes = consecutive
+//     levels -> coalesced streaming loads, ten in flight per thread);
+//   * a thread keeps its level k and walks over column blocks, so the hot loop has no integer division.
+// One 1008..1024-thread CTA per SM (171 KB of shared memory).  Arithmetic identical to k_aop_scalar -> bit-exact.
+template <bool ONEH>
+__global__ void __launch_bounds__(1024, 1) k_aop_scalar_direct(const __grid_constant__ AopParams P, int nrhp, int cpb,
+                                                                const float *__restrict__ qm, const float *__restrict__ rh,
+                                                                float *__restrict__ tau, float *__restrict__ ssa,
+                                                                float *__restrict__ g) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int nrow = P.nqa * P.nch * nrhp;
+  float4 *pairA = reinterpret_cast<float4 *>(smraw);                              // [row][8]
+  float *ssaT = reinterpret_cast<float *>(smraw + (size_t)nrow * 128);            // [a][n][isnap-1]
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < nrow * 8; idx += blockDim.x) {
+    const int row = idx >> 3;
+    const int irh = row % nrhp, an = row / nrhp, n = an % P.nch, a = an / P.nch;
+    const TracerDesc &d = P.d[a];
+    const int i0 = min(irh, d.nrh - 1), i1 = min(irh + 1, d.nrh - 1), co = d.nrh * P.chidx0[n];
+    pairA[idx] = make_float4(d.bext[co + i0], d.bext[co + i1], d.g[co + i0], d.g[co + i1]);
+  }
+  for (int idx = tid; idx < P.nqa * P.nch * NRHHASH; idx += blockDim.x) {
+    const int is = idx % NRHHASH, an = idx / NRHHASH, n = an % P.nch, a = an / P.nch;
+    const TracerDesc &d = P.d[a];
+    const int h = ONEH ? 0 : P.hcls[a];
+    const float arh = __ldg(P.hrha[h] + is), oma = __fsub_rn(1.f, arh);
+    const int irh = __ldg(P.hrhi[h] + is) - 1, i0 = min(irh, d.nrh - 1), i1 = min(irh + 1, d.nrh - 1), co = d.nrh * P.chidx0[n];
+    const float bext = __fadd_rn(__fmul_rn(d.bext[co + i0], oma), __fmul_rn(d.bext[co + i1], arh));
+    const float bsca = __fadd_rn(__fmul_rn(d.bsca[co + i0], oma), __fmul_rn(d.bsca[co + i1], arh));
+    ssaT[idx] = __fdiv_rn(bsca, bext);
+  }
+  __syncthreads();
+  const int col = tid / P.km, k = tid - col * P.km;          // cpb columns per block and step; the thread keeps its level k
+  if (col >= cpb) return;
+  const float4 *pA = pairA + (tid & 7);
+  const int nblk = (P.nobs + cpb - 1) / cpb;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int i = blk * cpb + col;
+    if (i >= P.nobs) continue;
+    const int isnap = snap_index(__ldcs(rh + k + (size_t)P.km * i));
+    const float *qcol = qm + k + (size_t)P.km * P.nq * i;
+    int irh0, irh1 = 0; float arh0, oma0, arh1 = 0.f, oma1 = 0.f;
+    arh0 = __ldg(P.hrha[0] + isnap - 1); irh0 = __ldg(P.hrhi[0] + isnap - 1) - 1; oma0 = __fsub_rn(1.f, arh0);
+    if (!ONEH) { arh1 = __ldg(P.hrha[1] + isnap - 1); irh1 = __ldg(P.hrhi[1] + isnap - 1) - 1; oma1 = __fsub_rn(1.f, arh1); }
+    const float *sT = ssaT + isnap - 1;
+    for (int n = 0; n < P.nch; n++) {
+      float t = 0.f, s = 0.f, gg = 0.f;
+      auto body = [&](int a, float q) {
+        const bool h1 = ONEH ? false : (P.hcls[a] != 0);
+        const int irh = h1 ? irh1 : irh0;
+        const float arh = h1 ? arh1 : arh0, oma = h1 ? oma1 : oma0;
+        const int an = a * P.nch + n;
+        const float4 A = pA[(an * nrhp + irh) * 8];
+        const float ssa_ = sT[an * NRHHASH];
+        const float bext = __fadd_rn(__fmul_rn(A.x, oma), __fmul_rn(A.y, arh));
+        const float gas = __fadd_rn(__fmul_rn(A.z, oma), __fmul_rn(A.w, arh));
+        const float tau_ = __fmul_rn(bext, q);
+        t = __fadd_rn(t, tau_);
+        s = __fadd_rn(s, __fmul_rn(ssa_, tau_));
+        gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(gas, ssa_), tau_));
+      };
+      int a0 = 0;
+      for (; a0 + 10 <= P.nqa; a0 += 10) {                   // full batches: ten loads in flight, no predicates
+        float q[10];
+#pragma unroll
+        for (int u = 0; u < 10; u++) q[u] = __ldcs(qcol + P.qoff[a0 + u]);
+#pragma unroll
+        for (int u = 0; u < 10; u++) body(a0 + u, q[u]);
+      }
+      for (; a0 < P.nqa; a0++) body(a0, __ldcs(qcol + P.qoff[a0]));
+      if (t > 0.f) s = __fdiv_rn(s, t);
+      float dd = __fmul_rn(s, t);
+      if (dd > 0.f) gg = __fdiv_rn(gg, dd);
+      const size_t o = k + (size_t)P.km * (n + (size_t)P.nch * i);
+      __stcs(tau + o, t); __stcs(ssa + o, s); __stcs(g + o, gg);
+    }
+  }
+}
+
 // ---- getAOPvector (MieObs_py.F90:391-446).  Block = 32 consecutive voxel-channels (lanes) x NW warps.
 // Phase 1: per-(voxel,tracer) query parameters -> shared memory; warp 0 forms tau/ssa/g.
 // Phase 2: warps split the moment axis in chunks of MCH moments x 6 matrix elements kept in registers;
@@ -825,6 +912,22 @@ extern "C" int ab200_get_aop_scalar_dev(ab200_mie *h, int km, int nobs, int nch,
   if (e || rc_) return e ? e : rc_;
   long nout = (long)km * nch * nobs;
   if (nout == 0) return 0;
+  // direct kernel (bank-replicated row table + snapped ssa table in shared memory, qm straight from HBM into registers) when the
+  // tables fit one SM; AB200_AOP_DIRECT=0 falls back to the tiled/TMA kernel
+  {
+    bool direct = P.nqa > 0 && P.nh <= MAXH && km <= 1024;
+    if (const char *e = getenv("AB200_AOP_DIRECT")) direct = direct && atoi(e) != 0;
+    const size_t smem = (size_t)P.nqa * nch * P.nrh_max * 128 + (size_t)P.nqa * nch * NRHHASH * 4;
+    if (direct && smem <= 220 * 1024) {
+      auto kern = (P.nh == 1) ? k_aop_scalar_direct<true> : k_aop_scalar_direct<false>;
+      AB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int cpb = std::max(1, 1024 / km), threads = std::min(1024, (cpb * km + 31) / 32 * 32);
+      const int grid = std::min((nobs + cpb - 1) / cpb, 148);
+      kern<<<grid, threads, smem, (cudaStream_t)stream>>>(P, P.nrh_max, cpb, qm, rh, tau, ssa, g);
+      AB_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
   // tiled/TMA kernel whenever its layout preconditions hold; the generic kernel takes the rest (and the
   // tail columns that do not fill a tile)
   int done_cols = 0;

@@ -36,9 +36,11 @@ HDFN int eig_lda(int n) { return n | 1; }                                  // od
 HDFN int eigen_scratch_doubles(int n, int NM) { return n * (n + 1) + n * eig_lda(n) + 18 * n + 6 * (NM + 1) + 8; }
 
 // one Jacobi rotation of the column pair (a,b) of A (length n).  NR > 0: both columns live in registers (n <= NR).
+// The squared column norms travel with the columns (na2, nb2: recomputed exactly at the start of every sweep, updated here
+// with  |a'|^2 = |a|^2 - t (a.b),  |b'|^2 = |b|^2 + t (a.b)), so a rotation needs one dot product instead of three.
 template <int NR>
-DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n) {
-  double al = 0.0, be = 0.0, ga = 0.0;
+DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n, double &na2, double &nb2) {
+  double al = na2, be = nb2, ga = 0.0;
   if (NR > 0) {
     double ra[NR > 0 ? NR : 1], rb[NR > 0 ? NR : 1];
     const bool full = (n == NR);                   // warp-uniform: no row masking needed
@@ -49,11 +51,11 @@ DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n) {
 #pragma unroll
       for (int r = 0; r < NR; r++) { ra[r] = r < n ? a[r] : 0.0; rb[r] = r < n ? b[r] : 0.0; }
     }
-    // four partial sums per dot product: 12 independent FMA chains
-    double alp[4] = {0.0, 0.0, 0.0, 0.0}, bep[4] = {0.0, 0.0, 0.0, 0.0}, gap[4] = {0.0, 0.0, 0.0, 0.0};
+    // eight partial sums: independent FMA chains
+    double gap[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int r = 0; r < NR; r++) { alp[r & 3] += ra[r] * ra[r]; bep[r & 3] += rb[r] * rb[r]; gap[r & 3] += ra[r] * rb[r]; }
-    al = (alp[0] + alp[1]) + (alp[2] + alp[3]); be = (bep[0] + bep[1]) + (bep[2] + bep[3]); ga = (gap[0] + gap[1]) + (gap[2] + gap[3]);
+    for (int r = 0; r < NR; r++) gap[r & 7] += ra[r] * rb[r];
+    ga = ((gap[0] + gap[1]) + (gap[2] + gap[3])) + ((gap[4] + gap[5]) + (gap[6] + gap[7]));
     // rel = |cos(a,b)|; the rotation uses  t = 2 ga / (d + sign(d) sqrt(d^2 + 4 ga^2)),  d = be - al  (one sqrt, one
     // divide and one rsqrt on the dependent chain; rel itself is off the chain)
     const double rel = fabs(ga) * rsqrt(al * be + 1.0e-300);
@@ -62,6 +64,7 @@ DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n) {
       const double rt = sqrt(d * d + g2 * g2);
       const double t = g2 / (d >= 0.0 ? d + rt : d - rt);
       const double c = rsqrt(1.0 + t * t), s = c * t;
+      na2 = al - t * ga; nb2 = be + t * ga;
       if (full) {
 #pragma unroll
         for (int r = 0; r < NR; r++) { a[r] = c * ra[r] - s * rb[r]; b[r] = s * ra[r] + c * rb[r]; }
@@ -73,12 +76,13 @@ DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n) {
     }
     return rel;
   } else {
-    for (int r = 0; r < n; r++) { const double x = a[r], y = b[r]; al += x * x; be += y * y; ga += x * y; }
+    for (int r = 0; r < n; r++) ga += a[r] * b[r];
     const double rel = fabs(ga) / sqrt(al * be + 1.0e-300);
     if (rel > 1.0e-15) {
       const double ze = (be - al) / (2.0 * ga);
       const double t = (ze >= 0.0 ? 1.0 : -1.0) / (fabs(ze) + sqrt(1.0 + ze * ze));
       const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+      na2 = al - t * ga; nb2 = be + t * ga;
       for (int r = 0; r < n; r++) { const double x = a[r], y = b[r]; a[r] = c * x - s * y; b[r] = s * x + c * y; }
     }
     return rel;
@@ -236,18 +240,27 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   // ---- one-sided Jacobi, round-robin ordering, one column pair per lane
   {
     const int np = n + (n & 1), half = np / 2;
+    double *nrm2 = sig;                                     // squared column norms (sig is only written after the sweeps)
     for (int sweep = 0; sweep < 30; sweep++) {
       double offmax = 0.0;
+      for (int c = T.rank; c < n; c += T.size) {
+        const double *col = A + c * LDA;
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r + 1 < n; r += 2) { s0 += col[r] * col[r]; s1 += col[r + 1] * col[r + 1]; }
+        if (n & 1) s0 += col[n - 1] * col[n - 1];
+        nrm2[c] = s0 + s1;
+      }
+      T.sync();
       for (int st = 0; st < np - 1; st++) {
         for (int t = T.rank; t < half; t += T.size) {
           int a, b;
           if (t == 0) { a = np - 1; b = st; } else { a = st + t; if (a >= np - 1) a -= np - 1; b = st - t; if (b < 0) b += np - 1; }
           if (a < n && b < n) {
             double rel;
-            if (n <= 12) rel = jacobi_pair<12>(A + a * LDA, A + b * LDA, n);
-            else if (n <= 24) rel = jacobi_pair<24>(A + a * LDA, A + b * LDA, n);
-            else if (n <= 36) rel = jacobi_pair<36>(A + a * LDA, A + b * LDA, n);
-            else rel = jacobi_pair<0>(A + a * LDA, A + b * LDA, n);
+            if (n <= 12) rel = jacobi_pair<12>(A + a * LDA, A + b * LDA, n, nrm2[a], nrm2[b]);
+            else if (n <= 24) rel = jacobi_pair<24>(A + a * LDA, A + b * LDA, n, nrm2[a], nrm2[b]);
+            else if (n <= 36) rel = jacobi_pair<36>(A + a * LDA, A + b * LDA, n, nrm2[a], nrm2[b]);
+            else rel = jacobi_pair<0>(A + a * LDA, A + b * LDA, n, nrm2[a], nrm2[b]);
             if (rel > offmax) offmax = rel;
           }
         }
