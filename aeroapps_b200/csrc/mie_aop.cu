@@ -420,15 +420,17 @@ __global__ void __launch_bounds__(1024, 1) k_aop_scalar_direct(const __grid_cons
     arh0 = __ldg(P.hrha[0] + isnap - 1); irh0 = __ldg(P.hrhi[0] + isnap - 1) - 1; oma0 = __fsub_rn(1.f, arh0);
     if (!ONEH) { arh1 = __ldg(P.hrha[1] + isnap - 1); irh1 = __ldg(P.hrhi[1] + isnap - 1) - 1; oma1 = __fsub_rn(1.f, arh1); }
     const float *sT = ssaT + isnap - 1;
+    const char *qb = reinterpret_cast<const char *>(qcol);      // full pointer + unsigned byte offsets: one IMAD.WIDE per load
     for (int n = 0; n < P.nch; n++) {
       float t = 0.f, s = 0.f, gg = 0.f;
-      auto body = [&](int a, float q) {
+      // running table positions of tracer a: row block (a nch + n) nrhp of pairA, (a nch + n) NRHHASH of ssaT
+      const int dA = P.nch * nrhp * 8, dS = P.nch * NRHHASH;
+      auto body = [&](int a, float q, const float4 *pa, const float *ps) {
         const bool h1 = ONEH ? false : (P.hcls[a] != 0);
         const int irh = h1 ? irh1 : irh0;
         const float arh = h1 ? arh1 : arh0, oma = h1 ? oma1 : oma0;
-        const int an = a * P.nch + n;
-        const float4 A = pA[(an * nrhp + irh) * 8];
-        const float ssa_ = sT[an * NRHHASH];
+        const float4 A = pa[irh * 8];
+        const float ssa_ = *ps;
         const float bext = __fadd_rn(__fmul_rn(A.x, oma), __fmul_rn(A.y, arh));
         const float gas = __fadd_rn(__fmul_rn(A.z, oma), __fmul_rn(A.w, arh));
         const float tau_ = __fmul_rn(bext, q);
@@ -436,15 +438,19 @@ __global__ void __launch_bounds__(1024, 1) k_aop_scalar_direct(const __grid_cons
         s = __fadd_rn(s, __fmul_rn(ssa_, tau_));
         gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(gas, ssa_), tau_));
       };
+      const float4 *pa = pA + n * nrhp * 8;
+      const float *ps = sT + n * NRHHASH;
       int a0 = 0;
       for (; a0 + 10 <= P.nqa; a0 += 10) {                   // full batches: ten loads in flight, no predicates
         float q[10];
 #pragma unroll
-        for (int u = 0; u < 10; u++) q[u] = __ldcs(qcol + P.qoff[a0 + u]);
+        for (int u = 0; u < 10; u++) q[u] = __ldcs(reinterpret_cast<const float *>(qb + (size_t)(4u * (unsigned)P.qoff[a0 + u])));
 #pragma unroll
-        for (int u = 0; u < 10; u++) body(a0 + u, q[u]);
+        for (int u = 0; u < 10; u++) body(a0 + u, q[u], pa + u * dA, ps + u * dS);
+        pa += 10 * dA; ps += 10 * dS;
       }
-      for (; a0 < P.nqa; a0++) body(a0, __ldcs(qcol + P.qoff[a0]));
+      for (; a0 < P.nqa; a0++, pa += dA, ps += dS)
+        body(a0, __ldcs(reinterpret_cast<const float *>(qb + (size_t)(4u * (unsigned)P.qoff[a0]))), pa, ps);
       if (t > 0.f) s = __fdiv_rn(s, t);
       float dd = __fmul_rn(s, t);
       if (dd > 0.f) gg = __fdiv_rn(gg, dd);
