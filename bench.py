@@ -169,8 +169,14 @@ class AopScalarWorkload:
     def roofline(self, kernel_ms):
         pk = peaks()
         achieved = self.units_per_step * self.bytes_per_unit / (kernel_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "k_aop_scalar", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["_source"],
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01b_rt_traffic.json")
+        if os.path.exists(tp) and self.nobs == 48600:
+            tj = json.load(open(tp)).get("k_aop_scalar")
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        return {"bound": "hbm", "kernel": "k_aop_scalar_direct", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["_source"],
                 "bytes_per_unit": self.bytes_per_unit}
 
 
@@ -305,7 +311,7 @@ class RtVectorWorkload:
         ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         tot = (st["flops_eigen"] + st["flops_bvp"]) / ((st["ms_eigen"] + st["ms_bvp"] + st["ms_setup"]) * 1e-3) / 1e12
         traffic, tnote = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_rt_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r01b_rt_traffic.json")
         if os.path.exists(tp) and self.nobs == 2048:
             tj = json.load(open(tp)).get(dom)
             if tj:
