@@ -32,7 +32,7 @@ struct TableDev {
   float *pool = nullptr;   // everything below lives in this allocation
   int nch = 0, nrh = 0, nbin = 0, nmom = 0, npol = 0;
   long o_rh, o_bext, o_bsca, o_bbck, o_g, o_refr, o_refi, o_pback, o_pmom, o_reff, o_gf, o_rhop, o_rhod,
-      o_vol, o_area, o_rha, o_rhi, total;
+      o_vol, o_area, o_rha, o_rhi, o_pmom2, total;   // o_pmom2: pmom rows pre-paired (T[irh], T[min(irh+1,nrh-1)]) as float2
   bool loaded = false;
   std::vector<int> h_rhi;      // host copies of the RH hash (to find tables that hash identically)
   std::vector<float> h_rha;
@@ -108,6 +108,13 @@ __global__ void k_polint(const double *__restrict__ lam, const double *__restric
   }
 }
 
+// rows of a (nrh, ...) table pre-paired for the RH interpolation: dst[i] = (T[irh], T[min(irh+1, nrh-1)])
+__global__ void k_pair_rows(const float *__restrict__ src, float2 *__restrict__ dst, int nrh, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int irh = (int)(i % nrh);
+    dst[i] = make_float2(src[i], src[i - irh + min(irh + 1, nrh - 1)]);
+  }
+}
 __global__ void k_fill(float *dst, float v, long n) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) dst[t] = v;
 }
@@ -169,6 +176,7 @@ __device__ __forceinline__ float lerp2(const float *__restrict__ a, const Snap &
 // per active tracer, per call.  3-D pointers are pre-offset to the tracer's bin; 2-D ones (vol,area) too.
 struct TracerDesc {
   const float *bext, *bsca, *g, *bbck, *refr, *refi, *pback, *pmom, *vol, *area;
+  const float2 *pmom2;                      // pmom with pre-paired RH rows (same indexing as pmom)
   const float *rha; const int *rhi;
   int nrh, n3, nmomt, npol_, sph, qidx;     // n3 = nrh*nch*nbin (stride of m); qidx = tracer slot in qm
   int p22off, pad;                          // offset of pback(...,5); 0 (P22:=P11) when the table has nPol<5
@@ -460,88 +468,96 @@ __global__ void __launch_bounds__(1024, 1) k_aop_scalar_direct(const __grid_cons
   }
 }
 
-// ---- getAOPvector (MieObs_py.F90:391-446).  Block = 32 consecutive voxel-channels (lanes) x NW warps.
-// Phase 1: per-(voxel,tracer) query parameters -> shared memory; warp 0 forms tau/ssa/g.
-// Phase 2: warps split the moment axis in chunks of MCH moments x 6 matrix elements kept in registers;
-// tracer loop outermost (the reference's accumulation order), P22:=P11 / P44:=P33 overwrite after each
+// ---- getAOPvector (MieObs_py.F90:391-446).  Every warp owns 32 consecutive voxel-channels (lanes); the VEC_NW warps of a block
+// walk over the moment axis TOGETHER (chunks of VEC_MCH moments x 6 matrix elements kept in registers, one block barrier per
+// chunk), so a table line fetched from L2 for one warp is an L1 hit for the other warps of the block: the lanes of a warp
+// gather inside one 36-row stretch of a table whose rows are pre-paired as (T[irh], T[irhp1]) float2 -- one 8-byte load per
+// element.  (With each warp on its own chunk the kernel was bound by L2 -> L1 traffic: 250 KB per voxel, L1 hit rate 5 %.)
+// Phase 1 (per warp): per-(voxel,tracer) query parameters -> shared memory, tau/ssa/g in the reference's accumulation order.
+// Phase 2: tracer loop outermost inside a chunk (the reference's accumulation order), P22:=P11 / P44:=P33 overwrite after each
 // spherical tracer.  Output writes are 128-B coalesced (lanes = consecutive k).
 #define VEC_NW 8
-#define VEC_MCH 4
+#define VEC_MCH 8
 __global__ void __launch_bounds__(32 * VEC_NW) k_aop_vector(const __grid_constant__ AopParams P,
                                                             const float *__restrict__ qm,
                                                             const float *__restrict__ rh, float *__restrict__ tau,
                                                             float *__restrict__ ssa, float *__restrict__ g,
                                                             float *__restrict__ pmom) {
-  __shared__ float s_tau[MAXQ][32], s_ssa[MAXQ][32], s_gas[MAXQ][32], s_arh[MAXQ][32];
-  __shared__ int s_irh[MAXQ][32];
-  __shared__ float s_den[32];
+  extern __shared__ float vsm[];                           // per warp: tau_, ssa_, arh [nqa][32] float, irh [nqa][32] int
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *s_tau = vsm + (size_t)warp * 4 * P.nqa * 32, *s_ssa = s_tau + P.nqa * 32, *s_arh = s_ssa + P.nqa * 32;
+  int *s_irh = reinterpret_cast<int *>(s_arh + P.nqa * 32);
   const long nout = (long)P.km * P.nch * P.nobs;
-  const long o = (long)blockIdx.x * 32 + lane;
+  const long o = ((long)blockIdx.x * VEC_NW + warp) * 32 + lane;
   const bool valid = o < nout;
   int k = 0, n = 0; long i = 0;
   if (valid) { k = (int)(o % P.km); long r = o / P.km; n = (int)(r % P.nch); i = r / P.nch; }
   const int ch = P.chidx0[n];
-
+  float den;
   {
     const int isnap = valid ? snap_index(__ldg(rh + k + (long)P.km * i)) : 1;
     const float *qcol = qm + k + (long)P.km * P.nq * i;
-    for (int a = warp; a < P.nqa; a += VEC_NW) {
+    float t = 0.f, s = 0.f, gg = 0.f;
+    for (int a = 0; a < P.nqa; a++) {
       const TracerDesc &d = P.d[a];
       Snap sn = make_snap(d, isnap);
       const int co = d.nrh * ch;
-      float bext = lerp2(d.bext + co, sn);
-      float bsca = lerp2(d.bsca + co, sn);
-      float gas = lerp2(d.g + co, sn);
-      float q = valid ? __ldcs(qcol + (long)P.km * d.qidx) : 0.f;
-      s_tau[a][lane] = __fmul_rn(bext, q);
-      s_ssa[a][lane] = __fdiv_rn(bsca, bext);
-      s_gas[a][lane] = gas;
-      s_arh[a][lane] = sn.arh;
-      s_irh[a][lane] = sn.irh | (sn.irhp1 << 16);
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    float t = 0.f, s = 0.f, gg = 0.f;
-    for (int a = 0; a < P.nqa; a++) {
-      float tau_ = s_tau[a][lane], ssa_ = s_ssa[a][lane];
+      const float bext = lerp2(d.bext + co, sn), bsca = lerp2(d.bsca + co, sn), gas = lerp2(d.g + co, sn);
+      const float q = valid ? __ldcs(qcol + (long)P.km * d.qidx) : 0.f;
+      const float tau_ = __fmul_rn(bext, q), ssa_ = __fdiv_rn(bsca, bext);
+      s_tau[a * 32 + lane] = tau_; s_ssa[a * 32 + lane] = ssa_; s_arh[a * 32 + lane] = sn.arh; s_irh[a * 32 + lane] = sn.irh;
       t = __fadd_rn(t, tau_);
       s = __fadd_rn(s, __fmul_rn(ssa_, tau_));
-      gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(s_gas[a][lane], ssa_), tau_));
+      gg = __fadd_rn(gg, __fmul_rn(__fmul_rn(gas, ssa_), tau_));
     }
     if (t > 0.f) s = __fdiv_rn(s, t);
-    float dd = __fmul_rn(s, t);
-    if (dd > 0.f) gg = __fdiv_rn(gg, dd);
-    s_den[lane] = dd;
+    den = __fmul_rn(s, t);
+    if (den > 0.f) gg = __fdiv_rn(gg, den);
     if (valid) { tau[o] = t; ssa[o] = s; g[o] = gg; }
   }
-  __syncthreads();
-  const float den = s_den[lane];
+  __syncwarp();
   const int nchunk = (P.nmom + VEC_MCH - 1) / VEC_MCH;
-  for (int mc = warp; mc < nchunk; mc += VEC_NW) {
+  for (int mc = 0; mc < nchunk; mc++) {
+    __syncthreads();                                       // keeps the warps of the block on the same table lines (L1 reuse)
     const int m0 = mc * VEC_MCH;
     float acc[VEC_MCH][6];
 #pragma unroll
     for (int mm = 0; mm < VEC_MCH; mm++)
 #pragma unroll
       for (int p = 0; p < 6; p++) acc[mm][p] = 0.f;
+    int mcl[VEC_MCH];                                       // moment index of each slot of the chunk (clamped in the tail chunk)
+#pragma unroll
+    for (int mm = 0; mm < VEC_MCH; mm++) mcl[mm] = min(m0 + mm, P.nmom - 1);
     for (int a = 0; a < P.nqa; a++) {
       const TracerDesc &d = P.d[a];
-      const float tau_ = s_tau[a][lane], ssa_ = s_ssa[a][lane], arh = s_arh[a][lane];
+      const float tau_ = s_tau[a * 32 + lane], ssa_ = s_ssa[a * 32 + lane], arh = s_arh[a * 32 + lane];
       const float oma = __fsub_rn(1.f, arh);
-      const int pk = s_irh[a][lane];
-      const float *b0 = d.pmom + d.nrh * ch + (pk & 0xffff);
-      const float *b1 = d.pmom + d.nrh * ch + (pk >> 16);
+      const float2 *b = d.pmom2 + d.nrh * ch + s_irh[a * 32 + lane];
+      const int n3 = d.n3;
+      const long pstride = (long)n3 * d.nmomt;
 #pragma unroll
-      for (int p = 0; p < 6; p++) {
+      for (int p = 0; p < 6; p += 2) {
         if (p < d.npol_) {
+          const bool two = (p + 1 < d.npol_);
+          const float2 *bp = b + pstride * p, *bq = bp + pstride;
+          float2 v2[VEC_MCH], w2[VEC_MCH];                   // all the loads of two rows first: 2 VEC_MCH gathers in flight
+#pragma unroll
+          for (int mm = 0; mm < VEC_MCH; mm++) v2[mm] = __ldg(bp + (long)n3 * mcl[mm]);
+          if (two) {
+#pragma unroll
+            for (int mm = 0; mm < VEC_MCH; mm++) w2[mm] = __ldg(bq + (long)n3 * mcl[mm]);
+          }
 #pragma unroll
           for (int mm = 0; mm < VEC_MCH; mm++) {
-            const int m = min(m0 + mm, P.nmom - 1);
-            const long off = (long)d.n3 * (m + (long)d.nmomt * p);
-            float v = __fadd_rn(__fmul_rn(__ldg(b0 + off), oma), __fmul_rn(__ldg(b1 + off), arh));
+            const float v = __fadd_rn(__fmul_rn(v2[mm].x, oma), __fmul_rn(v2[mm].y, arh));
             acc[mm][p] = __fadd_rn(acc[mm][p], __fmul_rn(__fmul_rn(v, ssa_), tau_));
+          }
+          if (two) {
+#pragma unroll
+            for (int mm = 0; mm < VEC_MCH; mm++) {
+              const float v = __fadd_rn(__fmul_rn(w2[mm].x, oma), __fmul_rn(w2[mm].y, arh));
+              acc[mm][p + 1] = __fadd_rn(acc[mm][p + 1], __fmul_rn(__fmul_rn(v, ssa_), tau_));
+            }
           }
         }
       }
@@ -780,6 +796,7 @@ extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh
   T.o_refr = take(n3); T.o_refi = take(n3); T.o_pback = take(n3 * npol); T.o_pmom = take(n3 * nmom * npol);
   T.o_reff = take(n2); T.o_gf = take(n2); T.o_rhop = take(n2); T.o_rhod = take(n2); T.o_vol = take(n2);
   T.o_area = take(n2); T.o_rha = take(NRHHASH); T.o_rhi = take(NRHHASH);
+  T.o_pmom2 = take(2 * n3 * nmom * npol);
   T.total = o;
   AB_CUDA_OK(cudaMalloc(&T.pool, sizeof(float) * T.total));
   // stage raw doubles
@@ -809,6 +826,7 @@ extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh
   interp(d_refr, T.o_refr, 1, 1, 1, 0, -999.f); interp(d_refi, T.o_refi, 1, 1, 1, 1, -999.f);
   interp(d_pback, T.o_pback, 1, 1, npol, 0, 1.f);
   if (nmom > 0) interp(d_pmom, T.o_pmom, nmom, nmom_file, npol, 0, 0.f);
+  if (nmom > 0) { const long n = n3 * nmom * npol; k_pair_rows<<<grid_for(n, 256), 256>>>(P + T.o_pmom, reinterpret_cast<float2 *>(P + T.o_pmom2), nrh, n); }
   k_derived<<<(int)((n2 + 127) / 128), 128>>>(d_reff, d_gf, d_rhop, nrh, nbin, P + T.o_reff, P + T.o_gf, P + T.o_rhop,
                                               P + T.o_rhod, P + T.o_vol, P + T.o_area);
   k_rhhash<<<(std::max(NRHHASH, nrh) + 127) / 128, 128>>>(d_rh, nrh, P + T.o_rh, P + T.o_rha, (int *)(P + T.o_rhi));
@@ -878,6 +896,7 @@ static int build_params(ab200_mie *h, int km, int nobs, int nch, int nq, const f
     d.bext = B + T.o_bext + b3; d.bsca = B + T.o_bsca + b3; d.g = B + T.o_g + b3; d.bbck = B + T.o_bbck + b3;
     d.refr = B + T.o_refr + b3; d.refi = B + T.o_refi + b3; d.pback = B + T.o_pback + b3;
     d.pmom = B + T.o_pmom + b3; d.vol = B + T.o_vol + b2; d.area = B + T.o_area + b2;
+    d.pmom2 = reinterpret_cast<const float2 *>(B + T.o_pmom2) + b3;
     d.rha = B + T.o_rha; d.rhi = (const int *)(B + T.o_rhi);
     d.nrh = T.nrh; d.n3 = (int)n3; d.nmomt = T.nmom; d.qidx = iq;
     d.p22off = T.npol >= 5 ? (int)(4 * n3) : 0;
@@ -993,7 +1012,9 @@ extern "C" int ab200_get_aop_vector_dev(ab200_mie *h, int km, int nobs, int nch,
   if (e || rc_) return e ? e : rc_;
   long nout = (long)km * nch * nobs;
   if (nout == 0) return 0;
-  k_aop_vector<<<(unsigned)((nout + 31) / 32), 32 * VEC_NW, 0, (cudaStream_t)stream>>>(P, qm, rh, tau, ssa, g, pmom);
+  const size_t vsmem = (size_t)VEC_NW * 4 * P.nqa * 32 * 4;
+  AB_CUDA_OK(cudaFuncSetAttribute(k_aop_vector, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(vsmem, 1024)));
+  k_aop_vector<<<(unsigned)((nout + 32 * VEC_NW - 1) / (32 * VEC_NW)), 32 * VEC_NW, vsmem, (cudaStream_t)stream>>>(P, qm, rh, tau, ssa, g, pmom);
   AB_CUDA_OK(cudaGetLastError());
   return 0;
 }

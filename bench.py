@@ -216,6 +216,7 @@ class RtVectorWorkload:
         tau, ssa, g, pmom, rc = mie.getaopvector([550.0], st["vnames"], 0, st["qm"], st["rh"], self.nmom, 6)
         self.aop_e2e_voxels_per_s = self.km * self.nobs / (time.perf_counter() - t0)
         assert rc == 0
+        self.aop_vector = self._time_aop_vector(mie, st)
         pe, ze, te = MieObs_.getedgevars(st["airdens"], st["delp"], 1.0)
         self.mie, self.state = mie, st                       # kept for the fused-pipeline leg
         pmom = pmom.astype(np.float64); pmom[..., 1] *= -1.0; pmom[..., 3] *= -1.0
@@ -227,6 +228,40 @@ class RtVectorWorkload:
         return dict(channels=ch, ROT=F(ROT), depol=depol, alpha=np.zeros_like(F(ROT)), tau=F(tau), ssa=F(ssa), pmom=F(pmom),
                     pe=F(pe), he=F(ze), te=F(te), albedo=F(rng.uniform(0.02, 0.4, (n, 1))), sza=rng.uniform(0, 75, n),
                     raa=rng.uniform(0, 180, n), vza=rng.uniform(0, 65, n), flux=np.ones((1, n), order="F"))
+
+    def _time_aop_vector(self, mie, st):
+        """k_aop_vector (getAOPvector with the nMom x 6 phase-matrix moments) on device-resident inputs: voxels/s and the
+        HBM bandwidth its algorithmic bytes (4 (nq+1) + 4 nch (3 + nMom nPol) per voxel) amount to"""
+        import ctypes as C
+        import torch
+        from aeroapps_b200._lib import lib, check
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nq, nvox = len(st["vnames"]), self.km * self.nobs
+        d_qm = torch.from_numpy(np.ascontiguousarray(st["qm"].T)).to(dev); d_rh = torch.from_numpy(np.ascontiguousarray(st["rh"].T)).to(dev)
+        outs = [torch.empty(nvox, dtype=torch.float32, device=dev) for _ in range(3)]
+        d_pm = torch.empty(nvox * self.nmom * 6, dtype=torch.float32, device=dev)
+        ch = np.array([550.0], np.float32); vn = self.mt.pad_names(st["vnames"])
+        p = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_float))
+        rc = C.c_int(0)
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def run():
+            check(lib().ab200_get_aop_vector_dev(mie.handle, self.km, self.nobs, 1, nq, ch.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 vn.ctypes.data_as(C.c_char_p), p(d_qm), p(d_rh), self.nmom, 6, p(outs[0]), p(outs[1]),
+                                                 p(outs[2]), p(d_pm), C.c_void_p(stream), C.byref(rc)), "aop_vector_dev")
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(5):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        bpu = 4 * (nq + 1) + 4 * (3 + self.nmom * 6)
+        gbs = nvox * bpu / (ms * 1e-3) / 1e9
+        pk = peaks()
+        return {"kernel": "k_aop_vector", "voxels_per_s": nvox / (ms * 1e-3), "ms": ms, "bytes_per_unit": bpu, "achieved_gbs": gbs,
+                "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "voxels": nvox, "nMom": self.nmom, "nPol": 6}
 
     def setup_gpu(self, torch, dev):
         import ctypes as C
@@ -572,6 +607,7 @@ def main():
         if rank == 0:
             out["aop"] = {k: aop[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "config")}
             out["aop"]["vector_e2e_voxels_per_s_nmom300"] = getattr(wl, "aop_e2e_voxels_per_s", None)
+            out["aop"]["vector"] = getattr(wl, "aop_vector", None)
     if rank == 0:
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
