@@ -82,6 +82,40 @@ struct WarpTeam {
   }
 };
 
+// two warps (2j, 2j+1 of the CTA, i.e. two different schedulers) working on one problem: K2 with twice the warps per SM for the
+// same shared-memory footprint.  Collectives: named barrier 1 + j (64 threads) and a 4-double exchange area `xch`.
+struct DuoTeam {
+  int rank;
+  static constexpr int size = 64;
+  int bar;
+  double *xch;
+  DEVFN DuoTeam(double *exchange) : rank(((threadIdx.x >> 5) & 1) * 32 + (threadIdx.x & 31)), bar(1 + (threadIdx.x >> 6)), xch(exchange) {}
+  DEVFN void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+  DEVFN double sum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    sync();
+    if ((rank & 31) == 0) xch[rank >> 5] = v;
+    sync();
+    return xch[0] + xch[1];
+  }
+  DEVFN double bcast0(double v) const { sync(); if (rank == 0) xch[2] = v; sync(); return xch[2]; }
+  DEVFN double argmax(double v, int &idx) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    sync();
+    if ((rank & 31) == 0) { xch[rank >> 5] = v; xch[2 + (rank >> 5)] = (double)idx; }
+    sync();
+    const double v0 = xch[0], v1 = xch[1]; const int i0 = (int)xch[2], i1 = (int)xch[3];
+    if (v1 > v0 || (v1 == v0 && i1 < i0)) { idx = i1; return v1; }
+    idx = i0; return v0;
+  }
+};
+
 // whole CTA; scratch must hold 64 doubles + 64 ints
 struct BlockTeam {
   int rank, size;

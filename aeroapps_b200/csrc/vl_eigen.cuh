@@ -89,6 +89,35 @@ DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n, do
   }
 }
 
+#ifndef AB_HOST_MODEL
+// the same rotation with the rows of the pair split over two neighbouring lanes (h = 0: rows [0, nh), h = 1: rows [nh, n)):
+// half the registers and half the dependent work per lane; the dot product is completed with one shuffle.  NRH >= rows per lane.
+template <int NRH>
+DEVFN double jacobi_halfpair(double *AB_RESTRICT a, double *AB_RESTRICT b, int r0, int nr, double &na2, double &nb2, bool writer, unsigned mask) {
+  double ra[NRH], rb[NRH];
+#pragma unroll
+  for (int r = 0; r < NRH; r++) { ra[r] = r < nr ? a[r0 + r] : 0.0; rb[r] = r < nr ? b[r0 + r] : 0.0; }
+  double gap[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int r = 0; r < NRH; r++) gap[r & 3] += ra[r] * rb[r];
+  double ga = (gap[0] + gap[1]) + (gap[2] + gap[3]);
+  ga += __shfl_xor_sync(mask, ga, 1);
+  const double al = na2, be = nb2;
+  const double rel = fabs(ga) * rsqrt(al * be + 1.0e-300);
+  if (rel > 1.0e-15) {
+    const double d = be - al, g2 = 2.0 * ga;
+    const double rt = sqrt(d * d + g2 * g2);
+    const double t = g2 / (d >= 0.0 ? d + rt : d - rt);
+    const double c = rsqrt(1.0 + t * t), s = c * t;
+    if (writer) { na2 = al - t * ga; nb2 = be + t * ga; }
+#pragma unroll
+    for (int r = 0; r < NRH; r++)
+      if (r < nr) { a[r0 + r] = c * ra[r] - s * rb[r]; b[r0 + r] = s * ra[r] + c * rb[r]; }
+  }
+  return rel;
+}
+#endif
+
 // back-transformation of eigenvector column e:  y = C u (in place in the column),  x = C^-T u (returned through xg)
 template <int NR>
 DEVFN void eig_backtransform(const double *AB_RESTRICT B1, int LDB, double *AB_RESTRICT col, double isig, int n, double *AB_RESTRICT xg) {
@@ -252,6 +281,31 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
       }
       T.sync();
       for (int st = 0; st < np - 1; st++) {
+#ifndef AB_HOST_MODEL
+        if constexpr (Team::size == 64) {
+          // two warps per problem: warp w takes the pairs [w ppw, (w+1) ppw), two lanes per pair (row halves)
+          const int ppw = (half + 1) / 2, w = T.rank >> 5, lane = T.rank & 31, h = lane & 1;
+          const int t = w * ppw + (lane >> 1);
+          const bool act = (lane >> 1) < ppw && t < half;
+          int a = 0, b = 0;
+          if (act) { if (t == 0) { a = np - 1; b = st; } else { a = st + t; if (a >= np - 1) a -= np - 1; b = st - t; if (b < 0) b += np - 1; } }
+          const bool run = act && a < n && b < n;
+          const unsigned rmask = __ballot_sync(0xffffffffu, run);
+          const int nh = (n + 1) / 2, r0 = h ? nh : 0, nr = h ? n - nh : nh;
+          double rel = 0.0;
+          // (the shuffle inside needs both lanes of a pair: pairs are either fully active or fully idle)
+          if (run) {
+            double na2 = nrm2[a], nb2 = nrm2[b];
+            if (n <= 12) rel = jacobi_halfpair<6>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
+            else if (n <= 24) rel = jacobi_halfpair<12>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
+            else rel = jacobi_halfpair<18>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
+            if (h == 0) { nrm2[a] = na2; nrm2[b] = nb2; }
+          }
+          if (rel > offmax) offmax = rel;
+          T.sync();
+          continue;
+        }
+#endif
         for (int t = T.rank; t < half; t += T.size) {
           int a, b;
           if (t == 0) { a = np - 1; b = st; } else { a = st + t; if (a >= np - 1) a -= np - 1; b = st - t; if (b < 0) b += np - 1; }

@@ -48,6 +48,20 @@ __global__ void __launch_bounds__(256) k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, c
   eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)warp * scr_doubles);
 }
 
+// two warps per (pixel, layer) problem (DuoTeam): same shared memory per problem, twice the warps per SM
+template <int S>
+__global__ void __launch_bounds__(256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
+                                                        const int *__restrict__ active, int nactive, int scr_doubles) {
+  extern __shared__ double smem_d[];
+  const int duo = threadIdx.x >> 6, ppc = blockDim.x >> 6;
+  const long prob = (long)blockIdx.x * ppc + duo;
+  if (prob >= (long)nactive * X.L) return;                  // both warps of a duo leave together: no barrier is left short
+  const int p = active[prob / X.L], k = (int)(prob % X.L);
+  double *scr = smem_d + (size_t)duo * (scr_doubles + 4);
+  DuoTeam T(scr + scr_doubles);
+  eigen_problem<S>(T, X, Z, QD, pq, m, p, k, scr);
+}
+
 // VAR: forward-elimination variant, one kernel each (own register allocation): 0 = blocked look-ahead (vl_bvp.cuh, the default),
 // 1 = the same with the window in a per-CTA HBM scratch ("large n"), 3 = warp-specialised (vl_bvp3.cuh), 4 = register-resident
 // window (vl_bvp4.cuh)
@@ -289,7 +303,11 @@ int run_vlidort(const RunDesc &R) {
   if (wpc >= 4) wpc /= 2;
   if (const char *e = getenv("AB200_VL_EIGEN_WARPS")) wpc = std::max(1, std::min(wpc, atoi(e)));      // tuning knob
   if (wpc < 1) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory eigen scratch"); return AB200_ERR_ARG; }
-  const size_t eig_smem = (size_t)wpc * scr_d * 8;
+  // two warps per problem (k_vl_eigen_duo) when the register-resident Jacobi applies (n <= 36); AB200_VL_EIGEN_DUO=0 switches it off
+  bool duo = n <= 36 && n >= 24;
+  if (const char *e = getenv("AB200_VL_EIGEN_DUO")) duo = duo && atoi(e) != 0;
+  const size_t eig_smem = duo ? (size_t)wpc * (scr_d + 4) * 8 : (size_t)wpc * scr_d * 8;
+  if (duo) ke = (S == 1) ? (const void *)k_vl_eigen_duo<1> : (const void *)k_vl_eigen_duo<3>;
   AB_CUDA_OK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
   const size_t setup_smem = (size_t)(12 * (L + 1) + 2 * (R.nMom + 1) + 2 * 4 + 16) * 8;
 
@@ -384,7 +402,10 @@ int run_vlidort(const RunDesc &R) {
       const int egrid = (int)((nprob + wpc - 1) / wpc);
       const double *pqm = d_pq + (size_t)m * (NM + 1) * N * 3;
       cudaEventRecord(ev[0], st);
-      if (S == 1) k_vl_eigen<1><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+      if (duo) {
+        if (S == 1) k_vl_eigen_duo<1><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+        else k_vl_eigen_duo<3><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+      } else if (S == 1) k_vl_eigen<1><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
       else k_vl_eigen<3><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
       cudaEventRecord(ev[1], st);
       const int bgrid = std::min(nactive, bvp_grid_max);
