@@ -47,7 +47,7 @@ def test_scalar_lambert(mods, N, planpar, nobs, nch):
     assert rel(R, ref["reflectance"], ref["reflectance"]) < TOL
 
 
-@pytest.mark.parametrize("N,planpar,nobs", [(6, False, 12), (12, True, 6), (4, False, 3)])
+@pytest.mark.parametrize("N,planpar,nobs", [(6, False, 12), (12, True, 6), (4, False, 3), (9, False, 3), (10, True, 2)])
 def test_vector_lambert(mods, N, planpar, nobs):
     VP, vg = mods
     sc = vg.synthetic_scene(nobs, nmom=80, seed=60 + N)
