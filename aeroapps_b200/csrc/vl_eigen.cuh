@@ -90,7 +90,7 @@ DEVFN double jacobi_pair(double *AB_RESTRICT a, double *AB_RESTRICT b, int n, do
 }
 
 #ifndef AB_HOST_MODEL
-// the same rotation with the rows of the pair split over two neighbouring lanes (h = 0: rows [0, nh), h = 1: rows [nh, n)):
+// the same rotation with the rows of the pair split over two lanes 16 apart (h = 0: rows [0, nh), h = 1: rows [nh, n)):
 // half the registers and half the dependent work per lane; the dot product is completed with one shuffle.  NRH >= rows per lane.
 template <int NRH>
 DEVFN double jacobi_halfpair(double *AB_RESTRICT a, double *AB_RESTRICT b, int r0, int nr, double &na2, double &nb2, bool writer, unsigned mask) {
@@ -101,7 +101,7 @@ DEVFN double jacobi_halfpair(double *AB_RESTRICT a, double *AB_RESTRICT b, int r
 #pragma unroll
   for (int r = 0; r < NRH; r++) gap[r & 3] += ra[r] * rb[r];
   double ga = (gap[0] + gap[1]) + (gap[2] + gap[3]);
-  ga += __shfl_xor_sync(mask, ga, 1);
+  ga += __shfl_xor_sync(mask, ga, 16);
   const double al = na2, be = nb2;
   const double rel = fabs(ga) * rsqrt(al * be + 1.0e-300);
   if (rel > 1.0e-15) {
@@ -283,10 +283,12 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
       for (int st = 0; st < np - 1; st++) {
 #ifndef AB_HOST_MODEL
         if constexpr (Team::size == 64) {
-          // two warps per problem: warp w takes the pairs [w ppw, (w+1) ppw), two lanes per pair (row halves)
-          const int ppw = (half + 1) / 2, w = T.rank >> 5, lane = T.rank & 31, h = lane & 1;
-          const int t = w * ppw + (lane >> 1);
-          const bool act = (lane >> 1) < ppw && t < half;
+          // two warps per problem: warp w takes the pairs [w ppw, (w+1) ppw), two lanes per pair (row halves).  The two halves of a
+          // pair sit 16 lanes apart: a half-warp then only holds equal halves of consecutive columns, whose 8-byte words fall
+          // into distinct banks (odd LDA) -- with neighbouring lanes a third of the column traffic was bank conflicts
+          const int ppw = (half + 1) / 2, w = T.rank >> 5, lane = T.rank & 31, h = lane >> 4;
+          const int t = w * ppw + (lane & 15);
+          const bool act = (lane & 15) < ppw && t < half;
           int a = 0, b = 0;
           if (act) { if (t == 0) { a = np - 1; b = st; } else { a = st + t; if (a >= np - 1) a -= np - 1; b = st - t; if (b < 0) b += np - 1; } }
           const bool run = act && a < n && b < n;
