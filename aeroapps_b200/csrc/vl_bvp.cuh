@@ -43,9 +43,10 @@ struct VLConv {                  // per pixel, persistent over the Fourier loop
 HDFN int bvp_cols(int n) { return 4 * n + 1; }
 HDFN int bvp_stride(int n) { return (4 * n + 1) | 1; }                         // odd row stride
 constexpr int BVP_NB = 8;                                                        // panel width of the blocked elimination
+constexpr int BVP_LS = BVP_NB + 1;   // row stride of the multiplier panels: odd, so that the per-row stores of a panel column are conflict-free
 // big region: forward phase = window + double-buffered panel arrays; backward phase = two buffers of pivot rows
 HDFN size_t bvp_big_doubles(int n) {
-  const size_t fwd = (size_t)3 * n * bvp_stride(n) + 2 * ((size_t)3 * n * BVP_NB + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB);
+  const size_t fwd = (size_t)3 * n * bvp_stride(n) + 2 * ((size_t)3 * n * BVP_LS + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB);
   const size_t bwd = (size_t)2 * (2 * n) * bvp_cols(n);
   return ((fwd > bwd ? fwd : bwd) + 1) & ~(size_t)1;
 }
@@ -53,7 +54,7 @@ HDFN size_t bvp_smem_doubles(int n) { return bvp_big_doubles(n) + 8 * n + 16; }
 // "large n" layout (3*nstreams*nstokes rows no longer fit the 227 KB of shared memory, e.g. nstokes 3 x 16 streams): the
 // window lives in a per-CTA HBM scratch (L1/L2 resident), shared memory keeps the panel arrays and ONE buffer of pivot rows
 HDFN size_t bvp_big_doubles_g(int n) {
-  const size_t fwd = 2 * ((size_t)3 * n * BVP_NB + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB);
+  const size_t fwd = 2 * ((size_t)3 * n * BVP_LS + (size_t)BVP_NB * bvp_stride(n) + BVP_NB * BVP_NB);
   const size_t bwd = (size_t)(2 * n) * bvp_cols(n);
   return ((fwd > bwd ? fwd : bwd) + 1) & ~(size_t)1;
 }
@@ -82,7 +83,7 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
     if (upd && act[u]) {
 #pragma unroll
       for (int jj = 0; jj < BVP_NB; jj++) {
-        const double l = jj < nbp ? LpP[r * BVP_NB + jj] : 0.0;
+        const double l = jj < nbp ? LpP[r * BVP_LS + jj] : 0.0;
 #pragma unroll
         for (int j = 0; j < BVP_NB; j++) if (j < nb) pv[u][j] -= l * UbP[jj * Cs + jc0 + j];
       }
@@ -127,12 +128,12 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
 #pragma unroll
             for (int jj = 0; jj < BVP_NB; jj++) if (jj > j) pv[u][jj] -= l * prow[jj];
           }
-          if (r < R) LpN[r * BVP_NB + j] = l;                    // multipliers straight to shared memory
+          if (r < R) LpN[r * BVP_LS + j] = l;                    // multipliers straight to shared memory
         }
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < RU; u++) { const int r = T.rank + PW * u; if (r < R) LpN[r * BVP_NB + j] = 0.0; }
+      for (int u = 0; u < RU; u++) { const int r = T.rank + PW * u; if (r < R) LpN[r * BVP_LS + j] = 0.0; }
     }
   }
 #pragma unroll
@@ -142,12 +143,12 @@ DEVFN void bvp_panel(const Team &T, double *AB_RESTRICT W, int Cs, int R, int *s
   if (!pfail) {
     for (int idx = T.rank; idx < BVP_NB * BVP_NB; idx += PW) {
       const int j = idx / BVP_NB, jj = idx % BVP_NB;
-      if (j < nb) LUpN[idx] = (jj < j) ? LpN[pivrow[jc0 + j] * BVP_NB + jj] : 0.0;
+      if (j < nb) LUpN[idx] = (jj < j) ? LpN[pivrow[jc0 + j] * BVP_LS + jj] : 0.0;
     }
     T.psync();
     for (int idx = T.rank; idx < BVP_NB * BVP_NB; idx += PW) {
       const int j = idx / BVP_NB, jj = idx % BVP_NB;
-      if (j < nb) LpN[pivrow[jc0 + j] * BVP_NB + jj] = 0.0;
+      if (j < nb) LpN[pivrow[jc0 + j] * BVP_LS + jj] = 0.0;
     }
   }
   if (pfail && T.rank == 0) iflag[0] = 1;
@@ -202,7 +203,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
   double *xnext = xcur + n2;              // 2n
   double *red = xnext + n2;               // 4n scratch
   double *Lp = wglob ? scr : W + (size_t)R * Cs;   // 2 x (R x NB) multipliers of the current / next panel
-  double *Ub = Lp + (size_t)2 * R * BVP_NB;   // 2 x (NB x Cs) finished pivot rows of the current / next panel
+  double *Ub = Lp + (size_t)2 * R * BVP_LS;   // 2 x (NB x Cs) finished pivot rows of the current / next panel
   double *LUp = Ub + (size_t)2 * BVP_NB * Cs; // 2 x (NB x NB) multipliers of the pivot rows inside the panel
   int *state = iscr;                      // R : -1 unused, 0 active, 1+t pivot number t
   int *pivrow = state + R;                // 2n
@@ -349,8 +350,8 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
         const int jc0 = P * BVP_NB, nb = (n2 - jc0 < BVP_NB) ? n2 - jc0 : BVP_NB;
         const bool has_next = P + 1 < npanel;
         const int jc1 = jc0 + nb, nb1 = has_next ? ((n2 - jc1 < BVP_NB) ? n2 - jc1 : BVP_NB) : 0;
-        double *LpC = Lp + (size_t)(P & 1) * R * BVP_NB, *UbC = Ub + (size_t)(P & 1) * BVP_NB * Cs;
-        double *LpN = Lp + (size_t)((P + 1) & 1) * R * BVP_NB, *UbN = Ub + (size_t)((P + 1) & 1) * BVP_NB * Cs;
+        double *LpC = Lp + (size_t)(P & 1) * R * BVP_LS, *UbC = Ub + (size_t)(P & 1) * BVP_NB * Cs;
+        double *LpN = Lp + (size_t)((P + 1) & 1) * R * BVP_LS, *UbN = Ub + (size_t)((P + 1) & 1) * BVP_NB * Cs;
         double *LUpN = LUp + ((P + 1) & 1) * BVP_NB * BVP_NB;
         const int *rflagC = rflag + (P & 1) * R;
         if (has_next) {
@@ -360,7 +361,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
             if (j < nb1) {
               double a = W[(size_t)r * Cs + jc1 + j];
 #pragma unroll
-              for (int jj = 0; jj < BVP_NB; jj++) a -= LpC[r * BVP_NB + jj] * UbC[jj * Cs + jc1 + j];
+              for (int jj = 0; jj < BVP_NB; jj++) a -= LpC[r * BVP_LS + jj] * UbC[jj * Cs + jc1 + j];
               W[(size_t)r * Cs + jc1 + j] = a;
             }
           }
@@ -390,7 +391,7 @@ DEVFN void bvp_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLQuad
 #pragma unroll
             for (int rr = 0; rr < RG; rr++)
 #pragma unroll
-              for (int j = 0; j < BVP_NB; j++) l[rr][j] = (r0 + rr < R) ? LpC[(r0 + rr) * BVP_NB + j] : 0.0;
+              for (int j = 0; j < BVP_NB; j++) l[rr][j] = (r0 + rr < R) ? LpC[(r0 + rr) * BVP_LS + j] : 0.0;
             for (int c = cbeg + lane; c < Cc; c += 2 * LW) {
               const int c2 = c + LW;
               const bool two = c2 < Cc;
