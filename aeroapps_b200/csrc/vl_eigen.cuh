@@ -301,6 +301,7 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
             if (n <= 12) rel = jacobi_halfpair<6>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
             else if (n <= 24) rel = jacobi_halfpair<12>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
             else rel = jacobi_halfpair<18>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
+            __syncwarp(rmask);                                 // the partner lane has read the old norms (racecheck-clean ordering)
             if (h == 0) { nrm2[a] = na2; nrm2[b] = nb2; }
           }
           if (rel > offmax) offmax = rel;
