@@ -1030,14 +1030,27 @@ extern "C" int ab200_get_aop_scalar(ab200_mie *h, int km, int nobs, int nch, int
   AB_CUDA_OK(h->ws_out.reserve(4 * 3 * nout + 256));
   float *d_qm = h->ws_in.as<float>(), *d_rh = d_qm + nin_q;
   float *d_tau = h->ws_out.as<float>(), *d_ssa = d_tau + nout, *d_g = d_ssa + nout;
-  AB_CUDA_OK(cudaMemcpyAsync(d_qm, qm, 4 * nin_q, cudaMemcpyHostToDevice, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(d_rh, rh, 4 * nin_r, cudaMemcpyHostToDevice, 0));
-  int e = ab200_get_aop_scalar_dev(h, km, nobs, nch, nq, channels, vname, d_qm, d_rh, d_tau, d_ssa, d_g, 0, rc);
-  if (e) return e;
-  AB_CUDA_OK(cudaMemcpyAsync(tau, d_tau, 4 * nout, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(ssa, d_ssa, 4 * nout, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(g, d_g, 4 * nout, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaStreamSynchronize(0));
+  // large calls: four slices of columns on two streams, so that the upload of slice c+1 overlaps the kernel and the download of
+  // slice c (columns are the slowest dimension of every array: plain 1-D slices); the call is PCIe bound either way
+  const int nslice = (nobs >= 4096) ? 4 : 1;
+  static cudaStream_t sst[2] = {nullptr, nullptr};
+  if (nslice > 1 && !sst[0]) { AB_CUDA_OK(cudaStreamCreateWithFlags(&sst[0], cudaStreamNonBlocking)); AB_CUDA_OK(cudaStreamCreateWithFlags(&sst[1], cudaStreamNonBlocking)); }
+  const int per = (nobs + nslice - 1) / nslice;
+  for (int c = 0; c < nslice; c++) {
+    const int j0 = c * per, w = std::min(per, nobs - j0);
+    if (w <= 0) break;
+    cudaStream_t st = nslice > 1 ? sst[c & 1] : (cudaStream_t)0;
+    const size_t oq = (size_t)km * nq * j0, orh = (size_t)km * j0, oo = (size_t)km * nch * j0;
+    AB_CUDA_OK(cudaMemcpyAsync(d_qm + oq, qm + oq, 4 * (size_t)km * nq * w, cudaMemcpyHostToDevice, st));
+    AB_CUDA_OK(cudaMemcpyAsync(d_rh + orh, rh + orh, 4 * (size_t)km * w, cudaMemcpyHostToDevice, st));
+    int e = ab200_get_aop_scalar_dev(h, km, w, nch, nq, channels, vname, d_qm + oq, d_rh + orh, d_tau + oo, d_ssa + oo, d_g + oo, st, rc);
+    if (e) return e;
+    AB_CUDA_OK(cudaMemcpyAsync(tau + oo, d_tau + oo, 4 * (size_t)km * nch * w, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaMemcpyAsync(ssa + oo, d_ssa + oo, 4 * (size_t)km * nch * w, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaMemcpyAsync(g + oo, d_g + oo, 4 * (size_t)km * nch * w, cudaMemcpyDeviceToHost, st));
+  }
+  if (nslice > 1) { AB_CUDA_OK(cudaStreamSynchronize(sst[0])); AB_CUDA_OK(cudaStreamSynchronize(sst[1])); }
+  else AB_CUDA_OK(cudaStreamSynchronize(0));
   return 0;
 }
 
