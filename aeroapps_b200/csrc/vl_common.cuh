@@ -80,6 +80,35 @@ struct WarpTeam {
     }
     return v;
   }
+  // the K3 interface (panel sub-team = the whole warp): lets one warp run a whole boundary-value problem when nstokes*nstreams is
+  // small (3n <= 64 window rows), several pixels per CTA
+  static constexpr int PW = 32, PRU = 2;
+  DEVFN void psync() const { __syncwarp(); }
+  DEVFN double pargmax(double v, int &idx) const {
+    const unsigned long long key = v < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(v);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const bool cand = (hi == mh) && (lo == ml);
+    idx = (int)__reduce_min_sync(0xffffffffu, cand ? (unsigned)idx : 0x7fffffffu);
+    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  }
+  template <int N_>
+  DEVFN void pbcast_n(double (&v)[N_], int j0, int owner) const {
+#pragma unroll
+    for (int j = 0; j < N_; j++) if (j >= j0) v[j] = __shfl_sync(0xffffffffu, v[j], owner);
+  }
+  DEVFN int wfetch(int *ctr) const {
+    int g = 0;
+    if (rank == 0) g = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, g, 0);
+  }
+  DEVFN void load_begin(double *dst, const double *src, size_t n) const {
+    __syncwarp();
+    for (size_t i = rank; i < n; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
+  DEVFN void load_wait() const {}
 };
 
 // two warps (2j, 2j+1 of the CTA, i.e. two different schedulers) working on one problem: K2 with twice the warps per SM for the

@@ -97,6 +97,35 @@ __global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLS
   }
 }
 
+// K3 for small problems (3 nstokes nstreams <= 64 window rows, e.g. the scalar 8-stream configuration): one WARP per pixel with its
+// own window in shared memory, several pixels per CTA -- the 384-thread kernel above leaves the SM almost idle on a 24 x 33 window
+template <int S>
+__global__ void __launch_bounds__(256) k_vl_bvp_warp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
+                                                     int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
+                                                     int *__restrict__ next_count, double *__restrict__ work, size_t work_per_warp,
+                                                     int smem_doubles_per_warp) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int n = S * QD.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  double *scr = smem_d + (size_t)warp * smem_doubles_per_warp;
+  for (int i = lane; i < smem_doubles_per_warp; i += 32) scr[i] = 0.0;
+  __syncwarp();
+  int *iscr = reinterpret_cast<int *>(scr + bvp_smem_doubles(n));
+  WarpTeam T;
+  const int gw = blockIdx.x * wpc + warp;
+  double *Ug = work + (size_t)gw * work_per_warp;
+  for (int a = gw; a < nactive; a += gridDim.x * wpc) {
+    const int p = active[a];
+    if (Z.fail[p]) {
+      if (lane == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
+    } else {
+      bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, scr, iscr, Ug);
+    }
+    __syncwarp();
+    if (lane == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
+    __syncwarp();
+  }
+}
+
 // K0a: exact direct-bounce BRDF of every pixel + the wrappers' BR outputs (nobs,nch)
 __global__ void k_vl_brdf_exact(VLBrdf B, int npix, const unsigned char *__restrict__ skip, double *BR, double *BR_Q, double *BR_U) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,7 +321,21 @@ int run_vlidort(const RunDesc &R) {
   AB_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvp_smem));
   AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bvp_per_sm, kb, bvp_threads, bvp_smem));
   bvp_per_sm = std::max(1, std::min(bvp_per_sm, 8));
-  const int bvp_grid_max = nsm * bvp_per_sm;
+  // small problems (3n <= 64 window rows): one warp per pixel, 4 pixels per CTA (k_vl_bvp_warp); AB200_VL_BVP_WARP=0 switches it off
+  bool warp_bvp = !use_v3 && !big_n && 3 * n <= 64;
+  if (const char *e = getenv("AB200_VL_BVP_WARP")) warp_bvp = warp_bvp && atoi(e) != 0;
+  const int wb_wpc = 4;
+  const size_t wb_smem_d = (bvp_smem_doubles(n) + (size_t)(13 * n + 32 + 1) / 2 + 2 + 1) & ~(size_t)1;     // per warp, doubles (ints behind)
+  const size_t wb_smem = wb_smem_d * 8 * wb_wpc;
+  auto kw = (S == 1) ? (const void *)k_vl_bvp_warp<1> : (const void *)k_vl_bvp_warp<3>;
+  int wb_per_sm = 1;
+  if (warp_bvp) {
+    AB_CUDA_OK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb_smem));
+    AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wb_per_sm, kw, 32 * wb_wpc, wb_smem));
+    wb_per_sm = std::max(1, std::min(wb_per_sm, 16));
+  }
+  // (work buffers: one per concurrently running solver = CTA of the block kernel, or warp of the warp kernel)
+  const int bvp_grid_max = warp_bvp ? nsm * wb_per_sm * wb_wpc : nsm * bvp_per_sm;
   const size_t work_per_cta = bvp_work_doubles(n, L);
   const size_t bvp_work_bytes = (size_t)bvp_grid_max * (work_per_cta + (big_n ? bvp_window_doubles(n) : 0)) * 8;
   // K2 geometry
@@ -410,6 +453,11 @@ int run_vlidort(const RunDesc &R) {
       cudaEventRecord(ev[1], st);
       const int bgrid = std::min(nactive, bvp_grid_max);
       int *cnt = counts + 1 + m;
+      if (warp_bvp) {
+        const int wgrid = std::min((nactive + wb_wpc - 1) / wb_wpc, nsm * wb_per_sm);
+        if (S == 1) k_vl_bvp_warp<1><<<wgrid, 32 * wb_wpc, wb_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, (int)wb_smem_d);
+        else k_vl_bvp_warp<3><<<wgrid, 32 * wb_wpc, wb_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, (int)wb_smem_d);
+      } else
       kbf<<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());

@@ -444,7 +444,48 @@ class RtVectorCxWorkload(RtVectorWorkload):
         return n * self.nch, time.perf_counter() - t0
 
 
-WORKLOADS = {"aop_scalar": AopScalarWorkload, "rt_vector": RtVectorWorkload, "rt_vector_cx": RtVectorCxWorkload}
+class RtScalarWorkload(RtVectorWorkload):
+    """BASELINE.json configs[1]: scalar VLIDORT (nstokes = 1), 8 streams, 72 layers, Lambertian surface, nMom = 64 (not the headline
+    workload; `python bench.py --workload rt_scalar`).  Only the reference-style host entry exists for the scalar form, so the
+    device-resident leg runs the same call: `value` includes the PCIe copies here and equals `e2e` up to noise."""
+    name = "vlidort_scalar_n8_l72_lambert"
+    metric = "VLIDORT pixels/sec (scalar nstokes=1, 8 streams, 72 layers, nMom=64, FO + delta-M, Lambertian surface)"
+    km, nobs, nch, N, S, nmom = 72, 16384, 1, 8, 1, 64
+
+    def setup_gpu(self, torch, dev):
+        super().setup_gpu(torch, dev)
+        g = np.zeros(self.km * self.nobs)                      # the scalar wrapper takes g but does not use it
+        self.h["g"] = torch.from_numpy(g).pin_memory()
+        self.h_out = [torch.empty(self.nobs * self.nch, dtype=torch.float64).pin_memory() for _ in range(2)]
+        keys = ["ROT", "depol", "tau", "ssa", "g", "pmom", "pe", "he", "te", "albedo", "sza", "raa", "vza"]
+        self.h2d = sum(self.h[k].numel() * 8 for k in keys)
+        self.d2h = 2 * self.nobs * self.nch * 8
+
+    def step_e2e(self):
+        C, h, p = self.C, self.h, self._p
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_vlidort_scalar_lambert(
+            self.km, self.nch, self.nobs, p(h["channels"]), self.N, int(self.plane_parallel), self.nmom, 6, p(h["ROT"]), p(h["depol"]),
+            p(h["tau"]), p(h["ssa"]), p(h["g"]), p(h["pmom"]), p(h["pe"]), p(h["he"]), p(h["te"]), p(h["albedo"]), p(h["sza"]),
+            p(h["raa"]), p(h["vza"]), C.c_double(1e15), 0, p(self.h_out[0]), p(self.h_out[1]), C.byref(rc)), "scalar_lambert")
+        assert rc.value == 0
+
+    def step_gpu(self, stream):
+        self.step_e2e()
+
+    def step_cpu(self, nthreads):
+        from concurrent.futures import ThreadPoolExecutor
+        s, n, vg = self.cpu_scene, self.sample_cols, self.vg
+        edges = np.linspace(0, n, nthreads + 1).astype(int)
+        rng = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(lambda ab: vg.vlidort_run(1, self.N, self.plane_parallel, s["ROT"], s["depol"], s["tau"], s["ssa"], s["pmom"], s["he"],
+                                                  s["sza"], s["raa"], s["vza"], albedo=s["albedo"], scalar_glue=True, obs_range=ab), rng))
+        return n * self.nch, time.perf_counter() - t0
+
+
+WORKLOADS = {"aop_scalar": AopScalarWorkload, "rt_vector": RtVectorWorkload, "rt_vector_cx": RtVectorCxWorkload, "rt_scalar": RtScalarWorkload}
 DEFAULT_WORKLOAD = "rt_vector_cx"
 
 
