@@ -111,6 +111,32 @@ struct WarpTeam {
   DEVFN void load_wait() const {}
 };
 
+// W = 8 or 16 neighbouring lanes of a warp working on one problem (small nstokes*nstreams: several problems per warp); every
+// collective carries the sub-team's lane mask, so the sub-teams of a warp may diverge freely
+template <int W>
+struct SubWarpTeam {
+  int rank;
+  static constexpr int size = W;
+  unsigned mask;
+  DEVFN SubWarpTeam() : rank(threadIdx.x & (W - 1)), mask(((1u << W) - 1u) << ((threadIdx.x & 31) & ~(W - 1))) {}
+  DEVFN void sync() const { __syncwarp(mask); }
+  DEVFN double sum(double v) const {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+  }
+  DEVFN double bcast0(double v) const { return __shfl_sync(mask, v, 0, W); }
+  DEVFN double argmax(double v, int &idx) const {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+      double ov = __shfl_xor_sync(mask, v, o);
+      int oi = __shfl_xor_sync(mask, idx, o);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    return v;
+  }
+};
+
 // two warps (2j, 2j+1 of the CTA, i.e. two different schedulers) working on one problem: K2 with twice the warps per SM for the
 // same shared-memory footprint.  Collectives: named barrier 1 + j (64 threads) and a 4-double exchange area `xch`.
 struct DuoTeam {

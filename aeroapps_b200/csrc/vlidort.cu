@@ -48,6 +48,21 @@ __global__ void __launch_bounds__(256) k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, c
   eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)warp * scr_doubles);
 }
 
+// W lanes per (pixel, layer) problem (SubWarpTeam): 32 / W problems per warp for small nstokes*nstreams (the scalar 8-stream
+// configuration keeps 4 of 32 lanes busy with one problem per warp)
+template <int S, int W>
+__global__ void __launch_bounds__(256) k_vl_eigen_sub(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
+                                                      const int *__restrict__ active, int nactive, int scr_doubles) {
+  extern __shared__ double smem_d[];
+  constexpr int SUBS = 32 / W;
+  const int slot = (threadIdx.x >> 5) * SUBS + ((threadIdx.x & 31) / W), spc = (blockDim.x >> 5) * SUBS;
+  const long prob = (long)blockIdx.x * spc + slot;
+  if (prob >= (long)nactive * X.L) return;
+  const int p = active[prob / X.L], k = (int)(prob % X.L);
+  SubWarpTeam<W> T;
+  eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)slot * scr_doubles);
+}
+
 // two warps per (pixel, layer) problem (DuoTeam): same shared memory per problem, twice the warps per SM
 template <int S>
 __global__ void __launch_bounds__(256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
@@ -351,7 +366,18 @@ int run_vlidort(const RunDesc &R) {
   if (const char *e = getenv("AB200_VL_EIGEN_DUO")) duo = duo && atoi(e) != 0;
   const size_t eig_smem = duo ? (size_t)wpc * (scr_d + 4) * 8 : (size_t)wpc * scr_d * 8;
   if (duo) ke = (S == 1) ? (const void *)k_vl_eigen_duo<1> : (const void *)k_vl_eigen_duo<3>;
-  AB_CUDA_OK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_smem));
+  // sub-warp teams for small problems: 8 lanes per problem up to n = 8, 16 up to n = 16 (AB200_VL_EIGEN_SUB=0 switches them off)
+  int subw = (n <= 8) ? 8 : (n <= 16 ? 16 : 32);
+  if (const char *e = getenv("AB200_VL_EIGEN_SUB")) { if (atoi(e) == 0) subw = 32; }
+  const int subs = 32 / subw;
+  size_t eig_smem_sub = 0;
+  int sub_warps = 4;
+  if (subw < 32) {
+    ke = (S == 1) ? (subw == 8 ? (const void *)k_vl_eigen_sub<1, 8> : (const void *)k_vl_eigen_sub<1, 16>)
+                  : (subw == 8 ? (const void *)k_vl_eigen_sub<3, 8> : (const void *)k_vl_eigen_sub<3, 16>);
+    eig_smem_sub = (size_t)sub_warps * subs * scr_d * 8;
+  }
+  AB_CUDA_OK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(subw < 32 ? eig_smem_sub : eig_smem)));
   const size_t setup_smem = (size_t)(12 * (L + 1) + 2 * (R.nMom + 1) + 2 * 4 + 16) * 8;
 
   size_t chunk = npix;
@@ -445,7 +471,13 @@ int run_vlidort(const RunDesc &R) {
       const int egrid = (int)((nprob + wpc - 1) / wpc);
       const double *pqm = d_pq + (size_t)m * (NM + 1) * N * 3;
       cudaEventRecord(ev[0], st);
-      if (duo) {
+      if (subw < 32) {
+        const int spc = sub_warps * subs, sgrid = (int)((nprob + spc - 1) / spc);
+        if (S == 1) { if (subw == 8) k_vl_eigen_sub<1, 8><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+                      else k_vl_eigen_sub<1, 16><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d); }
+        else { if (subw == 8) k_vl_eigen_sub<3, 8><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+               else k_vl_eigen_sub<3, 16><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d); }
+      } else if (duo) {
         if (S == 1) k_vl_eigen_duo<1><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
         else k_vl_eigen_duo<3><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
       } else if (S == 1) k_vl_eigen<1><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
