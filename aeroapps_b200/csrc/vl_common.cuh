@@ -139,12 +139,14 @@ struct SubWarpTeam {
 
 // two warps (2j, 2j+1 of the CTA, i.e. two different schedulers) working on one problem: K2 with twice the warps per SM for the
 // same shared-memory footprint.  Collectives: named barrier 1 + j (64 threads) and a 4-double exchange area `xch`.
-struct DuoTeam {
+template <int MAXHALF>
+struct DuoTeamT {
   int rank;
   static constexpr int size = 64;
+  static constexpr int maxhalf = MAXHALF;       // rows of a Jacobi half-pair kept in registers (18: n <= 36, 24: n <= 48)
   int bar;
   double *xch;
-  DEVFN DuoTeam(double *exchange) : rank(((threadIdx.x >> 5) & 1) * 32 + (threadIdx.x & 31)), bar(1 + (threadIdx.x >> 6)), xch(exchange) {}
+  DEVFN DuoTeamT(double *exchange) : rank(((threadIdx.x >> 5) & 1) * 32 + (threadIdx.x & 31)), bar(1 + (threadIdx.x >> 6)), xch(exchange) {}
   DEVFN void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
   DEVFN double sum(double v) const {
 #pragma unroll
@@ -170,6 +172,7 @@ struct DuoTeam {
     idx = i0; return v0;
   }
 };
+using DuoTeam = DuoTeamT<18>;
 
 // whole CTA; scratch must hold 64 doubles + 64 ints
 struct BlockTeam {

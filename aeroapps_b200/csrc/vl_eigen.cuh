@@ -300,7 +300,8 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
             double na2 = nrm2[a], nb2 = nrm2[b];
             if (n <= 12) rel = jacobi_halfpair<6>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
             else if (n <= 24) rel = jacobi_halfpair<12>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
-            else rel = jacobi_halfpair<18>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
+            else if (Team::maxhalf <= 18 || n <= 36) rel = jacobi_halfpair<18>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
+            else rel = jacobi_halfpair<(Team::maxhalf > 18 ? Team::maxhalf : 18)>(A + a * LDA, A + b * LDA, r0, nr, na2, nb2, h == 0, rmask);
             __syncwarp(rmask);                                 // the partner lane has read the old norms (racecheck-clean ordering)
             if (h == 0) { nrm2[a] = na2; nrm2[b] = nb2; }
           }

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_vl_eigen_sub(VLPix X, VLSol Z, VLQuad Q
 }
 
 // two warps per (pixel, layer) problem (DuoTeam): same shared memory per problem, twice the warps per SM
-template <int S>
+template <int S, int MAXHALF = 18>
 __global__ void __launch_bounds__(256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
                                                         const int *__restrict__ active, int nactive, int scr_doubles) {
   extern __shared__ double smem_d[];
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQua
   if (prob >= (long)nactive * X.L) return;                  // both warps of a duo leave together: no barrier is left short
   const int p = active[prob / X.L], k = (int)(prob % X.L);
   double *scr = smem_d + (size_t)duo * (scr_doubles + 4);
-  DuoTeam T(scr + scr_doubles);
+  DuoTeamT<MAXHALF> T(scr + scr_doubles);
   eigen_problem<S>(T, X, Z, QD, pq, m, p, k, scr);
 }
 
@@ -361,11 +361,13 @@ int run_vlidort(const RunDesc &R) {
   if (wpc >= 4) wpc /= 2;
   if (const char *e = getenv("AB200_VL_EIGEN_WARPS")) wpc = std::max(1, std::min(wpc, atoi(e)));      // tuning knob
   if (wpc < 1) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory eigen scratch"); return AB200_ERR_ARG; }
-  // two warps per problem (k_vl_eigen_duo) when the register-resident Jacobi applies (n <= 36); AB200_VL_EIGEN_DUO=0 switches it off
-  bool duo = n <= 36 && n >= 24;
+  // two warps per problem (k_vl_eigen_duo) when the register-resident half-pair Jacobi applies (24 <= n <= 48); AB200_VL_EIGEN_DUO=0 switches it off
+  bool duo = n <= 48 && n >= 24;                            // (the row halves of a pair live in registers: 24 rows at most)
   if (const char *e = getenv("AB200_VL_EIGEN_DUO")) duo = duo && atoi(e) != 0;
   const size_t eig_smem = duo ? (size_t)wpc * (scr_d + 4) * 8 : (size_t)wpc * scr_d * 8;
-  if (duo) ke = (S == 1) ? (const void *)k_vl_eigen_duo<1> : (const void *)k_vl_eigen_duo<3>;
+  const bool duo_big = duo && n > 36;                       // own kernel: the 24-row register path must not cost the n <= 36 kernel registers
+  if (duo) ke = duo_big ? ((S == 1) ? (const void *)k_vl_eigen_duo<1, 24> : (const void *)k_vl_eigen_duo<3, 24>)
+                        : ((S == 1) ? (const void *)k_vl_eigen_duo<1> : (const void *)k_vl_eigen_duo<3>);
   // sub-warp teams for small problems: 8 lanes per problem up to n = 8, 16 up to n = 16 (AB200_VL_EIGEN_SUB=0 switches them off)
   int subw = (n <= 8) ? 8 : (n <= 16 ? 16 : 32);
   if (const char *e = getenv("AB200_VL_EIGEN_SUB")) { if (atoi(e) == 0) subw = 32; }
@@ -477,6 +479,9 @@ int run_vlidort(const RunDesc &R) {
                       else k_vl_eigen_sub<1, 16><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d); }
         else { if (subw == 8) k_vl_eigen_sub<3, 8><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
                else k_vl_eigen_sub<3, 16><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d); }
+      } else if (duo_big) {
+        if (S == 1) k_vl_eigen_duo<1, 24><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
+        else k_vl_eigen_duo<3, 24><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
       } else if (duo) {
         if (S == 1) k_vl_eigen_duo<1><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
         else k_vl_eigen_duo<3><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
