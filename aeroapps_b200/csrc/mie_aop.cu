@@ -785,7 +785,9 @@ extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh
   if (nrh > 0xffff) { ab200_set_error("load_table: nrh too large"); return AB200_ERR_ARG; }
   const int nmom = h->nmom;
   if (nmom > 0 && (!pmom || nmom > nmom_file)) return 99;     // Chem_MieTableMod.F90:300-304
-  if (nmom == 0) npol = 6;                                    // nPol_table default, :270
+  // npol is the table file's own nPol (4 for spherical species, 6 for dust) also when the handle keeps no moments: pback is staged
+  // and interpolated with exactly that many components (the reference leaves nPol_table unset in that case, :336-339,366)
+  if (npol < 1 || npol > 6) { ab200_set_error("load_table: nPol of the table must be 1..6"); return AB200_ERR_ARG; }
   TableDev &T = h->tab[species];
   if (T.pool) { cudaFree(T.pool); T.pool = nullptr; }
   T.nch = h->nch; T.nrh = nrh; T.nbin = nbin; T.nmom = nmom; T.npol = npol;

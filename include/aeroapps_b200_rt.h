@@ -37,6 +37,9 @@ int ab200_vlidort_vector_lambert_dev(int km, int nch, int nobs, int nstreams, in
                                      void *stream, int *rc);
 /* algorithmic FLOP counters (SURVEY.md 8(d) formula) and kernel-launch counter since the last reset */
 int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long *n_launches);
+/* ms_ops: share of ms_bvp spent building the layer interaction operators; flops_exec: flops the default (interaction-principle)
+ * boundary-value kernels execute, while flops_bvp is the band-LU count of SURVEY.md 8(d) */
+int ab200_vlidort_stats3(double *ms_ops, double *flops_exec);
 
 /* ---- BRDF surfaces.  Surface set-up: RTSI/VLIDORT2p8p3/VLIDORT_SurfaceMod.F90 (CoxMunk :816-1042, GissCoxMunk :586-814,
  * LANDMODIS :1376-1596) + the VBRDF supplement (vsup/vbrdf).  Outputs (nobs,nch).  BR = exact direct-bounce BRDF

@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         src = os.path.join(_HERE, "vl_hostmodel.cpp")
-        hdrs = [os.path.join(_HERE, "..", "..", "aeroapps_b200", "csrc", f) for f in ("vl_common.cuh", "vl_setup.cuh", "vl_eigen.cuh", "vl_bvp.cuh", "vl_brdf.cuh")]
+        hdrs = [os.path.join(_HERE, "..", "..", "aeroapps_b200", "csrc", f) for f in ("vl_common.cuh", "vl_setup.cuh", "vl_eigen.cuh", "vl_bvp.cuh", "vl_brdf.cuh", "vl_linalg.cuh", "vl_layerops.cuh", "vl_add.cuh")]
         newest = max(os.path.getmtime(f) for f in [src] + hdrs)
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _SO, src])

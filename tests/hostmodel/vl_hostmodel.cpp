@@ -2,11 +2,12 @@
 // SerialTeam, so that their mathematics can be compared with the CPU oracle in the GPU-less build container.
 // Not part of the shipped library; the product has no CPU path.
 #define AB_HOST_MODEL 1
-#include "../../aeroapps_b200/csrc/vl_bvp.cuh"
+#include "../../aeroapps_b200/csrc/vl_add.cuh"
 #include "../../aeroapps_b200/csrc/vl_brdf.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 using namespace vlk;
 
 extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int nPol, int planpar, int lambertian,
@@ -61,6 +62,11 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
   std::vector<double> pq((size_t)(NM + 1) * N * 3), tmp(3 * (NM + 2));
   std::vector<double> escr(eigen_scratch_doubles(n, NM) + 64), bscr(bvp_smem_doubles(n) + 64), Ug(bvp_work_doubles(n, L));
   std::vector<int> iscr(13 * n + 32);
+  // default K3: interaction-principle solver (vl_layerops.cuh + vl_add.cuh); AB_HM_LEGACY_BVP=1: the windowed band elimination
+  const bool legacy = getenv("AB_HM_LEGACY_BVP") != nullptr || n > 64;
+  VLOps O;
+  std::vector<double> ork((size_t)L * n * n), otk(ork), osp(ork), osm(ork), osu((size_t)L * n), osd(osu);
+  std::vector<double> oscr(ops_smem_doubles(n) + 64), ascr(add_smem_doubles(n) + 64), awork(add_work_doubles(n, L));
   for (int p = 0; p < npix; p++) {
     status[p] = ibuf[(size_t)p * 4 + 1]; nfourier[p] = 0;
     for (int o = 0; o < 4; o++) stokes[(size_t)p * 4 + o] = 0.0;
@@ -81,8 +87,24 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
       }
       if (fail[p]) { status[p] = 4; break; }
       const double acc = (max_fourier_override >= 0) ? -1.0 : accuracy;
-      if (S == 1) bvp_pixel<1>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
-      else bvp_pixel<3>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
+      if (legacy) {
+        if (S == 1) bvp_pixel<1>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
+        else bvp_pixel<3>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
+      } else {
+        O.rk = ork.data() - q0 * n * n; O.tk = otk.data() - q0 * n * n; O.spT = osp.data() - q0 * n * n; O.smT = osm.data() - q0 * n * n;
+        O.sgu = osu.data() - q0 * n; O.sgd = osd.data() - q0 * n;
+        for (int k = 0; k < L; k++) {
+          if (S == 1) layer_ops_problem<1>(T, X, Z, O, p, k, oscr.data(), iscr.data());
+          else layer_ops_problem<3>(T, X, Z, O, p, k, oscr.data(), iscr.data());
+        }
+        if (getenv("AB_HM_DEBUG")) {
+          auto chk = [&](const char *nm, std::vector<double> &v) { for (size_t i = 0; i < v.size(); i++) if (!(v[i] == v[i])) { fprintf(stderr, "m=%d p=%d NaN in %s at %zu (layer %zu)\n", m, p, nm, i, i / (v.size() / L)); break; } };
+          chk("rk", ork); chk("tk", otk); chk("sp", osp); chk("sm", osm); chk("sgu", osu); chk("sgd", osd); chk("xp", xp); chk("xn", xn); chk("tde", tde); chk("wu", wu);
+        }
+        if (fail[p]) { status[p] = 4; break; }
+        if (S == 1) add_pixel<1>(T, X, Z, O, QD, SFc, CV, lambertian, acc, m, p, ascr.data(), iscr.data(), awork.data());
+        else add_pixel<3>(T, X, Z, O, QD, SFc, CV, lambertian, acc, m, p, ascr.data(), iscr.data(), awork.data());
+      }
       if (cstate[(size_t)p * 4 + 3]) { status[p] = 4; break; }
       nfourier[p] = m;
     }

@@ -135,3 +135,40 @@ def test_full_size_c90_properties(env):
     ref = o.getaopscalar([550.0], st["vnames"], np.asfortranarray(st["qm"][:, :, idx]), np.asfortranarray(st["rh"][:, idx]))
     assert same(np.asfortranarray(tau[:, :, idx]), ref[0]) and same(np.asfortranarray(ssa[:, :, idx]), ref[1])
     assert same(np.asfortranarray(g[:, :, idx]), ref[2])
+
+
+def test_aop_vector_nmom300_npol6_bit_exact(built):
+    """the bench / BASELINE moment count (nMom = 300, nPol = 6: LV/polar_vlidort.py:49, GV/geo_vlidort_pars.F90:14): every one of
+    the 1800 moment elements per voxel bit-identical to the oracle, 48 columns x 72 levels, 20 tracers, two channels"""
+    from aeroapps_b200 import MieObs_
+    from oracle import mie_oracle as orc
+    tables = mt.synthetic_tables(nmom=300)
+    chan = [388e-9, 550e-9]
+    mie, o = MieObs_.ChemMie(chan, 300, tables), orc.OracleMie(chan, 300, tables)
+    st = mt.synthetic_state(nobs=48, km=72, seed=300)
+    st["rh"][3, 5] = 1.2; st["rh"][0, 0] = -0.1
+    got = mie.getaopvector([550.0, 388.0], st["vnames"], 0, st["qm"], st["rh"], 300, 6)
+    ref = o.getaopvector([550.0, 388.0], st["vnames"], st["qm"], st["rh"], 300, 6)
+    assert got[-1] == ref[-1] == 0
+    assert got[3].shape == (72, 2, 48, 300, 6)
+    for a, b in zip(got[:4], ref[:4]):
+        assert same(a, b)
+
+
+def test_scalar_handle_with_4_component_tables(built):
+    """a handle created with n_moments = 0 from tables whose pback has 4 components (every species but dust)
+    must not read past the caller's pback buffer; getext's depolarisation reads P22 through it"""
+    from aeroapps_b200 import MieObs_
+    from oracle import mie_oracle as orc
+    tables = mt.synthetic_tables(nmom=0)
+    chan = [550e-9]
+    mie, o = MieObs_.ChemMie(chan, 0, tables), orc.OracleMie(chan, 0, tables)
+    st = mt.synthetic_state(nobs=7, km=72, seed=44)
+    got = mie.getaopscalar([550.0], st["vnames"], 0, st["qm"], st["rh"])
+    ref = o.getaopscalar([550.0], st["vnames"], st["qm"], st["rh"])
+    for a, b in zip(got[:3], ref[:3]):
+        assert same(a, b)
+    got = mie.getext([550.0], st["vnames"], 0, st["qc"], st["qm"], st["rh"])
+    ref = o.getext([550.0], st["vnames"], st["qc"], st["qm"], st["rh"])
+    for n, a, b in zip(["ext", "sca", "bsc", "absc_sfc", "absc_toa", "depol"], got[:6], ref[:6]):
+        assert (ulp_close(a, b, 1) if n.startswith("absc") else same(a, b)), n
