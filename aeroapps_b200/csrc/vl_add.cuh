@@ -13,37 +13,29 @@
 //                           Rs_{L+1}, Ss_{L+1} = the surface (Lambertian / BRDF Fourier component, BVP_SURFACE_SETUP_HOM/_BEAM)
 //   down-sweep, k = 1 .. L: I_dn(bot_k) = Y_k I_dn(top_k) + y_k,   u(bot_k) = Rs_{k+1} I_dn(bot_k) + Ss_{k+1},  I_dn(top_1) = 0
 //                           a + b = S+ (in_dn + in_u),  a - b = S- (in_dn - in_u)                 (LCON, MCON of the layer)
-// Work: one n x n elimination with n + 1 right-hand sides and three n x n products per layer (8.7 n^3 flops against the
-// 37 n^3 of the block-bidiagonal LU), 36 chained pivot columns per layer instead of 72, and 60 KB of shared memory per pixel
-// instead of 125 KB, so three pixels share an SM.  The layer source terms are accumulated top-down with the running user-stream
+// Work: one n x n inversion and four n x n products per layer (10 n^3 flops against the 37 n^3 of the block-bidiagonal LU), 36
+// chained pivot columns per layer instead of 72, and 60 KB of shared memory per pixel instead of 125 KB, so three pixels share an SM.  The layer source terms are accumulated top-down with the running user-stream
 // transmittance (the reference recurses bottom-up: same sum, different association).
 #pragma once
 #include "vl_bvp.cuh"
 #include "vl_layerops.cuh"
-#ifdef AB_HM_TRACE
-#include <cstdio>
-#endif
 
 namespace vlk {
 
-HDFN int add_ldy(int n) { return (n + 1) | 1; }
-// team scratch (doubles): Rs, Rk, Tk (n x ldn), Aug (n x ldw; later Zb n x ldy), Yb (n x ldy), 12 vectors, 3 pivot words
-HDFN size_t add_smem_doubles(int n) {
-  return 3 * (size_t)n * ops_ldn(n) + (size_t)n * ops_ldw(n) + (size_t)n * add_ldy(n) + 12 * n + 4;
-}
+// team scratch (doubles): Rs, Rk, Tk, QE (1 - R Rs, then its inverse, then Rs Y), Yb: n x ld each (ld = mat_ld(n)); 14 vectors;
+// inverse work; ints: 2n
+HDFN size_t add_smem_doubles(int n, bool cta) { return 5 * (size_t)n * mat_ld(n) + 14 * n + inv_work_doubles(n, cta); }
 // per-team global scratch (doubles): per layer Y^T, (Rs Y)^T (n x n each), y, Rs y + Ss (n each)
 HDFN size_t add_work_doubles(int n, int L) { return (size_t)L * (2 * (size_t)n * n + 2 * n); }
 
 template <int S, class Team>
 DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps &O, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
                      int lambertian, double accuracy, int m, int p, double *scr, int *piv, double *Wg) {
-  const int N = QD.N, n = S * N, L = X.L, NM = X.NM;
-  const int ldn = ops_ldn(n), ldw = ops_ldw(n), ldy = add_ldy(n);
-  double *Rs = scr, *Rk = Rs + (size_t)n * ldn, *Tk = Rk + (size_t)n * ldn, *Aug = Tk + (size_t)n * ldn, *Zb = Aug;
-  double *Yb = Aug + (size_t)n * ldw;
-  double *Ss = Yb + (size_t)n * ldy, *Sn = Ss + n, *su = Sn + n, *sd = su + n, *dinv = sd + n, *xv = dinv + n, *xb = xv + n,
-         *ub = xb + n, *inp = ub + n, *inm = inp + n, *av = inm + n, *bv = av + n;
-  unsigned long long *best = reinterpret_cast<unsigned long long *>(bv + n);
+  const int N = QD.N, n = S * N, L = X.L, NM = X.NM, ld = mat_ld(n);
+  double *Rs = scr, *Rk = Rs + (size_t)n * ld, *Tk = Rk + (size_t)n * ld, *QE = Tk + (size_t)n * ld, *Yb = QE + (size_t)n * ld, *Zb = QE;
+  double *Ss = Yb + (size_t)n * ld, *Sn = Ss + n, *su = Sn + n, *sd = su + n, *vv = sd + n, *yv = vv + n, *zz = yv + n, *xv = zz + n,
+         *xb = xv + n, *ub = xb + n, *inp = ub + n, *inm = inp + n, *av = inm + n, *bv = av + n;
+  double *wk = bv + n;
   const double *sc = X.scal + (size_t)p * 16;
   const int *ib = X.ibuf + (size_t)p * 4;
   int *cst = CV.state + (size_t)p * 4;
@@ -79,7 +71,7 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
       else v = SFAC * a * (nq == 16 ? BF[((size_t)(4 * o1 + o2) * N + i) * N + j] : ((o1 | o2) == 0 ? BF[(size_t)i * N + j] : 0.0));
       if (o1 > 1) v = -v;
     }
-    Rs[(size_t)r * ldn + c] = v;
+    Rs[(size_t)r * ld + c] = v;
   }
   for (int r = T.rank; r < n; r += T.size) {
     const int i = r / S, o1 = r % S;
@@ -99,52 +91,54 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
     const double *Rg = O.rk + q * n * n, *Tg = O.tk + q * n * n;
     for (int idx = T.rank; idx < n * n; idx += T.size) {
       const int r = idx / n, c = idx % n;
-      Rk[(size_t)r * ldn + c] = Rg[idx];
-      const double t = Tg[idx];
-      Tk[(size_t)r * ldn + c] = t; Aug[(size_t)r * ldw + n + c] = t;
+      Rk[(size_t)r * ld + c] = Rg[idx]; Tk[(size_t)r * ld + c] = Tg[idx];
     }
     for (int r = T.rank; r < n; r += T.size) { su[r] = O.sgu[q * n + r]; sd[r] = O.sgd[q * n + r]; }
     T.sync();
-    // Aug = [1 - R_k Rs | Tm_k | R_k Ss + sg_dn]
-    team_gemm_auto(T, n, n, n, Rk, ldn, Rs, ldn, [&](int r, int c, double acc) { Aug[(size_t)r * ldw + c] = (r == c ? 1.0 : 0.0) - acc; });
+    // QE = 1 - R_k Rs,   vv = R_k Ss + sg_dn
+    team_mm(T, n, n, n, Rk, ld, Rs, ld, [&](int r, int c, double acc) { QE[(size_t)r * ld + c] = (r == c ? 1.0 : 0.0) - acc; });
     for (int r = T.rank; r < n; r += T.size) {
-      const double *Rr = Rk + (size_t)r * ldn;
+      const double *Rr = Rk + (size_t)r * ld;
       double v = sd[r];
       for (int c = 0; c < n; c++) v += Rr[c] * Ss[c];
-      Aug[(size_t)r * ldw + 2 * n] = v;
-    }
-    if (!team_gauss_jordan(T, n, 2 * n + 1, Aug, ldw, piv, best)) { if (T.rank == 0) { cst[0] = 0; cst[3] = 4; } return; }
-    for (int e = T.rank; e < n; e += T.size) dinv[e] = 1.0 / Aug[(size_t)piv[e] * ldw + e];
-    T.sync();
-    // Yb = [Y | y]; Y^T and y to the team's global scratch for the down-sweep
-    double *Wk = Wg + (size_t)k * wl;
-    for (int idx = T.rank; idx < n * (n + 1); idx += T.size) {
-      const int j = idx / n, c = idx % n;                      // j = column of [Y | y] (slow), c = row (fast): coalesced stores
-      const double v = Aug[(size_t)piv[c] * ldw + n + j] * dinv[c];
-      Yb[(size_t)c * ldy + j] = v;
-      if (j < n) Wk[idx] = v; else Wk[2 * (size_t)n * n + c] = v;
+      vv[r] = v;
     }
     T.sync();
-    // Zb = Rs [Y | y]      (overwrites the augmented array)
-    team_gemm_auto(T, n, n + 1, n, Rs, ldn, Yb, ldy, [&](int r, int c, double acc) { Zb[(size_t)r * ldy + c] = acc; });
-    T.sync();
-    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, r = idx % n; Wk[(size_t)n * n + idx] = Zb[(size_t)r * ldy + j]; }
+    if (!team_inverse(T, n, QE, QE, ld, wk, piv)) { if (T.rank == 0) { cst[0] = 0; cst[3] = 4; } return; }     // QE <- E_k
+    // Yb = E_k Tm_k,  yv = E_k vv
+    team_mm(T, n, n, n, QE, ld, Tk, ld, [&](int r, int c, double acc) { Yb[(size_t)r * ld + c] = acc; });
     for (int r = T.rank; r < n; r += T.size) {
-      Wk[2 * (size_t)n * n + n + r] = Zb[(size_t)r * ldy + n] + Ss[r];          // u(bot_k) = (Rs Y) I_dn(top_k) + this
-      const double *Tr = Tk + (size_t)r * ldn;
+      const double *Er = QE + (size_t)r * ld;
+      double v = 0.0;
+      for (int c = 0; c < n; c++) v += Er[c] * vv[c];
+      yv[r] = v;
+    }
+    T.sync();
+    // Y^T and y to the team's global scratch for the down-sweep;  Zb = Rs Y (overwrites E),  zz = Rs y
+    double *Wk = Wg + (size_t)k * wl;
+    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, c = idx % n; Wk[idx] = Yb[(size_t)c * ld + j]; }
+    team_mm(T, n, n, n, Rs, ld, Yb, ld, [&](int r, int c, double acc) { Zb[(size_t)r * ld + c] = acc; });
+    for (int r = T.rank; r < n; r += T.size) {
+      const double *Rr = Rs + (size_t)r * ld;
+      double v = 0.0;
+      for (int c = 0; c < n; c++) v += Rr[c] * yv[c];
+      zz[r] = v;
+      Wk[2 * (size_t)n * n + r] = yv[r];
+      Wk[2 * (size_t)n * n + n + r] = v + Ss[r];               // u(bot_k) = (Rs Y) I_dn(top_k) + this
+    }
+    T.sync();
+    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, r = idx % n; Wk[(size_t)n * n + idx] = Zb[(size_t)r * ld + j]; }
+    for (int r = T.rank; r < n; r += T.size) {
+      const double *Tr = Tk + (size_t)r * ld;
       double v = su[r];
-      for (int c = 0; c < n; c++) v += Tr[c] * (Ss[c] + Zb[(size_t)c * ldy + n]);
+      for (int c = 0; c < n; c++) v += Tr[c] * (Ss[c] + zz[c]);
       Sn[r] = v;
     }
     // Rs <- R_k + Tm_k (Rs Y)       (nobody reads the old Rs any more)
-    team_gemm_auto(T, n, n, n, Tk, ldn, Zb, ldy, [&](int r, int c, double acc) { Rs[(size_t)r * ldn + c] = Rk[(size_t)r * ldn + c] + acc; });
+    team_mm(T, n, n, n, Tk, ld, Zb, ld, [&](int r, int c, double acc) { Rs[(size_t)r * ld + c] = Rk[(size_t)r * ld + c] + acc; });
     T.sync();
     for (int r = T.rank; r < n; r += T.size) Ss[r] = Sn[r];
     T.sync();
-#ifdef AB_HM_TRACE
-    { bool bad = false; for (int i = 0; i < n * ldn; i++) if (!(Rs[i] == Rs[i])) bad = true; for (int i = 0; i < n; i++) if (!(Ss[i] == Ss[i])) bad = true;
-      if (bad) { fprintf(stderr, "up-sweep NaN after layer %d (m=%d)\n", k, m); for (int c = 0; c < n; c++) fprintf(stderr, " piv[%d]=%d dinv=%g\n", c, piv[c], dinv[c]); return; } }
-#endif
   }
 
   // ---- down-sweep fused with the layer source terms (WHOLELAYER_STERM_UP) accumulated top-down

@@ -40,6 +40,7 @@ inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }     // CUDA's rsqrt
 
 struct SerialTeam {
   static constexpr int rank = 0, size = 1;
+  static constexpr bool is_cta = false;       // true: a whole CTA (threadIdx/blockDim/__syncthreads forms of vl_linalg.cuh apply)
   DEVFN void sync() const {}
   DEVFN double sum(double v) const { return v; }
   DEVFN double bcast0(double v) const { return v; }
@@ -63,6 +64,7 @@ DEVFN unsigned vl_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_s
 struct WarpTeam {
   int rank;
   static constexpr int size = 32;
+  static constexpr bool is_cta = false;
   DEVFN WarpTeam() : rank(threadIdx.x & 31) {}
   DEVFN void sync() const { __syncwarp(); }
   DEVFN double sum(double v) const {
@@ -177,6 +179,7 @@ using DuoTeam = DuoTeamT<18>;
 // whole CTA; scratch must hold 64 doubles + 64 ints
 struct BlockTeam {
   int rank, size;
+  static constexpr bool is_cta = true;
   double *sd; int *si;
   unsigned long long *mbar;      // optional mbarrier (shared memory) for load_begin/load_wait
   mutable unsigned mphase;

@@ -26,19 +26,16 @@ struct VLOps {                   // per problem q = p*L + k
   double *sgu, *sgd;             // [q][n]
 };
 
-HDFN int ops_ldn(int n) { return n | 1; }
-HDFN int ops_ldw(int n) { return (2 * n + 1) | 1; }
-// team scratch in doubles: Aug (n x ldw), Bm, Sb, Gp (n x ldn each), 5 vectors, 3 pivot words; ints: n pivots
-HDFN size_t ops_smem_doubles(int n) { return (size_t)n * ops_ldw(n) + 3 * (size_t)n * ops_ldn(n) + 5 * n + 4; }
+// team scratch in doubles: Am (later E), Bm, Gp (later R), Tb: n x ld each (ld = mat_ld(n)); 4 boundary vectors; inverse work; ints: 2n
+HDFN size_t ops_smem_doubles(int n, bool cta) { return 4 * (size_t)n * mat_ld(n) + 4 * n + inv_work_doubles(n, cta); }
 
 template <int S, class Team>
 DEVFN void layer_ops_problem(const Team &T, const VLPix &X, const VLSol &Z, const VLOps &O, int p, int k, double *scr, int *piv) {
-  const int n = Z.n, L = X.L, ldn = ops_ldn(n), ldw = ops_ldw(n);
+  const int n = Z.n, L = X.L, ld = mat_ld(n);
   const size_t q = (size_t)p * L + k;
-  double *Aug = scr, *Bm = Aug + (size_t)n * ldw, *Sb = Bm + (size_t)n * ldn, *Gp = Sb + (size_t)n * ldn;
-  double *wdt = Gp + (size_t)n * ldn, *wut = wdt + n, *wdb = wut + n, *wub = wdb + n;   // w_dn(top), w_u(top), w_dn(bot), w_u(bot)
-  double *dinv = wub + n;
-  unsigned long long *best = reinterpret_cast<unsigned long long *>(dinv + n);
+  double *Am = scr, *Bm = Am + (size_t)n * ld, *Gp = Bm + (size_t)n * ld, *Tb = Gp + (size_t)n * ld;
+  double *wdt = Tb + (size_t)n * ld, *wut = wdt + n, *wdb = wut + n, *wub = wdb + n;   // w_dn(top), w_u(top), w_dn(bot), w_u(bot)
+  double *wk = wub + n;
   const double *XP = Z.xp + q * n * n, *XN = Z.xn + q * n * n, *td = Z.tde + q * n;
   const double *WU = Z.wupper + q * 2 * n, *WL = Z.wlower + q * 2 * n;
   for (int r = T.rank; r < n; r += T.size) {
@@ -50,30 +47,21 @@ DEVFN void layer_ops_problem(const Team &T, const VLPix &X, const VLSol &Z, cons
     for (int idx = T.rank; idx < n * n; idx += T.size) {
       const int e = idx / n, r = idx % n;                      // global [e][r]: consecutive lanes read consecutive words
       const double P = XP[idx], M = XN[idx], t = td[e];
-      Aug[(size_t)r * ldw + e] = P + s * M * t;
-      Bm[(size_t)r * ldn + e] = M + s * P * t;
+      Am[(size_t)r * ld + e] = P + s * M * t;
+      Bm[(size_t)r * ld + e] = M + s * P * t;
     }
-    for (int idx = T.rank; idx < n * n; idx += T.size) { const int r = idx / n, c = idx % n; Aug[(size_t)r * ldw + n + c] = (r == c) ? 1.0 : 0.0; }
-    if (!team_gauss_jordan(T, n, 2 * n, Aug, ldw, piv, best)) { if (T.rank == 0) Z.fail[p] = 1; return; }
-    // S(e, r) = Aug[piv[e]][n + r] / Aug[piv[e]][e]
+    T.sync();
+    if (!team_inverse(T, n, Am, Am, ld, wk, piv)) { if (T.rank == 0) Z.fail[p] = 1; return; }      // Am <- S = (P +- M t)^-1, S(e, r)
     double *ST = sgn ? O.smT + q * n * n : O.spT + q * n * n;
-    for (int e = T.rank; e < n; e += T.size) dinv[e] = 1.0 / Aug[(size_t)piv[e] * ldw + e];
-    T.sync();
-    for (int idx = T.rank; idx < n * n; idx += T.size) {
-      const int r = idx / n, e = idx % n;
-      const double v = Aug[(size_t)piv[e] * ldw + n + r] * dinv[e];
-      Sb[(size_t)e * ldn + r] = v;
-      ST[idx] = v;
-    }
-    T.sync();
+    for (int idx = T.rank; idx < n * n; idx += T.size) { const int r = idx / n, e = idx % n; ST[idx] = Am[(size_t)e * ld + r]; }
     if (!sgn) {
-      team_gemm_auto(T, n, n, n, Bm, ldn, Sb, ldn, [&](int r, int c, double acc) { Gp[(size_t)r * ldn + c] = acc; });
+      team_mm(T, n, n, n, Bm, ld, Am, ld, [&](int r, int c, double acc) { Gp[(size_t)r * ld + c] = acc; });
     } else {
-      // R -> Gp (in place, element by element), Tm -> the dead augmented array
-      team_gemm_auto(T, n, n, n, Bm, ldn, Sb, ldn, [&](int r, int c, double acc) {
-        const double gp = Gp[(size_t)r * ldn + c];
-        Gp[(size_t)r * ldn + c] = 0.5 * (gp + acc);
-        Aug[(size_t)r * ldw + c] = 0.5 * (gp - acc);
+      // R -> Gp (in place, element by element), Tm -> Tb
+      team_mm(T, n, n, n, Bm, ld, Am, ld, [&](int r, int c, double acc) {
+        const double gp = Gp[(size_t)r * ld + c];
+        Gp[(size_t)r * ld + c] = 0.5 * (gp + acc);
+        Tb[(size_t)r * ld + c] = 0.5 * (gp - acc);
       });
     }
     T.sync();
@@ -81,10 +69,10 @@ DEVFN void layer_ops_problem(const Team &T, const VLPix &X, const VLSol &Z, cons
   double *Rg = O.rk + q * n * n, *Tg = O.tk + q * n * n;
   for (int idx = T.rank; idx < n * n; idx += T.size) {
     const int r = idx / n, c = idx % n;
-    Rg[idx] = Gp[(size_t)r * ldn + c]; Tg[idx] = Aug[(size_t)r * ldw + c];
+    Rg[idx] = Gp[(size_t)r * ld + c]; Tg[idx] = Tb[(size_t)r * ld + c];
   }
   for (int r = T.rank; r < n; r += T.size) {
-    const double *Rr = Gp + (size_t)r * ldn, *Tr = Aug + (size_t)r * ldw;
+    const double *Rr = Gp + (size_t)r * ld, *Tr = Tb + (size_t)r * ld;
     double su = wut[r], sd = wdb[r];
     for (int c = 0; c < n; c++) { su -= Rr[c] * wdt[c] + Tr[c] * wub[c]; sd -= Tr[c] * wdt[c] + Rr[c] * wub[c]; }
     O.sgu[q * n + r] = su; O.sgd[q * n + r] = sd;

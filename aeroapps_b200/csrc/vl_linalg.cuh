@@ -105,10 +105,17 @@ DEVFN bool team_gauss_jordan(const Team &T, int n, int W, double *AB_RESTRICT G,
     for (int item = T.rank; item < nitem; item += T.size) {
       const int r = item % n, cg = item / n;
       if (r == p) continue;
-      double *row = G + (size_t)r * ld;
+      double *AB_RESTRICT row = G + (size_t)r * ld;          // r != p: the two rows never overlap
+      const double *AB_RESTRICT pr = prow;
       const double f = row[c] * ipiv;
       if (f != 0.0) {
-        for (int j = c + 1 + cg; j < W; j += CG) row[j] -= f * prow[j];
+        int j = c + 1 + cg;
+        for (; j + 3 * CG < W; j += 4 * CG) {                 // loads first: four independent updates in flight
+          const double p0 = pr[j], p1 = pr[j + CG], p2 = pr[j + 2 * CG], p3 = pr[j + 3 * CG];
+          const double a0 = row[j], a1 = row[j + CG], a2 = row[j + 2 * CG], a3 = row[j + 3 * CG];
+          row[j] = a0 - f * p0; row[j + CG] = a1 - f * p1; row[j + 2 * CG] = a2 - f * p2; row[j + 3 * CG] = a3 - f * p3;
+        }
+        for (; j < W; j += CG) row[j] -= f * pr[j];
       }
       if (cg == 0 && c + 1 < n) {
         const bool u = r < 64 ? ((used0 >> r) & 1ull) : ((used1 >> (r - 64)) & 1ull);
@@ -120,6 +127,185 @@ DEVFN bool team_gauss_jordan(const Team &T, int n, int W, double *AB_RESTRICT G,
   }
   T.sync();
   return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// E = A^-1 for an n x n matrix in team scratch (row stride ld).  Generic form (host model, warp teams): Gauss-Jordan on [A | 1] in
+// the work array wk (n x ldw doubles, ldw = (2n)|1) + 3 pivot words; A is left untouched.
+HDFN int inv_ldw(int n) { return (2 * n) | 1; }
+HDFN size_t inv_work_doubles_generic(int n) { return (size_t)n * inv_ldw(n) + n + 4; }
+HDFN size_t inv_work_doubles_cta(int n) { return 4 * (size_t)n + 4; }       // scratch of the CTA form below
+template <class Team>
+DEVFN bool team_inverse_generic(const Team &T, int n, const double *A, int lda, double *E, int lde, double *wk, int *piv) {
+  const int ldw = inv_ldw(n);
+  double *dinv = wk + (size_t)n * ldw;
+  unsigned long long *best = reinterpret_cast<unsigned long long *>(dinv + n);
+  for (int idx = T.rank; idx < n * n; idx += T.size) {
+    const int r = idx / n, c = idx % n;
+    wk[(size_t)r * ldw + c] = A[(size_t)r * lda + c]; wk[(size_t)r * ldw + n + c] = (r == c) ? 1.0 : 0.0;
+  }
+  if (!team_gauss_jordan(T, n, 2 * n, wk, ldw, piv, best)) return false;
+  for (int e = T.rank; e < n; e += T.size) dinv[e] = 1.0 / wk[(size_t)piv[e] * ldw + e];
+  T.sync();
+  for (int idx = T.rank; idx < n * n; idx += T.size) { const int e = idx / n, r = idx % n; E[(size_t)e * lde + r] = wk[(size_t)piv[e] * ldw + n + r] * dinv[e]; }
+  T.sync();
+  return true;
+}
+
+#ifndef AB_HOST_MODEL
+// 1/x to full double precision from the hardware approximation + two Newton steps (the quotient only scales elimination multipliers)
+DEVFN double vl_fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  return y;
+}
+
+// CTA form: in-place Gauss-Jordan inversion with the matrix REGISTER-RESIDENT.  Thread (r, cg) of the first n*CG threads (CG =
+// blockDim / n column groups) keeps the elements a(r, cg + CG*jj), jj < NJ, of row r in registers for the whole elimination; per
+// pivot column only the pivot row travels through shared memory (one broadcast load per element and update).  Partial pivoting
+// over the rows that have not been pivots, no row swaps, no row scaling: piv[c] = pivot row of step c, stepof[r] = its inverse;
+// the physical column c holds, after step c, the column of the inverse that belongs to row piv[c] (the unit column it replaces
+// is implicit before).  E(stepof[r], piv[j]) = a(r, j) / pivot(stepof[r]).
+// Two barriers per pivot column: (A) column c of every row published -> every warp finds the pivot row by itself (two warp-wide
+// integer max reductions on (|value| bits, row)), (B) pivot row published.
+// Scratch: prow_s (n doubles), col_s (2n), dinv_s (n); ints piv (n), stepof (n).
+template <int NJ>
+DEVFN bool cta_inverse(int n, const double *A, int lda, double *E, int lde, double *wk, int *piv) {
+  const int CG = blockDim.x / n, rank = threadIdx.x, lane = threadIdx.x & 31;
+  const bool active = rank < n * CG;
+  const int r = rank % n, cg = rank / n;
+  double *prow_s = wk, *col_s = wk + n, *dinv_s = wk + 3 * n;
+  int *stepof = piv + n;
+  double a[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; jj++) { const int j = cg + CG * jj; a[jj] = (active && j < n) ? A[(size_t)r * lda + j] : 0.0; }
+  if (active && cg == 0) col_s[r] = a[0];
+  unsigned long long usedmask = 0ull;                          // rows that have been pivots (n <= 64), the same in every thread
+  bool ok = true;
+  for (int c = 0; c < n; c++) {
+    __syncthreads();                                           // (A) column c published by every row
+    const double *cs = col_s + (c & 1) * n;
+    double *cn = col_s + ((c + 1) & 1) * n;
+    // pivot search, redundantly in every warp (no atomics, no extra barrier): two candidates per lane, two 32-bit max reductions
+    unsigned long long key = 0ull;
+    for (int rr = lane; rr < n; rr += 32) {
+      if (!((usedmask >> rr) & 1ull)) { const unsigned long long k2 = vl_pivot_key(cs[rr], rr); key = k2 > key ? k2 : key; }
+    }
+    const unsigned hi = (unsigned)(key >> 32), mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)key : 0u);
+    key = ((unsigned long long)mh << 32) | ml;
+    if ((key >> 7) == 0ull) { ok = false; break; }
+    const int p = (int)(key & 127ull);
+    usedmask |= 1ull << p;
+    if (rank == 0) { piv[c] = p; stepof[p] = c; }
+    const bool isp = active && r == p;
+    if (isp) {
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) { const int j = cg + CG * jj; if (j < n) prow_s[j] = a[jj]; }
+    }
+    __syncthreads();                                           // (B) pivot row published
+    const double ipiv = vl_fast_rcp(prow_s[c]);
+    if (active) {
+      if (!isp) {
+        const double f = cs[r] * ipiv;
+#pragma unroll
+        for (int jj = 0; jj < NJ; jj++) {
+          const int j = cg + CG * jj;
+          if (j < n) {
+            a[jj] = (j == c) ? -f : a[jj] - f * prow_s[j];
+            if (j == c + 1) cn[r] = a[jj];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < NJ; jj++) {
+          const int j = cg + CG * jj;
+          if (j == c) { dinv_s[c] = ipiv; a[jj] = 1.0; }
+          if (j == c + 1 && j < n) cn[r] = a[jj];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (ok && active) {
+    const int cr = stepof[r];
+    const double di = dinv_s[cr];
+#pragma unroll
+    for (int jj = 0; jj < NJ; jj++) { const int j = cg + CG * jj; if (j < n) E[(size_t)cr * lde + piv[j]] = a[jj] * di; }
+  }
+  __syncthreads();
+  return ok;
+}
+
+// C = A B for a CTA out of shared memory with 16-byte loads: A (M x K, lda even), B (K x N, ldb even), both 16-byte aligned; every
+// item owns a TM x 2 register tile, two k per step.  epi2(r, c, v0, v1) receives the finished pair (r, c), (r, c + 1) (c even; the
+// second value belongs to column c + 1, which the caller ignores when c + 1 == N).
+template <int TM, class Epi2>
+DEVFN void cta_gemm2(int M, int N, int K, const double *AB_RESTRICT A, int lda, const double *AB_RESTRICT B, int ldb, Epi2 epi2) {
+  const int tn = (N + 1) / 2, tm = (M + TM - 1) / TM;
+  for (int item = threadIdx.x; item < tm * tn; item += blockDim.x) {
+    const int r0 = (item / tn) * TM, c0 = (item % tn) * 2;
+    double acc0[TM], acc1[TM];
+#pragma unroll
+    for (int i = 0; i < TM; i++) { acc0[i] = 0.0; acc1[i] = 0.0; }
+    const double *ar[TM];
+#pragma unroll
+    for (int i = 0; i < TM; i++) ar[i] = A + (size_t)(r0 + i < M ? r0 + i : M - 1) * lda;
+    const double *b = B + c0;
+    int k = 0;
+#pragma unroll 2
+    for (; k + 1 < K; k += 2) {
+      const double2 b0 = *reinterpret_cast<const double2 *>(b + (size_t)k * ldb), b1 = *reinterpret_cast<const double2 *>(b + (size_t)(k + 1) * ldb);
+#pragma unroll
+      for (int i = 0; i < TM; i++) {
+        const double2 a2 = *reinterpret_cast<const double2 *>(ar[i] + k);
+        acc0[i] += a2.x * b0.x; acc1[i] += a2.x * b0.y;
+        acc0[i] += a2.y * b1.x; acc1[i] += a2.y * b1.y;
+      }
+    }
+    if (k < K) {
+      const double2 b0 = *reinterpret_cast<const double2 *>(b + (size_t)k * ldb);
+#pragma unroll
+      for (int i = 0; i < TM; i++) { const double av = ar[i][k]; acc0[i] += av * b0.x; acc1[i] += av * b0.y; }
+    }
+#pragma unroll
+    for (int i = 0; i < TM; i++) if (r0 + i < M) epi2(r0 + i, c0, acc0[i], acc1[i]);
+  }
+}
+#endif
+
+// ---- what the solvers call: one leading dimension for every n x n team matrix (even, >= n + 2: 16-byte rows, room for the pair tiles)
+HDFN int mat_ld(int n) { return ((n + 1) / 2) * 2 + 2; }
+HDFN size_t inv_work_doubles(int n, bool cta) { return cta ? inv_work_doubles_cta(n) : inv_work_doubles_generic(n); }
+
+// E = A^-1 (E may be A itself for CTA teams); piv: 2n ints
+template <class Team>
+DEVFN bool team_inverse(const Team &T, int n, double *A, double *E, int ld, double *wk, int *piv) {
+#ifndef AB_HOST_MODEL
+  if constexpr (Team::is_cta) {
+    const int CG = T.size / n, nj = (n + CG - 1) / CG;
+    if (nj <= 6) return cta_inverse<6>(n, A, ld, E, ld, wk, piv);
+    if (nj <= 10) return cta_inverse<10>(n, A, ld, E, ld, wk, piv);
+    return cta_inverse<13>(n, A, ld, E, ld, wk, piv);
+  }
+#endif
+  return team_inverse_generic(T, n, A, ld, E, ld, wk, piv);
+}
+
+// C(r, c) = sum_k A(r, k) B(k, c) handed to epi(r, c, value); A, B in team scratch with the leading dimension mat_ld(n)
+template <class Team, class Epi>
+DEVFN void team_mm(const Team &T, int M, int N, int K, const double *A, int lda, const double *B, int ldb, Epi epi) {
+#ifndef AB_HOST_MODEL
+  if constexpr (Team::is_cta) {
+    auto epi2 = [&](int r, int c, double v0, double v1) { epi(r, c, v0); if (c + 1 < N) epi(r, c + 1, v1); };
+    if (M * ((N + 1) / 2) <= 3 * (int)blockDim.x) cta_gemm2<3>(M, N, K, A, lda, B, ldb, epi2);
+    else cta_gemm2<6>(M, N, K, A, lda, B, ldb, epi2);
+    return;
+  }
+#endif
+  team_gemm_auto(T, M, N, K, A, lda, B, ldb, epi);
 }
 
 }  // namespace vlk

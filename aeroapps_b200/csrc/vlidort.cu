@@ -1,24 +1,24 @@
-// Stage B -- VLIDORT drop-in entry points on B200: kernel wrappers, chunked host driver, C ABI.
-// Kernels: k_vl_setup (K1, CTA per pixel), k_vl_eigen (K2, warp per pixel-layer), k_vl_bvp (K3, persistent CTAs,
-// one pixel at a time), k_vl_finish.  The Fourier loop runs on the host; pixels that have converged drop out
-// of the device-side active list, so later components only launch work for the pixels that still need it.
-#include "../../include/aeroapps_b200.h"
-#include "common.h"
-#include "vl_add.cuh"
-#ifdef AB200_BVP_VARIANTS            // opt-in build (make EXTRA=-DAB200_BVP_VARIANTS): the two experimental forward eliminations of round 1
-#include "vl_bvp3.cuh"
-#include "vl_bvp4.cuh"
-#endif
+// Stage B -- VLIDORT drop-in entry points on B200: chunked host driver and C ABI, plus the light kernels (K0 BRDF, K1 setup,
+// finish, Rayleigh).  The heavy kernels live in vl_k2_eigen.cu (K2), vl_k3_add.cu (K2b, K3) and vl_k3_band.cu (K3, band form).
+// The Fourier loop runs on the host; pixels that have converged drop out of the device-side active list, so later components
+// only launch work for the pixels that still need it.
+// State: one context per CUDA device (workspace arena, staging buffers), serialised by a per-device mutex; the diagnostics of
+// the most recent call are per host thread.  Nothing is tied to "the device that was current first".
+#include "vl_launch.h"
 #include "vl_brdf.cuh"
 #include <algorithm>
-#include <vector>
 #include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
 
 using namespace vlk;
 
 struct VLStats { double ms_setup, ms_eigen, ms_bvp, flops_eigen, flops_bvp; long n_eigen_problems, n_bvp_problems, n_launches; long npix; double ms_ops, flops_exec; };
-static VLStats g_stats;
-static std::vector<int> g_last_nfourier, g_last_status;
+static VLStats g_stats;                      // summed over devices and host threads (g_stats_mu)
+static std::mutex g_stats_mu;
+static thread_local std::vector<int> g_last_nfourier, g_last_status;      // diagnostics of this host thread's most recent call
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_vl_setup(VLIn in, VLPix X, int p0) {
@@ -37,190 +37,6 @@ __global__ void __launch_bounds__(128) k_vl_setup(VLIn in, VLPix X, int p0) {
   Xl.tdmubar -= (size_t)p0 * L; Xl.tduserm -= (size_t)p0 * L; Xl.emult_up -= (size_t)p0 * L; Xl.sigma_p -= (size_t)p0 * L;
   Xl.itrans_userm -= (size_t)p0 * L; Xl.scal -= (size_t)p0 * 16; Xl.ibuf -= (size_t)p0 * 4; Xl.layscat -= (size_t)p0 * (NM + 1) * L;
   setup_pixel(T, inl, Xl, p0 + pl, smem_d);
-}
-
-template <int S>
-__global__ void __launch_bounds__(256) k_vl_eigen(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m, const int *__restrict__ active,
-                           int nactive, int scr_doubles) {
-  extern __shared__ double smem_d[];
-  const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const long prob = (long)blockIdx.x * wpc + warp;
-  if (prob >= (long)nactive * X.L) return;
-  const int p = active[prob / X.L], k = (int)(prob % X.L);
-  WarpTeam T;
-  eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)warp * scr_doubles);
-}
-
-// W lanes per (pixel, layer) problem (SubWarpTeam): 32 / W problems per warp for small nstokes*nstreams (the scalar 8-stream
-// configuration keeps 4 of 32 lanes busy with one problem per warp)
-template <int S, int W>
-__global__ void __launch_bounds__(256) k_vl_eigen_sub(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
-                                                      const int *__restrict__ active, int nactive, int scr_doubles) {
-  extern __shared__ double smem_d[];
-  constexpr int SUBS = 32 / W;
-  const int slot = (threadIdx.x >> 5) * SUBS + ((threadIdx.x & 31) / W), spc = (blockDim.x >> 5) * SUBS;
-  const long prob = (long)blockIdx.x * spc + slot;
-  if (prob >= (long)nactive * X.L) return;
-  const int p = active[prob / X.L], k = (int)(prob % X.L);
-  SubWarpTeam<W> T;
-  eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)slot * scr_doubles);
-}
-
-// two warps per (pixel, layer) problem (DuoTeam): same shared memory per problem, twice the warps per SM
-template <int S, int MAXHALF = 18>
-__global__ void __launch_bounds__(256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
-                                                        const int *__restrict__ active, int nactive, int scr_doubles) {
-  extern __shared__ double smem_d[];
-  const int duo = threadIdx.x >> 6, ppc = blockDim.x >> 6;
-  const long prob = (long)blockIdx.x * ppc + duo;
-  if (prob >= (long)nactive * X.L) return;                  // both warps of a duo leave together: no barrier is left short
-  const int p = active[prob / X.L], k = (int)(prob % X.L);
-  double *scr = smem_d + (size_t)duo * (scr_doubles + 4);
-  DuoTeamT<MAXHALF> T(scr + scr_doubles);
-  eigen_problem<S>(T, X, Z, QD, pq, m, p, k, scr);
-}
-
-// VAR: forward-elimination variant, one kernel each (own register allocation): 0 = blocked look-ahead (vl_bvp.cuh, the default),
-// 1 = the same with the window in a per-CTA HBM scratch ("large n"), 3 = warp-specialised (vl_bvp3.cuh), 4 = register-resident
-// window (vl_bvp4.cuh)
-template <int S, int VAR>
-__global__ void __launch_bounds__(384) k_vl_bvp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
-                                                int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
-                                                int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta, int v3,
-                                                int smem_doubles, double *__restrict__ wglob) {
-  extern __shared__ __align__(16) double smem_d[];
-  __shared__ double sd[64];
-  __shared__ int si[64];
-  const int n = S * QD.N;
-  (void)v3;
-#ifdef AB200_BVP_VARIANTS
-  int *iscr = reinterpret_cast<int *>(smem_d + (VAR == 4 ? b4_smem_doubles(n) : (VAR == 3 ? b3_smem_doubles(n) : (VAR == 1 ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)))));
-#else
-  int *iscr = reinterpret_cast<int *>(smem_d + (VAR == 1 ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)));
-#endif
-  double *wg = (VAR == 1) ? wglob + (size_t)blockIdx.x * bvp_window_doubles(n) : nullptr;
-  __shared__ unsigned long long mbar;
-  for (int i = threadIdx.x; i < smem_doubles; i += blockDim.x) smem_d[i] = 0.0;      // no stale NaN patterns in never-written padding
-  BlockTeam T(sd, si, &mbar);
-  double *Ug = work + (size_t)blockIdx.x * work_per_cta;
-  for (int a = blockIdx.x; a < nactive; a += gridDim.x) {
-    const int p = active[a];
-    if (Z.fail[p]) {
-      if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
-    } else {
-#ifdef AB200_BVP_VARIANTS
-      if constexpr (VAR == 4) bvp_pixel_v4<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
-      else if constexpr (VAR == 3) bvp_pixel_v3<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
-      else
-#endif
-      if constexpr (VAR == 1) bvp_pixel<S, BlockTeam, true>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug, wg);
-      else bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, smem_d, iscr, Ug);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
-    __syncthreads();
-  }
-}
-
-// K3 for small problems (3 nstokes nstreams <= 64 window rows, e.g. the scalar 8-stream configuration): one WARP per pixel with its
-// own window in shared memory, several pixels per CTA -- the 384-thread kernel above leaves the SM almost idle on a 24 x 33 window
-template <int S>
-__global__ void __launch_bounds__(256) k_vl_bvp_warp(VLPix X, VLSol Z, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
-                                                     int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
-                                                     int *__restrict__ next_count, double *__restrict__ work, size_t work_per_warp,
-                                                     int smem_doubles_per_warp) {
-  extern __shared__ __align__(16) double smem_d[];
-  const int n = S * QD.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-  double *scr = smem_d + (size_t)warp * smem_doubles_per_warp;
-  for (int i = lane; i < smem_doubles_per_warp; i += 32) scr[i] = 0.0;
-  __syncwarp();
-  int *iscr = reinterpret_cast<int *>(scr + bvp_smem_doubles(n));
-  WarpTeam T;
-  const int gw = blockIdx.x * wpc + warp;
-  double *Ug = work + (size_t)gw * work_per_warp;
-  for (int a = gw; a < nactive; a += gridDim.x * wpc) {
-    const int p = active[a];
-    if (Z.fail[p]) {
-      if (lane == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
-    } else {
-      bvp_pixel<S>(T, X, Z, QD, SF, CV, lambertian, accuracy, m, p, scr, iscr, Ug);
-    }
-    __syncwarp();
-    if (lane == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
-    __syncwarp();
-  }
-}
-
-// K2b: layer interaction operators (vl_layerops.cuh), one CTA per (pixel, layer) problem
-template <int S>
-__global__ void __launch_bounds__(128) k_vl_layer_ops(VLPix X, VLSol Z, VLOps O, const int *__restrict__ active, int nactive) {
-  extern __shared__ __align__(16) double smem_d[];
-  __shared__ double sd[64];
-  __shared__ int si[64];
-  const long prob = blockIdx.x;
-  const int p = active[prob / X.L], k = (int)(prob % X.L);
-  BlockTeam T(sd, si);
-  layer_ops_problem<S>(T, X, Z, O, p, k, smem_d, reinterpret_cast<int *>(smem_d + ops_smem_doubles(Z.n)));
-}
-// small problems: one warp per (pixel, layer) problem, WPC problems per CTA
-template <int S>
-__global__ void __launch_bounds__(256) k_vl_layer_ops_warp(VLPix X, VLSol Z, VLOps O, const int *__restrict__ active, int nactive, int per_warp) {
-  extern __shared__ __align__(16) double smem_d[];
-  const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const long prob = (long)blockIdx.x * wpc + warp;
-  if (prob >= (long)nactive * X.L) return;
-  const int p = active[prob / X.L], k = (int)(prob % X.L);
-  double *scr = smem_d + (size_t)warp * per_warp;
-  WarpTeam T;
-  layer_ops_problem<S>(T, X, Z, O, p, k, scr, reinterpret_cast<int *>(scr + ops_smem_doubles(Z.n)));
-}
-
-// K3 (default): interaction-principle solver (vl_add.cuh), persistent CTAs of 128 threads, three per SM at nstokes*nstreams = 36
-template <int S>
-__global__ void __launch_bounds__(128, 3) k_vl_add(VLPix X, VLSol Z, VLOps O, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
-                                                   int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
-                                                   int *__restrict__ next_count, double *__restrict__ work, size_t work_per_cta) {
-  extern __shared__ __align__(16) double smem_d[];
-  __shared__ double sd[64];
-  __shared__ int si[64];
-  BlockTeam T(sd, si);
-  int *piv = reinterpret_cast<int *>(smem_d + add_smem_doubles(Z.n));
-  double *Wg = work + (size_t)blockIdx.x * work_per_cta;
-  for (int a = blockIdx.x; a < nactive; a += gridDim.x) {
-    const int p = active[a];
-    if (Z.fail[p]) {
-      if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
-    } else {
-      add_pixel<S>(T, X, Z, O, QD, SF, CV, lambertian, accuracy, m, p, smem_d, piv, Wg);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
-    __syncthreads();
-  }
-}
-// small problems: one warp per pixel
-template <int S>
-__global__ void __launch_bounds__(256) k_vl_add_warp(VLPix X, VLSol Z, VLOps O, VLQuad QD, VLSurf SF, VLConv CV, int lambertian, double accuracy,
-                                                     int m, const int *__restrict__ active, int nactive, int *__restrict__ next_list,
-                                                     int *__restrict__ next_count, double *__restrict__ work, size_t work_per_warp, int per_warp) {
-  extern __shared__ __align__(16) double smem_d[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-  double *scr = smem_d + (size_t)warp * per_warp;
-  int *piv = reinterpret_cast<int *>(scr + add_smem_doubles(Z.n));
-  WarpTeam T;
-  const int gw = blockIdx.x * wpc + warp;
-  double *Wg = work + (size_t)gw * work_per_warp;
-  for (int a = gw; a < nactive; a += gridDim.x * wpc) {
-    const int p = active[a];
-    if (Z.fail[p]) {
-      if (lane == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
-    } else {
-      add_pixel<S>(T, X, Z, O, QD, SF, CV, lambertian, accuracy, m, p, scr, piv, Wg);
-    }
-    __syncwarp();
-    if (lane == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
-    __syncwarp();
-  }
 }
 
 // K0a: exact direct-bounce BRDF of every pixel + the wrappers' BR outputs (nobs,nch)
@@ -343,7 +159,24 @@ struct DevArena {                      // one allocation carved into aligned pie
   }
   template <class T> T *take(size_t n) { off = (off + 255) / 256 * 256; T *p = reinterpret_cast<T *>(base + off); off += n * sizeof(T); return p; }
 };
-DevArena g_arena;          // grow-only; released by ab200_vlidort_release()
+
+// per-device state: the grow-only workspace arena of run_vlidort and the staging buffers of the entry points.  A call locks the
+// context of the device that is current on its host thread; calls on different devices run concurrently.
+struct VLContext {
+  std::mutex mu;
+  DevArena arena;
+  DevBuf io, tab, diag, rot;
+};
+std::mutex g_ctx_mu;
+std::map<int, std::unique_ptr<VLContext>> g_ctx;
+VLContext &vl_context() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto &p = g_ctx[dev];
+  if (!p) p.reset(new VLContext);
+  return *p;
+}
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -360,19 +193,36 @@ struct RunDesc {
   // device outputs (nobs,nch)
   double *radiance, *reflectance, *Q, *U; int *nfourier, *status;
   cudaStream_t stream;
+  int nadir_already;                // sharded calls: an earlier slab of the same call has already switched FOCORR_NADIR on (RunDesc is memset to 0)
 };
 
-int run_vlidort(const RunDesc &R) {
+struct EventSet {                      // RAII: destroyed on every return path
+  cudaEvent_t e[4];
+  EventSet() { for (auto &x : e) cudaEventCreate(&x); }
+  ~EventSet() { for (auto &x : e) cudaEventDestroy(x); }
+};
+
+// the caller holds C.mu
+int run_vlidort(VLContext &C, const RunDesc &R) {
   const int S = R.S, N = R.N, L = R.km, n = S * N, NM = std::min(2 * N - 1, R.nMom), npix = R.nobs * R.nch;
   if (npix == 0) return 0;
   if (N < 1 || N > 32 || L < 1 || L > MAXLAY || (S != 1 && S != 3) || 2 * N > MAXMOM) { ab200_set_error("vlidort: unsupported nstreams/nlayers/nstokes"); return AB200_ERR_ARG; }
   cudaStream_t st = R.stream;
-  // ---- sizes
-  const size_t per_pix_state = (size_t)L * 8 * 8 + (size_t)(NM + 1) * L * 4 * 8 + 16 * 8 + 4 * 4 + (size_t)(NM + 1) * L;
-  // K3 variant: interaction-principle solver (vl_add.cuh) for nstokes*nstreams <= 64; AB200_VL_BVP_LEGACY=1 (or larger problems)
-  // selects the windowed band elimination of vl_bvp.cuh
+  int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  VLStats stats; memset(&stats, 0, sizeof stats);
+  // ---- kernel plans.  K3: interaction-principle solver (vl_add.cuh) for nstokes*nstreams <= 64; AB200_VL_BVP_LEGACY=1 (or larger
+  //      problems) selects the windowed band elimination of vl_bvp.cuh
   bool use_add = n <= 64;
   if (const char *e = getenv("AB200_VL_BVP_LEGACY")) use_add = use_add && atoi(e) == 0;
+  EigenPlan PE; AddPlan PA; BandPlan PB;
+  if (int e = vl_eigen_plan(PE, S, N, NM)) return e;
+  if (use_add) { if (int e = vl_add_plan(PA, S, N, L, nsm)) return e; }
+  else { if (int e = vl_band_plan(PB, S, N, L, nsm)) return e; }
+  const int solvers = use_add ? PA.grid_max : PB.grid_max;
+  const size_t work_per_solver = use_add ? PA.work_per_solver : PB.work_per_solver;
+  const size_t bvp_work_bytes = (size_t)solvers * (work_per_solver + (use_add ? 0 : PB.window)) * 8;
+  // ---- sizes
+  const size_t per_pix_state = (size_t)L * 8 * 8 + (size_t)(NM + 1) * L * 4 * 8 + 16 * 8 + 4 * 4 + (size_t)(NM + 1) * L;
   const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + (6 + 2 * S) * n + 2 * n + 2 * 2 * n + (use_add ? 4 * (size_t)n * n + 2 * n : 0)) * 8;
   size_t per_pix_brdf = 0; int brdf_nscr = 0; size_t brdf_smem = 0;
   if (R.brdf) {
@@ -390,113 +240,7 @@ int run_vlidort(const RunDesc &R) {
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   size_t budget = (size_t)(ws_gb * 1e9);
-  budget = std::min(budget, (size_t)(0.6 * (double)(freeb + g_arena.cap)));
-  // K3 geometry
-  const int bvp_threads = 384;
-  // warp-specialised forward elimination (vl_bvp3.cuh): opt-in with AB200_VL_BVP_V3=1 while it is slower than the blocked
-  // look-ahead one (measured 2426 vs 2893 pixels/s on configs[2]); needs its window (3n+16 rows) to fit 128 row slots
-  int use_v3 = 0;
-#ifdef AB200_BVP_VARIANTS
-  if (const char *e = getenv("AB200_VL_BVP_V3"))
-    use_v3 = (atoi(e) != 0 && b3_supported(n) && (b3_smem_doubles(n) * 8 + b3_smem_ints(n) * 4 <= 227 * 1024)) ? 3 : 0;
-  // register-resident forward elimination (vl_bvp4.cuh): opt-in with AB200_VL_BVP_V4=1 (n > 24) or =2 (every supported n).
-  // Parity green; measured 1316 ms vs 1189 ms of K3 time per 3 bench steps, so the blocked look-ahead one stays the default
-  {
-    int v4 = 0;
-    if (const char *e = getenv("AB200_VL_BVP_V4")) v4 = atoi(e);
-    if (!use_v3 && v4 && b4_supported(n) && (v4 >= 2 || n > 24)) use_v3 = 4;
-  }
-#endif
-  // default variant: when the 3n x (4n+1) window does not fit the 227 KB of shared memory (e.g. nstokes 3 x 16 streams) it moves
-  // to a per-CTA HBM scratch ("large n" layout, vl_bvp.cuh)
-  const bool big_n = !use_v3 && (bvp_smem_doubles(n) * 8 + (size_t)(13 * n + 32) * 4 > 227 * 1024);
-#ifdef AB200_BVP_VARIANTS
-  const size_t bvp_smem_d = use_v3 == 4 ? b4_smem_doubles(n) : (use_v3 ? b3_smem_doubles(n) : (big_n ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n)));
-  const size_t bvp_smem = bvp_smem_d * 8 + (use_v3 == 3 ? b3_smem_ints(n) : (size_t)(13 * n + 32)) * 4;
-#else
-  const size_t bvp_smem_d = big_n ? bvp_smem_doubles_g(n) : bvp_smem_doubles(n);
-  const size_t bvp_smem = bvp_smem_d * 8 + (size_t)(13 * n + 32) * 4;
-#endif
-  int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  int bvp_per_sm = 1;
-  const int var = use_v3 ? use_v3 : (big_n ? 1 : 0);
-  using bvp_fn = void (*)(VLPix, VLSol, VLQuad, VLSurf, VLConv, int, double, int, const int *, int, int *, int *, double *, size_t, int, int, double *);
-#ifdef AB200_BVP_VARIANTS
-  const bvp_fn kbf = (S == 1) ? (var == 4 ? k_vl_bvp<1, 4> : var == 3 ? k_vl_bvp<1, 3> : var == 1 ? k_vl_bvp<1, 1> : k_vl_bvp<1, 0>)
-                              : (var == 4 ? k_vl_bvp<3, 4> : var == 3 ? k_vl_bvp<3, 3> : var == 1 ? k_vl_bvp<3, 1> : k_vl_bvp<3, 0>);
-#else
-  const bvp_fn kbf = (S == 1) ? (var == 1 ? k_vl_bvp<1, 1> : k_vl_bvp<1, 0>) : (var == 1 ? k_vl_bvp<3, 1> : k_vl_bvp<3, 0>);
-#endif
-  auto kb = (const void *)kbf;
-  auto ke = (S == 1) ? (const void *)k_vl_eigen<1> : (const void *)k_vl_eigen<3>;
-  if (!use_add) {
-    if (bvp_smem > 227 * 1024) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory BVP window"); return AB200_ERR_ARG; }
-    AB_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvp_smem));
-    AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bvp_per_sm, kb, bvp_threads, bvp_smem));
-    bvp_per_sm = std::max(1, std::min(bvp_per_sm, 8));
-  }
-  // small problems (3n <= 64 window rows): one warp per pixel, 4 pixels per CTA (k_vl_bvp_warp); AB200_VL_BVP_WARP=0 switches it off
-  bool warp_bvp = !use_add && !use_v3 && !big_n && 3 * n <= 64;
-  if (const char *e = getenv("AB200_VL_BVP_WARP")) warp_bvp = warp_bvp && atoi(e) != 0;
-  const int wb_wpc = 4;
-  const size_t wb_smem_d = (bvp_smem_doubles(n) + (size_t)(13 * n + 32 + 1) / 2 + 2 + 1) & ~(size_t)1;     // per warp, doubles (ints behind)
-  const size_t wb_smem = wb_smem_d * 8 * wb_wpc;
-  auto kw = (S == 1) ? (const void *)k_vl_bvp_warp<1> : (const void *)k_vl_bvp_warp<3>;
-  int wb_per_sm = 1;
-  if (warp_bvp) {
-    AB_CUDA_OK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb_smem));
-    AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wb_per_sm, kw, 32 * wb_wpc, wb_smem));
-    wb_per_sm = std::max(1, std::min(wb_per_sm, 16));
-  }
-  // interaction-principle solver: K2b (one CTA or warp per layer problem) + K3 (persistent CTAs, or one warp per pixel for n <= 16)
-  const bool warp_add = use_add && n <= 16;
-  const int add_wpc = 8;
-  const size_t ops_pw = (ops_smem_doubles(n) + (size_t)(n + 1) / 2 + 1 + 1) & ~(size_t)1, add_pw = (add_smem_doubles(n) + (size_t)(n + 1) / 2 + 1 + 1) & ~(size_t)1;
-  const size_t ops_smem = warp_add ? ops_pw * 8 * add_wpc : ops_smem_doubles(n) * 8 + (size_t)n * 4 + 16;
-  const size_t add_smem = warp_add ? add_pw * 8 * add_wpc : add_smem_doubles(n) * 8 + (size_t)n * 4 + 16;
-  int add_per_sm = 1;
-  if (use_add) {
-    auto ko = warp_add ? ((S == 1) ? (const void *)k_vl_layer_ops_warp<1> : (const void *)k_vl_layer_ops_warp<3>)
-                       : ((S == 1) ? (const void *)k_vl_layer_ops<1> : (const void *)k_vl_layer_ops<3>);
-    auto ka = warp_add ? ((S == 1) ? (const void *)k_vl_add_warp<1> : (const void *)k_vl_add_warp<3>)
-                       : ((S == 1) ? (const void *)k_vl_add<1> : (const void *)k_vl_add<3>);
-    if (ops_smem > 227 * 1024 || add_smem > 227 * 1024) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory solver"); return AB200_ERR_ARG; }
-    AB_CUDA_OK(cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
-    AB_CUDA_OK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)add_smem));
-    AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&add_per_sm, ka, warp_add ? 32 * add_wpc : 128, add_smem));
-    add_per_sm = std::max(1, std::min(add_per_sm, 8));
-  }
-  // (work buffers: one per concurrently running solver = CTA of the block kernel, or warp of the warp kernel)
-  const int bvp_grid_max = use_add ? (warp_add ? nsm * add_per_sm * add_wpc : nsm * add_per_sm) : (warp_bvp ? nsm * wb_per_sm * wb_wpc : nsm * bvp_per_sm);
-  const size_t work_per_cta = use_add ? add_work_doubles(n, L) : bvp_work_doubles(n, L);
-  const size_t bvp_work_bytes = (size_t)bvp_grid_max * (work_per_cta + (big_n && !use_add ? bvp_window_doubles(n) : 0)) * 8;
-  // K2 geometry
-  const int scr_d = eigen_scratch_doubles(n, NM);
-  // warps (= problems) resident per SM within the 227 KB opt-in limit; two CTAs per SM when possible: problems need a
-  // different number of Jacobi sweeps and a CTA only retires when its slowest warp does (measured: 2 x 4 warps beats 1 x 8)
-  int wpc = (int)std::min<size_t>(8, (226 * 1024) / ((size_t)scr_d * 8));
-  if (wpc >= 4) wpc /= 2;
-  if (const char *e = getenv("AB200_VL_EIGEN_WARPS")) wpc = std::max(1, std::min(wpc, atoi(e)));      // tuning knob
-  if (wpc < 1) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory eigen scratch"); return AB200_ERR_ARG; }
-  // two warps per problem (k_vl_eigen_duo) when the register-resident half-pair Jacobi applies (24 <= n <= 48); AB200_VL_EIGEN_DUO=0 switches it off
-  bool duo = n <= 48 && n >= 24;                            // (the row halves of a pair live in registers: 24 rows at most)
-  if (const char *e = getenv("AB200_VL_EIGEN_DUO")) duo = duo && atoi(e) != 0;
-  const size_t eig_smem = duo ? (size_t)wpc * (scr_d + 4) * 8 : (size_t)wpc * scr_d * 8;
-  const bool duo_big = duo && n > 36;                       // own kernel: the 24-row register path must not cost the n <= 36 kernel registers
-  if (duo) ke = duo_big ? ((S == 1) ? (const void *)k_vl_eigen_duo<1, 24> : (const void *)k_vl_eigen_duo<3, 24>)
-                        : ((S == 1) ? (const void *)k_vl_eigen_duo<1> : (const void *)k_vl_eigen_duo<3>);
-  // sub-warp teams for small problems: 8 lanes per problem up to n = 8, 16 up to n = 16 (AB200_VL_EIGEN_SUB=0 switches them off)
-  int subw = (n <= 8) ? 8 : (n <= 16 ? 16 : 32);
-  if (const char *e = getenv("AB200_VL_EIGEN_SUB")) { if (atoi(e) == 0) subw = 32; }
-  const int subs = 32 / subw;
-  size_t eig_smem_sub = 0;
-  int sub_warps = 4;
-  if (subw < 32) {
-    ke = (S == 1) ? (subw == 8 ? (const void *)k_vl_eigen_sub<1, 8> : (const void *)k_vl_eigen_sub<1, 16>)
-                  : (subw == 8 ? (const void *)k_vl_eigen_sub<3, 8> : (const void *)k_vl_eigen_sub<3, 16>);
-    eig_smem_sub = (size_t)sub_warps * subs * scr_d * 8;
-  }
-  AB_CUDA_OK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(subw < 32 ? eig_smem_sub : eig_smem)));
+  budget = std::min(budget, (size_t)(0.6 * (double)(freeb + C.arena.cap)));
   const size_t setup_smem = (size_t)(12 * (L + 1) + 2 * (R.nMom + 1) + 2 * 4 + 16) * 8;
 
   size_t chunk = npix;
@@ -504,8 +248,8 @@ int run_vlidort(const RunDesc &R) {
   else chunk = 1;
   chunk = std::max<size_t>(1, chunk);
   const size_t total_bytes = chunk * per_pix + chunk * 64 + bvp_work_bytes + (size_t)(NM + 1) * (NM + 1) * N * 3 * 8 + (size_t)npix + (64 << 20);
-  AB_CUDA_OK(g_arena.reserve(total_bytes));
-  DevArena &A = g_arena;
+  AB_CUDA_OK(C.arena.reserve(total_bytes));
+  DevArena &A = C.arena;
   VLPix X; X.L = L; X.NM = NM; X.S = S; X.npix = (int)chunk;
   X.deltau = A.take<double>(chunk * L); X.og = A.take<double>(chunk * (NM + 1) * L * 4);
   X.avsec = A.take<double>(chunk * L); X.itrans = A.take<double>(chunk * L); X.tdmubar = A.take<double>(chunk * L);
@@ -526,8 +270,8 @@ int run_vlidort(const RunDesc &R) {
   VLConv CV; CV.total = A.take<double>(chunk * 4); CV.state = A.take<int>(chunk * 4);
   int *listA = A.take<int>(chunk), *listB = A.take<int>(chunk), *counts = A.take<int>(2 * (NM + 4));
   double *d_pq = A.take<double>((size_t)(NM + 1) * N * 3 * (NM + 1));
-  double *work = A.take<double>((size_t)bvp_grid_max * work_per_cta);
-  double *wglob = (big_n && !use_add) ? A.take<double>((size_t)bvp_grid_max * bvp_window_doubles(n)) : nullptr;
+  double *work = A.take<double>((size_t)solvers * work_per_solver);
+  double *wglob = (!use_add && PB.window) ? A.take<double>((size_t)solvers * PB.window) : nullptr;
   unsigned char *d_skip = A.take<unsigned char>(npix);
   VLBrdf Bd; VLSurf SFb; memset(&SFb, 0, sizeof SFb);
   if (R.brdf) {
@@ -556,6 +300,7 @@ int run_vlidort(const RunDesc &R) {
     const std::vector<unsigned char> &sk = *R.h_skip;
     for (int j = 0; j < R.nobs && nadir_from == R.nobs; j++)
       if ((*R.h_sza)[j] == 0.0) for (int i = 0; i < R.nch; i++) if (!sk[(size_t)j * R.nch + i]) { nadir_from = j; break; }
+    if (R.nadir_already) nadir_from = 0;
     AB_CUDA_OK(cudaMemcpyAsync(d_skip, sk.data(), npix, cudaMemcpyHostToDevice, st));
   }
   VLIn in; memset(&in, 0, sizeof in);
@@ -566,14 +311,13 @@ int run_vlidort(const RunDesc &R) {
   in.albedo = R.albedo; in.sza = R.sza; in.raa = R.raa; in.vza = R.vza; in.flux_factor = R.flux_factor; in.exactdb = R.exactdb;
   in.skip = d_skip;
   const double accuracy = (double)0.0001f;
-  cudaEvent_t ev[4];
-  for (auto &e : ev) cudaEventCreate(&e);
+  EventSet EV; cudaEvent_t *ev = EV.e;
 
   for (size_t p0 = 0; p0 < (size_t)npix; p0 += chunk) {
     const int nc = (int)std::min<size_t>(chunk, npix - p0);
     AB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * (NM + 4), st));
     cudaEventRecord(ev[0], st);
-    if (R.brdf) { k_vl_brdf_fourier<<<nc, 256, brdf_smem, st>>>(Bd, (int)p0, d_skip, brdf_nscr); g_stats.n_launches += 1; }
+    if (R.brdf) { k_vl_brdf_fourier<<<nc, 256, brdf_smem, st>>>(Bd, (int)p0, d_skip, brdf_nscr); stats.n_launches += 1; }
     k_vl_setup<<<nc, 128, setup_smem, st>>>(in, X, (int)p0);
     k_vl_init_active<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, Z, nc, listA, counts);
     cudaEventRecord(ev[1], st);
@@ -581,8 +325,8 @@ int run_vlidort(const RunDesc &R) {
     int nactive = 0;
     AB_CUDA_OK(cudaMemcpyAsync(&nactive, counts, sizeof(int), cudaMemcpyDeviceToHost, st));
     AB_CUDA_OK(cudaStreamSynchronize(st));
-    float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); g_stats.ms_setup += ms;
-    // BRDF pointers are indexed with the global pixel inside bvp_pixel via SF; shift them to the chunk
+    float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); stats.ms_setup += ms;
+    // BRDF pointers are indexed with the chunk-local pixel inside the solvers via SF; shift caller-supplied arrays to the chunk
     VLSurf SFc = R.surf;
     if (R.brdf) SFc = SFb;                                   // chunk-local arrays, rewritten for every chunk
     else if (!R.lambertian) {
@@ -592,63 +336,34 @@ int run_vlidort(const RunDesc &R) {
     int *cur = listA, *nxt = listB;
     for (int m = 0; m <= NM && nactive > 0; m++) {
       const long nprob = (long)nactive * L;
-      const int egrid = (int)((nprob + wpc - 1) / wpc);
       const double *pqm = d_pq + (size_t)m * (NM + 1) * N * 3;
-      cudaEventRecord(ev[0], st);
-      if (subw < 32) {
-        const int spc = sub_warps * subs, sgrid = (int)((nprob + spc - 1) / spc);
-        if (S == 1) { if (subw == 8) k_vl_eigen_sub<1, 8><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-                      else k_vl_eigen_sub<1, 16><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d); }
-        else { if (subw == 8) k_vl_eigen_sub<3, 8><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-               else k_vl_eigen_sub<3, 16><<<sgrid, 32 * sub_warps, eig_smem_sub, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d); }
-      } else if (duo_big) {
-        if (S == 1) k_vl_eigen_duo<1, 24><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-        else k_vl_eigen_duo<3, 24><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-      } else if (duo) {
-        if (S == 1) k_vl_eigen_duo<1><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-        else k_vl_eigen_duo<3><<<egrid, 64 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-      } else if (S == 1) k_vl_eigen<1><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-      else k_vl_eigen<3><<<egrid, 32 * wpc, eig_smem, st>>>(X, Z, QD, pqm, m, cur, nactive, scr_d);
-      cudaEventRecord(ev[1], st);
-      const int bgrid = std::min(nactive, bvp_grid_max);
       int *cnt = counts + 1 + m;
+      cudaEventRecord(ev[0], st);
+      vl_eigen_launch(PE, X, Z, QD, pqm, m, cur, nactive, st);
+      cudaEventRecord(ev[1], st);
       if (use_add) {
-        if (warp_add) {
-          const int ogrid = (int)((nprob + add_wpc - 1) / add_wpc), agrid = std::min((nactive + add_wpc - 1) / add_wpc, nsm * add_per_sm);
-          if (S == 1) k_vl_layer_ops_warp<1><<<ogrid, 32 * add_wpc, ops_smem, st>>>(X, Z, O, cur, nactive, (int)ops_pw);
-          else k_vl_layer_ops_warp<3><<<ogrid, 32 * add_wpc, ops_smem, st>>>(X, Z, O, cur, nactive, (int)ops_pw);
-          cudaEventRecord(ev[3], st);
-          if (S == 1) k_vl_add_warp<1><<<agrid, 32 * add_wpc, add_smem, st>>>(X, Z, O, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, (int)add_pw);
-          else k_vl_add_warp<3><<<agrid, 32 * add_wpc, add_smem, st>>>(X, Z, O, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, (int)add_pw);
-        } else {
-          if (S == 1) k_vl_layer_ops<1><<<(unsigned)nprob, 128, ops_smem, st>>>(X, Z, O, cur, nactive);
-          else k_vl_layer_ops<3><<<(unsigned)nprob, 128, ops_smem, st>>>(X, Z, O, cur, nactive);
-          cudaEventRecord(ev[3], st);
-          if (S == 1) k_vl_add<1><<<bgrid, 128, add_smem, st>>>(X, Z, O, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
-          else k_vl_add<3><<<bgrid, 128, add_smem, st>>>(X, Z, O, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta);
-        }
-        g_stats.n_launches += 1;
-        // executed flops of the two kernels: 2 x (3 n^3 elimination + 2 n^3 product) per layer, and 3 n^3 + 3 x 2 n^3 per layer
-        g_stats.flops_exec += (double)nprob * 19.0 * (double)n * n * n;
-      } else if (warp_bvp) {
-        const int wgrid = std::min((nactive + wb_wpc - 1) / wb_wpc, nsm * wb_per_sm);
-        if (S == 1) k_vl_bvp_warp<1><<<wgrid, 32 * wb_wpc, wb_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, (int)wb_smem_d);
-        else k_vl_bvp_warp<3><<<wgrid, 32 * wb_wpc, wb_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, (int)wb_smem_d);
-      } else
-      kbf<<<bgrid, bvp_threads, bvp_smem, st>>>(X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, work_per_cta, use_v3, (int)bvp_smem_d, wglob);
+        vl_ops_launch(PA, X, Z, O, cur, nactive, st);
+        cudaEventRecord(ev[3], st);
+        vl_add_launch(PA, X, Z, O, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, st);
+        stats.n_launches += 1;
+        // executed flops of the two kernels per layer: 2 x (2 n^3 inversion + 2 n^3 product), and 2 n^3 inversion + 4 x 2 n^3 products
+        stats.flops_exec += (double)nprob * 18.0 * (double)n * n * n;
+      } else {
+        vl_band_launch(PB, X, Z, QD, SFc, CV, R.lambertian, accuracy, m, cur, nactive, nxt, cnt, work, wglob, st);
+      }
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());
-      g_stats.n_eigen_problems += nprob; g_stats.n_bvp_problems += nactive; g_stats.n_launches += 2;
+      stats.n_eigen_problems += nprob; stats.n_bvp_problems += nactive; stats.n_launches += 2;
       {  // algorithmic flops of SURVEY.md 8(d): eigen part (2+25+2) n^3 + 4 S^3 N^2 (2N-m); BVP part (14/3)(2n)^3 + 12 (2n)^2
         const double n3 = (double)n * n * n;
-        g_stats.flops_eigen += (double)nprob * (29.0 * n3 + 4.0 * S * S * S * (double)N * N * (2 * N - m));
-        g_stats.flops_bvp += (double)nprob * ((14.0 / 3.0) * 8.0 * n3 + 12.0 * 4.0 * n * n);
+        stats.flops_eigen += (double)nprob * (29.0 * n3 + 4.0 * S * S * S * (double)N * N * (2 * N - m));
+        stats.flops_bvp += (double)nprob * ((14.0 / 3.0) * 8.0 * n3 + 12.0 * 4.0 * n * n);
       }
       AB_CUDA_OK(cudaMemcpyAsync(&nactive, cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
       AB_CUDA_OK(cudaStreamSynchronize(st));
       float m1 = 0, m2 = 0, m3 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);
-      if (use_add) { cudaEventElapsedTime(&m3, ev[1], ev[3]); g_stats.ms_ops += m3; }
-      g_stats.ms_eigen += m1; g_stats.ms_bvp += m2;
+      if (use_add) { cudaEventElapsedTime(&m3, ev[1], ev[3]); stats.ms_ops += m3; }
+      stats.ms_eigen += m1; stats.ms_bvp += m2;
       std::swap(cur, nxt);
     }
     k_vl_finish<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, (int)p0, nc, R.nch, R.nobs, R.sza, R.MISSING, S, R.radiance, R.reflectance, R.Q, R.U,
@@ -656,8 +371,14 @@ int run_vlidort(const RunDesc &R) {
     AB_CUDA_OK(cudaGetLastError());
     AB_CUDA_OK(cudaStreamSynchronize(st));
   }
-  for (auto &e : ev) cudaEventDestroy(e);
-  g_stats.npix += npix; g_stats.n_launches += 3 * ((npix + chunk - 1) / chunk);
+  stats.npix += npix; stats.n_launches += 3 * ((npix + chunk - 1) / chunk);
+  {
+    std::lock_guard<std::mutex> lk(g_stats_mu);
+    g_stats.ms_setup += stats.ms_setup; g_stats.ms_eigen += stats.ms_eigen; g_stats.ms_bvp += stats.ms_bvp; g_stats.ms_ops += stats.ms_ops;
+    g_stats.flops_eigen += stats.flops_eigen; g_stats.flops_bvp += stats.flops_bvp; g_stats.flops_exec += stats.flops_exec;
+    g_stats.n_eigen_problems += stats.n_eigen_problems; g_stats.n_bvp_problems += stats.n_bvp_problems; g_stats.n_launches += stats.n_launches;
+    g_stats.npix += stats.npix;
+  }
   return 0;
 }
 
@@ -678,10 +399,16 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
   if (npix == 0) return 0;
   const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
   size_t bytes = 8 * (n_rot * (alpha ? 4 : 3) + n_pm + n_he + npix * (1 + (flux_factor ? 1 : 0)) + 3 * (size_t)nobs + nch + 4 * npix) + 8 * npix + 4096 * 16;
-  static DevBuf io;
-  AB_CUDA_OK(io.reserve(bytes));
-  char *b = io.as<char>(); size_t off = 0;
-  auto put = [&](const double *src, size_t n) -> double * { off = align256(off); double *d = (double *)(b + off); off += n * 8; if (src) cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, 0); return d; };
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  AB_CUDA_OK(C.io.reserve(bytes));
+  char *b = C.io.as<char>(); size_t off = 0;
+  cudaError_t cpe = cudaSuccess;
+  auto put = [&](const double *src, size_t n) -> double * {
+    off = align256(off); double *d = (double *)(b + off); off += n * 8;
+    if (src) { cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, 0); if (e != cudaSuccess) cpe = e; }
+    return d;
+  };
   RunDesc R; memset(&R, 0, sizeof R);
   R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
   R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING;
@@ -697,7 +424,8 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
     for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || is_missing_h(albedo[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
   }
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = 0;
-  int e = run_vlidort(R);
+  AB_CUDA_OK(cpe);
+  int e = run_vlidort(C, R);
   if (e) return e;
   AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * npix, cudaMemcpyDeviceToHost, 0));
   AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * npix, cudaMemcpyDeviceToHost, 0));
@@ -715,14 +443,13 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
 struct SurfArgs { int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; const double *alpha = nullptr, *flux_factor = nullptr; };
 
 // pixel-independent BRDF tables -> device
-int build_brdf_tables(VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, cudaStream_t st) {
+int build_brdf_tables(VLContext &C, VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, cudaStream_t st) {
   std::vector<double> h;
   brdf_host_tables(B, kind, S, scalar_glue, N, NM, nch, nobs, h);
-  static DevBuf tab;
-  AB_CUDA_OK(tab.reserve(h.size() * 8));
-  AB_CUDA_OK(cudaMemcpyAsync(tab.as<double>(), h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+  AB_CUDA_OK(C.tab.reserve(h.size() * 8));
+  AB_CUDA_OK(cudaMemcpyAsync(C.tab.as<double>(), h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
   AB_CUDA_OK(cudaStreamSynchronize(st));
-  brdf_rebase_tables(B, h.data(), tab.as<double>());
+  brdf_rebase_tables(B, h.data(), C.tab.as<double>());
   return 0;
 }
 
@@ -740,13 +467,15 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   const bool cx = (sa.kind != SURF_MODIS);
   const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
   const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + 5 * (size_t)nobs + 2 * nch + 6 * npix + 7 * npix + 16 * npix) + 16 * npix + 4096 * 32;
-  static DevBuf io;
-  AB_CUDA_OK(io.reserve(dev ? 8 * (16 * npix + 7 * npix) + 16 * npix + 4096 * 8 : bytes));
-  char *b = io.as<char>(); size_t off = 0;
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * npix + 7 * npix) + 16 * npix + 4096 * 8 : bytes));
+  char *b = C.io.as<char>(); size_t off = 0;
+  cudaError_t cpe = cudaSuccess;
   auto put = [&](const double *src, size_t n) -> double * {
     if (dev && src) return const_cast<double *>(src);
     off = align256(off); double *d = (double *)(b + off); off += n * 8;
-    if (src) cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st);
+    if (src) { cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) cpe = e; }
     return d;
   };
   RunDesc R; memset(&R, 0, sizeof R);
@@ -786,13 +515,14 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   AB_CUDA_OK(cudaMemcpyAsync(d_skip0, skip.data(), npix, cudaMemcpyHostToDevice, st));
   VLBrdf B;
   const int NM = std::min(2 * nstreams - 1, nMom);
-  if (int e = build_brdf_tables(B, sa.kind, S, scalar_glue, nstreams, NM, nch, nobs, st)) return e;
+  AB_CUDA_OK(cpe);
+  if (int e = build_brdf_tables(C, B, sa.kind, S, scalar_glue, nstreams, NM, nch, nobs, st)) return e;
   B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
   B.exactdb = d_exact;
   off = align256(off); B.wsa_fail = (int *)(b + off); off += 4 * npix;
   k_vl_brdf_exact<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(B, (int)npix, d_skip0, d_BR, d_BRQ, d_BRU);
   AB_CUDA_OK(cudaGetLastError());
-  g_stats.n_launches += 1;
+  { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.n_launches += 1; }
   if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel not run
     std::vector<double> h_br(npix);
     AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * npix, cudaMemcpyDeviceToHost, st));
@@ -801,7 +531,7 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   }
   R.exactdb = d_exact; R.brdf = &B;
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
-  if (int e = run_vlidort(R)) return e;
+  if (int e = run_vlidort(C, R)) return e;
   g_last_nfourier.resize(npix); g_last_status.resize(npix);
   AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * npix, cudaMemcpyDeviceToHost, st));
   AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * npix, cudaMemcpyDeviceToHost, st));
@@ -853,9 +583,10 @@ extern "C" int ab200_rot_calc(int km, int nch, int nobs, const double *channels,
   if (km > 72) { *rc = 3; return 3; }
   const size_t ne = (size_t)(km + 1) * nobs, nr = (size_t)km * nobs * nch;
   if (nr == 0) return 0;
-  static DevBuf io;
-  AB_CUDA_OK(io.reserve(8 * (3 * ne + nr + 2 * nch) + 4096));
-  double *d = io.as<double>();
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  AB_CUDA_OK(C.rot.reserve(8 * (3 * ne + nr + 2 * nch) + 4096));
+  double *d = C.rot.as<double>();
   double *d_pe = d, *d_he = d + ne, *d_te = d + 2 * ne, *d_ch = d + 3 * ne, *d_dp = d_ch + nch, *d_rot = d_dp + nch;
   cudaMemcpyAsync(d_pe, pe, 8 * ne, cudaMemcpyHostToDevice, 0); cudaMemcpyAsync(d_he, he, 8 * ne, cudaMemcpyHostToDevice, 0);
   cudaMemcpyAsync(d_te, te, 8 * ne, cudaMemcpyHostToDevice, 0); cudaMemcpyAsync(d_ch, channels, 8 * nch, cudaMemcpyHostToDevice, 0);
@@ -885,6 +616,7 @@ extern "C" long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long
 }
 
 extern "C" int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long *n_launches) {
+  std::lock_guard<std::mutex> lk(g_stats_mu);
   if (flops_eigen) *flops_eigen = g_stats.flops_eigen;
   if (flops_bvp) *flops_bvp = g_stats.flops_bvp;
   if (n_launches) *n_launches = g_stats.n_launches;
@@ -894,6 +626,7 @@ extern "C" int ab200_vlidort_stats2(double *flops_eigen, double *flops_bvp, long
 // ms_ops: the share of ms_bvp spent in K2b (layer interaction operators); flops_exec: flops the interaction-principle kernels
 // actually execute (flops_bvp stays the SURVEY 8(d) band-LU count the roofline is quoted on)
 extern "C" int ab200_vlidort_stats3(double *ms_ops, double *flops_exec) {
+  std::lock_guard<std::mutex> lk(g_stats_mu);
   if (ms_ops) *ms_ops = g_stats.ms_ops;
   if (flops_exec) *flops_exec = g_stats.flops_exec;
   return 0;
@@ -924,17 +657,18 @@ extern "C" int ab200_vlidort_vector_lambert_dev(int km, int nch, int nobs, int n
     const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
     for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || is_missing_h(h_alb[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
   }
-  static DevBuf diag;
-  AB_CUDA_OK(diag.reserve(8 * npix + 512));
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  AB_CUDA_OK(C.diag.reserve(8 * npix + 512));
   RunDesc R; memset(&R, 0, sizeof R);
   R.S = 3; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
   R.lambertian = 1; R.scalar_glue = 0; R.MISSING = MISSING;
   R.ROT = ROT; R.depol = depol; R.alpha = alpha; R.tau = tau; R.ssa = ssa; R.pmom = pmom; R.he = he; R.albedo = albedo;
   R.sza = sza; R.raa = raa; R.vza = vza; R.flux_factor = flux_factor;
   R.radiance = radiance; R.reflectance = reflectance; R.Q = Q; R.U = U;
-  R.nfourier = diag.as<int>(); R.status = diag.as<int>() + npix;
+  R.nfourier = C.diag.as<int>(); R.status = C.diag.as<int>() + npix;
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
-  return run_vlidort(R);
+  return run_vlidort(C, R);
 }
 
 // ---- BRDF surfaces (argument lists follow LV/VLIDORT_POLAR_py.F90:137-213 VECTOR_BRDF_MODIS, :673-745 VECTOR_GissCX,
@@ -1040,6 +774,7 @@ extern "C" int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstrea
 
 extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,
                                    int reset) {
+  std::lock_guard<std::mutex> lk(g_stats_mu);
   if (ms_setup) *ms_setup = g_stats.ms_setup;
   if (ms_eigen) *ms_eigen = g_stats.ms_eigen;
   if (ms_bvp) *ms_bvp = g_stats.ms_bvp;
@@ -1051,8 +786,12 @@ extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *m
 }
 
 extern "C" int ab200_vlidort_release(void) {
-  if (g_arena.base) cudaFree(g_arena.base);
-  g_arena.base = nullptr; g_arena.cap = 0; g_arena.off = 0;
+  // frees the workspaces of the device that is current on the calling thread
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  if (C.arena.base) cudaFree(C.arena.base);
+  C.arena.base = nullptr; C.arena.cap = 0; C.arena.off = 0;
+  C.io.release(); C.tab.release(); C.diag.release(); C.rot.release();
   return 0;
 }
 

@@ -66,7 +66,7 @@ extern "C" int hm_vlidort(int S, int N, int km, int nch, int nobs, int nMom, int
   const bool legacy = getenv("AB_HM_LEGACY_BVP") != nullptr || n > 64;
   VLOps O;
   std::vector<double> ork((size_t)L * n * n), otk(ork), osp(ork), osm(ork), osu((size_t)L * n), osd(osu);
-  std::vector<double> oscr(ops_smem_doubles(n) + 64), ascr(add_smem_doubles(n) + 64), awork(add_work_doubles(n, L));
+  std::vector<double> oscr(ops_smem_doubles(n, false) + 64), ascr(add_smem_doubles(n, false) + 64), awork(add_work_doubles(n, L));
   for (int p = 0; p < npix; p++) {
     status[p] = ibuf[(size_t)p * 4 + 1]; nfourier[p] = 0;
     for (int o = 0; o < 4; o++) stokes[(size_t)p * 4 + o] = 0.0;
