@@ -198,8 +198,72 @@ def scalar_brdf_modis(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, 
     return (*outs, rc.value)
 
 
+# ---- multi-geometry forms: the generic Fortran interfaces VLIDORT_Vector_Lambert / VLIDORT_Vector_CX / VLIDORT_Vector_LandMODIS over
+#      SingleGeom / MultiGeom (GV/VLIDORT_LAMBERT.F90:14-17,346-520, GV/VLIDORT_BRDF_CX.F90:27-30,766-947, GV/VLIDORT_BRDF_MODIS.F90:413).
+#      solar_zenith, relat_azymuth, sensor_zenith are (nobs,ngeom); outputs (nobs,nch,ngeom).  With one sun per observation (the 60 view
+#      angles per column of LV/polar_vlidort.py:935-950) the eigenproblems and the boundary-value solve are shared by all views.
+def _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs):
+    a = [np.asfortranarray(np.asarray(x, dtype=np.float64).reshape(nobs, -1)) for x in (solar_zenith, relat_azymuth, sensor_zenith)]
+    ngeom = a[1].shape[1]
+    if a[0].shape[1] == 1 and ngeom > 1:
+        a[0] = np.asfortranarray(np.repeat(a[0], ngeom, axis=1))
+    assert a[0].shape == a[1].shape == a[2].shape == (nobs, ngeom), "angles must be (nobs, ngeom)"
+    return a[0], a[1], a[2], ngeom
+
+
+def vector_lambert_multigeom(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, albedo,
+                             solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """returns (radiance, reflectance, Q, U (nobs,nch,ngeom), rc)"""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor = (_F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    sza, raa, vza, ngeom = _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs)
+    ch, dp = _v(channels), _v(depol)
+    outs = [np.zeros((nobs, nch, ngeom), order="F") for _ in range(4)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_lambert_multigeom(km, nch, nobs, ngeom, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                       _p(ROT), _p(dp), _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te),
+                                                       _p(albedo), _p(sza), _p(raa), _p(vza), _p(flux_factor), C.c_double(MISSING),
+                                                       int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_lambert_multigeom")
+    return (*outs, rc.value)
+
+
+def vector_cx_multigeom(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
+                        relat_azymuth, sensor_zenith, MISSING, verbose):
+    """returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U (nobs,nch,ngeom), rc)"""
+    ROT, tau, ssa, pmom, pe, he, te = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    sza, raa, vza, ngeom = _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs)
+    ch, dp, u, v, m = _v(channels), _v(depol), _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch, ngeom), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_cx_multigeom(km, nch, nobs, ngeom, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                  _p(ROT), _p(dp), _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m),
+                                                  _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs],
+                                                  C.byref(rc)), "ab200_vlidort_vector_cx_multigeom")
+    return (*outs, rc.value)
+
+
+def vector_brdf_modis_multigeom(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, kernel_wt, param,
+                                solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U (nobs,nch,ngeom), rc)"""
+    ROT, tau, ssa, pmom, pe, he, te, kernel_wt, param = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, kernel_wt, param))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    sza, raa, vza, ngeom = _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs)
+    ch, dp = _v(channels), _v(depol)
+    outs = [np.zeros((nobs, nch, ngeom), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_brdf_modis_multigeom(km, nch, nobs, ngeom, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom,
+                                                          nPol, kernel_wt.shape[0], param.shape[0], _p(ROT), _p(dp), _p(tau), _p(ssa),
+                                                          _p(pmom), _p(pe), _p(he), _p(te), _p(kernel_wt), _p(param), _p(sza), _p(raa),
+                                                          _p(vza), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs],
+                                                          C.byref(rc)), "ab200_vlidort_vector_brdf_modis_multigeom")
+    return (*outs, rc.value)
+
+
 def last_diag():
-    """(nfourier, status) per pixel (nobs, nch) of the most recent VLIDORT call -- diagnostics, not in the reference."""
+    """(nfourier, status) per pixel p = j*nch + i (per pixel-view (j*nch + i)*ngeom + g for the multi-geometry forms) of this
+    thread's most recent VLIDORT call -- diagnostics, not in the reference."""
     lib().ab200_vlidort_last_diag.restype = C.c_long
     n = lib().ab200_vlidort_last_diag(None, None, C.c_long(0))
     nf = np.zeros(n, np.int32); st = np.zeros(n, np.int32)

@@ -8,13 +8,15 @@
 // (2n x 72 unknowns, band half-width 3n-1, 5184 chained pivot columns at n = 36).  K2b (vl_layerops.cuh) has already reduced every
 // layer to its n x n reflection / transmission operators R_k, Tm_k and source vectors; here the SAME linear system is solved by
 // block elimination over interfaces:
-//   up-sweep, k = L .. 1:   Rs_k = R_k + Tm_k Rs_{k+1} E_k Tm_k,   E_k = (1 - R_k Rs_{k+1})^-1     (reflection of everything below)
+//   up-sweep, k = L .. 1:   Rs_k = R_k + Tm_k Rs_{k+1} E_k Tm_k,   E_k = (1 - R_k Rs_{k+1})^-1     (reflection of everything below;
+//                           E_k applied as the product prod_j (1 + (R_k Rs_{k+1})^(2^j)), see the loop)
 //                           Ss_k = sg_up + Tm_k (Ss_{k+1} + Rs_{k+1} y_k),   [Y_k | y_k] = E_k [Tm_k | R_k Ss_{k+1} + sg_dn]
 //                           Rs_{L+1}, Ss_{L+1} = the surface (Lambertian / BRDF Fourier component, BVP_SURFACE_SETUP_HOM/_BEAM)
 //   down-sweep, k = 1 .. L: I_dn(bot_k) = Y_k I_dn(top_k) + y_k,   u(bot_k) = Rs_{k+1} I_dn(bot_k) + Ss_{k+1},  I_dn(top_1) = 0
 //                           a + b = S+ (in_dn + in_u),  a - b = S- (in_dn - in_u)                 (LCON, MCON of the layer)
-// Work: one n x n inversion and four n x n products per layer (10 n^3 flops against the 37 n^3 of the block-bidiagonal LU), 36
-// chained pivot columns per layer instead of 72, and 60 KB of shared memory per pixel instead of 125 KB, so three pixels share an SM.  The layer source terms are accumulated top-down with the running user-stream
+// Work: 6 - 8 n x n products per layer for a typical column (12 - 16 n^3 flops against the 37 n^3 of the block-bidiagonal LU), all
+// of them register-tiled products out of shared memory with no pivot-column chain (the reference's LU has 5184 chained columns per
+// pixel and Fourier term), and 66 KB of shared memory per pixel instead of 125 KB, so three pixels share an SM.  The layer source terms are accumulated top-down with the running user-stream
 // transmittance (the reference recurses bottom-up: same sum, different association).
 #pragma once
 #include "vl_bvp.cuh"
@@ -22,23 +24,28 @@
 
 namespace vlk {
 
-// team scratch (doubles): Rs, Rk, Tk, QE (1 - R Rs, then its inverse, then Rs Y), Yb: n x ld each (ld = mat_ld(n)); 14 vectors;
-// inverse work; ints: 2n
-HDFN size_t add_smem_doubles(int n, bool cta) { return 5 * (size_t)n * mat_ld(n) + 14 * n + inv_work_doubles(n, cta); }
+// team scratch (doubles): Rs, Rk, two Q arrays, two Y arrays: n x ld each (ld = mat_ld(n)); 13 vectors
+HDFN size_t add_smem_doubles(int n, bool) { return 6 * (size_t)n * mat_ld(n) + 13 * n + 2; }
 // per-team global scratch (doubles): per layer Y^T, (Rs Y)^T (n x n each), y, Rs y + Ss (n each)
 HDFN size_t add_work_doubles(int n, int L) { return (size_t)L * (2 * (size_t)n * n + 2 * n); }
+
+// an eigenproblem or the boundary-value solve failed: every view of the pixel leaves the Fourier loop with status 4
+template <class Team>
+DEVFN void add_fail_pixel(const Team &T, const VLPix &X, const VLConv &CV, int p) {
+  for (int g = T.rank; g < X.G; g += T.size) { int *c = CV.state + (size_t)(view0(X, p) + g) * 4; c[0] = 0; c[3] = 4; }
+  if (T.rank == 0) CV.col_active[p] = 0;
+}
 
 template <int S, class Team>
 DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps &O, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
                      int lambertian, double accuracy, int m, int p, double *scr, int *piv, double *Wg) {
   const int N = QD.N, n = S * N, L = X.L, NM = X.NM, ld = mat_ld(n);
-  double *Rs = scr, *Rk = Rs + (size_t)n * ld, *Tk = Rk + (size_t)n * ld, *QE = Tk + (size_t)n * ld, *Yb = QE + (size_t)n * ld, *Zb = QE;
-  double *Ss = Yb + (size_t)n * ld, *Sn = Ss + n, *su = Sn + n, *sd = su + n, *vv = sd + n, *yv = vv + n, *zz = yv + n, *xv = zz + n,
+  double *Rs = scr, *Rk = Rs + (size_t)n * ld, *QA = Rk + (size_t)n * ld, *QB = QA + (size_t)n * ld, *YA = QB + (size_t)n * ld, *YB = YA + (size_t)n * ld;
+  double *Ss = YB + (size_t)n * ld, *Sn = Ss + n, *su = Sn + n, *sd = su + n, *yv = sd + n, *zz = yv + n, *xv = zz + n,
          *xb = xv + n, *ub = xb + n, *inp = ub + n, *inm = inp + n, *av = inm + n, *bv = av + n;
-  double *wk = bv + n;
-  const double *sc = X.scal + (size_t)p * 16;
-  const int *ib = X.ibuf + (size_t)p * 4;
-  int *cst = CV.state + (size_t)p * 4;
+  const int G = X.G, v0 = view0(X, p);                        // p = pixel; its views are v0 .. v0 + G - 1
+  const double *sc = X.scal + (size_t)v0 * 16;                // sun, flux, albedo: the same for every view of the pixel
+  const int *ib = X.ibuf + (size_t)v0 * 4;
   const double cos_sza = sc[0], albedo = sc[4], FLUXF = sc[5];
   const int cutoff = ib[0];
   const bool refl_direct = ib[2] != 0;
@@ -46,16 +53,12 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
   if (lambertian) { if (m != 0) include_surface = false; else if (albedo == 0.0) include_surface = false; }
   const double SFAC = (m == 0) ? 2.0 : 1.0, DELTA_FACTOR = (m == 0) ? 1.0 : 2.0;
   const bool localbeam = include_surface && refl_direct;
-  const double *BF = nullptr, *BF0 = nullptr, *UBF = nullptr;
+  const double *BF = nullptr, *BF0 = nullptr;
   const int nq = SF.nq;
   if (!lambertian) {
     BF = SF.brdf_f + ((size_t)p * SF.nmfour + m) * SF.nq * N * N;
     BF0 = SF.brdf_f_0 + ((size_t)p * SF.nmfour + m) * SF.nq * N;
-    UBF = SF.user_brdf_f + ((size_t)p * SF.nmfour + m) * SF.nq * N;
   }
-  auto UBFq = [&](int o1, int o2, int jj) -> double {
-    return nq == 16 ? UBF[(size_t)(4 * o1 + o2) * N + jj] : ((o1 | o2) == 0 ? UBF[jj] : 0.0);
-  };
   double attn = 0.0;
   if (localbeam) attn = FLUXF * (4.0 * cos_sza / DELTA_FACTOR) / PI4 * sc[3];
   const size_t q0 = (size_t)p * L;
@@ -85,45 +88,59 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
   }
   T.sync();
 
-  // ---- up-sweep
+  // ---- up-sweep.  E_k = (1 - Q)^-1, Q = R_k Rs, is never formed: reflectances are contractions (spectral radius of Q < 1), so
+  //      E_k [Tm_k | v] = prod_j (1 + Q^(2^j)) [Tm_k | v]   -- one product per factor and one squaring per level, no pivoting,
+  //      no pivot-column chain; the loop stops when the next factor is 1 to working precision (2 - 3 levels for the optically
+  //      thin layers that make up most of a column, 6 - 7 for a thick cloud over a bright surface).
   for (int k = L - 1; k >= 0; k--) {
     const size_t q = q0 + k;
     const double *Rg = O.rk + q * n * n, *Tg = O.tk + q * n * n;
+    double *Qc = QA, *Qn = QB, *Yc = YA, *Yn = YB, *yc = yv, *yn = zz;
     for (int idx = T.rank; idx < n * n; idx += T.size) {
       const int r = idx / n, c = idx % n;
-      Rk[(size_t)r * ld + c] = Rg[idx]; Tk[(size_t)r * ld + c] = Tg[idx];
+      Rk[(size_t)r * ld + c] = Rg[idx]; Yc[(size_t)r * ld + c] = Tg[idx];
     }
     for (int r = T.rank; r < n; r += T.size) { su[r] = O.sgu[q * n + r]; sd[r] = O.sgd[q * n + r]; }
     T.sync();
-    // QE = 1 - R_k Rs,   vv = R_k Ss + sg_dn
-    team_mm(T, n, n, n, Rk, ld, Rs, ld, [&](int r, int c, double acc) { QE[(size_t)r * ld + c] = (r == c ? 1.0 : 0.0) - acc; });
+    // Q = R_k Rs,   y = R_k Ss + sg_dn
+    double qmax = 0.0;
+    team_mm(T, n, n, n, Rk, ld, Rs, ld, [&](int r, int c, double acc) { Qc[(size_t)r * ld + c] = acc; qmax = fmax(qmax, fabs(acc)); });
     for (int r = T.rank; r < n; r += T.size) {
       const double *Rr = Rk + (size_t)r * ld;
       double v = sd[r];
       for (int c = 0; c < n; c++) v += Rr[c] * Ss[c];
-      vv[r] = v;
+      yc[r] = v;
     }
-    T.sync();
-    if (!team_inverse(T, n, QE, QE, ld, wk, piv)) { if (T.rank == 0) { cst[0] = 0; cst[3] = 4; } return; }     // QE <- E_k
-    // Yb = E_k Tm_k,  yv = E_k vv
-    team_mm(T, n, n, n, QE, ld, Tk, ld, [&](int r, int c, double acc) { Yb[(size_t)r * ld + c] = acc; });
-    for (int r = T.rank; r < n; r += T.size) {
-      const double *Er = QE + (size_t)r * ld;
-      double v = 0.0;
-      for (int c = 0; c < n; c++) v += Er[c] * vv[c];
-      yv[r] = v;
+    { int dummy = 0; qmax = T.argmax(qmax, dummy) * (double)n; }          // >= the max-row-sum norm of Q; the collective also orders Q, y
+    bool okq = true;
+    for (int lev = 0; qmax > 1.0e-17; lev++) {
+      if (lev > 14 || !(qmax < 1.0e30)) { okq = false; break; }           // not a contraction (or NaN input): fail the pixel
+      // [Y | y] <- (1 + Q) [Y | y]
+      team_mm(T, n, n, n, Qc, ld, Yc, ld, [&](int r, int c, double acc) { Yn[(size_t)r * ld + c] = Yc[(size_t)r * ld + c] + acc; });
+      for (int r = T.rank; r < n; r += T.size) {
+        const double *Qr = Qc + (size_t)r * ld;
+        double v = yc[r];
+        for (int c = 0; c < n; c++) v += Qr[c] * yc[c];
+        yn[r] = v;
+      }
+      { double *t = Yc; Yc = Yn; Yn = t; t = yc; yc = yn; yn = t; }
+      if (qmax * qmax <= 1.0e-17) { T.sync(); break; }                    // the next factor 1 + Q^2 is 1 to working precision
+      double q2 = 0.0;
+      team_mm(T, n, n, n, Qc, ld, Qc, ld, [&](int r, int c, double acc) { Qn[(size_t)r * ld + c] = acc; q2 = fmax(q2, fabs(acc)); });
+      { double *t = Qc; Qc = Qn; Qn = t; }
+      { int dummy = 0; qmax = T.argmax(q2, dummy) * (double)n; }
     }
-    T.sync();
-    // Y^T and y to the team's global scratch for the down-sweep;  Zb = Rs Y (overwrites E),  zz = Rs y
-    double *Wk = Wg + (size_t)k * wl;
-    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, c = idx % n; Wk[idx] = Yb[(size_t)c * ld + j]; }
-    team_mm(T, n, n, n, Rs, ld, Yb, ld, [&](int r, int c, double acc) { Zb[(size_t)r * ld + c] = acc; });
+    if (!okq) { add_fail_pixel(T, X, CV, p); return; }
+    // Y^T and y to the team's global scratch for the down-sweep;  Zb = Rs Y,  zb = Rs y;  Tm_k comes back into the other free array
+    double *Wk = Wg + (size_t)k * wl, *Zb = Qn, *Tk = Qc, *zb = yn;
+    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, c = idx % n; Wk[idx] = Yc[(size_t)c * ld + j]; Tk[(size_t)j * ld + c] = Tg[idx]; }
+    team_mm(T, n, n, n, Rs, ld, Yc, ld, [&](int r, int c, double acc) { Zb[(size_t)r * ld + c] = acc; });
     for (int r = T.rank; r < n; r += T.size) {
       const double *Rr = Rs + (size_t)r * ld;
       double v = 0.0;
-      for (int c = 0; c < n; c++) v += Rr[c] * yv[c];
-      zz[r] = v;
-      Wk[2 * (size_t)n * n + r] = yv[r];
+      for (int c = 0; c < n; c++) v += Rr[c] * yc[c];
+      zb[r] = v;
+      Wk[2 * (size_t)n * n + r] = yc[r];
       Wk[2 * (size_t)n * n + n + r] = v + Ss[r];               // u(bot_k) = (Rs Y) I_dn(top_k) + this
     }
     T.sync();
@@ -131,7 +148,7 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
     for (int r = T.rank; r < n; r += T.size) {
       const double *Tr = Tk + (size_t)r * ld;
       double v = su[r];
-      for (int c = 0; c < n; c++) v += Tr[c] * (Ss[c] + zz[c]);
+      for (int c = 0; c < n; c++) v += Tr[c] * (Ss[c] + zb[c]);
       Sn[r] = v;
     }
     // Rs <- R_k + Tm_k (Rs Y)       (nobody reads the old Rs any more)
@@ -141,17 +158,21 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
     T.sync();
   }
 
-  // ---- down-sweep fused with the layer source terms (WHOLELAYER_STERM_UP) accumulated top-down
-  double part[S];
+  // ---- down-sweep: interface fields and LCON / MCON of every layer (shared by all views); the layer source terms
+  //      (WHOLELAYER_STERM_UP) are accumulated top-down per view: thread (g, ep) owns view g and the eigensolutions e = ep, ep + EP, ...
+  const int EP = (T.size / G) > 0 ? T.size / G : 1, nslot = G * EP;      // slot = (view g, partition ep of the eigensolutions)
+  double *red = Rs, *trn = red + (size_t)nslot * S;           // the matrix arrays are free now: partial sums and user transmittances
+  for (int slot = T.rank; slot < nslot; slot += T.size) {
 #pragma unroll
-  for (int o = 0; o < S; o++) part[o] = 0.0;
+    for (int o = 0; o < S; o++) red[(size_t)slot * S + o] = 0.0;
+    trn[slot] = 1.0;
+  }
   for (int r = T.rank; r < n; r += T.size) xv[r] = 0.0;       // no diffuse downwelling at TOA
-  double trans = 1.0;
   T.sync();
   for (int k = 0; k < L; k++) {
     const size_t q = q0 + k;
     const double *Wk = Wg + (size_t)k * wl;
-    const double *YT = Wk, *ZT = Wk + (size_t)n * n, *yv = Wk + 2 * (size_t)n * n, *zv = yv + n;
+    const double *YT = Wk, *ZT = Wk + (size_t)n * n, *yw = Wk + 2 * (size_t)n * n, *zw = yw + n;
     const bool scat = X.layscat[((size_t)p * (NM + 1) + m) * L + k] != 0;
     for (int item = T.rank; item < 2 * n; item += T.size) {
       const int which = item / n, r = item % n;
@@ -163,7 +184,7 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
         s2 += MT[(size_t)(c + 2) * n + r] * xv[c + 2]; s3 += MT[(size_t)(c + 3) * n + r] * xv[c + 3];
       }
       for (; c < n; c++) s0 += MT[(size_t)c * n + r] * xv[c];
-      const double v = (s0 + s1) + (s2 + s3) + (which ? zv[r] : yv[r]);
+      const double v = (s0 + s1) + (s2 + s3) + (which ? zw[r] : yw[r]);
       if (which) ub[r] = v; else xb[r] = v;
     }
     T.sync();
@@ -191,66 +212,85 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
       }
       T.sync();
       const bool beam = (k + 1 <= cutoff);
-      const double wdel = X.tdmubar[pixL(X, p) + k], itr = X.itrans[pixL(X, p) + k], itw = -itr * wdel;
-      const double emu = X.emult_up[pixL(X, p) + k], sgp = X.sigma_p[pixL(X, p) + k], itu = X.itrans_userm[pixL(X, p) + k];
-      const double udel = X.tduserm[pixL(X, p) + k], dl = X.deltau[pixL(X, p) + k];
-      for (int e = T.rank; e < n; e += T.size) {
-        const double lc = 0.5 * (av[e] + bv[e]), mc = 0.5 * (av[e] - bv[e]);
-        const double h1 = Z.hm1[q * n + e], h2 = Z.hm2[q * n + e];
-        double cd = lc * h2, cu = mc * h1;
-        if (beam) {
-          const double gm = Z.gam_m[q * n + e], gp = Z.gam_p[q * n + e];
-          double SD;
-          if (fabs(gm) < TAYLOR_SMALL) SD = itu * taylor_series_2(gm, sgp, dl, 1.0, wdel * udel, 1.0);
-          else SD = (itr * h2 - emu) / gm;
-          const double SU = (itw * h1 + emu) / gp;
-          cd += SD * Z.aterm[q * n + e]; cu += SU * Z.bterm[q * n + e];
+      const double wdel = X.tdmubar[pixL(X, p) + k], itr = X.itrans[pixL(X, p) + k], itw = -itr * wdel, dl = X.deltau[pixL(X, p) + k];
+      for (int slot = T.rank; slot < nslot; slot += T.size) {
+        const int vg = slot % G, ep = slot / G, pv = v0 + vg;
+        if (CV.state[(size_t)pv * 4] != 1) continue;          // views that have converged keep their sums
+        const double emu = X.emult_up[pixL(X, pv) + k], sgp = X.sigma_p[pixL(X, pv) + k], itu = X.itrans_userm[pixL(X, pv) + k];
+        const double udel = X.tduserm[pixL(X, pv) + k], trans = trn[slot];
+        const size_t qv = q * G + vg;
+        double part[S];
+#pragma unroll
+        for (int o = 0; o < S; o++) part[o] = 0.0;
+        for (int e = ep; e < n; e += EP) {
+          const double lc = 0.5 * (av[e] + bv[e]), mc = 0.5 * (av[e] - bv[e]);
+          const double h1 = Z.hm1[qv * n + e], h2 = Z.hm2[qv * n + e];
+          double cd = lc * h2, cu = mc * h1;
+          if (beam) {
+            const double gm = Z.gam_m[q * n + e], gp = Z.gam_p[q * n + e];
+            double SD;
+            if (fabs(gm) < TAYLOR_SMALL) SD = itu * taylor_series_2(gm, sgp, dl, 1.0, wdel * udel, 1.0);
+            else SD = (itr * h2 - emu) / gm;
+            const double SU = (itw * h1 + emu) / gp;
+            cd += SD * Z.aterm[q * n + e]; cu += SU * Z.bterm[q * n + e];
+          }
+#pragma unroll
+          for (int o = 0; o < S; o++) part[o] += cd * Z.uh_dn[(qv * n + e) * S + o] + cu * Z.uh_up[(qv * n + e) * S + o];
         }
 #pragma unroll
-        for (int o = 0; o < S; o++) part[o] += trans * (cd * Z.uh_dn[(q * n + e) * S + o] + cu * Z.uh_up[(q * n + e) * S + o]);
+        for (int o = 0; o < S; o++) red[(size_t)slot * S + o] += trans * part[o];
       }
     }
-    trans *= X.tduserm[pixL(X, p) + k];
+    for (int slot = T.rank; slot < nslot; slot += T.size) trn[slot] *= X.tduserm[pixL(X, v0 + slot % G) + k];
     T.sync();
     for (int r = T.rank; r < n; r += T.size) xv[r] = xb[r];
     T.sync();
   }
   // ---- BOA source: surface-reflected downwelling diffuse field at the bottom (GET_BOA_SOURCE); xv = I_dn(bot_L)
-  double boa[S];
+  if (include_surface) for (int r = T.rank; r < n; r += T.size) { const int i = r / S; inp[r] = QD.x[i] * QD.w[i] * xv[r]; }
+  T.sync();
+  // ---- per view: Fourier summation and convergence (VLIDORT_CONVERGE_OBSGEO); FLUX_MULTIPLIER = DELTA_FACTOR
+  for (int vg = T.rank; vg < G; vg += T.size) {
+    const int pv = v0 + vg;
+    int *cst = CV.state + (size_t)pv * 4;
+    if (cst[0] != 1) continue;
+    double cum[S], boa[S];
 #pragma unroll
-  for (int o = 0; o < S; o++) boa[o] = 0.0;
-  if (include_surface) {
-    for (int r = T.rank; r < n; r += T.size) { const int i = r / S; inp[r] = QD.x[i] * QD.w[i] * xv[r]; }
-    T.sync();
-    if (lambertian) {
-      double rr = 0.0;
-      for (int i = 0; i < N; i++) rr += inp[S * i];
-      boa[0] = SFAC * albedo * rr;
-    } else {
+    for (int o = 0; o < S; o++) { cum[o] = 0.0; boa[o] = 0.0; }
+    for (int t = 0; t < EP; t++) {
 #pragma unroll
-      for (int o1 = 0; o1 < S; o1++) {
+      for (int o = 0; o < S; o++) cum[o] += red[(size_t)(vg + G * t) * S + o];
+    }
+    const double trans = trn[vg];
+    if (include_surface) {
+      if (lambertian) {
         double rr = 0.0;
-        for (int jj = 0; jj < N; jj++) for (int o2 = 0; o2 < S; o2++) rr += inp[S * jj + o2] * UBFq(o1, o2, jj);
-        boa[o1] = SFAC * rr;
+        for (int i = 0; i < N; i++) rr += inp[S * i];
+        boa[0] = SFAC * albedo * rr;
+      } else {
+        const double *UBF = SF.user_brdf_f + ((size_t)pv * SF.nmfour + m) * SF.nq * N;
+#pragma unroll
+        for (int o1 = 0; o1 < S; o1++) {
+          double rr = 0.0;
+          for (int jj = 0; jj < N; jj++)
+            for (int o2 = 0; o2 < S; o2++)
+              rr += inp[S * jj + o2] * (nq == 16 ? UBF[(size_t)(4 * o1 + o2) * N + jj] : ((o1 | o2) == 0 ? UBF[jj] : 0.0));
+          boa[o1] = SFAC * rr;
+        }
       }
     }
-  }
-  double cum[S];
-#pragma unroll
-  for (int o = 0; o < S; o++) cum[o] = T.sum(part[o]) + trans * boa[o];
-  // ---- Fourier summation and convergence (VLIDORT_CONVERGE_OBSGEO); FLUX_MULTIPLIER = DELTA_FACTOR
-  if (T.rank == 0) {
-    double *tot = CV.total + (size_t)p * 4;
+    const double *scv = X.scal + (size_t)pv * 16;
+    double *tot = CV.total + (size_t)pv * 4;
     double sf[S];
 #pragma unroll
-    for (int o = 0; o < S; o++) sf[o] = DELTA_FACTOR * cum[o];
+    for (int o = 0; o < S; o++) sf[o] = DELTA_FACTOR * (cum[o] + trans * boa[o]);
     if (m == 0) {
 #pragma unroll
-      for (int o = 0; o < S; o++) tot[o] = sf[o] + sc[6 + o] + sc[9 + o];
+      for (int o = 0; o < S; o++) tot[o] = sf[o] + scv[6 + o] + scv[9 + o];
       cst[1] = 0; cst[2] = 0;
       if (NM == 0) cst[0] = 0;
     } else {
-      const double arg = sc[12] * (double)m * DEG_TO_RAD, cf = cos(arg), sf_ = sin(arg);
+      const double arg = scv[12] * (double)m * DEG_TO_RAD, cf = cos(arg), sf_ = sin(arg);
       const double t0 = cf * sf[0], tn0 = tot[0] + t0;
       int count = 0;
       if (t0 != 0.0) { if (fabs(t0 / tn0) < accuracy) count = 1; } else count = 1;
@@ -262,6 +302,13 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
       } else { cst[1] = 0; cst[2] = 2 * N - 1; }
       if (m >= NM) cst[0] = 0;
     }
+  }
+  T.sync();
+  // the pixel stays in the Fourier loop while any of its views does
+  if (T.rank == 0) {
+    int any = 0;
+    for (int g = 0; g < G; g++) any |= (CV.state[(size_t)(v0 + g) * 4] == 1);
+    CV.col_active[p] = any;
   }
 }
 

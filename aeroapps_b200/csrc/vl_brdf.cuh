@@ -25,7 +25,9 @@ HDFN bool surf_is_oci(int kind) { return kind == SURF_OCICX || kind == SURF_OCIG
 
 struct VLBrdf {
   int kind, N, NM, NB, nq, half_range, nch, nobs, bns;   // bns: BRDF nstokes (1 or 3)
-  const double *sza, *vza, *raa;            // (nobs)
+  int G;                                    // view geometries per observation (0 or 1: single geometry)
+  const double *sza;                        // (nobs)
+  const double *vza, *raa;                  // (nobs,G)
   const double *u10m, *v10m, *mr;           // (nobs) (nobs) (nch)      Cox-Munk family
   const double *kernel_wt, *param;          // (3,nch,nobs) (2,nch,nobs) MODIS RTLS
   const double *xb, *ab, *cxb, *sxb;        // [NB] azimuth quadrature (angles, weights, cos, sin)
@@ -33,8 +35,9 @@ struct VLBrdf {
   const double *sx, *ss, *ssw;              // [24] scaling quadrature: cosines, sines, cosine*weight
   double qx[32], qs[32];                    // stream cosines / sines
   // outputs
-  double *exactdb;                          // [npix][16]
-  double *brdf_f, *brdf_f_0, *user_brdf_f;  // chunk-local [pc][2N][nq][N][N], [pc][2N][nq][N], [pc][2N][nq][N]
+  double *exactdb;                          // [npix*G][16]   per pixel-view
+  double *brdf_f, *brdf_f_0;                // chunk-local, per pixel: [pc][2N][nq][N][N], [pc][2N][nq][N]
+  double *user_brdf_f;                      // chunk-local, per pixel-view: [pc*G + g][2N][nq][N]
   int *wsa_fail;                            // [npix]
 };
 
@@ -201,13 +204,14 @@ HDFN void surf_params(const VLBrdf &B, int j, int i, SurfPars &P) {
 HDFN int brdf_q16(int t) { return 4 * (t / 3) + (t % 3); }
 HDFN int brdf_cossin(int t) { return (t == 2 || t == 5) ? 2 : ((t == 6 || t == 7) ? 3 : 1); }
 
-// exact direct-bounce BRDF of one pixel (thread-level)
+// exact direct-bounce BRDF of one pixel-view p = (j*nch + i)*G + g (thread-level)
 HDFN void brdf_exact_pixel(const VLBrdf &B, int p) {
-  const int j = p / B.nch, i = p % B.nch;
+  const int G = B.G > 0 ? B.G : 1, pc = p / G, g = p % G;
+  const int j = pc / B.nch, i = pc % B.nch;
   SurfPars P; surf_params(B, j, i, P);
   const double mu0 = cos(B.sza[j] * DEG_TO_RAD), smu0 = sqrt(1.0 - mu0 * mu0);
-  const double muv = cos(B.vza[j] * DEG_TO_RAD), smuv = sqrt(1.0 - muv * muv);
-  const double phi = B.raa[j] * DEG_TO_RAD, cphi = cos(phi), sphi = sin(phi);
+  const double muv = cos(B.vza[j + (size_t)B.nobs * g] * DEG_TO_RAD), smuv = sqrt(1.0 - muv * muv);
+  const double phi = B.raa[j + (size_t)B.nobs * g] * DEG_TO_RAD, cphi = cos(phi), sphi = sin(phi);
   double ex[16];
   for (int q = 0; q < 16; q++) ex[q] = 0.0;
   for (int k = 0; k < P.nk; k++) {
@@ -223,21 +227,21 @@ HDFN void brdf_exact_pixel(const VLBrdf &B, int p) {
 HDFN size_t brdf_out_f(const VLBrdf &B) { return (size_t)2 * B.N * B.nq * B.N * B.N; }
 HDFN size_t brdf_out_f0(const VLBrdf &B) { return (size_t)2 * B.N * B.nq * B.N; }
 
-// Fourier components of one pixel.  pc = chunk-local pixel, p = global pixel.  scr: nscr doubles of team scratch
+// Fourier components of one pixel (all its views).  pc = chunk-local pixel, p = global pixel.  scr: nscr doubles of team scratch
 // (>= T.size + batch storage), batch storage = EB * nqs * NB with EB >= 1.
 template <class Team>
 DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr, int nscr) {
-  const int N = B.N, NB = B.NB, NM = B.NM, j = p / B.nch, i = p % B.nch;
+  const int N = B.N, NB = B.NB, NM = B.NM, j = p / B.nch, i = p % B.nch, G = B.G > 0 ? B.G : 1;
   SurfPars P; surf_params(B, j, i, P);
   const double mu0 = cos(B.sza[j] * DEG_TO_RAD), smu0 = sqrt(1.0 - mu0 * mu0);
-  const double muv = cos(B.vza[j] * DEG_TO_RAD), smuv = sqrt(1.0 - muv * muv);
-  double *OF = B.brdf_f + (size_t)pc * brdf_out_f(B), *OF0 = B.brdf_f_0 + (size_t)pc * brdf_out_f0(B), *OU = B.user_brdf_f + (size_t)pc * brdf_out_f0(B);
+  double *OF = B.brdf_f + (size_t)pc * brdf_out_f(B), *OF0 = B.brdf_f_0 + (size_t)pc * brdf_out_f0(B), *OU = B.user_brdf_f + (size_t)pc * G * brdf_out_f0(B);
   for (size_t t = T.rank; t < brdf_out_f(B); t += T.size) OF[t] = 0.0;
-  for (size_t t = T.rank; t < brdf_out_f0(B); t += T.size) { OF0[t] = 0.0; OU[t] = 0.0; }
+  for (size_t t = T.rank; t < brdf_out_f0(B); t += T.size) OF0[t] = 0.0;
+  for (size_t t = T.rank; t < (size_t)G * brdf_out_f0(B); t += T.size) OU[t] = 0.0;
   double *red = scr, *vals = scr + T.size;
   const int nqs = (B.nq == 16) ? 9 : 1;
   const int EB = (nscr - T.size) / (nqs * NB);
-  const int NE = N * N + 2 * N;                      // entries: (i,j) stream pairs, sun -> stream i, stream i -> user
+  const int NE = N * N + N + G * N;                  // entries: (i,j) stream pairs, sun -> stream i, stream i -> user view g
   const double help_w = B.half_range ? 1.0 : 0.5;
   // ---- white-sky albedo check over all kernels (serious status -> the last kernel contributes no Fourier terms)
   double total_wsa = 0.0;
@@ -271,7 +275,8 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
     const double f = P.fac[k];
     if (P.lam[k]) {
       for (int t = T.rank; t < N * N; t += T.size) OF[t] += f;                   // m = 0, element (1,1)
-      for (int t = T.rank; t < N; t += T.size) { OF0[t] += f; OU[t] += f; }
+      for (int t = T.rank; t < N; t += T.size) OF0[t] += f;
+      for (int t = T.rank; t < G * N; t += T.size) OU[(size_t)(t / N) * brdf_out_f0(B) + t % N] += f;
       T.sync();
       continue;
     }
@@ -283,7 +288,11 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
         double XI, SXI, XJ, SXJ;                                                // incident, reflected
         if (e < N * N) { const int ir = e / N, jc = e % N; XI = B.qx[jc]; SXI = B.qs[jc]; XJ = B.qx[ir]; SXJ = B.qs[ir]; }
         else if (e < N * N + N) { const int ir = e - N * N; XI = mu0; SXI = smu0; XJ = B.qx[ir]; SXJ = B.qs[ir]; }
-        else { const int jc = e - N * N - N; XI = B.qx[jc]; SXI = B.qs[jc]; XJ = muv; SXJ = smuv; }
+        else {
+          const int u = e - N * N - N, jc = u % N, g = u / N;
+          const double muv = cos(B.vza[j + (size_t)B.nobs * g] * DEG_TO_RAD);
+          XI = B.qx[jc]; SXI = B.qs[jc]; XJ = muv; SXJ = sqrt(1.0 - muv * muv);
+        }
         if (P.which[k] == 10) {
           double K[9]; brdf_giss_kernel(P.pars[k], XI, SXI, XJ, SXJ, B.cxb[b], B.sxb[b], K);
           if (nqs == 1) vals[(size_t)el * NB + b] = K[0];
@@ -305,7 +314,7 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
         const int q = (B.nq == 16) ? brdf_q16(t) : 0;
         if (e < N * N) OF[((size_t)m * B.nq + q) * N * N + e] += f * s;
         else if (e < N * N + N) OF0[((size_t)m * B.nq + q) * N + (e - N * N)] += f * s;
-        else OU[((size_t)m * B.nq + q) * N + (e - N * N - N)] += f * s;
+        else { const int u = e - N * N - N; OU[(size_t)(u / N) * brdf_out_f0(B) + ((size_t)m * B.nq + q) * N + u % N] += f * s; }
       }
       T.sync();
     }

@@ -35,9 +35,10 @@ struct VLSurf {                  // BRDF Fourier components per pixel (null poin
   int nq;                        // 1: only the (1,1) element is non-zero (scalar kernels), 16: Mueller layout
 };
 
-struct VLConv {                  // per pixel, persistent over the Fourier loop
-  double *total;                 // [p][4]
-  int *state;                    // [p][4]: 0 active(1)/done(0), 1 testconv, 2 fourier_saved, 3 failure code
+struct VLConv {                  // per pixel-view v, persistent over the Fourier loop
+  double *total;                 // [v][4]
+  int *state;                    // [v][4]: 0 active(1)/done(0), 1 testconv, 2 fourier_saved, 3 failure code
+  int *col_active;               // [c]: 1 while any view of pixel c is still in the Fourier loop
 };
 
 HDFN int bvp_cols(int n) { return 4 * n + 1; }

@@ -16,12 +16,13 @@
 
 namespace vlk {
 
-struct VLSol {                 // per problem q = p*L + k (structure of arrays)
+struct VLSol {                 // per problem q = c*L + k (pixel c, layer k; structure of arrays); G view geometries per pixel
   int n, S, N;
   double *keig, *tde;          // [q][n]
   double *xp, *xn;             // [q][e][r]   r = S*i + o, streams i < N (the i+N half follows by symmetry)
-  double *uh_dn, *uh_up;       // [q][e][S]   UHOM_UPDN, UHOM_UPUP
-  double *hm1, *hm2, *aterm, *bterm, *gam_m, *gam_p;   // [q][n]
+  double *uh_dn, *uh_up;       // [q][g][e][S]   UHOM_UPDN, UHOM_UPUP per view
+  double *hm1, *hm2;           // [q][g][n]      whole-layer multipliers per view
+  double *aterm, *bterm, *gam_m, *gam_p;   // [q][n]
   double *wupper, *wlower;     // [q][2N*S]
   int *fail;                   // [p] set !=0 when an eigenproblem fails
 };
@@ -170,15 +171,15 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   double *piu = KK + 12 * n;          // 3*(NM+1)  user-stream P,R,T
   double *pi0 = piu + 3 * (NM + 1);   // 3*(NM+1)  solar P,R,T
   const double *og = og_ptr(X, p);                          // [(l*L + k)*4]
-  const double *sc = X.scal + (size_t)p * 16;
-  const int *ib = X.ibuf + (size_t)p * 4;
-  const double usec = sc[2], FLUXF = sc[5];
+  const int G = X.G;
+  const double *sc = X.scal + (size_t)view0(X, p) * 16;     // sun / flux: the same for every view of the pixel
+  const int *ib = X.ibuf + (size_t)view0(X, p) * 4;
+  const double FLUXF = sc[5];
   const bool layscat = X.layscat[((size_t)p * (NM + 1) + m) * L + k] != 0;
   const double deltau = X.deltau[pixL(X, p) + k];
   double *XPg = Z.xp + q * n * n, *XNg = Z.xn + q * n * n;
 
-  // ---- generalized spherical functions at the user and solar cosines
-  if (T.rank == 0) pi_prt(m, NM, sc[1], piu);
+  // ---- generalized spherical functions at the solar cosine (the user cosines follow per view further down)
   if (T.rank == (T.size > 1 ? 1 : 0)) pi_prt(m, NM, sc[0], pi0);
   for (int r = T.rank; r < n; r += T.size) { const int i = r / S; sr[r] = sqrt(QD.w[i] * QD.x[i]); }
 
@@ -364,12 +365,26 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
     Z.keig[q * n + e] = ke;
     const double hlp = ke * deltau, tde = hlp > MAX_TAU_PATH ? 0.0 : exp(-hlp);
     Z.tde[q * n + e] = tde;
-    // HMULT (whole layer, upwelling user stream): vlidort_solutions.f90:1715-1745, zeta :1290-1305
-    const double rho_p = usec + ke, rho_m = usec - ke, udel = X.tduserm[pixL(X, p) + k];
-    const bool hs = fabs(rho_m) < TAYLOR_SMALL;
-    Z.hm1[q * n + e] = hs ? taylor_series_1(rho_m, deltau, udel, usec) : usec * (tde - udel) / rho_m;
-    Z.hm2[q * n + e] = usec * (1.0 - tde * udel) / rho_p;
   }
+  T.sync();
+  for (int idx = T.rank; idx < n * n; idx += T.size) { XPg[idx] = A[(idx / n) * LDA + (idx % n)]; XNg[idx] = B1[(idx / n) * LDB + (idx % n)]; }
+  // ---- per view geometry: whole-layer multipliers and user-stream solutions
+  for (int g = 0; g < G; g++) {
+  const size_t qv = q * G + g;
+  const double *scv = X.scal + ((size_t)view0(X, p) + g) * 16;
+  const double usec = scv[2], udel = X.tduserm[pixL(X, view0(X, p) + g) + k];
+  if (T.rank == 0) pi_prt(m, NM, scv[1], piu);
+  for (int e = T.rank; e < n; e += T.size) {
+    const double ke = sig[e];
+    if (!(ke > 0.0)) continue;
+    const double hlp = ke * deltau, tde = hlp > MAX_TAU_PATH ? 0.0 : exp(-hlp);
+    // HMULT (whole layer, upwelling user stream): vlidort_solutions.f90:1715-1745, zeta :1290-1305
+    const double rho_p = usec + ke, rho_m = usec - ke;
+    const bool hs = fabs(rho_m) < TAYLOR_SMALL;
+    Z.hm1[qv * n + e] = hs ? taylor_series_1(rho_m, deltau, udel, usec) : usec * (tde - udel) / rho_m;
+    Z.hm2[qv * n + e] = usec * (1.0 - tde * udel) / rho_p;
+  }
+  T.sync();
   // ---- user-stream operators: UHOM_UP/DN(o,e) = sum_r KK[..][r] X+-(r,e); item = (stream j, up/down)
   for (int idx = T.rank; idx < 2 * N; idx += T.size) {
     const int j = idx >> 1, ud = idx & 1;                                  // ud = 0: UHOM_UPDN, 1: UHOM_UPUP
@@ -417,16 +432,13 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
       }
   }
   T.sync();
-  for (int idx = T.rank; idx < n * n; idx += T.size) XPg[idx] = A[(idx / n) * LDA + (idx % n)];
   for (int e = T.rank; e < n; e += T.size) {
     const double *col = A + e * LDA, *xn = B1 + e * LDB;
-    double *xg = XNg + (size_t)e * n;
     double dn[S], up[S];
 #pragma unroll
     for (int o = 0; o < S; o++) { dn[o] = 0.0; up[o] = 0.0; }
     for (int r = 0; r < n; r++) {
       const double xp_ = col[r], xn_ = xn[r];
-      xg[r] = xn_;
 #pragma unroll
       for (int o = 0; o < S; o++) {
         dn[o] += KK[(0 * S + o) * n + r] * xp_ + KK[(1 * S + o) * n + r] * xn_;
@@ -434,8 +446,10 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
       }
     }
 #pragma unroll
-    for (int o = 0; o < S; o++) { Z.uh_dn[(q * n + e) * S + o] = dn[o]; Z.uh_up[(q * n + e) * S + o] = up[o]; }
+    for (int o = 0; o < S; o++) { Z.uh_dn[(qv * n + e) * S + o] = dn[o]; Z.uh_up[(qv * n + e) * S + o] = up[o]; }
   }
+  T.sync();
+  }   // views
   // ---- Green's function particular integral (solar beam)
   const bool active = layscat && (k + 1 <= ib[0]);
   double *WU = Z.wupper + q * (2 * n), *WL = Z.wlower + q * (2 * n);

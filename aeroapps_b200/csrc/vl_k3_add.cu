@@ -43,13 +43,10 @@ __global__ void __launch_bounds__(TPB, TPB == 128 ? 3 : 1) k_vl_add(VLPix X, VLS
   double *Wg = work + (size_t)blockIdx.x * work_per_cta;
   for (int a = blockIdx.x; a < nactive; a += gridDim.x) {
     const int p = active[a];
-    if (Z.fail[p]) {
-      if (threadIdx.x == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
-    } else {
-      add_pixel<S>(T, X, Z, O, QD, SF, CV, lambertian, accuracy, m, p, smem_d, piv, Wg);
-    }
+    if (Z.fail[p]) add_fail_pixel(T, X, CV, p);
+    else add_pixel<S>(T, X, Z, O, QD, SF, CV, lambertian, accuracy, m, p, smem_d, piv, Wg);
     __syncthreads();
-    if (threadIdx.x == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
+    if (threadIdx.x == 0 && CV.col_active[p]) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
     __syncthreads();
   }
 }
@@ -67,15 +64,48 @@ __global__ void __launch_bounds__(256) k_vl_add_warp(VLPix X, VLSol Z, VLOps O, 
   double *Wg = work + (size_t)gw * work_per_warp;
   for (int a = gw; a < nactive; a += gridDim.x * wpc) {
     const int p = active[a];
-    if (Z.fail[p]) {
-      if (lane == 0) { CV.state[(size_t)p * 4] = 0; CV.state[(size_t)p * 4 + 3] = 4; }
-    } else {
-      add_pixel<S>(T, X, Z, O, QD, SF, CV, lambertian, accuracy, m, p, scr, piv, Wg);
-    }
+    if (Z.fail[p]) add_fail_pixel(T, X, CV, p);
+    else add_pixel<S>(T, X, Z, O, QD, SF, CV, lambertian, accuracy, m, p, scr, piv, Wg);
     __syncwarp();
-    if (lane == 0 && CV.state[(size_t)p * 4] == 1) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
+    if (lane == 0 && CV.col_active[p]) { const int idx = atomicAdd(next_count, 1); next_list[idx] = p; }
     __syncwarp();
   }
+}
+
+// ---- self-test of the CTA linear algebra (tests/test_linalg_gpu.py): E = A^-1 by team_inverse and P = A E by team_mm, one CTA
+__global__ void k_vl_selftest_linalg(int n, const double *__restrict__ A, double *__restrict__ E, double *__restrict__ P, int *__restrict__ okflag) {
+  extern __shared__ __align__(16) double smem_d[];
+  __shared__ double sd[64];
+  __shared__ int si[64];
+  BlockTeam T(sd, si);
+  const int ld = mat_ld(n);
+  double *As = smem_d, *Es = As + (size_t)n * ld, *wk = Es + (size_t)n * ld;
+  int *piv = reinterpret_cast<int *>(wk + inv_work_doubles(n, true));
+  for (int idx = T.rank; idx < n * ld; idx += T.size) { const int r = idx / ld, c = idx % ld; As[idx] = c < n ? A[(size_t)r * n + c] : 0.0; Es[idx] = As[idx]; }
+  T.sync();
+  const bool ok = team_inverse(T, n, Es, Es, ld, wk, piv);
+  if (T.rank == 0) *okflag = ok ? 1 : 0;
+  if (!ok) return;
+  for (int idx = T.rank; idx < n * n; idx += T.size) E[idx] = Es[(size_t)(idx / n) * ld + idx % n];
+  team_mm(T, n, n, n, As, ld, Es, ld, [&](int r, int c, double acc) { P[(size_t)r * n + c] = acc; });
+}
+
+extern "C" int ab200_selftest_linalg(int n, int threads, const double *A, double *E, double *P) {
+  if (n < 1 || n > 64 || threads < 32 || threads > 512 || threads % 32) { ab200_set_error("selftest_linalg: bad arguments"); return AB200_ERR_ARG; }
+  const size_t nn = (size_t)n * n, smem = (2 * (size_t)n * mat_ld(n) + inv_work_doubles(n, true)) * 8 + (size_t)n * 8 + 16;
+  double *d = nullptr; int *dok = nullptr;
+  AB_CUDA_OK(cudaMalloc((void **)&d, 3 * nn * 8 + 16));
+  dok = reinterpret_cast<int *>(d + 3 * nn);
+  AB_CUDA_OK(cudaMemcpy(d, A, nn * 8, cudaMemcpyHostToDevice));
+  AB_CUDA_OK(cudaFuncSetAttribute((const void *)k_vl_selftest_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_vl_selftest_linalg<<<1, threads, smem>>>(n, d, d + nn, d + 2 * nn, dok);
+  AB_CUDA_OK(cudaGetLastError());
+  int ok = 0;
+  AB_CUDA_OK(cudaMemcpy(&ok, dok, 4, cudaMemcpyDeviceToHost));
+  AB_CUDA_OK(cudaMemcpy(E, d + nn, nn * 8, cudaMemcpyDeviceToHost));
+  AB_CUDA_OK(cudaMemcpy(P, d + 2 * nn, nn * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return ok ? 0 : 1;
 }
 
 namespace vlk {

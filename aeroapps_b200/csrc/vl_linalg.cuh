@@ -134,7 +134,7 @@ DEVFN bool team_gauss_jordan(const Team &T, int n, int W, double *AB_RESTRICT G,
 // the work array wk (n x ldw doubles, ldw = (2n)|1) + 3 pivot words; A is left untouched.
 HDFN int inv_ldw(int n) { return (2 * n) | 1; }
 HDFN size_t inv_work_doubles_generic(int n) { return (size_t)n * inv_ldw(n) + n + 4; }
-HDFN size_t inv_work_doubles_cta(int n) { return 4 * (size_t)n + 4; }       // scratch of the CTA form below
+HDFN size_t inv_work_doubles_cta(int n) { return (size_t)n * (n | 1) + 3 * n + 2; }       // scratch of the CTA form below
 template <class Team>
 DEVFN bool team_inverse_generic(const Team &T, int n, const double *A, int lda, double *E, int lde, double *wk, int *piv) {
   const int ldw = inv_ldw(n);
@@ -162,70 +162,70 @@ DEVFN double vl_fast_rcp(double x) {
   return y;
 }
 
-// CTA form: in-place Gauss-Jordan inversion with the matrix REGISTER-RESIDENT.  Thread (r, cg) of the first n*CG threads (CG =
-// blockDim / n column groups) keeps the elements a(r, cg + CG*jj), jj < NJ, of row r in registers for the whole elimination; per
-// pivot column only the pivot row travels through shared memory (one broadcast load per element and update).  Partial pivoting
-// over the rows that have not been pivots, no row swaps, no row scaling: piv[c] = pivot row of step c, stepof[r] = its inverse;
-// the physical column c holds, after step c, the column of the inverse that belongs to row piv[c] (the unit column it replaces
-// is implicit before).  E(stepof[r], piv[j]) = a(r, j) / pivot(stepof[r]).
-// Two barriers per pivot column: (A) column c of every row published -> every warp finds the pivot row by itself (two warp-wide
-// integer max reductions on (|value| bits, row)), (B) pivot row published.
-// Scratch: prow_s (n doubles), col_s (2n), dinv_s (n); ints piv (n), stepof (n).
-template <int NJ>
-DEVFN bool cta_inverse(int n, const double *A, int lda, double *E, int lde, double *wk, int *piv) {
-  const int CG = blockDim.x / n, rank = threadIdx.x, lane = threadIdx.x & 31;
+// CTA form: in-place Gauss-Jordan inversion with the matrix REGISTER-RESIDENT and mirrored in shared memory.  Thread (r, cg) of the
+// first n*CG threads (CG = blockDim / n column groups) keeps the elements a(r, cg + CG*jj), jj < NJ, of row r in registers for the
+// whole elimination and stores every updated element to the mirror Mw (n x ldm, ldm odd: conflict-free for lanes over rows), from
+// which the other threads take the pivot row (broadcast loads); the next pivot column (multipliers, pivot candidates) travels through
+// a double-buffered column array, so that column c of the mirror can be overwritten in step c -- ONE barrier per pivot column.  Partial pivoting over the rows that have not been pivots (every warp finds the pivot by itself: float magnitudes
+// with the row number in the low 6 bits, one warp-wide integer max), no row swaps, no row scaling: piv[c] = pivot row of step c,
+// stepof[r] = its inverse; the physical column c holds, after step c, the column of the inverse that belongs to row piv[c] (the
+// unit column it replaces is implicit before).  E(stepof[r], piv[j]) = a(r, j) / pivot(stepof[r]).
+// The pivot row's threads rewrite their mirror entries with unchanged values in their own step (benign).
+// N_, CG_ > 0: compile-time n and column-group count (n = 36 with 128 threads: 3 groups of 12 columns).
+// Scratch: Mw (n x ldm doubles), dinv_s (n), column buffer (2n); ints piv (n), stepof (n).
+HDFN int inv_ldm(int n) { return n | 1; }
+template <int NJ, int N_, int CG_>
+DEVFN bool cta_inverse(int n_, const double *A, int lda, double *E, int lde, double *wk, int *piv) {
+  const int n = N_ > 0 ? N_ : n_, CG = CG_ > 0 ? CG_ : (int)blockDim.x / n, ldm = inv_ldm(n);
+  const int rank = threadIdx.x, lane = threadIdx.x & 31;
   const bool active = rank < n * CG;
-  const int r = rank % n, cg = rank / n;
-  double *prow_s = wk, *col_s = wk + n, *dinv_s = wk + 3 * n;
+  const int r = active ? rank % n : 0, cg = active ? rank / n : 0;
+  double *Mw = wk, *dinv_s = wk + (size_t)n * ldm, *colb = dinv_s + n;
   int *stepof = piv + n;
   double a[NJ];
+  double *mrow = Mw + (size_t)r * ldm + cg;
 #pragma unroll
-  for (int jj = 0; jj < NJ; jj++) { const int j = cg + CG * jj; a[jj] = (active && j < n) ? A[(size_t)r * lda + j] : 0.0; }
-  if (active && cg == 0) col_s[r] = a[0];
-  unsigned long long usedmask = 0ull;                          // rows that have been pivots (n <= 64), the same in every thread
+  for (int jj = 0; jj < NJ; jj++) {
+    const int j = cg + CG * jj;
+    a[jj] = (active && j < n) ? A[(size_t)r * lda + j] : 0.0;
+    if (active && j < n) mrow[CG * jj] = a[jj];
+  }
+  if (active && cg == 0) colb[r] = a[0];                       // column 0
+  unsigned used0 = 0u, used1 = 0u;                             // rows that have been pivots (n <= 64), the same in every thread
   bool ok = true;
   for (int c = 0; c < n; c++) {
-    __syncthreads();                                           // (A) column c published by every row
-    const double *cs = col_s + (c & 1) * n;
-    double *cn = col_s + ((c + 1) & 1) * n;
-    // pivot search, redundantly in every warp (no atomics, no extra barrier): two candidates per lane, two 32-bit max reductions
-    unsigned long long key = 0ull;
-    for (int rr = lane; rr < n; rr += 32) {
-      if (!((usedmask >> rr) & 1ull)) { const unsigned long long k2 = vl_pivot_key(cs[rr], rr); key = k2 > key ? k2 : key; }
+    __syncthreads();                                           // every update of step c - 1 is in the mirror / the column buffer
+    const double *cs = colb + (c & 1) * n;                     // column c as of the end of step c - 1
+    double *cn = colb + ((c + 1) & 1) * n;
+    // pivot search, redundantly in every warp: rows lane and lane + 32 of column c
+    unsigned key = 0u;
+    if (lane < n && !((used0 >> lane) & 1u)) key = (__float_as_uint(fabsf((float)cs[lane])) & ~63u) | (unsigned)lane;
+    if (lane + 32 < n && !((used1 >> lane) & 1u)) {
+      const unsigned k2 = (__float_as_uint(fabsf((float)cs[lane + 32])) & ~63u) | (unsigned)(lane + 32);
+      key = k2 > key ? k2 : key;
     }
-    const unsigned hi = (unsigned)(key >> 32), mh = __reduce_max_sync(0xffffffffu, hi);
-    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)key : 0u);
-    key = ((unsigned long long)mh << 32) | ml;
-    if ((key >> 7) == 0ull) { ok = false; break; }
-    const int p = (int)(key & 127ull);
-    usedmask |= 1ull << p;
+    key = __reduce_max_sync(0xffffffffu, key);
+    if ((key >> 6) == 0u) { ok = false; break; }
+    const int p = (int)(key & 63u);
+    if (p < 32) used0 |= 1u << p; else used1 |= 1u << (p - 32);
     if (rank == 0) { piv[c] = p; stepof[p] = c; }
-    const bool isp = active && r == p;
-    if (isp) {
-#pragma unroll
-      for (int jj = 0; jj < NJ; jj++) { const int j = cg + CG * jj; if (j < n) prow_s[j] = a[jj]; }
-    }
-    __syncthreads();                                           // (B) pivot row published
-    const double ipiv = vl_fast_rcp(prow_s[c]);
+    const double ipiv = vl_fast_rcp(cs[p]);
     if (active) {
-      if (!isp) {
-        const double f = cs[r] * ipiv;
+      const bool isp = (r == p);
+      const double f = isp ? 0.0 : cs[r] * ipiv;
+      const double vc = isp ? 1.0 : -f;                        // what column c becomes (the implicit unit column of row p)
+      const double *pr = Mw + (size_t)p * ldm + cg;
+      const int dc = c - cg;                                   // this thread holds column c iff dc == CG * jj for some jj
 #pragma unroll
-        for (int jj = 0; jj < NJ; jj++) {
-          const int j = cg + CG * jj;
-          if (j < n) {
-            a[jj] = (j == c) ? -f : a[jj] - f * prow_s[j];
-            if (j == c + 1) cn[r] = a[jj];
-          }
-        }
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < NJ; jj++) {
-          const int j = cg + CG * jj;
-          if (j == c) { dinv_s[c] = ipiv; a[jj] = 1.0; }
-          if (j == c + 1 && j < n) cn[r] = a[jj];
+      for (int jj = 0; jj < NJ; jj++) {
+        if (N_ > 0 || cg + CG * jj < n) {
+          const double v = a[jj] - f * pr[CG * jj];            // (for column c the loaded pivot-row value is not used)
+          a[jj] = (CG * jj == dc) ? vc : v;
+          mrow[CG * jj] = a[jj];
+          if (CG * jj == dc + 1) cn[r] = a[jj];                // column c + 1 for the next step
         }
       }
+      if (isp && dc >= 0 && dc % CG == 0) dinv_s[c] = ipiv;
     }
   }
   __syncthreads();
@@ -286,9 +286,10 @@ DEVFN bool team_inverse(const Team &T, int n, double *A, double *E, int ld, doub
 #ifndef AB_HOST_MODEL
   if constexpr (Team::is_cta) {
     const int CG = T.size / n, nj = (n + CG - 1) / CG;
-    if (nj <= 6) return cta_inverse<6>(n, A, ld, E, ld, wk, piv);
-    if (nj <= 10) return cta_inverse<10>(n, A, ld, E, ld, wk, piv);
-    return cta_inverse<13>(n, A, ld, E, ld, wk, piv);
+    if (n == 36 && CG == 3) return cta_inverse<12, 36, 3>(n, A, ld, E, ld, wk, piv);
+    if (nj <= 6) return cta_inverse<6, 0, 0>(n, A, ld, E, ld, wk, piv);
+    if (nj <= 10) return cta_inverse<10, 0, 0>(n, A, ld, E, ld, wk, piv);
+    return cta_inverse<13, 0, 0>(n, A, ld, E, ld, wk, piv);
   }
 #endif
   return team_inverse_generic(T, n, A, ld, E, ld, wk, piv);

@@ -13,6 +13,7 @@ struct VLIn {                 // device pointers in the reference's Fortran layo
   int km, nch, nobs, nMom, nPol, S, N, nfine;
   int planpar, lambertian, scalar_glue;
   int nadir_from_obs;         // first obs index that runs with FOCORR_NADIR (reference state quirk), nobs if none
+  int ngeom;                  // view geometries per observation (>= 1): pixel-view pv = (j*nch + i)*ngeom + g
   double MISSING, earth_radius;
   const double *ROT;          // (km,nobs,nch)
   const double *depol;        // (nch)
@@ -21,25 +22,30 @@ struct VLIn {                 // device pointers in the reference's Fortran layo
   const double *pmom;         // (km,nch,nobs,nMom,nPol)
   const double *ze;           // (km+1,nobs) [m]
   const double *albedo;       // (nobs,nch)   (Lambertian)
-  const double *sza, *raa, *vza;   // (nobs)
+  const double *sza;          // (nobs): one sun per observation
+  const double *raa, *vza;    // (nobs,ngeom)
   const double *flux_factor;  // (nch,nobs) or null (=1)
-  const double *exactdb;      // (npix,16) exact direct-bounce BRDF (non-Lambertian) or null
-  const unsigned char *skip;  // (npix) 1 = pixel not run (MISSING inputs), 2 = not run, outputs -500 (RTLS BR < 0); may be null
+  const double *exactdb;      // (npix*ngeom,16) exact direct-bounce BRDF per pixel-view (non-Lambertian) or null
+  const unsigned char *skip;  // (npix*ngeom) 1 = pixel-view not run (MISSING inputs), 2 = not run, outputs -500 (RTLS BR < 0); may be null
 };
 
-// per-pixel state produced by K1 and consumed by K2/K3 (structure of arrays, pixel-major)
+// per-pixel state produced by K1 and consumed by K2/K3 (structure of arrays).  A pixel c = (observation, channel) owns G view
+// geometries that share the sun, the atmosphere and the surface; everything that does not depend on the viewing direction is
+// stored per pixel [c], the rest per pixel-view [v] with v = c*G + g.  The single-geometry entry points have G = 1 (v == c).
 struct VLPix {
-  int L, NM, S, npix;
-  double *deltau;      // [p][L]   delta-M scaled
-  double *og;          // [p][(NM+1)][L][4]  omega' * (g11,g12,g22,g33)'
-  double *avsec, *itrans, *tdmubar, *tduserm, *emult_up, *sigma_p, *itrans_userm;   // [p][L]
-  double *scal;        // [p][16]: 0 cos_sza 1 ustream 2 usec 3 trans_solar_beam 4 albedo 5 flux 6.. fo_ss(3) 9.. fo_db(3) 12 raa
-  int *ibuf;           // [p][4]: 0 beam_cutoff (1-based) 1 status 2 do_reflected_directbeam
-  unsigned char *layscat;   // [p][(NM+1)][L]
+  int L, NM, S, npix, G;
+  double *deltau;      // [c][L]   delta-M scaled
+  double *og;          // [c][(NM+1)][L][4]  omega' * (g11,g12,g22,g33)'
+  double *avsec, *itrans, *tdmubar;                      // [c][L]   solar beam
+  double *tduserm, *emult_up, *sigma_p, *itrans_userm;   // [v][L]   user stream
+  double *scal;        // [v][16]: 0 cos_sza 1 ustream 2 usec 3 trans_solar_beam 4 albedo 5 flux 6.. fo_ss(3) 9.. fo_db(3) 12 raa
+  int *ibuf;           // [v][4]: 0 beam_cutoff (1-based) 1 status 2 do_reflected_directbeam
+  unsigned char *layscat;   // [c][(NM+1)][L]
 };
 
-DEVFN size_t pixL(const VLPix &X, int p) { return (size_t)p * X.L; }
+DEVFN size_t pixL(const VLPix &X, int p) { return (size_t)p * X.L; }                 // p: pixel for the [c] arrays, pixel-view for the [v] arrays
 DEVFN double *og_ptr(const VLPix &X, int p) { return X.og + (size_t)p * (X.NM + 1) * X.L * 4; }
+DEVFN int view0(const VLPix &X, int c) { return c * X.G; }                           // first pixel-view of pixel c
 
 // Sum_k ext[k-1]*sunpath(k) for a direct (FindSunPaths_D) or tangent (FindSunPaths_T) solar path that starts at
 // radius Radstart inside layer N (1-based), local solar zenith thstart.  radii[0..L].
@@ -134,8 +140,10 @@ HDFN void gauss01(int n, double *x, double *w) {           // GETQUAD2 (FO_geome
 // scratch (doubles): 12*(L+1) + 2*(nMom+1) + 2*nfine
 template <class Team>
 DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, double *scr) {
+  // p = pixel-view; the views of a pixel all write the same values to the pixel's [c] arrays (every view needs them here anyway)
   const int L = in.km, S = in.S, N = in.N, nMom = in.nMom, NM = X.NM;
-  const int j = p / in.nch, i = p % in.nch;
+  const int G = in.ngeom > 0 ? in.ngeom : 1, pc = p / G, g = p % G;
+  const int j = pc / in.nch, i = pc % in.nch;
   int *ib = X.ibuf + (size_t)p * 4;
   double *sc = X.scal + (size_t)p * 16;
   if (in.skip && in.skip[p]) { if (T.rank == 0) ib[1] = (in.skip[p] == 2) ? 98 : 99; return; }
@@ -157,8 +165,8 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
   double *xf = gs2 + (nMom + 1);
   double *wf = xf + (in.nfine > 0 ? in.nfine : 1);
 
-  const double sza = in.sza[j], vza = in.vza[j];
-  double raa = in.raa[j];
+  const double sza = in.sza[j], vza = in.vza[j + (size_t)in.nobs * g];
+  double raa = in.raa[j + (size_t)in.nobs * g];
   const double depol = in.depol[i];
   const double FLUX = in.flux_factor ? in.flux_factor[i + (size_t)in.nch * j] : 1.0;
   const double albedo = in.lambertian ? in.albedo[j + (size_t)in.nobs * i] : 0.0;
@@ -175,7 +183,7 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
   for (int k = T.rank; k <= L; k += T.size) H[k] = in.ze[k + (size_t)(L + 1) * j] * f32_1em3;
   T.sync();
   // ---- glue: layer optical properties
-  double *ogp = og_ptr(X, p);
+  double *ogp = og_ptr(X, pc);
   for (int k = T.rank; k < L; k += T.size) {
     const double ray = in.ROT[k + (size_t)L * (j + (size_t)in.nobs * i)];
     const double alp = in.alpha ? in.alpha[k + (size_t)L * (j + (size_t)in.nobs * i)] : 0.0;
@@ -199,8 +207,8 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
     fac1[k] = 1.0 - fdel * w; trunc[k] = fdel;
     double dsc = tau_ext * fac1[k], wsc = w * fac2 / fac1[k];
     if (wsc > 0.999999999) wsc = 0.999999999; else if (wsc < 1.0e-9) wsc = 1.0e-9;
-    X.deltau[pixL(X, p) + k] = dsc;
-    unsigned char *ls = X.layscat + (size_t)p * (NM + 1) * L;
+    X.deltau[pixL(X, pc) + k] = dsc;
+    unsigned char *ls = X.layscat + (size_t)pc * (NM + 1) * L;
     int nzero_tail = 0;                          // number of zero g11 input moments in l = m..NM, built from the top
     for (int l = NM; l >= 0; l--) {
       double a1 = 0, a2 = 0, a5 = 0, a3 = 0;     // aerosol P11, P12, P22, P33 moments (index l+1 in pmom)
@@ -259,10 +267,10 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
   if (T.rank == 0) tslant[0] = 0.0;
   T.sync();
   // ---- QSPREP (sequential in the layer index)
-  double *avsec = X.avsec + pixL(X, p), *itrans = X.itrans + pixL(X, p), *tdmubar = X.tdmubar + pixL(X, p);
+  double *avsec = X.avsec + pixL(X, pc), *itrans = X.itrans + pixL(X, pc), *tdmubar = X.tdmubar + pixL(X, pc);
   double *tduserm = X.tduserm + pixL(X, p), *emult = X.emult_up + pixL(X, p), *sigp = X.sigma_p + pixL(X, p);
   double *itu = X.itrans_userm + pixL(X, p);
-  const double *dsc = X.deltau + pixL(X, p);
+  const double *dsc = X.deltau + pixL(X, pc);
   if (T.rank == 0) {
     int cutoff = L;
     if (in.planpar) {

@@ -26,25 +26,26 @@ __global__ void __launch_bounds__(128) k_vl_setup(VLIn in, VLPix X, int p0) {
   __shared__ double sd[64];
   __shared__ int si[64];
   BlockTeam T(sd, si);
-  const int pl = blockIdx.x;                 // pixel index inside the chunk
-  // the inputs are indexed by the global pixel, the per-pixel state by the chunk-local pixel
+  const int vl = blockIdx.x;                 // pixel-view index inside the chunk (p0 = first pixel of the chunk)
+  // the inputs are indexed by the global pixel-view, the state by the chunk-local one -> give setup_pixel a state view whose
+  // arrays start p0 pixels (p0*G pixel-views) "before" the chunk
   VLPix Xl = X;
-  VLIn inl = in;
-  // shift input pixel numbering: setup_pixel derives (j,i) from p, outputs are addressed with the same p
-  // -> give it a state view whose arrays start p0 pixels "before" the chunk
-  const int L = X.L, NM = X.NM;
+  const int L = X.L, NM = X.NM, G = X.G;
+  const size_t v0 = (size_t)p0 * G;
   Xl.deltau -= (size_t)p0 * L; Xl.og -= (size_t)p0 * (NM + 1) * L * 4; Xl.avsec -= (size_t)p0 * L; Xl.itrans -= (size_t)p0 * L;
-  Xl.tdmubar -= (size_t)p0 * L; Xl.tduserm -= (size_t)p0 * L; Xl.emult_up -= (size_t)p0 * L; Xl.sigma_p -= (size_t)p0 * L;
-  Xl.itrans_userm -= (size_t)p0 * L; Xl.scal -= (size_t)p0 * 16; Xl.ibuf -= (size_t)p0 * 4; Xl.layscat -= (size_t)p0 * (NM + 1) * L;
-  setup_pixel(T, inl, Xl, p0 + pl, smem_d);
+  Xl.tdmubar -= (size_t)p0 * L; Xl.layscat -= (size_t)p0 * (NM + 1) * L;
+  Xl.tduserm -= v0 * L; Xl.emult_up -= v0 * L; Xl.sigma_p -= v0 * L; Xl.itrans_userm -= v0 * L; Xl.scal -= v0 * 16; Xl.ibuf -= v0 * 4;
+  setup_pixel(T, in, Xl, (int)v0 + vl, smem_d);
 }
 
 // K0a: exact direct-bounce BRDF of every pixel + the wrappers' BR outputs (nobs,nch)
+// (pixel-views p = (j*nch + i)*G + g; BR outputs (nobs,nch,G))
 __global__ void k_vl_brdf_exact(VLBrdf B, int npix, const unsigned char *__restrict__ skip, double *BR, double *BR_Q, double *BR_U) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
-  const int j = p / B.nch, i = p % B.nch;
-  const size_t o = j + (size_t)B.nobs * i;
+  const int G = B.G > 0 ? B.G : 1, pc = p / G, g = p % G;
+  const int j = pc / B.nch, i = pc % B.nch;
+  const size_t o = j + (size_t)B.nobs * (i + (size_t)B.nch * g);
   if (skip[p]) { for (int q = 0; q < 16; q++) B.exactdb[(size_t)p * 16 + q] = 0.0; BR[o] = 0.0; if (BR_Q) { BR_Q[o] = 0.0; BR_U[o] = 0.0; } return; }
   brdf_exact_pixel(B, p);
   double br = B.exactdb[(size_t)p * 16];
@@ -67,25 +68,25 @@ __global__ void __launch_bounds__(256) k_vl_brdf_fourier(VLBrdf B, int p0, const
   __shared__ double sd[64];
   __shared__ int si[64];
   const int pc = blockIdx.x, p = p0 + pc;
-  if (skip[p]) return;
+  if (skip[(size_t)p * (B.G > 0 ? B.G : 1)]) return;          // (the screening of a pixel is that of its first view)
   BlockTeam T(sd, si);
   brdf_pixel(T, B, p, pc, smem_d, nscr);
 }
 
 // outputs in the drop-in layout (nobs,nch); reflectance uses the single-precision pi of the glue
 // (VLIDORT_ScatMod.F90:344,596)
-__global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int npix_chunk, int nch, int nobs, const double *__restrict__ sza,
+__global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int nview_chunk, int nch, int nobs, const double *__restrict__ sza,
                             double MISSING, int S, double *radiance, double *reflectance, double *Q, double *U,
                             int *nfourier, int *status) {
-  const int pl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pl >= npix_chunk) return;
-  const int p = p0 + pl, j = p / nch, i = p % nch;
-  const size_t o = j + (size_t)nobs * i;
-  const int st0 = X.ibuf[(size_t)pl * 4 + 1];
-  const int fail = CV.state[(size_t)pl * 4 + 3];
+  const int vl = blockIdx.x * blockDim.x + threadIdx.x;     // chunk-local pixel-view
+  if (vl >= nview_chunk) return;
+  const int G = X.G, p = p0 * G + vl, pc = p / G, g = p % G, j = pc / nch, i = pc % nch;
+  const size_t o = j + (size_t)nobs * (i + (size_t)nch * g);   // outputs (nobs,nch[,G])
+  const int st0 = X.ibuf[(size_t)vl * 4 + 1];
+  const int fail = CV.state[(size_t)vl * 4 + 3];
   const int st = st0 != 0 ? st0 : fail;
   if (status) status[p] = st;
-  if (nfourier) nfourier[p] = CV.state[(size_t)pl * 4 + 2];
+  if (nfourier) nfourier[p] = CV.state[(size_t)vl * 4 + 2];
   if (st != 0) {
     const double fill = (st == 98) ? -500.0 : MISSING;     // 98: RTLS bidirectional reflectance < 0 (GV/VLIDORT_BRDF_MODIS.F90:368-377)
     radiance[o] = fill; reflectance[o] = fill;
@@ -94,21 +95,28 @@ __global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int npix_chunk, int nch,
     return;
   }
   const double pi_f = (double)3.14159274101257324f;      // 4.*atan(1.0) in real*4
-  const double I = CV.total[(size_t)pl * 4];
+  const double I = CV.total[(size_t)vl * 4];
   radiance[o] = I;
-  reflectance[o] = (pi_f * I) / (cos(sza[j] * pi_f / 180.0) * X.scal[(size_t)pl * 16 + 5]);
-  if (Q) Q[o] = S > 1 ? CV.total[(size_t)pl * 4 + 1] : 0.0;
-  if (U) U[o] = S > 1 ? CV.total[(size_t)pl * 4 + 2] : 0.0;
+  reflectance[o] = (pi_f * I) / (cos(sza[j] * pi_f / 180.0) * X.scal[(size_t)vl * 16 + 5]);
+  if (Q) Q[o] = S > 1 ? CV.total[(size_t)vl * 4 + 1] : 0.0;
+  if (U) U[o] = S > 1 ? CV.total[(size_t)vl * 4 + 2] : 0.0;
 }
 
+// one thread per pixel of the chunk: a pixel enters the Fourier loop when any of its views passed the input checks
 __global__ void k_vl_init_active(VLPix X, VLConv CV, VLSol Z, int npix_chunk, int *list, int *count) {
   const int pl = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl >= npix_chunk) return;
-  const bool ok = X.ibuf[(size_t)pl * 4 + 1] == 0;
-  CV.state[(size_t)pl * 4] = ok ? 1 : 0; CV.state[(size_t)pl * 4 + 1] = 0; CV.state[(size_t)pl * 4 + 2] = 0; CV.state[(size_t)pl * 4 + 3] = 0;
-  for (int o = 0; o < 4; o++) CV.total[(size_t)pl * 4 + o] = 0.0;
+  int any = 0;
+  for (int g = 0; g < X.G; g++) {
+    const size_t v = (size_t)pl * X.G + g;
+    const bool ok = X.ibuf[v * 4 + 1] == 0;
+    CV.state[v * 4] = ok ? 1 : 0; CV.state[v * 4 + 1] = 0; CV.state[v * 4 + 2] = 0; CV.state[v * 4 + 3] = 0;
+    for (int o = 0; o < 4; o++) CV.total[v * 4 + o] = 0.0;
+    any |= ok;
+  }
   Z.fail[pl] = 0;
-  if (ok) { const int idx = atomicAdd(count, 1); list[idx] = pl; }
+  CV.col_active[pl] = any;
+  if (any) { const int idx = atomicAdd(count, 1); list[idx] = pl; }
 }
 
 // Rayleigh optical thickness (VLIDORT_ROT_CALC): one thread per (layer, obs, channel)
@@ -182,6 +190,7 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct RunDesc {
   int S, N, km, nch, nobs, nMom, nPol, planpar, lambertian, scalar_glue;
+  int ngeom;                        // view geometries per observation (0 or 1: single geometry); raa, vza (nobs,ngeom), outputs (nobs,nch,ngeom)
   double MISSING;
   // device inputs (Fortran layouts)
   const double *ROT, *depol, *alpha, *tau, *ssa, *pmom, *he, *albedo, *sza, *raa, *vza, *flux_factor;
@@ -205,6 +214,8 @@ struct EventSet {                      // RAII: destroyed on every return path
 // the caller holds C.mu
 int run_vlidort(VLContext &C, const RunDesc &R) {
   const int S = R.S, N = R.N, L = R.km, n = S * N, NM = std::min(2 * N - 1, R.nMom), npix = R.nobs * R.nch;
+  const int G = R.ngeom > 1 ? R.ngeom : 1;
+  const size_t nview = (size_t)npix * G;
   if (npix == 0) return 0;
   if (N < 1 || N > 32 || L < 1 || L > MAXLAY || (S != 1 && S != 3) || 2 * N > MAXMOM) { ab200_set_error("vlidort: unsupported nstreams/nlayers/nstokes"); return AB200_ERR_ARG; }
   cudaStream_t st = R.stream;
@@ -214,6 +225,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   //      problems) selects the windowed band elimination of vl_bvp.cuh
   bool use_add = n <= 64;
   if (const char *e = getenv("AB200_VL_BVP_LEGACY")) use_add = use_add && atoi(e) == 0;
+  if (G > 1 && !use_add) { ab200_set_error("vlidort: the multi-geometry entries need the interaction-principle solver (nstokes*nstreams <= 64)"); return AB200_ERR_ARG; }
   EigenPlan PE; AddPlan PA; BandPlan PB;
   if (int e = vl_eigen_plan(PE, S, N, NM)) return e;
   if (use_add) { if (int e = vl_add_plan(PA, S, N, L, nsm)) return e; }
@@ -222,19 +234,19 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   const size_t work_per_solver = use_add ? PA.work_per_solver : PB.work_per_solver;
   const size_t bvp_work_bytes = (size_t)solvers * (work_per_solver + (use_add ? 0 : PB.window)) * 8;
   // ---- sizes
-  const size_t per_pix_state = (size_t)L * 8 * 8 + (size_t)(NM + 1) * L * 4 * 8 + 16 * 8 + 4 * 4 + (size_t)(NM + 1) * L;
-  const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + (6 + 2 * S) * n + 2 * n + 2 * 2 * n + (use_add ? 4 * (size_t)n * n + 2 * n : 0)) * 8;
+  const size_t per_pix_state = (size_t)L * 4 * 8 + (size_t)(NM + 1) * L * 4 * 8 + (size_t)(NM + 1) * L + (size_t)G * ((size_t)L * 4 * 8 + 16 * 8 + 4 * 4);
+  const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + 6 * n + 4 * n + (size_t)G * (2 + 2 * S) * n + (use_add ? 4 * (size_t)n * n + 2 * n : 0)) * 8;
   size_t per_pix_brdf = 0; int brdf_nscr = 0; size_t brdf_smem = 0;
   if (R.brdf) {
     const VLBrdf &B0 = *R.brdf;
-    per_pix_brdf = (brdf_out_f(B0) + 2 * brdf_out_f0(B0)) * 8;
-    const int nqs = (B0.nq == 16) ? 9 : 1, NE = N * N + 2 * N;
+    per_pix_brdf = (brdf_out_f(B0) + (1 + (size_t)G) * brdf_out_f0(B0)) * 8;
+    const int nqs = (B0.nq == 16) ? 9 : 1, NE = N * N + N + G * N;
     const size_t want = (size_t)NE * nqs * B0.NB, cap = 20000;
     brdf_nscr = 256 + (int)std::min(want, std::max<size_t>(cap, (size_t)nqs * B0.NB));
     brdf_smem = (size_t)brdf_nscr * 8;
     AB_CUDA_OK(cudaFuncSetAttribute((const void *)k_vl_brdf_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brdf_smem));
   }
-  const size_t per_pix = per_pix_state + per_pix_sol + 4 * 8 + 4 * 4 + 4 * 3 + per_pix_brdf;
+  const size_t per_pix = per_pix_state + per_pix_sol + (size_t)G * (4 * 8 + 4 * 4) + 4 * 4 + per_pix_brdf;
   double ws_gb = 24.0;
   if (const char *e = getenv("AB200_VL_WORKSPACE_GB")) ws_gb = atof(e);
   size_t freeb = 0, totalb = 0;
@@ -247,19 +259,20 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   if (budget > bvp_work_bytes + (64 << 20)) chunk = std::min<size_t>(npix, (budget - bvp_work_bytes - (64 << 20)) / per_pix);
   else chunk = 1;
   chunk = std::max<size_t>(1, chunk);
-  const size_t total_bytes = chunk * per_pix + chunk * 64 + bvp_work_bytes + (size_t)(NM + 1) * (NM + 1) * N * 3 * 8 + (size_t)npix + (64 << 20);
+  const size_t total_bytes = chunk * per_pix + chunk * 64 + bvp_work_bytes + (size_t)(NM + 1) * (NM + 1) * N * 3 * 8 + nview + (64 << 20);
   AB_CUDA_OK(C.arena.reserve(total_bytes));
   DevArena &A = C.arena;
-  VLPix X; X.L = L; X.NM = NM; X.S = S; X.npix = (int)chunk;
+  const size_t vchunk = chunk * G;                         // pixel-views per chunk
+  VLPix X; X.L = L; X.NM = NM; X.S = S; X.npix = (int)chunk; X.G = G;
   X.deltau = A.take<double>(chunk * L); X.og = A.take<double>(chunk * (NM + 1) * L * 4);
   X.avsec = A.take<double>(chunk * L); X.itrans = A.take<double>(chunk * L); X.tdmubar = A.take<double>(chunk * L);
-  X.tduserm = A.take<double>(chunk * L); X.emult_up = A.take<double>(chunk * L); X.sigma_p = A.take<double>(chunk * L);
-  X.itrans_userm = A.take<double>(chunk * L); X.scal = A.take<double>(chunk * 16); X.ibuf = A.take<int>(chunk * 4);
+  X.tduserm = A.take<double>(vchunk * L); X.emult_up = A.take<double>(vchunk * L); X.sigma_p = A.take<double>(vchunk * L);
+  X.itrans_userm = A.take<double>(vchunk * L); X.scal = A.take<double>(vchunk * 16); X.ibuf = A.take<int>(vchunk * 4);
   X.layscat = A.take<unsigned char>(chunk * (NM + 1) * L);
   VLSol Z; Z.n = n; Z.S = S; Z.N = N;
   const size_t nq = chunk * L;
   Z.keig = A.take<double>(nq * n); Z.tde = A.take<double>(nq * n); Z.xp = A.take<double>(nq * n * n); Z.xn = A.take<double>(nq * n * n);
-  Z.uh_dn = A.take<double>(nq * n * S); Z.uh_up = A.take<double>(nq * n * S); Z.hm1 = A.take<double>(nq * n); Z.hm2 = A.take<double>(nq * n);
+  Z.uh_dn = A.take<double>(nq * G * n * S); Z.uh_up = A.take<double>(nq * G * n * S); Z.hm1 = A.take<double>(nq * G * n); Z.hm2 = A.take<double>(nq * G * n);
   Z.aterm = A.take<double>(nq * n); Z.bterm = A.take<double>(nq * n); Z.gam_m = A.take<double>(nq * n); Z.gam_p = A.take<double>(nq * n);
   Z.wupper = A.take<double>(nq * 2 * n); Z.wlower = A.take<double>(nq * 2 * n); Z.fail = A.take<int>(chunk);
   VLOps O; memset(&O, 0, sizeof O);
@@ -267,16 +280,16 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
     O.rk = A.take<double>(nq * n * n); O.tk = A.take<double>(nq * n * n); O.spT = A.take<double>(nq * n * n); O.smT = A.take<double>(nq * n * n);
     O.sgu = A.take<double>(nq * n); O.sgd = A.take<double>(nq * n);
   }
-  VLConv CV; CV.total = A.take<double>(chunk * 4); CV.state = A.take<int>(chunk * 4);
+  VLConv CV; CV.total = A.take<double>(vchunk * 4); CV.state = A.take<int>(vchunk * 4); CV.col_active = A.take<int>(chunk);
   int *listA = A.take<int>(chunk), *listB = A.take<int>(chunk), *counts = A.take<int>(2 * (NM + 4));
   double *d_pq = A.take<double>((size_t)(NM + 1) * N * 3 * (NM + 1));
   double *work = A.take<double>((size_t)solvers * work_per_solver);
   double *wglob = (!use_add && PB.window) ? A.take<double>((size_t)solvers * PB.window) : nullptr;
-  unsigned char *d_skip = A.take<unsigned char>(npix);
+  unsigned char *d_skip = A.take<unsigned char>(nview);
   VLBrdf Bd; VLSurf SFb; memset(&SFb, 0, sizeof SFb);
   if (R.brdf) {
-    Bd = *R.brdf;
-    Bd.brdf_f = A.take<double>(chunk * brdf_out_f(Bd)); Bd.brdf_f_0 = A.take<double>(chunk * brdf_out_f0(Bd)); Bd.user_brdf_f = A.take<double>(chunk * brdf_out_f0(Bd));
+    Bd = *R.brdf; Bd.G = G;
+    Bd.brdf_f = A.take<double>(chunk * brdf_out_f(Bd)); Bd.brdf_f_0 = A.take<double>(chunk * brdf_out_f0(Bd)); Bd.user_brdf_f = A.take<double>(vchunk * brdf_out_f0(Bd));
     SFb.brdf_f = Bd.brdf_f; SFb.brdf_f_0 = Bd.brdf_f_0; SFb.user_brdf_f = Bd.user_brdf_f; SFb.user_brdf_f_0 = nullptr; SFb.nmfour = 2 * N; SFb.nq = Bd.nq;
   }
   if (A.off > A.cap) { ab200_set_error("vlidort: internal workspace accounting error"); return AB200_ERR_ARG; }
@@ -299,13 +312,13 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   {
     const std::vector<unsigned char> &sk = *R.h_skip;
     for (int j = 0; j < R.nobs && nadir_from == R.nobs; j++)
-      if ((*R.h_sza)[j] == 0.0) for (int i = 0; i < R.nch; i++) if (!sk[(size_t)j * R.nch + i]) { nadir_from = j; break; }
+      if ((*R.h_sza)[j] == 0.0) for (int i = 0; i < R.nch; i++) if (!sk[((size_t)j * R.nch + i) * G]) { nadir_from = j; break; }
     if (R.nadir_already) nadir_from = 0;
-    AB_CUDA_OK(cudaMemcpyAsync(d_skip, sk.data(), npix, cudaMemcpyHostToDevice, st));
+    AB_CUDA_OK(cudaMemcpyAsync(d_skip, sk.data(), nview, cudaMemcpyHostToDevice, st));
   }
   VLIn in; memset(&in, 0, sizeof in);
   in.km = L; in.nch = R.nch; in.nobs = R.nobs; in.nMom = R.nMom; in.nPol = R.nPol; in.S = S; in.N = N; in.nfine = 3;
-  in.planpar = R.planpar; in.lambertian = R.lambertian; in.scalar_glue = R.scalar_glue; in.nadir_from_obs = nadir_from;
+  in.planpar = R.planpar; in.lambertian = R.lambertian; in.scalar_glue = R.scalar_glue; in.nadir_from_obs = nadir_from; in.ngeom = G;
   in.MISSING = R.MISSING; in.earth_radius = 6371.0;
   in.ROT = R.ROT; in.depol = R.depol; in.alpha = R.alpha; in.tau = R.tau; in.ssa = R.ssa; in.pmom = R.pmom; in.ze = R.he;
   in.albedo = R.albedo; in.sza = R.sza; in.raa = R.raa; in.vza = R.vza; in.flux_factor = R.flux_factor; in.exactdb = R.exactdb;
@@ -318,7 +331,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
     AB_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int) * 2 * (NM + 4), st));
     cudaEventRecord(ev[0], st);
     if (R.brdf) { k_vl_brdf_fourier<<<nc, 256, brdf_smem, st>>>(Bd, (int)p0, d_skip, brdf_nscr); stats.n_launches += 1; }
-    k_vl_setup<<<nc, 128, setup_smem, st>>>(in, X, (int)p0);
+    k_vl_setup<<<nc * G, 128, setup_smem, st>>>(in, X, (int)p0);
     k_vl_init_active<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, Z, nc, listA, counts);
     cudaEventRecord(ev[1], st);
     AB_CUDA_OK(cudaGetLastError());
@@ -366,12 +379,12 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
       stats.ms_eigen += m1; stats.ms_bvp += m2;
       std::swap(cur, nxt);
     }
-    k_vl_finish<<<(nc + 255) / 256, 256, 0, st>>>(X, CV, (int)p0, nc, R.nch, R.nobs, R.sza, R.MISSING, S, R.radiance, R.reflectance, R.Q, R.U,
+    k_vl_finish<<<(nc * G + 255) / 256, 256, 0, st>>>(X, CV, (int)p0, nc * G, R.nch, R.nobs, R.sza, R.MISSING, S, R.radiance, R.reflectance, R.Q, R.U,
                                                   R.nfourier, R.status);
     AB_CUDA_OK(cudaGetLastError());
     AB_CUDA_OK(cudaStreamSynchronize(st));
   }
-  stats.npix += npix; stats.n_launches += 3 * ((npix + chunk - 1) / chunk);
+  stats.npix += (long)nview; stats.n_launches += 3 * ((npix + chunk - 1) / chunk);
   {
     std::lock_guard<std::mutex> lk(g_stats_mu);
     g_stats.ms_setup += stats.ms_setup; g_stats.ms_eigen += stats.ms_eigen; g_stats.ms_bvp += stats.ms_bvp; g_stats.ms_ops += stats.ms_ops;
@@ -384,8 +397,17 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
 
 bool is_missing_h(double x, double MISSING) { return std::fabs(x / MISSING - 1.0) < (double)0.001f; }
 
-// host-pointer front end shared by the Lambertian entry points
-int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+// true when every geometry of every observation has the sun of the first one (solar_zenith (nobs,ngeom)): one beam per pixel
+bool same_sun(const double *sza, int nobs, int ngeom) {
+  for (int g = 1; g < ngeom; g++) for (int j = 0; j < nobs; j++) if (sza[j + (size_t)nobs * g] != sza[j]) return false;
+  return true;
+}
+
+// host-pointer front end shared by the Lambertian entry points.  ngeom > 1: multi-geometry form -- solar_zenith, relat_azymuth,
+// sensor_zenith are (nobs,ngeom), the outputs (nobs,nch,ngeom); the layer eigenproblems and the boundary-value solve are done once
+// per pixel and Fourier term for all views (they do not depend on the viewing direction).  Geometries with different suns are
+// solved one geometry at a time.
+int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int ngeom, int nstreams, int plane_parallel, int nMom, int nPol,
                  const double *ROT, const double *depol, const double *alpha, const double *tau, const double *ssa,
                  const double *pmom, const double *he, const double *albedo, const double *sza, const double *raa,
                  const double *vza, const double *flux_factor, double MISSING, double *radiance, double *reflectance,
@@ -395,10 +417,23 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
   if (nstreams > 25) { *rc = 2; return 2; }
   if (km > 72) { *rc = 3; return 3; }
   if (nMom > 1000) { *rc = 5; return 5; }
-  const size_t npix = (size_t)nobs * nch;
+  const int G = ngeom > 1 ? ngeom : 1;
+  const size_t npix = (size_t)nobs * nch, nview = npix * G;
   if (npix == 0) return 0;
+  if (G > 1 && (!same_sun(sza, nobs, G) || S * nstreams > 64)) {
+    std::vector<int> nf(nview), stt(nview);
+    for (int g = 0; g < G; g++) {
+      const size_t og = npix * g, oa = (size_t)nobs * g;
+      if (int e = lambert_host(S, scalar_glue, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, he,
+                               albedo, sza + oa, raa + oa, vza + oa, flux_factor, MISSING, radiance + og, reflectance + og,
+                               Q ? Q + og : nullptr, U ? U + og : nullptr, rc)) return e;
+      for (size_t p = 0; p < npix; p++) { nf[p * G + g] = g_last_nfourier[p]; stt[p * G + g] = g_last_status[p]; }
+    }
+    g_last_nfourier = nf; g_last_status = stt;
+    return 0;
+  }
   const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
-  size_t bytes = 8 * (n_rot * (alpha ? 4 : 3) + n_pm + n_he + npix * (1 + (flux_factor ? 1 : 0)) + 3 * (size_t)nobs + nch + 4 * npix) + 8 * npix + 4096 * 16;
+  size_t bytes = 8 * (n_rot * (alpha ? 4 : 3) + n_pm + n_he + npix * (1 + (flux_factor ? 1 : 0)) + (1 + 2 * (size_t)G) * nobs + nch + 4 * nview) + 8 * nview + 4096 * 16;
   VLContext &C = vl_context();
   std::lock_guard<std::mutex> lock(C.mu);
   AB_CUDA_OK(C.io.reserve(bytes));
@@ -411,29 +446,34 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int nstreams
   };
   RunDesc R; memset(&R, 0, sizeof R);
   R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
-  R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING;
+  R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G;
   R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.alpha = alpha ? put(alpha, n_rot) : nullptr; R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
-  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.albedo = put(albedo, npix); R.sza = put(sza, nobs); R.raa = put(raa, nobs); R.vza = put(vza, nobs);
+  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.albedo = put(albedo, npix); R.sza = put(sza, nobs);
+  R.raa = put(raa, (size_t)nobs * G); R.vza = put(vza, (size_t)nobs * G);
   R.flux_factor = flux_factor ? put(flux_factor, npix) : nullptr;
-  R.radiance = put(nullptr, npix); R.reflectance = put(nullptr, npix); R.Q = put(nullptr, npix); R.U = put(nullptr, npix);
-  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * npix; off = align256(off); R.status = (int *)(b + off); off += 4 * npix;
+  R.radiance = put(nullptr, nview); R.reflectance = put(nullptr, nview); R.Q = put(nullptr, nview); R.U = put(nullptr, nview);
+  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * nview; off = align256(off); R.status = (int *)(b + off); off += 4 * nview;
   std::vector<double> h_sza(sza, sza + nobs);
-  std::vector<unsigned char> skip(npix, 0);
+  std::vector<unsigned char> skip(nview, 0);
+  // screening as in the reference: the angles of the first geometry and the albedo (GV/VLIDORT_LAMBERT.F90:271-299,449-472)
   for (int j = 0; j < nobs; j++) {
     const bool ma = is_missing_h(sza[j], MISSING) || is_missing_h(vza[j], MISSING) || is_missing_h(raa[j], MISSING);
-    for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || is_missing_h(albedo[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
+    for (int i = 0; i < nch; i++) {
+      const unsigned char sk = (ma || is_missing_h(albedo[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
+      for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
+    }
   }
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = 0;
   AB_CUDA_OK(cpe);
   int e = run_vlidort(C, R);
   if (e) return e;
-  AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * npix, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * npix, cudaMemcpyDeviceToHost, 0));
-  if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * npix, cudaMemcpyDeviceToHost, 0));
-  if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * npix, cudaMemcpyDeviceToHost, 0));
-  g_last_nfourier.resize(npix); g_last_status.resize(npix);
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * npix, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * npix, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * nview, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * nview, cudaMemcpyDeviceToHost, 0));
+  if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * nview, cudaMemcpyDeviceToHost, 0));
+  if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * nview, cudaMemcpyDeviceToHost, 0));
+  g_last_nfourier.resize(nview); g_last_status.resize(nview);
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * nview, cudaMemcpyDeviceToHost, 0));
   AB_CUDA_OK(cudaStreamSynchronize(0));
   return 0;
 }
@@ -454,7 +494,7 @@ int build_brdf_tables(VLContext &C, VLBrdf &B, int kind, int S, int scalar_glue,
 }
 
 // front end of the Cox-Munk / GISS Cox-Munk / MODIS RTLS wrappers; dev: every array pointer is a device pointer
-int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
+int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int ngeom, int nstreams, int plane_parallel, int nMom, int nPol,
                const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
                const double *he, const double *sza, const double *raa, const double *vza, double MISSING, const SurfArgs &sa,
                double *radiance, double *reflectance, double *Q, double *U, cudaStream_t st, int *rc) {
@@ -462,14 +502,33 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   if (nstreams > 25) { *rc = 2; return 2; }
   if (km > 72) { *rc = 3; return 3; }
   if (nMom > 1000) { *rc = 5; return 5; }
-  const size_t npix = (size_t)nobs * nch;
+  const int G = ngeom > 1 ? ngeom : 1;
+  const size_t npix = (size_t)nobs * nch, nview = npix * G;
   if (npix == 0) return 0;
+  if (G > 1 && (dev || !same_sun(sza, nobs, G) || S * nstreams > 64)) {
+    if (dev) { ab200_set_error("brdf multi-geometry: host-pointer entry only"); return AB200_ERR_ARG; }
+    // geometries with their own suns: one geometry at a time (solar_zenith, relat_azymuth, sensor_zenith (nobs,ngeom); outputs (nobs,nch,ngeom))
+    std::vector<int> nf(nview), stt(nview);
+    for (int g = 0; g < G; g++) {
+      const size_t og = npix * g, oa = (size_t)nobs * g;
+      SurfArgs s1 = sa;
+      if (sa.BR) s1.BR = sa.BR + og;
+      if (sa.BR_Q) s1.BR_Q = sa.BR_Q + og;
+      if (sa.BR_U) s1.BR_U = sa.BR_U + og;
+      if (int e = brdf_front(false, S, scalar_glue, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he,
+                             sza + oa, raa + oa, vza + oa, MISSING, s1, radiance + og, reflectance + og, Q ? Q + og : nullptr,
+                             U ? U + og : nullptr, st, rc)) return e;
+      for (size_t p = 0; p < npix; p++) { nf[p * G + g] = g_last_nfourier[p]; stt[p * G + g] = g_last_status[p]; }
+    }
+    g_last_nfourier = nf; g_last_status = stt;
+    return 0;
+  }
   const bool cx = (sa.kind != SURF_MODIS);
   const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
-  const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + 5 * (size_t)nobs + 2 * nch + 6 * npix + 7 * npix + 16 * npix) + 16 * npix + 4096 * 32;
+  const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + (3 + 2 * (size_t)G) * nobs + 2 * nch + 6 * npix + 7 * nview + 16 * nview) + 16 * nview + 4096 * 32;
   VLContext &C = vl_context();
   std::lock_guard<std::mutex> lock(C.mu);
-  AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * npix + 7 * npix) + 16 * npix + 4096 * 8 : bytes));
+  AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * nview + 7 * nview) + 16 * nview + 4096 * 8 : bytes));
   char *b = C.io.as<char>(); size_t off = 0;
   cudaError_t cpe = cudaSuccess;
   auto put = [&](const double *src, size_t n) -> double * {
@@ -480,24 +539,24 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   };
   RunDesc R; memset(&R, 0, sizeof R);
   R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
-  R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING;
+  R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G;
   R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
-  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.sza = put(sza, nobs); R.raa = put(raa, nobs); R.vza = put(vza, nobs);
+  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.sza = put(sza, nobs); R.raa = put(raa, (size_t)nobs * G); R.vza = put(vza, (size_t)nobs * G);
   R.alpha = sa.alpha ? put(sa.alpha, n_rot) : nullptr; R.flux_factor = sa.flux_factor ? put(sa.flux_factor, npix) : nullptr;
   const double *d_u = cx ? put(sa.u10m, nobs) : nullptr, *d_v = cx ? put(sa.v10m, nobs) : nullptr, *d_mr = cx ? put(sa.mr, nch) : nullptr;
   const double *d_kw = cx ? nullptr : put(sa.kernel_wt, 3 * npix), *d_pr = cx ? nullptr : put(sa.param, 2 * npix);
-  double *d_exact = put(nullptr, 16 * npix);
+  double *d_exact = put(nullptr, 16 * nview);
   double *d_BR, *d_BRQ, *d_BRU;
   if (dev) {
     R.radiance = radiance; R.reflectance = reflectance; R.Q = Q; R.U = U; d_BR = sa.BR; d_BRQ = sa.BR_Q; d_BRU = sa.BR_U;
   } else {
-    R.radiance = put(nullptr, npix); R.reflectance = put(nullptr, npix); R.Q = put(nullptr, npix); R.U = put(nullptr, npix);
-    d_BR = put(nullptr, npix); d_BRQ = put(nullptr, npix); d_BRU = put(nullptr, npix);
+    R.radiance = put(nullptr, nview); R.reflectance = put(nullptr, nview); R.Q = put(nullptr, nview); R.U = put(nullptr, nview);
+    d_BR = put(nullptr, nview); d_BRQ = put(nullptr, nview); d_BRU = put(nullptr, nview);
   }
-  if (!d_BR) d_BR = put(nullptr, npix);
-  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * npix; off = align256(off); R.status = (int *)(b + off); off += 4 * npix;
-  off = align256(off); unsigned char *d_skip0 = (unsigned char *)(b + off); off += npix;
-  // host copies for the MISSING screening
+  if (!d_BR) d_BR = put(nullptr, nview);
+  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * nview; off = align256(off); R.status = (int *)(b + off); off += 4 * nview;
+  off = align256(off); unsigned char *d_skip0 = (unsigned char *)(b + off); off += nview;
+  // host copies for the MISSING screening (first geometry, as the reference's multi-geometry wrappers)
   std::vector<double> h_sza(nobs), h_vza(nobs), h_raa(nobs), h_u, h_v, h_mr;
   auto fetch = [&](std::vector<double> &hv, const double *src, size_t n) {
     hv.resize(n);
@@ -506,43 +565,50 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   fetch(h_sza, sza, nobs); fetch(h_vza, vza, nobs); fetch(h_raa, raa, nobs);
   if (cx) { fetch(h_u, sa.u10m, nobs); fetch(h_v, sa.v10m, nobs); fetch(h_mr, sa.mr, nch); }
   if (dev) AB_CUDA_OK(cudaStreamSynchronize(st));
-  std::vector<unsigned char> skip(npix, 0);
+  std::vector<unsigned char> skip(nview, 0);
   for (int j = 0; j < nobs; j++) {
     const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
     const bool mw = cx && (is_missing_h(h_u[j], MISSING) || is_missing_h(h_v[j], MISSING));
-    for (int i = 0; i < nch; i++) skip[(size_t)j * nch + i] = (ma || mw || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
+    for (int i = 0; i < nch; i++) {
+      const unsigned char sk = (ma || mw || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
+      for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
+    }
   }
-  AB_CUDA_OK(cudaMemcpyAsync(d_skip0, skip.data(), npix, cudaMemcpyHostToDevice, st));
+  AB_CUDA_OK(cudaMemcpyAsync(d_skip0, skip.data(), nview, cudaMemcpyHostToDevice, st));
   VLBrdf B;
   const int NM = std::min(2 * nstreams - 1, nMom);
   AB_CUDA_OK(cpe);
   if (int e = build_brdf_tables(C, B, sa.kind, S, scalar_glue, nstreams, NM, nch, nobs, st)) return e;
+  B.G = G;
   B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
   B.exactdb = d_exact;
   off = align256(off); B.wsa_fail = (int *)(b + off); off += 4 * npix;
-  k_vl_brdf_exact<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(B, (int)npix, d_skip0, d_BR, d_BRQ, d_BRU);
+  k_vl_brdf_exact<<<(unsigned)((nview + 127) / 128), 128, 0, st>>>(B, (int)nview, d_skip0, d_BR, d_BRQ, d_BRU);
   AB_CUDA_OK(cudaGetLastError());
   { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.n_launches += 1; }
-  if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel not run
-    std::vector<double> h_br(npix);
-    AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * npix, cudaMemcpyDeviceToHost, st));
+  if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel-view not run
+    std::vector<double> h_br(nview);
+    AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * nview, cudaMemcpyDeviceToHost, st));
     AB_CUDA_OK(cudaStreamSynchronize(st));
-    for (int j = 0; j < nobs; j++) for (int i = 0; i < nch; i++) if (!skip[(size_t)j * nch + i] && h_br[j + (size_t)nobs * i] < 0) skip[(size_t)j * nch + i] = 2;
+    for (int j = 0; j < nobs; j++) for (int i = 0; i < nch; i++) for (int g = 0; g < G; g++) {
+      unsigned char &sk = skip[((size_t)j * nch + i) * G + g];
+      if (!sk && h_br[j + (size_t)nobs * (i + (size_t)nch * g)] < 0) sk = 2;
+    }
   }
   R.exactdb = d_exact; R.brdf = &B;
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
   if (int e = run_vlidort(C, R)) return e;
-  g_last_nfourier.resize(npix); g_last_status.resize(npix);
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * npix, cudaMemcpyDeviceToHost, st));
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * npix, cudaMemcpyDeviceToHost, st));
+  g_last_nfourier.resize(nview); g_last_status.resize(nview);
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * nview, cudaMemcpyDeviceToHost, st));
   if (!dev) {
-    AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * npix, cudaMemcpyDeviceToHost, st));
-    AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * npix, cudaMemcpyDeviceToHost, st));
-    if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * npix, cudaMemcpyDeviceToHost, st));
-    if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * npix, cudaMemcpyDeviceToHost, st));
-    if (sa.BR) AB_CUDA_OK(cudaMemcpyAsync(sa.BR, d_BR, 8 * npix, cudaMemcpyDeviceToHost, st));
-    if (sa.BR_Q) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_Q, d_BRQ, 8 * npix, cudaMemcpyDeviceToHost, st));
-    if (sa.BR_U) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_U, d_BRU, 8 * npix, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * nview, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * nview, cudaMemcpyDeviceToHost, st));
+    if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * nview, cudaMemcpyDeviceToHost, st));
+    if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * nview, cudaMemcpyDeviceToHost, st));
+    if (sa.BR) AB_CUDA_OK(cudaMemcpyAsync(sa.BR, d_BR, 8 * nview, cudaMemcpyDeviceToHost, st));
+    if (sa.BR_Q) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_Q, d_BRQ, 8 * nview, cudaMemcpyDeviceToHost, st));
+    if (sa.BR_U) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_U, d_BRU, 8 * nview, cudaMemcpyDeviceToHost, st));
   }
   AB_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
@@ -559,7 +625,7 @@ extern "C" int ab200_vlidort_scalar_lambert(int km, int nch, int nobs, const dou
                                             const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL,
                                             double *reflectance_VL, int *rc) {
   (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
-  return lambert_host(1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, nullptr, tau, ssa, pmom, he, albedo,
+  return lambert_host(1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, nullptr, tau, ssa, pmom, he, albedo,
                       solar_zenith, relat_azymuth, sensor_zenith, nullptr, MISSING, radiance_VL, reflectance_VL, nullptr, nullptr, rc);
 }
 
@@ -572,7 +638,7 @@ extern "C" int ab200_vlidort_vector_lambert(int km, int nch, int nobs, const dou
                                             int verbose, double *radiance_VL, double *reflectance_VL, double *Q, double *U,
                                             int *rc) {
   (void)channels; (void)pe; (void)te; (void)verbose;
-  return lambert_host(3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, he, albedo,
+  return lambert_host(3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, he, albedo,
                       solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, radiance_VL, reflectance_VL, Q, U, rc);
 }
 
@@ -681,21 +747,21 @@ extern "C" int ab200_vlidort_vector_cx(AB_CX_ARGS, double *radiance_VL_SURF, dou
                                        double *U, double *BR_Q, double *BR_U, int *rc) {
   (void)channels; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
-  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 extern "C" int ab200_vlidort_vector_gisscx(AB_CX_ARGS, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
                                            double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
   (void)channels; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
-  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 extern "C" int ab200_vlidort_vector_ocicx(AB_CX_ARGS, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
                                           double *U, double *BR_Q, double *BR_U, int *rc) {
   (void)channels; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_OCICX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
-  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 extern "C" int ab200_vlidort_vector_ocigisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
@@ -708,7 +774,7 @@ extern "C" int ab200_vlidort_vector_ocigisscx(int km, int nch, int nobs, const d
                                               double *U, double *BR_Q, double *BR_U, int *rc) {
   (void)channels; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_OCIGISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U, alpha, flux_factor};
-  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 extern "C" int ab200_vlidort_scalar_gisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
@@ -720,7 +786,7 @@ extern "C" int ab200_vlidort_scalar_gisscx(int km, int nch, int nobs, const doub
                                            double *reflectance_VL_SURF, double *BRDF, int *rc) {
   (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BRDF, nullptr, nullptr};
-  return brdf_front(false, 1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
 }
 extern "C" int ab200_vlidort_scalar_cx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
@@ -731,7 +797,7 @@ extern "C" int ab200_vlidort_scalar_cx(int km, int nch, int nobs, const double *
                                        double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc) {
   (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BRDF, nullptr, nullptr};
-  return brdf_front(false, 1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
 }
 extern "C" int ab200_vlidort_vector_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
@@ -745,7 +811,7 @@ extern "C" int ab200_vlidort_vector_brdf_modis(int km, int nch, int nobs, const 
   (void)channels; (void)pe; (void)te; (void)verbose;
   if (nkernel != 3 || nparam != 2) { ab200_set_error("vector_brdf_modis: nkernel must be 3 and nparam 2 (GV/VLIDORT_BRDF_MODIS.F90:224-225)"); return AB200_ERR_ARG; }
   SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U};
-  return brdf_front(false, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 extern "C" int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
@@ -757,7 +823,7 @@ extern "C" int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const 
                                                double *reflectance_VL_SURF, double *BR, int *rc) {
   (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, nullptr, nullptr};
-  return brdf_front(false, 1, 1, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+  return brdf_front(false, 1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
 }
 // device-pointer variant of ab200_vlidort_vector_cx (every array resident in HBM, outputs too)
@@ -768,8 +834,57 @@ extern "C" int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstrea
                                            double MISSING, double *radiance, double *reflectance, double *BR, double *Q, double *U,
                                            void *stream, int *rc) {
   SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BR, nullptr, nullptr};
-  return brdf_front(true, 3, 0, km, nch, nobs, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, sza, raa, vza,
+  return brdf_front(true, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, sza, raa, vza,
                     MISSING, sa, radiance, reflectance, Q, U, (cudaStream_t)stream, rc);
+}
+
+// ---- multi-geometry forms (generic VLIDORT_Vector_Lambert / VLIDORT_Vector_CX over SingleGeom / MultiGeom, GV/VLIDORT_LAMBERT.F90:
+//      14-17,346-520, GV/VLIDORT_BRDF_CX.F90:27-30,766-947).  solar_zenith, relat_azymuth, sensor_zenith are (nobs,ngeom), the outputs
+//      (nobs,nch,ngeom); the albedo of the first geometry is used for all (VLIDORT_SurfaceLamb_MultiGeom, V283/VLIDORT_SurfaceMod.F90:
+//      564-582).  ngeom is not capped at the reference's MAX_USER_OBSGEOMS = 2.  When all geometries of an observation share the sun
+//      (polar_vlidort's 60 view angles per column, LV/polar_vlidort.py:935-950) the layer eigenproblems and the boundary-value solve
+//      are done once per pixel and Fourier term; every view keeps its own Fourier convergence, as in per-view calls.
+extern "C" int ab200_vlidort_vector_lambert_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                      int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                                      const double *alpha, const double *tau, const double *ssa, const double *pmom,
+                                                      const double *pe, const double *he, const double *te, const double *albedo,
+                                                      const double *solar_zenith, const double *relat_azymuth,
+                                                      const double *sensor_zenith, const double *flux_factor, double MISSING,
+                                                      int verbose, double *radiance_VL, double *reflectance_VL, double *Q, double *U,
+                                                      int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (ngeom < 1) { ab200_set_error("multigeom: ngeom must be >= 1"); return AB200_ERR_ARG; }
+  return lambert_host(3, 0, km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, he, albedo,
+                      solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, radiance_VL, reflectance_VL, Q, U, rc);
+}
+extern "C" int ab200_vlidort_vector_cx_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                 int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                                 const double *tau, const double *ssa, const double *pmom, const double *pe,
+                                                 const double *he, const double *te, const double *U10m, const double *V10m,
+                                                 const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                                 const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                                 double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q,
+                                                 double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (ngeom < 1) { ab200_set_error("multigeom: ngeom must be >= 1"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_CX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_brdf_modis_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                         int plane_parallel, int nMom, int nPol, int nkernel, int nparam,
+                                                         const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                                         const double *pmom, const double *pe, const double *he, const double *te,
+                                                         const double *kernel_wt, const double *param, const double *solar_zenith,
+                                                         const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                                                         int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                                         double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (ngeom < 1) { ab200_set_error("multigeom: ngeom must be >= 1"); return AB200_ERR_ARG; }
+  if (nkernel != 3 || nparam != 2) { ab200_set_error("vector_brdf_modis: nkernel must be 3 and nparam 2 (GV/VLIDORT_BRDF_MODIS.F90:224-225)"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 
 extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,

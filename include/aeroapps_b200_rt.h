@@ -140,11 +140,45 @@ int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch, int nq, co
                              const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
                              double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
 
-/* diagnostics of the most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i; returns npix */
+/* ---- multi-geometry forms: the generic interfaces VLIDORT_Vector_Lambert / VLIDORT_Vector_CX / VLIDORT_Vector_LandMODIS over
+ * SingleGeom / MultiGeom (GV/VLIDORT_LAMBERT.F90:14-17,346-350; GV/VLIDORT_BRDF_CX.F90:27-30,766; GV/VLIDORT_BRDF_MODIS.F90:413).
+ * solar_zenith, relat_azymuth, sensor_zenith (nobs,ngeom); outputs (nobs,nch,ngeom); albedo (nobs,nch) = the reference's
+ * albedo(:,:,1) (VLIDORT_SurfaceLamb_MultiGeom uses the first geometry's albedo, V283/VLIDORT_SurfaceMod.F90:564-582).  ngeom is not
+ * capped at the reference's MAX_USER_OBSGEOMS = 2.  One sun per observation (LV/polar_vlidort.py:935-950: 60 view angles per column):
+ * eigenproblems and boundary-value solve once per pixel and Fourier term, per-view post-processing and Fourier convergence;
+ * geometries with their own suns are solved one geometry at a time. */
+int ab200_vlidort_vector_lambert_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                           int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                           const double *alpha, const double *tau, const double *ssa, const double *pmom,
+                                           const double *pe, const double *he, const double *te, const double *albedo,
+                                           const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                           const double *flux_factor, double MISSING, int verbose, double *radiance_VL,
+                                           double *reflectance_VL, double *Q, double *U, int *rc);
+int ab200_vlidort_vector_cx_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams, int plane_parallel,
+                                      int nMom, int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                      const double *pmom, const double *pe, const double *he, const double *te, const double *U10m,
+                                      const double *V10m, const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                      const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                      double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+int ab200_vlidort_vector_brdf_modis_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                              int plane_parallel, int nMom, int nPol, int nkernel, int nparam, const double *ROT,
+                                              const double *depol, const double *tau, const double *ssa, const double *pmom,
+                                              const double *pe, const double *he, const double *te, const double *kernel_wt,
+                                              const double *param, const double *solar_zenith, const double *relat_azymuth,
+                                              const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                              double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q,
+                                              double *BR_U, int *rc);
+
+/* diagnostics of the calling thread's most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i (per pixel-view
+ * (j*nch + i)*ngeom + g for the multi-geometry forms); returns their number */
 long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap);
 /* accumulated device timings (CUDA events) of the three kernels and problem counts; reset != 0 clears them */
 int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,
                         int reset);
+/* self-test of the CTA linear algebra of the boundary-value kernels (tests/test_linalg_gpu.py): E = A^-1 (register-resident
+ * Gauss-Jordan with partial pivoting) and P = A E (16-byte-load product) for one n x n row-major matrix, one CTA of `threads`
+ * threads.  Returns 0, or 1 when the matrix is singular to working precision. */
+int ab200_selftest_linalg(int n, int threads, const double *A, double *E, double *P);
 /* frees the grow-only device workspace */
 int ab200_vlidort_release(void);
 #endif

@@ -26,10 +26,44 @@ class VLOutput(C.Structure):
 
 
 _lib = None
+_native = None
+_use_native = False
+
+
+def _cpu_tag():
+    """identifies the host CPU: a -march=native build must never run on another machine (the tree travels to the GPU box)"""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        key = "".join(l for l in txt.splitlines() if l.startswith(("model name", "flags")))[:20000]
+    except OSError:
+        key = "unknown"
+    return hashlib.sha1(key.encode()).hexdigest()[:12]
+
+
+def use_native(on=True):
+    """bench.py's CPU arms: time a -O3 -march=native build of the same sources (built on first use, on the host that runs it, into
+    oracle/_native/).  The portable -O2 build stays the checker of the parity tests.  Returns True when the native build is active."""
+    global _native, _use_native
+    if on and _native is None:
+        d = os.path.join(_HERE, "_native")
+        so = os.path.join(d, f"libvlidort_oracle_{_cpu_tag()}.so")
+        try:
+            if not os.path.exists(so):
+                os.makedirs(d, exist_ok=True)
+                subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-shared", "-o", so,
+                                       os.path.join(_HERE, "vlidort_oracle.cpp"), os.path.join(_HERE, "vbrdf_oracle.cpp"), "-lm"])
+            _native = C.CDLL(so)
+        except Exception:
+            _native = False
+    _use_native = bool(on and _native)
+    return _use_native
 
 
 def lib():
     global _lib
+    if _use_native:
+        return _native
     if _lib is None:
         if not os.path.exists(_SO):
             subprocess.check_call(["make", "-s", "-C", _HERE])

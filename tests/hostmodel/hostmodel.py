@@ -28,16 +28,17 @@ def _p(a):
 
 
 def run(nstokes, nstreams, plane_parallel, sc, lambertian=True, scalar_glue=False, nfine=3, nadir_from_obs=None,
-        accuracy=float(np.float32(0.0001)), brdf=None, alpha=None, flux_factor=None, max_fourier=-1, surface=None):
+        accuracy=float(np.float32(0.0001)), brdf=None, alpha=None, flux_factor=None, max_fourier=-1, surface=None, ngeom=1):
+    """ngeom > 1: sc["raa"], sc["vza"] are (nobs, ngeom); results get a trailing ngeom axis"""
     F = lambda a: np.asfortranarray(a, dtype=np.float64)
     km, nch, nobs = sc["tau"].shape
-    npix = nobs * nch
+    npix = nobs * nch * ngeom
     stokes = np.zeros((npix, 4)); nf = np.zeros(npix, np.int32); st = np.zeros(npix, np.int32)
     b = {k: None for k in ("brdf_f", "brdf_f_0", "user_brdf_f", "user_brdf_f_0", "exactdb")}
     if brdf is not None:
         b = {k: np.ascontiguousarray(brdf[k], dtype=np.float64) for k in b}
     arrs = [F(sc["ROT"]), np.ascontiguousarray(sc["depol"], dtype=np.float64), None if alpha is None else F(alpha), F(sc["tau"]),
-            F(sc["ssa"]), F(sc["pmom"]), F(sc["he"]), F(sc["albedo"])] + [np.ascontiguousarray(sc[k], dtype=np.float64) for k in ("sza", "raa", "vza")]
+            F(sc["ssa"]), F(sc["pmom"]), F(sc["he"]), F(sc["albedo"])] + [np.ascontiguousarray(np.asarray(sc[k], dtype=np.float64).ravel(order="F")) for k in ("sza", "raa", "vza")]
     ff = None if flux_factor is None else F(flux_factor)
     kinds = {None: 0, "cx": 2, "gisscx": 3, "modis": 4, "ocicx": 5, "ocigisscx": 6}
     sk = kinds[surface]
@@ -47,12 +48,15 @@ def run(nstokes, nstreams, plane_parallel, sc, lambertian=True, scalar_glue=Fals
     elif sk == 4:
         sarr[3:] = [F(sc["kernel_wt"]), F(sc["param"])]
     BR = np.zeros(npix); wsa = np.zeros(npix, np.int32)
-    lib().hm_vlidort(int(nstokes), int(nstreams), km, nch, nobs, sc["nMom"], sc["nPol"], int(plane_parallel), int(lambertian),
+    lib().hm_vlidort(int(ngeom), int(nstokes), int(nstreams), km, nch, nobs, sc["nMom"], sc["nPol"], int(plane_parallel), int(lambertian),
                      int(scalar_glue), int(nfine), nobs if nadir_from_obs is None else int(nadir_from_obs), C.c_double(6371.0),
                      C.c_double(accuracy), *[_p(a) for a in arrs], _p(ff), _p(b["brdf_f"]), _p(b["brdf_f_0"]), _p(b["user_brdf_f"]),
                      _p(b["user_brdf_f_0"]), _p(b["exactdb"]), int(max_fourier), sk, *[_p(a) for a in sarr], _p(BR),
                      wsa.ctypes.data_as(C.POINTER(C.c_int)), _p(stokes), nf.ctypes.data_as(C.POINTER(C.c_int)),
                      st.ctypes.data_as(C.POINTER(C.c_int)))
+    if ngeom > 1:
+        out = (stokes.reshape(nobs, nch, ngeom, 4), nf.reshape(nobs, nch, ngeom), st.reshape(nobs, nch, ngeom))
+        return out + (BR.reshape(nobs, nch, ngeom),) if surface is not None else out
     if surface is not None:
-        return stokes.reshape(nobs, nch, 4), nf.reshape(nobs, nch), st.reshape(nobs, nch), BR.reshape(nobs, nch), wsa.reshape(nobs, nch)
+        return stokes.reshape(nobs, nch, 4), nf.reshape(nobs, nch), st.reshape(nobs, nch), BR.reshape(nobs, nch), wsa[:nobs * nch].reshape(nobs, nch)
     return stokes.reshape(nobs, nch, 4), nf.reshape(nobs, nch), st.reshape(nobs, nch)

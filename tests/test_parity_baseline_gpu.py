@@ -107,3 +107,43 @@ def test_geo_modis_4_channels(mods):
     rep = parity.parity_report("modis", 3, N, False, sc, got)
     _save("geo_modis_n12_4ch_nmom300", rep)
     assert rep["n"] + rep["n_special"] == 4 * nobs and rep["pass"], rep
+
+
+@pytest.mark.parametrize("kind", ["lambert", "cx"])
+def test_polar_multigeometry_60_views(mods, kind):
+    """BASELINE configs[4] call pattern (LV/polar_vlidort.py:935-950: 60 view angles per column, nstokes 3, 16 streams, nMom 300) through
+    the multi-geometry entries: ONE call solves the layer eigenproblems and the boundary-value problem once per column and Fourier
+    term; every one of the 60 views must equal the single-geometry oracle run of that view (bar as above) with its own Fourier count"""
+    VP, vg, parity = mods
+    nobs, N, G = 2, 16, 60
+    sc = vg.synthetic_scene(nobs, nmom=300, seed=20260106)
+    rng = np.random.default_rng(60)
+    vza = np.asfortranarray(rng.uniform(0.0, 65.0, (nobs, G))); raa = np.asfortranarray(rng.uniform(0.0, 180.0, (nobs, G)))
+    vza[0, 7] = 0.0
+    sza = np.asfortranarray(np.repeat(sc["sza"][:, None], G, axis=1))
+    if kind == "lambert":
+        alpha = np.zeros_like(sc["ROT"]); flux = np.ones((1, nobs), order="F")
+        I, R, Q, U, rc = VP.vector_lambert_multigeom(sc["channels"], N, False, sc["ROT"], sc["depol"], alpha, sc["tau"], sc["ssa"], sc["pmom"],
+                                                     sc["pe"], sc["he"], sc["te"], sc["albedo"], sza, raa, vza, flux, M, 0)
+    else:
+        I, R, BR, Q, U, BRQ, BRU, rc = VP.vector_cx_multigeom(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"],
+                                                              sc["pe"], sc["he"], sc["te"], sc["u10m"], sc["v10m"], sc["mr"], sza, raa, vza, M, 0)
+    assert rc == 0 and I.shape == (nobs, 1, G)
+    nf, st = VP.last_diag()
+    assert (st == 0).all()
+    # the same pixel-views as nobs*G independent observations for the oracle: observation index = g*nobs + j
+    rep = lambda a, ax: np.asfortranarray(np.concatenate([a] * G, axis=ax))
+    flat = dict(ROT=rep(sc["ROT"], 1), depol=sc["depol"], tau=rep(sc["tau"], 2), ssa=rep(sc["ssa"], 2), pmom=rep(sc["pmom"], 2), he=rep(sc["he"], 1),
+                albedo=rep(sc["albedo"], 0), sza=sza.ravel(order="F"), raa=raa.ravel(order="F"), vza=vza.ravel(order="F"),
+                u10m=np.tile(sc["u10m"], G), v10m=np.tile(sc["v10m"], G), mr=sc["mr"])
+    if kind == "lambert":
+        flat["alpha"] = np.zeros_like(flat["ROT"]); flat["flux"] = np.ones((1, nobs * G), order="F")
+    fl = lambda a: np.asfortranarray(a[:, 0, :].reshape(nobs * G, 1, order="F"))          # (nobs,1,G) -> (G*nobs, 1), index g*nobs + j
+    got = dict(radiance=fl(I), reflectance=fl(R), Q=fl(Q), U=fl(U), nfourier=fl(nf.reshape(nobs, 1, G)))
+    rep_ = parity.parity_report(kind, 3, N, False, flat, got)
+    _save(f"polar_multigeom60_{kind}_n16_nmom300", rep_)
+    assert rep_["n"] == nobs * G and rep_["pass"], rep_
+    if kind == "cx":
+        ref = parity.oracle_parallel(kind, 3, N, False, flat, obs=list(range(0, nobs * G, 7)))
+        sel = np.zeros(nobs * G, bool); sel[::7] = True
+        assert np.all(np.abs(fl(BR)[sel] - ref["BR"][sel]) <= 1e-12 * np.abs(ref["BR"][sel]) + 1e-30)
