@@ -24,10 +24,12 @@
 
 namespace vlk {
 
-// team scratch (doubles): Rs, Rk, two Q arrays, two Y arrays: n x ld each (ld = mat_ld(n)); 13 vectors
-HDFN size_t add_smem_doubles(int n, bool) { return 6 * (size_t)n * mat_ld(n) + 13 * n + 2; }
-// per-team global scratch (doubles): per layer Y^T, (Rs Y)^T (n x n each), y, Rs y + Ss (n each)
-HDFN size_t add_work_doubles(int n, int L) { return (size_t)L * (2 * (size_t)n * n + 2 * n); }
+// team scratch (doubles): six n x ld matrix arrays (ld = mat_ld(n)) used as Rs + five rotating arrays (R_k, two Q, two Y) in the up-sweep and
+// as two copy slots in the down-sweep; 14 vectors
+HDFN size_t add_smem_doubles(int n, bool) { return 6 * (size_t)n * mat_ld(n) + 14 * n + 2; }
+// per-team global scratch (doubles): per layer Y, Rs Y (n x ld each), y, Rs y + Ss (n each) -- one contiguous block per layer
+HDFN size_t add_layer_doubles(int n) { return 2 * (size_t)n * mat_ld(n) + 2 * n; }
+HDFN size_t add_work_doubles(int n, int L) { return (size_t)L * add_layer_doubles(n); }
 
 // an eigenproblem or the boundary-value solve failed: every view of the pixel leaves the Fourier loop with status 4
 template <class Team>
@@ -40,9 +42,10 @@ template <int S, class Team>
 DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps &O, const VLQuad &QD, const VLSurf &SF, const VLConv &CV,
                      int lambertian, double accuracy, int m, int p, double *scr, int *piv, double *Wg) {
   const int N = QD.N, n = S * N, L = X.L, NM = X.NM, ld = mat_ld(n);
-  double *Rs = scr, *Rk = Rs + (size_t)n * ld, *QA = Rk + (size_t)n * ld, *QB = QA + (size_t)n * ld, *YA = QB + (size_t)n * ld, *YB = YA + (size_t)n * ld;
-  double *Ss = YB + (size_t)n * ld, *Sn = Ss + n, *su = Sn + n, *sd = su + n, *yv = sd + n, *zz = yv + n, *xv = zz + n,
-         *xb = xv + n, *ub = xb + n, *inp = ub + n, *inm = inp + n, *av = inm + n, *bv = av + n;
+  const size_t nl = (size_t)n * ld;
+  double *Rs = scr, *pool = scr + nl;                         // pool: five matrix arrays whose roles rotate from layer to layer
+  double *Ss = scr + 6 * nl, *Sn = Ss + n, *su = Sn + n, *sd = su + n, *sun = sd + n, *sdn = sun + n, *yv = sdn + n, *zz = yv + n, *xv = zz + n,
+         *xb = xv + n, *ub = xb + n, *inp = ub + n, *inm = inp + n;
   const int G = X.G, v0 = view0(X, p);                        // p = pixel; its views are v0 .. v0 + G - 1
   const double *sc = X.scal + (size_t)v0 * 16;                // sun, flux, albedo: the same for every view of the pixel
   const int *ib = X.ibuf + (size_t)v0 * 4;
@@ -62,7 +65,7 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
   double attn = 0.0;
   if (localbeam) attn = FLUXF * (4.0 * cos_sza / DELTA_FACTOR) / PI4 * sc[3];
   const size_t q0 = (size_t)p * L;
-  const size_t wl = 2 * (size_t)n * n + 2 * n;              // scratch doubles per layer
+  const size_t wl = add_layer_doubles(n), ob = ops_block_doubles(n);
 
   // ---- surface: Rs = D * (reflection matrix), Ss = D * (reflected direct beam)      (BVP_SURFACE_SETUP_HOM / _BEAM :439-626,1625-1742)
   for (int idx = T.rank; idx < n * n; idx += T.size) {
@@ -92,16 +95,22 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
   //      E_k [Tm_k | v] = prod_j (1 + Q^(2^j)) [Tm_k | v]   -- one product per factor and one squaring per level, no pivoting,
   //      no pivot-column chain; the loop stops when the next factor is 1 to working precision (2 - 3 levels for the optically
   //      thin layers that make up most of a column, 6 - 7 for a thick cloud over a bright surface).
+  //      Copy channel 0 brings the next layer's operators [R | Tm] into two free arrays while the current layer finishes; channel 1
+  //      brings Tm_k back for the last product (the doubling overwrites the copy it started from); channel 2 the source vectors.
+  double *Rk = pool, *Yc = pool + nl, *Qc = pool + 2 * nl, *Qn = pool + 3 * nl, *Yn = pool + 4 * nl;
+  {
+    const double *blk = O.rt + (q0 + L - 1) * ob;
+    T.copy_begin(0, Rk, blk, nl);
+    T.copy_wait(0);
+    T.copy_begin(0, Yc, blk + nl, nl);
+    T.copy_wait(0);
+    T.copy_begin(2, su, blk + 2 * nl, 2 * (size_t)n);         // su, sd are adjacent
+    T.copy_wait(2);
+  }
+  T.sync();
   for (int k = L - 1; k >= 0; k--) {
-    const size_t q = q0 + k;
-    const double *Rg = O.rk + q * n * n, *Tg = O.tk + q * n * n;
-    double *Qc = QA, *Qn = QB, *Yc = YA, *Yn = YB, *yc = yv, *yn = zz;
-    for (int idx = T.rank; idx < n * n; idx += T.size) {
-      const int r = idx / n, c = idx % n;
-      Rk[(size_t)r * ld + c] = Rg[idx]; Yc[(size_t)r * ld + c] = Tg[idx];
-    }
-    for (int r = T.rank; r < n; r += T.size) { su[r] = O.sgu[q * n + r]; sd[r] = O.sgd[q * n + r]; }
-    T.sync();
+    const double *blk = O.rt + (q0 + k) * ob;
+    double *yc = yv, *yn = zz;
     // Q = R_k Rs,   y = R_k Ss + sg_dn
     double qmax = 0.0;
     team_mm(T, n, n, n, Rk, ld, Rs, ld, [&](int r, int c, double acc) { Qc[(size_t)r * ld + c] = acc; qmax = fmax(qmax, fabs(acc)); });
@@ -112,6 +121,7 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
       yc[r] = v;
     }
     { int dummy = 0; qmax = T.argmax(qmax, dummy) * (double)n; }          // >= the max-row-sum norm of Q; the collective also orders Q, y
+    T.sync();
     bool okq = true;
     for (int lev = 0; qmax > 1.0e-17; lev++) {
       if (lev > 14 || !(qmax < 1.0e30)) { okq = false; break; }           // not a contraction (or NaN input): fail the pixel
@@ -129,22 +139,32 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
       team_mm(T, n, n, n, Qc, ld, Qc, ld, [&](int r, int c, double acc) { Qn[(size_t)r * ld + c] = acc; q2 = fmax(q2, fabs(acc)); });
       { double *t = Qc; Qc = Qn; Qn = t; }
       { int dummy = 0; qmax = T.argmax(q2, dummy) * (double)n; }
+      T.sync();
     }
     if (!okq) { add_fail_pixel(T, X, CV, p); return; }
-    // Y^T and y to the team's global scratch for the down-sweep;  Zb = Rs Y,  zb = Rs y;  Tm_k comes back into the other free array
+    // Tm_k comes back into the array of the last Q (channel 1) while  Zb = Rs Y,  zb = Rs y  are formed;  Y and y go to the team's
+    // global scratch for the down-sweep as they are (row-major, padded)
     double *Wk = Wg + (size_t)k * wl, *Zb = Qn, *Tk = Qc, *zb = yn;
-    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, c = idx % n; Wk[idx] = Yc[(size_t)c * ld + j]; Tk[(size_t)j * ld + c] = Tg[idx]; }
+    T.copy_begin(1, Tk, blk + nl, nl);
+    if (k > 0) T.copy_begin(3, Yn, O.rt + (q0 + k - 1) * ob + nl, nl);    // the spare Y array: Tm of the next layer (channel 3)
+    for (int idx = T.rank; idx < (int)nl; idx += T.size) Wk[idx] = Yc[idx];
     team_mm(T, n, n, n, Rs, ld, Yc, ld, [&](int r, int c, double acc) { Zb[(size_t)r * ld + c] = acc; });
     for (int r = T.rank; r < n; r += T.size) {
       const double *Rr = Rs + (size_t)r * ld;
       double v = 0.0;
       for (int c = 0; c < n; c++) v += Rr[c] * yc[c];
       zb[r] = v;
-      Wk[2 * (size_t)n * n + r] = yc[r];
-      Wk[2 * (size_t)n * n + n + r] = v + Ss[r];               // u(bot_k) = (Rs Y) I_dn(top_k) + this
+      Wk[2 * nl + r] = yc[r];
+      Wk[2 * nl + n + r] = v + Ss[r];                          // u(bot_k) = (Rs Y) I_dn(top_k) + this
     }
-    T.sync();
-    for (int idx = T.rank; idx < n * n; idx += T.size) { const int j = idx / n, r = idx % n; Wk[(size_t)n * n + idx] = Zb[(size_t)r * ld + j]; }
+    // Y is in the scratch: its array takes the next layer's R (channel 0) while this layer finishes
+    if (k > 0) {
+      const double *nb = O.rt + (q0 + k - 1) * ob;
+      T.copy_begin(0, Yc, nb, nl);                             // (the barrier inside also orders Zb, zb)
+      T.copy_begin(2, sun, nb + 2 * nl, 2 * (size_t)n);        // sun, sdn are adjacent
+    } else T.sync();
+    for (int idx = T.rank; idx < (int)nl; idx += T.size) { const int c = idx % ld; Wk[nl + idx] = c < n ? Zb[idx] : 0.0; }
+    T.copy_wait(1);
     for (int r = T.rank; r < n; r += T.size) {
       const double *Tr = Tk + (size_t)r * ld;
       double v = su[r];
@@ -155,75 +175,92 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
     team_mm(T, n, n, n, Tk, ld, Zb, ld, [&](int r, int c, double acc) { Rs[(size_t)r * ld + c] = Rk[(size_t)r * ld + c] + acc; });
     T.sync();
     for (int r = T.rank; r < n; r += T.size) Ss[r] = Sn[r];
+    if (k > 0) {
+      // rotate the arrays: R_{k-1} sits in the old Y array, Tm_{k-1} in the spare one; the other three are free
+      double *nR = Yc, *nY = Yn, *f1 = Rk, *f2 = Qc, *f3 = Qn;
+      T.copy_wait(0); T.copy_wait(3); T.copy_wait(2);
+      for (int r = T.rank; r < 2 * n; r += T.size) su[r] = sun[r];        // (su, sd) <- (sun, sdn)
+      Rk = nR; Yc = nY; Qc = f1; Qn = f2; Yn = f3;
+    }
     T.sync();
   }
 
-  // ---- down-sweep: interface fields and LCON / MCON of every layer (shared by all views); the layer source terms
-  //      (WHOLELAYER_STERM_UP) are accumulated top-down per view: thread (g, ep) owns view g and the eigensolutions e = ep, ep + EP, ...
-  const int EP = (T.size / G) > 0 ? T.size / G : 1, nslot = G * EP;      // slot = (view g, partition ep of the eigensolutions)
-  double *red = Rs, *trn = red + (size_t)nslot * S;           // the matrix arrays are free now: partial sums and user transmittances
-  for (int slot = T.rank; slot < nslot; slot += T.size) {
-#pragma unroll
-    for (int o = 0; o < S; o++) red[(size_t)slot * S + o] = 0.0;
-    trn[slot] = 1.0;
-  }
+  // ---- down-sweep, pass 1: the interface fields, a chain over the layers, I_dn(top_1) = 0:
+  //          I_dn(bot_k) = Y_k I_dn(top_k) + y_k,   u(bot_k) = (Rs Y)_k I_dn(top_k) + (Rs y + Ss)_k
+  //      each layer's block [Y | Rs Y | y | .] comes back from the team's scratch through two alternating copy slots; the layer's
+  //      incoming fields minus the particular solution, in+ and in-, replace (y, .) in the scratch for pass 2
+  const size_t slotd = (wl + 1) & ~(size_t)1;
+  double *slot0 = pool, *slot1 = pool + slotd;                // 2 * slotd <= 5 nl
   for (int r = T.rank; r < n; r += T.size) xv[r] = 0.0;       // no diffuse downwelling at TOA
-  T.sync();
+  T.copy_begin(0, slot0, Wg, wl);
   for (int k = 0; k < L; k++) {
     const size_t q = q0 + k;
-    const double *Wk = Wg + (size_t)k * wl;
-    const double *YT = Wk, *ZT = Wk + (size_t)n * n, *yw = Wk + 2 * (size_t)n * n, *zw = yw + n;
-    const bool scat = X.layscat[((size_t)p * (NM + 1) + m) * L + k] != 0;
+    double *Wk = Wg + (size_t)k * wl;
+    const double *sl = (k & 1) ? slot1 : slot0;
+    if (k + 1 < L) T.copy_begin((k + 1) & 1, (k & 1) ? slot0 : slot1, Wg + (size_t)(k + 1) * wl, wl); else T.sync();
+    T.copy_wait(k & 1);
     for (int item = T.rank; item < 2 * n; item += T.size) {
       const int which = item / n, r = item % n;
-      const double *MT = which ? ZT : YT;
+      const double *Mr = sl + (which ? nl : 0) + (size_t)r * ld;
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int c = 0;
-      for (; c + 3 < n; c += 4) {
-        s0 += MT[(size_t)c * n + r] * xv[c]; s1 += MT[(size_t)(c + 1) * n + r] * xv[c + 1];
-        s2 += MT[(size_t)(c + 2) * n + r] * xv[c + 2]; s3 += MT[(size_t)(c + 3) * n + r] * xv[c + 3];
-      }
-      for (; c < n; c++) s0 += MT[(size_t)c * n + r] * xv[c];
-      const double v = (s0 + s1) + (s2 + s3) + (which ? zw[r] : yw[r]);
+      for (; c + 3 < n; c += 4) { s0 += Mr[c] * xv[c]; s1 += Mr[c + 1] * xv[c + 1]; s2 += Mr[c + 2] * xv[c + 2]; s3 += Mr[c + 3] * xv[c + 3]; }
+      for (; c < n; c++) s0 += Mr[c] * xv[c];
+      const double v = (s0 + s1) + (s2 + s3) + sl[2 * nl + (which ? n : 0) + r];
       if (which) ub[r] = v; else xb[r] = v;
     }
     T.sync();
-    if (scat) {
-      const double *WU = Z.wupper + q * 2 * n, *WL = Z.wlower + q * 2 * n;
-      for (int r = T.rank; r < n; r += T.size) {
-        const double sg = ((r % S) > 1) ? -1.0 : 1.0;
-        const double hd = xv[r] - WU[r], hu = ub[r] - sg * WL[n + r];
-        inp[r] = hd + hu; inm[r] = hd - hu;
-      }
-      T.sync();
-      const double *SpT = O.spT + q * n * n, *SmT = O.smT + q * n * n;
-      for (int item = T.rank; item < 2 * n; item += T.size) {
-        const int which = item / n, e = item % n;
-        const double *MT = which ? SmT : SpT, *in = which ? inm : inp;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int r = 0;
-        for (; r + 3 < n; r += 4) {
-          s0 += MT[(size_t)r * n + e] * in[r]; s1 += MT[(size_t)(r + 1) * n + e] * in[r + 1];
-          s2 += MT[(size_t)(r + 2) * n + e] * in[r + 2]; s3 += MT[(size_t)(r + 3) * n + e] * in[r + 3];
-        }
-        for (; r < n; r++) s0 += MT[(size_t)r * n + e] * in[r];
-        const double v = (s0 + s1) + (s2 + s3);
-        if (which) bv[e] = v; else av[e] = v;                  // a + b, a - b
-      }
-      T.sync();
-      const bool beam = (k + 1 <= cutoff);
-      const double wdel = X.tdmubar[pixL(X, p) + k], itr = X.itrans[pixL(X, p) + k], itw = -itr * wdel, dl = X.deltau[pixL(X, p) + k];
-      for (int slot = T.rank; slot < nslot; slot += T.size) {
-        const int vg = slot % G, ep = slot / G, pv = v0 + vg;
-        if (CV.state[(size_t)pv * 4] != 1) continue;          // views that have converged keep their sums
+    const double *WU = Z.wupper + q * 2 * n, *WL = Z.wlower + q * 2 * n;
+    for (int r = T.rank; r < n; r += T.size) {
+      const double sg = ((r % S) > 1) ? -1.0 : 1.0;
+      const double hd = xv[r] - WU[r], hu = ub[r] - sg * WL[n + r];
+      Wk[2 * nl + r] = hd + hu; Wk[2 * nl + n + r] = hd - hu;
+      xv[r] = xb[r];
+    }
+    T.sync();
+  }
+  // ---- pass 2a: LCON, MCON of every layer, all layers at once:  a + b = S+ in+,  a - b = S- in-   (results over the dead Y block)
+  for (int item = T.rank; item < L * n; item += T.size) {
+    const int k = item / n, e = item % n;
+    if (!X.layscat[((size_t)p * (NM + 1) + m) * L + k]) continue;
+    const size_t q = q0 + k;
+    const double *SpT = O.spT + q * n * n, *SmT = O.smT + q * n * n;
+    double *Wk = Wg + (size_t)k * wl;
+    const double *ip = Wk + 2 * nl, *im = ip + n;
+    double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
+    int r = 0;
+    for (; r + 1 < n; r += 2) {
+      s0 += SpT[(size_t)r * n + e] * ip[r]; s1 += SpT[(size_t)(r + 1) * n + e] * ip[r + 1];
+      d0 += SmT[(size_t)r * n + e] * im[r]; d1 += SmT[(size_t)(r + 1) * n + e] * im[r + 1];
+    }
+    if (r < n) { s0 += SpT[(size_t)r * n + e] * ip[r]; d0 += SmT[(size_t)r * n + e] * im[r]; }
+    const double ab = s0 + s1, amb = d0 + d1;
+    Wk[e] = 0.5 * (ab + amb); Wk[n + e] = 0.5 * (ab - amb);              // LCON(e), MCON(e)
+  }
+  T.sync();
+  // ---- pass 2b: layer source terms (WHOLELAYER_STERM_UP) accumulated top-down per view: slot = (view g, partition ep of the
+  //      eigensolutions); every slot walks down the layers with its running user-stream transmittance
+  const int EP = (T.size / G) > 0 ? T.size / G : 1, nslot = G * EP;
+  double *red = Rs, *trn = red + (size_t)nslot * S;           // the matrix arrays are free now
+  for (int slot = T.rank; slot < nslot; slot += T.size) {
+    const int vg = slot % G, ep = slot / G, pv = v0 + vg;
+    double acc[S], trans = 1.0;
+#pragma unroll
+    for (int o = 0; o < S; o++) acc[o] = 0.0;
+    const bool vact = CV.state[(size_t)pv * 4] == 1;          // views that have converged keep their sums
+    for (int k = 0; k < L; k++) {
+      const size_t q = q0 + k, qv = q * G + vg;
+      const double udel = X.tduserm[pixL(X, pv) + k];
+      if (vact && ep < n && X.layscat[((size_t)p * (NM + 1) + m) * L + k]) {
+        const double *Wk = Wg + (size_t)k * wl;
+        const bool beam = (k + 1 <= cutoff);
+        const double wdel = X.tdmubar[pixL(X, p) + k], itr = X.itrans[pixL(X, p) + k], itw = -itr * wdel, dl = X.deltau[pixL(X, p) + k];
         const double emu = X.emult_up[pixL(X, pv) + k], sgp = X.sigma_p[pixL(X, pv) + k], itu = X.itrans_userm[pixL(X, pv) + k];
-        const double udel = X.tduserm[pixL(X, pv) + k], trans = trn[slot];
-        const size_t qv = q * G + vg;
         double part[S];
 #pragma unroll
         for (int o = 0; o < S; o++) part[o] = 0.0;
         for (int e = ep; e < n; e += EP) {
-          const double lc = 0.5 * (av[e] + bv[e]), mc = 0.5 * (av[e] - bv[e]);
+          const double lc = Wk[e], mc = Wk[n + e];
           const double h1 = Z.hm1[qv * n + e], h2 = Z.hm2[qv * n + e];
           double cd = lc * h2, cu = mc * h1;
           if (beam) {
@@ -238,15 +275,14 @@ DEVFN void add_pixel(const Team &T, const VLPix &X, const VLSol &Z, const VLOps 
           for (int o = 0; o < S; o++) part[o] += cd * Z.uh_dn[(qv * n + e) * S + o] + cu * Z.uh_up[(qv * n + e) * S + o];
         }
 #pragma unroll
-        for (int o = 0; o < S; o++) red[(size_t)slot * S + o] += trans * part[o];
+        for (int o = 0; o < S; o++) acc[o] += trans * part[o];
       }
+      trans *= udel;
     }
-    for (int slot = T.rank; slot < nslot; slot += T.size) trn[slot] *= X.tduserm[pixL(X, v0 + slot % G) + k];
-    T.sync();
-    for (int r = T.rank; r < n; r += T.size) xv[r] = xb[r];
-    T.sync();
+#pragma unroll
+    for (int o = 0; o < S; o++) red[(size_t)slot * S + o] = acc[o];
+    trn[slot] = trans;
   }
-  // ---- BOA source: surface-reflected downwelling diffuse field at the bottom (GET_BOA_SOURCE); xv = I_dn(bot_L)
   if (include_surface) for (int r = T.rank; r < n; r += T.size) { const int i = r / S; inp[r] = QD.x[i] * QD.w[i] * xv[r]; }
   T.sync();
   // ---- per view: Fourier summation and convergence (VLIDORT_CONVERGE_OBSGEO); FLUX_MULTIPLIER = DELTA_FACTOR

@@ -57,6 +57,9 @@ struct SerialTeam {
   DEVFN void load_wait() const {}
   // next item of a shared work counter, one value per 32-lane group of the team
   DEVFN int wfetch(int *ctr) const { return (*ctr)++; }
+  // asynchronous copy of n doubles global -> team scratch on one of 4 channels: begin (collective) ... wait (collective)
+  DEVFN void copy_begin(int, double *dst, const double *src, size_t n) const { for (size_t i = 0; i < n; i++) dst[i] = src[i]; }
+  DEVFN void copy_wait(int) const {}
 };
 
 #ifndef AB_HOST_MODEL
@@ -111,6 +114,8 @@ struct WarpTeam {
     __syncwarp();
   }
   DEVFN void load_wait() const {}
+  DEVFN void copy_begin(int, double *dst, const double *src, size_t n) const { load_begin(dst, src, n); }
+  DEVFN void copy_wait(int) const {}
 };
 
 // W = 8 or 16 neighbouring lanes of a warp working on one problem (small nstokes*nstreams: several problems per warp); every
@@ -183,15 +188,45 @@ struct BlockTeam {
   double *sd; int *si;
   unsigned long long *mbar;      // optional mbarrier (shared memory) for load_begin/load_wait
   mutable unsigned mphase;
-  DEVFN BlockTeam(double *scratch_d, int *scratch_i, unsigned long long *bar = nullptr)
-      : rank(threadIdx.x), size(blockDim.x), sd(scratch_d), si(scratch_i), mbar(bar), mphase(0) {
-    if (bar) {
+  unsigned long long *cbar;      // optional 4 mbarriers for the copy_begin/copy_wait channels
+  mutable unsigned cphase;       // bit c = phase parity of channel c
+  DEVFN BlockTeam(double *scratch_d, int *scratch_i, unsigned long long *bar = nullptr, unsigned long long *chan = nullptr)
+      : rank(threadIdx.x), size(blockDim.x), sd(scratch_d), si(scratch_i), mbar(bar), mphase(0), cbar(chan), cphase(0) {
+    if (bar || chan) {
       if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vl_smem_u32(bar)), "r"(1));
+        if (bar) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vl_smem_u32(bar)), "r"(1));
+        if (chan) for (int c = 0; c < 4; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vl_smem_u32(chan + c)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
       __syncthreads();
     }
+  }
+  // channel c: 1-D TMA bulk copy global -> shared of n doubles (n*8 a multiple of 16, both sides 16-byte aligned), completion on the
+  // channel's mbarrier.  Collective: the barrier inside orders the team's earlier accesses to dst before the asynchronous write.
+  DEVFN void copy_begin(int c, double *dst, const double *src, size_t n) const {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (rank == 0) {
+      const unsigned bytes = (unsigned)(n * 8);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vl_smem_u32(cbar + c)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vl_smem_u32(dst)),
+                   "l"(src), "r"(bytes), "r"(vl_smem_u32(cbar + c))
+                   : "memory");
+    }
+  }
+  DEVFN void copy_wait(int c) const {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "VL_CWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra VL_CDONE;\n"
+        "bra VL_CWAIT;\n"
+        "VL_CDONE:\n"
+        "}" ::"r"(vl_smem_u32(cbar + c)),
+        "r"((cphase >> c) & 1u)
+        : "memory");
+    cphase ^= 1u << c;
   }
   // 1-D TMA bulk copy global -> shared (cp.async.bulk), n*8 bytes a multiple of 16, both sides 16-byte aligned.
   // Collective: orders the team's earlier generic-proxy accesses to dst/src before the asynchronous copy.

@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(TPB, TPB == 128 ? 3 : 1) k_vl_add(VLPix X, VLS
   extern __shared__ __align__(16) double smem_d[];
   __shared__ double sd[64];
   __shared__ int si[64];
-  BlockTeam T(sd, si);
+  __shared__ unsigned long long chan[4];
+  for (int i = threadIdx.x; i < (int)add_smem_doubles(Z.n, true); i += blockDim.x) smem_d[i] = 0.0;    // no stale NaN patterns in the padding
+  BlockTeam T(sd, si, nullptr, chan);
   int *piv = reinterpret_cast<int *>(smem_d + add_smem_doubles(Z.n, true));
   double *Wg = work + (size_t)blockIdx.x * work_per_cta;
   for (int a = blockIdx.x; a < nactive; a += gridDim.x) {

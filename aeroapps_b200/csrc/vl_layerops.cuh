@@ -21,10 +21,11 @@
 namespace vlk {
 
 struct VLOps {                   // per problem q = p*L + k
-  double *rk, *tk;               // [q][r][c]  row-major n x n
+  double *rt;                    // [q][2][n][ld]  R then Tm, row-major with the team-scratch leading dimension ld = mat_ld(n), followed by
+                                 //                sg_up, sg_dn [2][n]: one contiguous block of ops_block_doubles(n) per problem (one bulk copy)
   double *spT, *smT;             // [q][r][e]  = S+(e,r), S-(e,r): transposed so that lanes over e read consecutive words
-  double *sgu, *sgd;             // [q][n]
 };
+HDFN size_t ops_block_doubles(int n) { return 2 * (size_t)n * mat_ld(n) + 2 * n; }
 
 // team scratch in doubles: Am (later E), Bm, Gp (later R), Tb: n x ld each (ld = mat_ld(n)); 4 boundary vectors; inverse work; ints: 2n
 HDFN size_t ops_smem_doubles(int n, bool cta) { return 4 * (size_t)n * mat_ld(n) + 4 * n + inv_work_doubles(n, cta); }
@@ -66,16 +67,16 @@ DEVFN void layer_ops_problem(const Team &T, const VLPix &X, const VLSol &Z, cons
     }
     T.sync();
   }
-  double *Rg = O.rk + q * n * n, *Tg = O.tk + q * n * n;
-  for (int idx = T.rank; idx < n * n; idx += T.size) {
-    const int r = idx / n, c = idx % n;
-    Rg[idx] = Gp[(size_t)r * ld + c]; Tg[idx] = Tb[(size_t)r * ld + c];
+  double *Rg = O.rt + q * ops_block_doubles(n), *Tg = Rg + (size_t)n * ld, *sg = Tg + (size_t)n * ld;
+  for (int idx = T.rank; idx < n * ld; idx += T.size) {
+    const bool pad = (idx % ld) >= n;                          // zero padding: the block is copied as a whole by the solver
+    Rg[idx] = pad ? 0.0 : Gp[idx]; Tg[idx] = pad ? 0.0 : Tb[idx];
   }
   for (int r = T.rank; r < n; r += T.size) {
     const double *Rr = Gp + (size_t)r * ld, *Tr = Tb + (size_t)r * ld;
     double su = wut[r], sd = wdb[r];
     for (int c = 0; c < n; c++) { su -= Rr[c] * wdt[c] + Tr[c] * wub[c]; sd -= Tr[c] * wdt[c] + Rr[c] * wub[c]; }
-    O.sgu[q * n + r] = su; O.sgd[q * n + r] = sd;
+    sg[r] = su; sg[n + r] = sd;
   }
   T.sync();
 }

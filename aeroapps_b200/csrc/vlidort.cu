@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace vlk;
@@ -235,7 +236,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   const size_t bvp_work_bytes = (size_t)solvers * (work_per_solver + (use_add ? 0 : PB.window)) * 8;
   // ---- sizes
   const size_t per_pix_state = (size_t)L * 4 * 8 + (size_t)(NM + 1) * L * 4 * 8 + (size_t)(NM + 1) * L + (size_t)G * ((size_t)L * 4 * 8 + 16 * 8 + 4 * 4);
-  const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + 6 * n + 4 * n + (size_t)G * (2 + 2 * S) * n + (use_add ? 4 * (size_t)n * n + 2 * n : 0)) * 8;
+  const size_t per_pix_sol = (size_t)L * ((size_t)2 * n * n + 6 * n + 4 * n + (size_t)G * (2 + 2 * S) * n + (use_add ? 2 * (size_t)n * n + ops_block_doubles(n) : 0)) * 8;
   size_t per_pix_brdf = 0; int brdf_nscr = 0; size_t brdf_smem = 0;
   if (R.brdf) {
     const VLBrdf &B0 = *R.brdf;
@@ -277,8 +278,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   Z.wupper = A.take<double>(nq * 2 * n); Z.wlower = A.take<double>(nq * 2 * n); Z.fail = A.take<int>(chunk);
   VLOps O; memset(&O, 0, sizeof O);
   if (use_add) {
-    O.rk = A.take<double>(nq * n * n); O.tk = A.take<double>(nq * n * n); O.spT = A.take<double>(nq * n * n); O.smT = A.take<double>(nq * n * n);
-    O.sgu = A.take<double>(nq * n); O.sgd = A.take<double>(nq * n);
+    O.rt = A.take<double>(nq * ops_block_doubles(n)); O.spT = A.take<double>(nq * n * n); O.smT = A.take<double>(nq * n * n);
   }
   VLConv CV; CV.total = A.take<double>(vchunk * 4); CV.state = A.take<int>(vchunk * 4); CV.col_active = A.take<int>(chunk);
   int *listA = A.take<int>(chunk), *listB = A.take<int>(chunk), *counts = A.take<int>(2 * (NM + 4));
@@ -396,6 +396,54 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
 }
 
 bool is_missing_h(double x, double MISSING) { return std::fabs(x / MISSING - 1.0) < (double)0.001f; }
+
+// ---- observation slabs: a host-pointer call may be split over several devices (ab200_set_devices / AB200_DEVICES), every device owning
+//      a contiguous slab of observations -- the way the reference spreads pixels over MPI ranks (GV/geo_vlidort.F90:482-495); the
+//      "gather" is each device's D2H copy straight into its slab of the caller's arrays.
+struct Slab { int j0, nj, nobs; };        // observations [j0, j0 + nj) of a call with nobs observations
+
+int g_devices_req = -1;                   // -1: read AB200_DEVICES once (default 1); 0: all visible devices
+int vl_device_count() {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (g_devices_req < 0) { const char *e = getenv("AB200_DEVICES"); g_devices_req = e ? (strcmp(e, "all") == 0 ? 0 : std::max(0, atoi(e))) : 1; }
+  int vis = 1;
+  if (cudaGetDeviceCount(&vis) != cudaSuccess || vis < 1) vis = 1;
+  return g_devices_req == 0 ? vis : std::min(g_devices_req, vis);
+}
+
+// f(slab j0, slab nj, an earlier slab already ran an observation with solar_zenith == 0) -> error code; one host thread per device
+template <class F>
+int shard_obs(int nobs, int nadir_first, F f) {
+  const int nd = std::max(1, std::min(vl_device_count(), nobs));
+  if (nd == 1) return f(0, nobs, 0);
+  int cur = 0, vis = 1;
+  cudaGetDevice(&cur); cudaGetDeviceCount(&vis);
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::string> errs(nd);
+  std::vector<std::thread> th;
+  auto run = [&](int d) {
+    const int j0 = (int)((long)nobs * d / nd), j1 = (int)((long)nobs * (d + 1) / nd);
+    if (d > 0 && cudaSetDevice((cur + d) % vis) != cudaSuccess) { rcs[d] = AB200_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+    rcs[d] = f(j0, j1 - j0, nadir_first < j0 ? 1 : 0);
+    if (rcs[d]) errs[d] = ab200_last_error();
+  };
+  for (int d = 1; d < nd; d++) th.emplace_back(run, d);
+  run(0);
+  for (auto &t : th) t.join();
+  for (int d = 0; d < nd; d++) if (rcs[d]) { ab200_set_error(errs[d]); return rcs[d]; }
+  return 0;
+}
+
+// H2D of the slab of a Fortran array (inner, nobs, outer) -> compact device array (inner, nj, outer); D2H the other way round
+cudaError_t put_slab(double *d, const double *src, size_t inner, size_t outer, const Slab &sl, cudaStream_t st) {
+  if (sl.nj == sl.nobs || outer == 1) return cudaMemcpyAsync(d, src + inner * sl.j0, inner * sl.nj * outer * 8, cudaMemcpyHostToDevice, st);
+  return cudaMemcpy2DAsync(d, inner * sl.nj * 8, src + inner * sl.j0, inner * sl.nobs * 8, inner * sl.nj * 8, outer, cudaMemcpyHostToDevice, st);
+}
+cudaError_t get_slab(double *dst, const double *d, size_t inner, size_t outer, const Slab &sl, cudaStream_t st) {
+  if (sl.nj == sl.nobs || outer == 1) return cudaMemcpyAsync(dst + inner * sl.j0, d, inner * sl.nj * outer * 8, cudaMemcpyDeviceToHost, st);
+  return cudaMemcpy2DAsync(dst + inner * sl.j0, inner * sl.nobs * 8, d, inner * sl.nj * 8, inner * sl.nj * 8, outer, cudaMemcpyDeviceToHost, st);
+}
 
 // true when every geometry of every observation has the sun of the first one (solar_zenith (nobs,ngeom)): one beam per pixel
 bool same_sun(const double *sza, int nobs, int ngeom) {

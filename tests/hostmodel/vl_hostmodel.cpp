@@ -70,7 +70,7 @@ extern "C" int hm_vlidort(int ngeom, int S, int N, int km, int nch, int nobs, in
   // default K3: interaction-principle solver (vl_layerops.cuh + vl_add.cuh); AB_HM_LEGACY_BVP=1: the windowed band elimination
   const bool legacy = (getenv("AB_HM_LEGACY_BVP") != nullptr || n > 64) && G == 1;
   VLOps O;
-  std::vector<double> ork((size_t)L * n * n), otk(ork), osp(ork), osm(ork), osu((size_t)L * n), osd(osu);
+  std::vector<double> ort((size_t)L * ops_block_doubles(n)), osp((size_t)L * n * n), osm(osp);
   std::vector<double> oscr(ops_smem_doubles(n, false) + 64), ascr(add_smem_doubles(n, false) + 64), awork(add_work_doubles(n, L));
   for (int p = 0; p < npix; p++) {
     int any = 0;
@@ -104,8 +104,7 @@ extern "C" int hm_vlidort(int ngeom, int S, int N, int km, int nch, int nobs, in
         else bvp_pixel<3>(T, X, Z, QD, SFc, CV, lambertian, acc, m, p, bscr.data(), iscr.data(), Ug.data());
         colact[p] = cstate[(size_t)p * 4];
       } else {
-        O.rk = ork.data() - q0 * n * n; O.tk = otk.data() - q0 * n * n; O.spT = osp.data() - q0 * n * n; O.smT = osm.data() - q0 * n * n;
-        O.sgu = osu.data() - q0 * n; O.sgd = osd.data() - q0 * n;
+        O.rt = ort.data() - q0 * ops_block_doubles(n); O.spT = osp.data() - q0 * n * n; O.smT = osm.data() - q0 * n * n;
         for (int k = 0; k < L; k++) {
           if (S == 1) layer_ops_problem<1>(T, X, Z, O, p, k, oscr.data(), iscr.data());
           else layer_ops_problem<3>(T, X, Z, O, p, k, oscr.data(), iscr.data());
