@@ -7,6 +7,9 @@
 // host, vlidort.py:438-440, are one elementwise kernel here), hence bit-identical results.
 #include "../../include/aeroapps_b200.h"
 #include "common.h"
+#include <map>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -49,9 +52,22 @@ extern "C" int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch,
   const size_t o_ped = taked(ne), o_zed = taked(ne), o_ted = taked(ne), o_ch = taked(nch), o_rot = taked(nrot), o_dep = taked(nch),
                o_taud = taked(nvox), o_ssad = taked(nvox), o_pmd = taked(npm), o_u = taked(nobs), o_v = taked(nobs), o_mr = taked(nch),
                o_sza = taked(nobs), o_raa = taked(nobs), o_vza = taked(nobs), o_out = taked(5 * npix);
-  static DevBuf buf;
-  AB_CUDA_OK(buf.reserve(off + 256));
-  char *b = buf.as<char>();
+  // one grow-only staging buffer per device, serialised per device (calls on different devices run concurrently)
+  struct Ctx { std::mutex mu; DevBuf buf; };
+  static std::mutex reg_mu;
+  static std::map<int, std::unique_ptr<Ctx>> reg;
+  Ctx *ctx;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(reg_mu);
+    auto &u = reg[dev];
+    if (!u) u.reset(new Ctx);
+    ctx = u.get();
+  }
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  AB_CUDA_OK(ctx->buf.reserve(off + 256));
+  char *b = ctx->buf.as<char>();
   auto F = [&](size_t o) { return reinterpret_cast<float *>(b + o); };
   auto D = [&](size_t o) { return reinterpret_cast<double *>(b + o); };
   cudaStream_t st = 0;

@@ -451,10 +451,73 @@ bool same_sun(const double *sza, int nobs, int ngeom) {
   return true;
 }
 
+// one observation slab of a Lambertian call on the device that is current on this thread.  nf_out / st_out: the caller's diagnostics
+// arrays (all views of the call)
+int lambert_slab(int S, int scalar_glue, int km, int nch, const Slab &sl, int G, int nstreams, int plane_parallel, int nMom, int nPol,
+                 const double *ROT, const double *depol, const double *alpha, const double *tau, const double *ssa,
+                 const double *pmom, const double *he, const double *albedo, const double *sza, const double *raa,
+                 const double *vza, const double *flux_factor, double MISSING, int nadir_already, double *radiance, double *reflectance,
+                 double *Q, double *U, int *nf_out, int *st_out) {
+  const int nj = sl.nj, nobs = sl.nobs, j0 = sl.j0;
+  const size_t npix = (size_t)nj * nch, nview = npix * G;
+  const size_t n_rot = (size_t)km * nj * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nj;
+  size_t bytes = 8 * (n_rot * (alpha ? 4 : 3) + n_pm + n_he + npix * (1 + (flux_factor ? 1 : 0)) + (1 + 2 * (size_t)G) * nj + nch + 4 * nview) + 8 * nview + 4096 * 16;
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  AB_CUDA_OK(C.io.reserve(bytes));
+  char *b = C.io.as<char>(); size_t off = 0;
+  cudaError_t cpe = cudaSuccess;
+  // device array (inner, nj, outer) <- the slab of the host array (inner, nobs, outer); src == nullptr: space only
+  auto put = [&](const double *src, size_t inner, size_t outer) -> double * {
+    off = align256(off); double *d = (double *)(b + off); off += inner * nj * outer * 8;
+    if (src) { cudaError_t e = put_slab(d, src, inner, outer, sl, 0); if (e != cudaSuccess) cpe = e; }
+    return d;
+  };
+  auto putv = [&](const double *src, size_t n) -> double * {          // not indexed by the observation
+    off = align256(off); double *d = (double *)(b + off); off += n * 8;
+    cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, 0); if (e != cudaSuccess) cpe = e;
+    return d;
+  };
+  RunDesc R; memset(&R, 0, sizeof R);
+  R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nj; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
+  R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G; R.nadir_already = nadir_already;
+  R.ROT = put(ROT, km, nch); R.depol = putv(depol, nch); R.alpha = alpha ? put(alpha, km, nch) : nullptr;
+  R.tau = put(tau, (size_t)km * nch, 1); R.ssa = put(ssa, (size_t)km * nch, 1);
+  R.pmom = put(pmom, (size_t)km * nch, (size_t)nMom * nPol); R.he = put(he, km + 1, 1); R.albedo = put(albedo, 1, nch); R.sza = put(sza, 1, 1);
+  R.raa = put(raa, 1, G); R.vza = put(vza, 1, G);
+  R.flux_factor = flux_factor ? put(flux_factor, nch, 1) : nullptr;
+  R.radiance = put(nullptr, 1, (size_t)nch * G); R.reflectance = put(nullptr, 1, (size_t)nch * G); R.Q = put(nullptr, 1, (size_t)nch * G); R.U = put(nullptr, 1, (size_t)nch * G);
+  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * nview; off = align256(off); R.status = (int *)(b + off); off += 4 * nview;
+  std::vector<double> h_sza(sza + j0, sza + j0 + nj);
+  std::vector<unsigned char> skip(nview, 0);
+  // screening as in the reference: the angles of the first geometry and the albedo (GV/VLIDORT_LAMBERT.F90:271-299,449-472)
+  for (int j = 0; j < nj; j++) {
+    const int jg = j0 + j;
+    const bool ma = is_missing_h(sza[jg], MISSING) || is_missing_h(vza[jg], MISSING) || is_missing_h(raa[jg], MISSING);
+    for (int i = 0; i < nch; i++) {
+      const unsigned char sk = (ma || is_missing_h(albedo[jg + (size_t)nobs * i], MISSING)) ? 1 : 0;
+      for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
+    }
+  }
+  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = 0;
+  AB_CUDA_OK(cpe);
+  int e = run_vlidort(C, R);
+  if (e) return e;
+  AB_CUDA_OK(get_slab(radiance, R.radiance, 1, (size_t)nch * G, sl, 0));
+  AB_CUDA_OK(get_slab(reflectance, R.reflectance, 1, (size_t)nch * G, sl, 0));
+  if (Q) AB_CUDA_OK(get_slab(Q, R.Q, 1, (size_t)nch * G, sl, 0));
+  if (U) AB_CUDA_OK(get_slab(U, R.U, 1, (size_t)nch * G, sl, 0));
+  const size_t v0 = (size_t)j0 * nch * G;
+  AB_CUDA_OK(cudaMemcpyAsync(nf_out + v0, R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(st_out + v0, R.status, 4 * nview, cudaMemcpyDeviceToHost, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
 // host-pointer front end shared by the Lambertian entry points.  ngeom > 1: multi-geometry form -- solar_zenith, relat_azymuth,
 // sensor_zenith are (nobs,ngeom), the outputs (nobs,nch,ngeom); the layer eigenproblems and the boundary-value solve are done once
 // per pixel and Fourier term for all views (they do not depend on the viewing direction).  Geometries with different suns are
-// solved one geometry at a time.
+// solved one geometry at a time.  With more than one device selected the observations are split into one slab per device.
 int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int ngeom, int nstreams, int plane_parallel, int nMom, int nPol,
                  const double *ROT, const double *depol, const double *alpha, const double *tau, const double *ssa,
                  const double *pmom, const double *he, const double *albedo, const double *sza, const double *raa,
@@ -480,50 +543,19 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int ngeom, i
     g_last_nfourier = nf; g_last_status = stt;
     return 0;
   }
-  const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
-  size_t bytes = 8 * (n_rot * (alpha ? 4 : 3) + n_pm + n_he + npix * (1 + (flux_factor ? 1 : 0)) + (1 + 2 * (size_t)G) * nobs + nch + 4 * nview) + 8 * nview + 4096 * 16;
-  VLContext &C = vl_context();
-  std::lock_guard<std::mutex> lock(C.mu);
-  AB_CUDA_OK(C.io.reserve(bytes));
-  char *b = C.io.as<char>(); size_t off = 0;
-  cudaError_t cpe = cudaSuccess;
-  auto put = [&](const double *src, size_t n) -> double * {
-    off = align256(off); double *d = (double *)(b + off); off += n * 8;
-    if (src) { cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, 0); if (e != cudaSuccess) cpe = e; }
-    return d;
-  };
-  RunDesc R; memset(&R, 0, sizeof R);
-  R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
-  R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G;
-  R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.alpha = alpha ? put(alpha, n_rot) : nullptr; R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
-  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.albedo = put(albedo, npix); R.sza = put(sza, nobs);
-  R.raa = put(raa, (size_t)nobs * G); R.vza = put(vza, (size_t)nobs * G);
-  R.flux_factor = flux_factor ? put(flux_factor, npix) : nullptr;
-  R.radiance = put(nullptr, nview); R.reflectance = put(nullptr, nview); R.Q = put(nullptr, nview); R.U = put(nullptr, nview);
-  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * nview; off = align256(off); R.status = (int *)(b + off); off += 4 * nview;
-  std::vector<double> h_sza(sza, sza + nobs);
-  std::vector<unsigned char> skip(nview, 0);
-  // screening as in the reference: the angles of the first geometry and the albedo (GV/VLIDORT_LAMBERT.F90:271-299,449-472)
-  for (int j = 0; j < nobs; j++) {
-    const bool ma = is_missing_h(sza[j], MISSING) || is_missing_h(vza[j], MISSING) || is_missing_h(raa[j], MISSING);
-    for (int i = 0; i < nch; i++) {
-      const unsigned char sk = (ma || is_missing_h(albedo[j + (size_t)nobs * i], MISSING)) ? 1 : 0;
-      for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
-    }
+  // first observation with solar_zenith == 0.0 that is actually run: FOCORR_NADIR stays on from there (reference state quirk)
+  int nadir_first = nobs;
+  for (int j = 0; j < nobs && nadir_first == nobs; j++) {
+    if (sza[j] != 0.0 || is_missing_h(sza[j], MISSING) || is_missing_h(vza[j], MISSING) || is_missing_h(raa[j], MISSING)) continue;
+    for (int i = 0; i < nch; i++) if (!is_missing_h(albedo[j + (size_t)nobs * i], MISSING)) { nadir_first = j; break; }
   }
-  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = 0;
-  AB_CUDA_OK(cpe);
-  int e = run_vlidort(C, R);
-  if (e) return e;
-  AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * nview, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * nview, cudaMemcpyDeviceToHost, 0));
-  if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * nview, cudaMemcpyDeviceToHost, 0));
-  if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * nview, cudaMemcpyDeviceToHost, 0));
-  g_last_nfourier.resize(nview); g_last_status.resize(nview);
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * nview, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaStreamSynchronize(0));
-  return 0;
+  std::vector<int> nf(nview, 0), stt(nview, 0);
+  int e = shard_obs(nobs, nadir_first, [&](int j0, int nj, int nadir_already) {
+    return lambert_slab(S, scalar_glue, km, nch, Slab{j0, nj, nobs}, G, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom,
+                        he, albedo, sza, raa, vza, flux_factor, MISSING, nadir_already, radiance, reflectance, Q, U, nf.data(), stt.data());
+  });
+  g_last_nfourier.swap(nf); g_last_status.swap(stt);
+  return e;
 }
 
 
@@ -542,6 +574,114 @@ int build_brdf_tables(VLContext &C, VLBrdf &B, int kind, int S, int scalar_glue,
 }
 
 // front end of the Cox-Munk / GISS Cox-Munk / MODIS RTLS wrappers; dev: every array pointer is a device pointer
+// one observation slab of a BRDF-wrapper call on the device that is current on this thread (dev: every array pointer is a device
+// pointer and the slab is the whole call)
+int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl, int G, int nstreams, int plane_parallel, int nMom, int nPol,
+              const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
+              const double *he, const double *sza, const double *raa, const double *vza, double MISSING, const SurfArgs &sa,
+              int nadir_already, double *radiance, double *reflectance, double *Q, double *U, cudaStream_t st, int *nf_out, int *st_out) {
+  const int nj = sl.nj, nobs = sl.nobs, j0 = sl.j0;
+  const size_t npix = (size_t)nj * nch, nview = npix * G;
+  const bool cx = (sa.kind != SURF_MODIS);
+  const size_t n_rot = (size_t)km * nj * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nj;
+  const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + (3 + 2 * (size_t)G) * nj + 2 * nch + 6 * npix + 7 * nview + 16 * nview) + 16 * nview + 4096 * 32;
+  VLContext &C = vl_context();
+  std::lock_guard<std::mutex> lock(C.mu);
+  AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * nview + 7 * nview) + 16 * nview + 4096 * 8 : bytes));
+  char *b = C.io.as<char>(); size_t off = 0;
+  cudaError_t cpe = cudaSuccess;
+  auto put = [&](const double *src, size_t inner, size_t outer) -> double * {
+    if (dev && src) return const_cast<double *>(src);
+    off = align256(off); double *d = (double *)(b + off); off += inner * nj * outer * 8;
+    if (src) { cudaError_t e = put_slab(d, src, inner, outer, sl, st); if (e != cudaSuccess) cpe = e; }
+    return d;
+  };
+  auto putv = [&](const double *src, size_t n) -> double * {
+    if (dev) return const_cast<double *>(src);
+    off = align256(off); double *d = (double *)(b + off); off += n * 8;
+    cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) cpe = e;
+    return d;
+  };
+  RunDesc R; memset(&R, 0, sizeof R);
+  R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nj; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
+  R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G; R.nadir_already = nadir_already;
+  R.ROT = put(ROT, km, nch); R.depol = putv(depol, nch); R.tau = put(tau, (size_t)km * nch, 1); R.ssa = put(ssa, (size_t)km * nch, 1);
+  R.pmom = put(pmom, (size_t)km * nch, (size_t)nMom * nPol); R.he = put(he, km + 1, 1); R.sza = put(sza, 1, 1); R.raa = put(raa, 1, G); R.vza = put(vza, 1, G);
+  R.alpha = sa.alpha ? put(sa.alpha, km, nch) : nullptr; R.flux_factor = sa.flux_factor ? put(sa.flux_factor, nch, 1) : nullptr;
+  const double *d_u = cx ? put(sa.u10m, 1, 1) : nullptr, *d_v = cx ? put(sa.v10m, 1, 1) : nullptr, *d_mr = cx ? putv(sa.mr, nch) : nullptr;
+  const double *d_kw = cx ? nullptr : put(sa.kernel_wt, (size_t)3 * nch, 1), *d_pr = cx ? nullptr : put(sa.param, (size_t)2 * nch, 1);
+  double *d_exact = put(nullptr, 16, (size_t)nch * G);
+  double *d_BR, *d_BRQ, *d_BRU;
+  const size_t oo = (size_t)nch * G;
+  if (dev) {
+    R.radiance = radiance; R.reflectance = reflectance; R.Q = Q; R.U = U; d_BR = sa.BR; d_BRQ = sa.BR_Q; d_BRU = sa.BR_U;
+  } else {
+    R.radiance = put(nullptr, 1, oo); R.reflectance = put(nullptr, 1, oo); R.Q = put(nullptr, 1, oo); R.U = put(nullptr, 1, oo);
+    d_BR = put(nullptr, 1, oo); d_BRQ = put(nullptr, 1, oo); d_BRU = put(nullptr, 1, oo);
+  }
+  if (!d_BR) d_BR = put(nullptr, 1, oo);
+  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * nview; off = align256(off); R.status = (int *)(b + off); off += 4 * nview;
+  off = align256(off); unsigned char *d_skip0 = (unsigned char *)(b + off); off += nview;
+  // host copies for the MISSING screening (first geometry, as the reference's multi-geometry wrappers)
+  std::vector<double> h_sza(nj), h_vza(nj), h_raa(nj), h_u, h_v, h_mr;
+  auto fetch = [&](std::vector<double> &hv, const double *src, size_t n, size_t o) {
+    hv.resize(n);
+    if (dev) cudaMemcpyAsync(hv.data(), src, 8 * n, cudaMemcpyDeviceToHost, st); else std::copy(src + o, src + o + n, hv.begin());
+  };
+  fetch(h_sza, sza, nj, j0); fetch(h_vza, vza, nj, j0); fetch(h_raa, raa, nj, j0);
+  if (cx) { fetch(h_u, sa.u10m, nj, j0); fetch(h_v, sa.v10m, nj, j0); fetch(h_mr, sa.mr, nch, 0); }
+  if (dev) AB_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<unsigned char> skip(nview, 0);
+  for (int j = 0; j < nj; j++) {
+    const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
+    const bool mw = cx && (is_missing_h(h_u[j], MISSING) || is_missing_h(h_v[j], MISSING));
+    for (int i = 0; i < nch; i++) {
+      const unsigned char sk = (ma || mw || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
+      for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
+    }
+  }
+  AB_CUDA_OK(cudaMemcpyAsync(d_skip0, skip.data(), nview, cudaMemcpyHostToDevice, st));
+  VLBrdf B;
+  const int NM = std::min(2 * nstreams - 1, nMom);
+  AB_CUDA_OK(cpe);
+  if (int e = build_brdf_tables(C, B, sa.kind, S, scalar_glue, nstreams, NM, nch, nj, st)) return e;
+  B.G = G;
+  B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
+  B.exactdb = d_exact;
+  off = align256(off); B.wsa_fail = (int *)(b + off); off += 4 * npix;
+  k_vl_brdf_exact<<<(unsigned)((nview + 127) / 128), 128, 0, st>>>(B, (int)nview, d_skip0, d_BR, d_BRQ, d_BRU);
+  AB_CUDA_OK(cudaGetLastError());
+  { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.n_launches += 1; }
+  if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel-view not run
+    std::vector<double> h_br(nview);
+    AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * nview, cudaMemcpyDeviceToHost, st));
+    AB_CUDA_OK(cudaStreamSynchronize(st));
+    for (int j = 0; j < nj; j++) for (int i = 0; i < nch; i++) for (int g = 0; g < G; g++) {
+      unsigned char &sk = skip[((size_t)j * nch + i) * G + g];
+      if (!sk && h_br[j + (size_t)nj * (i + (size_t)nch * g)] < 0) sk = 2;
+    }
+  }
+  R.exactdb = d_exact; R.brdf = &B;
+  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
+  if (int e = run_vlidort(C, R)) return e;
+  const size_t v0 = (size_t)j0 * nch * G;
+  AB_CUDA_OK(cudaMemcpyAsync(nf_out + v0, R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(st_out + v0, R.status, 4 * nview, cudaMemcpyDeviceToHost, st));
+  if (!dev) {
+    AB_CUDA_OK(get_slab(radiance, R.radiance, 1, oo, sl, st));
+    AB_CUDA_OK(get_slab(reflectance, R.reflectance, 1, oo, sl, st));
+    if (Q) AB_CUDA_OK(get_slab(Q, R.Q, 1, oo, sl, st));
+    if (U) AB_CUDA_OK(get_slab(U, R.U, 1, oo, sl, st));
+    if (sa.BR) AB_CUDA_OK(get_slab(sa.BR, d_BR, 1, oo, sl, st));
+    if (sa.BR_Q) AB_CUDA_OK(get_slab(sa.BR_Q, d_BRQ, 1, oo, sl, st));
+    if (sa.BR_U) AB_CUDA_OK(get_slab(sa.BR_U, d_BRU, 1, oo, sl, st));
+  }
+  AB_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// front end of the Cox-Munk / GISS Cox-Munk / MODIS RTLS wrappers; dev: every array pointer is a device pointer.  Host-pointer calls are
+// split into one observation slab per selected device.
 int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int ngeom, int nstreams, int plane_parallel, int nMom, int nPol,
                const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
                const double *he, const double *sza, const double *raa, const double *vza, double MISSING, const SurfArgs &sa,
@@ -571,95 +711,26 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
     g_last_nfourier = nf; g_last_status = stt;
     return 0;
   }
-  const bool cx = (sa.kind != SURF_MODIS);
-  const size_t n_rot = (size_t)km * nobs * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nobs;
-  const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + (3 + 2 * (size_t)G) * nobs + 2 * nch + 6 * npix + 7 * nview + 16 * nview) + 16 * nview + 4096 * 32;
-  VLContext &C = vl_context();
-  std::lock_guard<std::mutex> lock(C.mu);
-  AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * nview + 7 * nview) + 16 * nview + 4096 * 8 : bytes));
-  char *b = C.io.as<char>(); size_t off = 0;
-  cudaError_t cpe = cudaSuccess;
-  auto put = [&](const double *src, size_t n) -> double * {
-    if (dev && src) return const_cast<double *>(src);
-    off = align256(off); double *d = (double *)(b + off); off += n * 8;
-    if (src) { cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) cpe = e; }
-    return d;
-  };
-  RunDesc R; memset(&R, 0, sizeof R);
-  R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nobs; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
-  R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G;
-  R.ROT = put(ROT, n_rot); R.depol = put(depol, nch); R.tau = put(tau, n_rot); R.ssa = put(ssa, n_rot);
-  R.pmom = put(pmom, n_pm); R.he = put(he, n_he); R.sza = put(sza, nobs); R.raa = put(raa, (size_t)nobs * G); R.vza = put(vza, (size_t)nobs * G);
-  R.alpha = sa.alpha ? put(sa.alpha, n_rot) : nullptr; R.flux_factor = sa.flux_factor ? put(sa.flux_factor, npix) : nullptr;
-  const double *d_u = cx ? put(sa.u10m, nobs) : nullptr, *d_v = cx ? put(sa.v10m, nobs) : nullptr, *d_mr = cx ? put(sa.mr, nch) : nullptr;
-  const double *d_kw = cx ? nullptr : put(sa.kernel_wt, 3 * npix), *d_pr = cx ? nullptr : put(sa.param, 2 * npix);
-  double *d_exact = put(nullptr, 16 * nview);
-  double *d_BR, *d_BRQ, *d_BRU;
+  std::vector<int> nf(nview, 0), stt(nview, 0);
+  int e;
   if (dev) {
-    R.radiance = radiance; R.reflectance = reflectance; R.Q = Q; R.U = U; d_BR = sa.BR; d_BRQ = sa.BR_Q; d_BRU = sa.BR_U;
+    e = brdf_slab(true, S, scalar_glue, km, nch, Slab{0, nobs, nobs}, G, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, sza,
+                  raa, vza, MISSING, sa, 0, radiance, reflectance, Q, U, st, nf.data(), stt.data());
   } else {
-    R.radiance = put(nullptr, nview); R.reflectance = put(nullptr, nview); R.Q = put(nullptr, nview); R.U = put(nullptr, nview);
-    d_BR = put(nullptr, nview); d_BRQ = put(nullptr, nview); d_BRU = put(nullptr, nview);
-  }
-  if (!d_BR) d_BR = put(nullptr, nview);
-  off = align256(off); R.nfourier = (int *)(b + off); off += 4 * nview; off = align256(off); R.status = (int *)(b + off); off += 4 * nview;
-  off = align256(off); unsigned char *d_skip0 = (unsigned char *)(b + off); off += nview;
-  // host copies for the MISSING screening (first geometry, as the reference's multi-geometry wrappers)
-  std::vector<double> h_sza(nobs), h_vza(nobs), h_raa(nobs), h_u, h_v, h_mr;
-  auto fetch = [&](std::vector<double> &hv, const double *src, size_t n) {
-    hv.resize(n);
-    if (dev) cudaMemcpyAsync(hv.data(), src, 8 * n, cudaMemcpyDeviceToHost, st); else std::copy(src, src + n, hv.begin());
-  };
-  fetch(h_sza, sza, nobs); fetch(h_vza, vza, nobs); fetch(h_raa, raa, nobs);
-  if (cx) { fetch(h_u, sa.u10m, nobs); fetch(h_v, sa.v10m, nobs); fetch(h_mr, sa.mr, nch); }
-  if (dev) AB_CUDA_OK(cudaStreamSynchronize(st));
-  std::vector<unsigned char> skip(nview, 0);
-  for (int j = 0; j < nobs; j++) {
-    const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
-    const bool mw = cx && (is_missing_h(h_u[j], MISSING) || is_missing_h(h_v[j], MISSING));
-    for (int i = 0; i < nch; i++) {
-      const unsigned char sk = (ma || mw || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
-      for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
+    const bool cx = (sa.kind != SURF_MODIS);
+    int nadir_first = nobs;       // first observation with solar_zenith == 0.0 that is actually run (FOCORR_NADIR state quirk)
+    for (int j = 0; j < nobs && nadir_first == nobs; j++) {
+      if (sza[j] != 0.0 || is_missing_h(sza[j], MISSING) || is_missing_h(vza[j], MISSING) || is_missing_h(raa[j], MISSING)) continue;
+      if (cx && (is_missing_h(sa.u10m[j], MISSING) || is_missing_h(sa.v10m[j], MISSING))) continue;
+      for (int i = 0; i < nch; i++) if (!(cx && is_missing_h(sa.mr[i], MISSING))) { nadir_first = j; break; }
     }
+    e = shard_obs(nobs, nadir_first, [&](int j0, int nj, int nadir_already) {
+      return brdf_slab(false, S, scalar_glue, km, nch, Slab{j0, nj, nobs}, G, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he,
+                       sza, raa, vza, MISSING, sa, nadir_already, radiance, reflectance, Q, U, st, nf.data(), stt.data());
+    });
   }
-  AB_CUDA_OK(cudaMemcpyAsync(d_skip0, skip.data(), nview, cudaMemcpyHostToDevice, st));
-  VLBrdf B;
-  const int NM = std::min(2 * nstreams - 1, nMom);
-  AB_CUDA_OK(cpe);
-  if (int e = build_brdf_tables(C, B, sa.kind, S, scalar_glue, nstreams, NM, nch, nobs, st)) return e;
-  B.G = G;
-  B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
-  B.exactdb = d_exact;
-  off = align256(off); B.wsa_fail = (int *)(b + off); off += 4 * npix;
-  k_vl_brdf_exact<<<(unsigned)((nview + 127) / 128), 128, 0, st>>>(B, (int)nview, d_skip0, d_BR, d_BRQ, d_BRU);
-  AB_CUDA_OK(cudaGetLastError());
-  { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.n_launches += 1; }
-  if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel-view not run
-    std::vector<double> h_br(nview);
-    AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * nview, cudaMemcpyDeviceToHost, st));
-    AB_CUDA_OK(cudaStreamSynchronize(st));
-    for (int j = 0; j < nobs; j++) for (int i = 0; i < nch; i++) for (int g = 0; g < G; g++) {
-      unsigned char &sk = skip[((size_t)j * nch + i) * G + g];
-      if (!sk && h_br[j + (size_t)nobs * (i + (size_t)nch * g)] < 0) sk = 2;
-    }
-  }
-  R.exactdb = d_exact; R.brdf = &B;
-  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
-  if (int e = run_vlidort(C, R)) return e;
-  g_last_nfourier.resize(nview); g_last_status.resize(nview);
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_nfourier.data(), R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, st));
-  AB_CUDA_OK(cudaMemcpyAsync(g_last_status.data(), R.status, 4 * nview, cudaMemcpyDeviceToHost, st));
-  if (!dev) {
-    AB_CUDA_OK(cudaMemcpyAsync(radiance, R.radiance, 8 * nview, cudaMemcpyDeviceToHost, st));
-    AB_CUDA_OK(cudaMemcpyAsync(reflectance, R.reflectance, 8 * nview, cudaMemcpyDeviceToHost, st));
-    if (Q) AB_CUDA_OK(cudaMemcpyAsync(Q, R.Q, 8 * nview, cudaMemcpyDeviceToHost, st));
-    if (U) AB_CUDA_OK(cudaMemcpyAsync(U, R.U, 8 * nview, cudaMemcpyDeviceToHost, st));
-    if (sa.BR) AB_CUDA_OK(cudaMemcpyAsync(sa.BR, d_BR, 8 * nview, cudaMemcpyDeviceToHost, st));
-    if (sa.BR_Q) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_Q, d_BRQ, 8 * nview, cudaMemcpyDeviceToHost, st));
-    if (sa.BR_U) AB_CUDA_OK(cudaMemcpyAsync(sa.BR_U, d_BRU, 8 * nview, cudaMemcpyDeviceToHost, st));
-  }
-  AB_CUDA_OK(cudaStreamSynchronize(st));
-  return 0;
+  g_last_nfourier.swap(nf); g_last_status.swap(stt);
+  return e;
 }
 
 }  // namespace
@@ -933,6 +1004,14 @@ extern "C" int ab200_vlidort_vector_brdf_modis_multigeom(int km, int nch, int no
   SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U};
   return brdf_front(false, 3, 0, km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+
+// number of devices the host-pointer Stage-B entries spread their observations over (one contiguous slab and one host thread per
+// device, starting with the device that is current on the calling thread).  n <= 0: every visible device.  Default: AB200_DEVICES, or 1
+// (rank-per-GPU mains such as geo_vlidort.x keep one device per process).  Returns the number that will be used.
+extern "C" int ab200_set_devices(int n) {
+  { static std::mutex mu; std::lock_guard<std::mutex> lk(mu); g_devices_req = n <= 0 ? 0 : n; }
+  return vl_device_count();
 }
 
 extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,

@@ -546,6 +546,30 @@ def time_aop_vector(wl, torch):
             "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "voxels": nvox, "nMom": wl.nmom, "nPol": 6}
 
 
+def in_library_leg(world, torch):
+    """strong scaling INSIDE the library (no torchrun ranks involved): one process, one call of the reference-style host entry
+    VLIDORT_Vector_LandMODIS on a FIXED geo_vlidort workload (BASELINE configs[3] shape: 2048 observations x 4 channels), observations
+    split into one slab per device by ab200_set_devices(world).  Rank 0 runs it while the other ranks wait."""
+    from aeroapps_b200._lib import lib
+    wl = RtGeoModisWorkload(nobs=2048)
+    wl.setup_gpu(torch, torch.device("cuda", torch.cuda.current_device()))
+    L = lib()
+    used = L.ab200_set_devices(world)
+    try:
+        wl.step_e2e()                                          # warm-up: per-device workspaces, kernel attributes
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            wl.step_e2e()
+        dt = (time.perf_counter() - t0) / 2
+    finally:
+        L.ab200_set_devices(1)
+    return {"value": wl.units_per_step / dt, "unit": wl.unit, "devices": int(used), "scaling": "strong", "ms_per_call": 1e3 * dt,
+            "units_per_call": wl.units_per_step, "config": wl.config(),
+            "entry": "ab200_vlidort_vector_brdf_modis (host pointers, pinned) with ab200_set_devices(N): one host thread and one "
+                     "observation slab per device, outputs copied by every device into its slab of the caller's arrays"}
+
+
 def cpu_arm(wl, cores, passes=1, warmup=0):
     """the reference algorithm's CPU restatement (oracle/, built -O3 -march=native on this host for the timing) on `cores` threads over
     the workload's bounded sample; returns (units/s, sample description)"""
@@ -765,6 +789,20 @@ def main():
                 out.setdefault("extras", {})[name] = x
             del xwl
             gc.collect(); torch.cuda.empty_cache()
+        # in-library multi-GPU: rank 0 alone drives all `world` devices through ONE library call.  The other ranks must leave their
+        # GPUs idle meanwhile, so they wait on the host (rendezvous-store key), not inside an NCCL barrier kernel.
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+            store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            out["in_library_multi_gpu"] = in_library_leg(world, torch)
+            if dist:
+                store.set("ab200_in_library_done", "1")
+        elif dist:
+            store.wait(["ab200_in_library_done"])
+        if dist:
+            dist.barrier()
     if rank == 0:
         print(json.dumps(out))
     if dist:

@@ -175,6 +175,11 @@ long ab200_vlidort_last_diag(int *nfourier_out, int *status_out, long cap);
 /* accumulated device timings (CUDA events) of the three kernels and problem counts; reset != 0 clears them */
 int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long *n_eigen, long *n_bvp, long *npix,
                         int reset);
+/* Multi-GPU inside the library (the reference spreads pixels over MPI ranks, GV/geo_vlidort.F90:482-495): the host-pointer Stage-B
+ * entries split their observations into one contiguous slab per device, one host thread per device, each device copying its slab
+ * of the results straight into the caller's arrays.  n <= 0: every visible device; default AB200_DEVICES, else 1 (rank-per-GPU
+ * mains keep one device per process).  Returns the number of devices that will be used. */
+int ab200_set_devices(int n);
 /* self-test of the CTA linear algebra of the boundary-value kernels (tests/test_linalg_gpu.py): E = A^-1 (register-resident
  * Gauss-Jordan with partial pivoting) and P = A E (16-byte-load product) for one n x n row-major matrix, one CTA of `threads`
  * threads.  Returns 0, or 1 when the matrix is singular to working precision. */
