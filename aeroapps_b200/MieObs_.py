@@ -67,6 +67,18 @@ class ChemMie:
         if check(rc, "ab200_mie_load_table") != 0:
             raise ValueError(f"optics table {species}: fewer moments on file than n_moments (rc={rc})")
 
+    def load_interpolated(self, species, nrh, nbin, npol, t):
+        """upload an already channel-interpolated float32 table, i.e. the contents of the reference's type(Chem_MieTable)
+        (CB/Chem_MieTableMod.F90:39-78) as the Fortran shim passes them; t maps the member names to flat arrays"""
+        sp = mt.SPECIES.index(species)
+        f = lambda k: (np.ascontiguousarray(t[k], np.float32).ctypes.data_as(C.POINTER(C.c_float)) if t.get(k) is not None else None)
+        rhi = np.ascontiguousarray(t["rhi"], np.int32)
+        rc = lib().ab200_mie_load_table_f32(
+            self._h, sp, int(nrh), int(nbin), int(npol), f("rh"), f("reff"), f("gf"), f("rhop"), f("rhod"), f("vol"), f("area"),
+            f("bext"), f("bsca"), f("bbck"), f("g"), f("refr"), f("refi"), f("pback"), f("pmom"),
+            rhi.ctypes.data_as(C.POINTER(C.c_int)), f("rha"))
+        check(rc, "ab200_mie_load_table_f32")
+
     def register_tracer(self, name, species, bin_):
         check(lib().ab200_mie_register_tracer(self._h, name.encode(), mt.SPECIES.index(species), int(bin_)), "register")
 

@@ -841,6 +841,56 @@ extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh
   return 0;
 }
 
+// A table the CALLER has already read and interpolated to the handle's channels: the contents of the reference's own
+// type(Chem_MieTable) after Chem_MieTableRead (Chem_MieTableMod.F90:55-83,238-719), float32, in that type's array orders.  This is what
+// the Fortran shims of VLIDORT_getAOPscalar / VLIDORT_getAOPvector hand over (the NetCDF read stays with the reference's reader).
+// pmom may be NULL when the handle keeps no moments; rhi holds the 1-based indices of the type.
+extern "C" int ab200_mie_load_table_f32(ab200_mie *h, int species, int nrh, int nbin, int npol, const float *rh, const float *reff,
+                                        const float *gf, const float *rhop, const float *rhod, const float *vol, const float *area,
+                                        const float *bext, const float *bsca, const float *bbck, const float *g, const float *refr,
+                                        const float *refi, const float *pback, const float *pmom, const int *rhi, const float *rha) {
+  if (!h || species < 0 || species >= AB200_NSPECIES || nrh < 1 || nbin < 1 || !rh || !reff || !bext || !bsca || !bbck || !g || !rhi || !rha) {
+    ab200_set_error("load_table_f32: bad argument"); return AB200_ERR_ARG;
+  }
+  if (nrh > 0xffff) { ab200_set_error("load_table_f32: nrh too large"); return AB200_ERR_ARG; }
+  if (npol < 1 || npol > 6) { ab200_set_error("load_table_f32: nPol of the table must be 1..6"); return AB200_ERR_ARG; }
+  const int nmom = h->nmom;
+  if (nmom > 0 && !pmom) return 99;
+  TableDev &T = h->tab[species];
+  if (T.pool) { cudaFree(T.pool); T.pool = nullptr; }
+  T.nch = h->nch; T.nrh = nrh; T.nbin = nbin; T.nmom = nmom; T.npol = npol;
+  const long n3 = (long)nrh * T.nch * nbin, n2 = (long)nrh * nbin;
+  long o = 0;
+  auto take = [&](long n) { long r = o; o += (n + 31) / 32 * 32; return r; };   // 128-B aligned sub-arrays (same carve-up as load_table)
+  T.o_rh = take(nrh); T.o_bext = take(n3); T.o_bsca = take(n3); T.o_bbck = take(n3); T.o_g = take(n3);
+  T.o_refr = take(n3); T.o_refi = take(n3); T.o_pback = take(n3 * npol); T.o_pmom = take(n3 * nmom * npol);
+  T.o_reff = take(n2); T.o_gf = take(n2); T.o_rhop = take(n2); T.o_rhod = take(n2); T.o_vol = take(n2);
+  T.o_area = take(n2); T.o_rha = take(NRHHASH); T.o_rhi = take(NRHHASH);
+  T.o_pmom2 = take(2 * n3 * nmom * npol);
+  T.total = o;
+  AB_CUDA_OK(cudaMalloc(&T.pool, sizeof(float) * T.total));
+  float *P = T.pool;
+  auto up = [&](long off, const float *src, long n, float fillv) -> cudaError_t {
+    if (src) return cudaMemcpy(P + off, src, 4 * n, cudaMemcpyHostToDevice);
+    if (n > 0) k_fill<<<grid_for(n, 256), 256>>>(P + off, fillv, n);
+    return cudaGetLastError();
+  };
+  AB_CUDA_OK(up(T.o_rh, rh, nrh, 0.f)); AB_CUDA_OK(up(T.o_bext, bext, n3, 0.f)); AB_CUDA_OK(up(T.o_bsca, bsca, n3, 0.f));
+  AB_CUDA_OK(up(T.o_bbck, bbck, n3, 0.f)); AB_CUDA_OK(up(T.o_g, g, n3, 0.f)); AB_CUDA_OK(up(T.o_refr, refr, n3, -999.f));
+  AB_CUDA_OK(up(T.o_refi, refi, n3, -999.f)); AB_CUDA_OK(up(T.o_pback, pback, n3 * npol, 1.f));
+  if (nmom > 0) AB_CUDA_OK(up(T.o_pmom, pmom, n3 * nmom * npol, 0.f));
+  AB_CUDA_OK(up(T.o_reff, reff, n2, 0.f)); AB_CUDA_OK(up(T.o_gf, gf, n2, -999.f)); AB_CUDA_OK(up(T.o_rhop, rhop, n2, -999.f));
+  AB_CUDA_OK(up(T.o_rhod, rhod, n2, -999.f)); AB_CUDA_OK(up(T.o_vol, vol, n2, 0.f)); AB_CUDA_OK(up(T.o_area, area, n2, 0.f));
+  AB_CUDA_OK(cudaMemcpy(P + T.o_rha, rha, 4 * NRHHASH, cudaMemcpyHostToDevice));
+  AB_CUDA_OK(cudaMemcpy(P + T.o_rhi, rhi, 4 * NRHHASH, cudaMemcpyHostToDevice));
+  if (nmom > 0) { const long n = n3 * nmom * npol; k_pair_rows<<<grid_for(n, 256), 256>>>(P + T.o_pmom, reinterpret_cast<float2 *>(P + T.o_pmom2), nrh, n); }
+  AB_CUDA_OK(cudaGetLastError());
+  AB_CUDA_OK(cudaDeviceSynchronize());
+  T.h_rhi.assign(rhi, rhi + NRHHASH); T.h_rha.assign(rha, rha + NRHHASH);
+  T.loaded = true;
+  return 0;
+}
+
 extern "C" long ab200_mie_get_table(ab200_mie *h, int species, const char *var, void *dst, long cap) {
   if (!h || species < 0 || species >= AB200_NSPECIES || !h->tab[species].loaded) return -1;
   TableDev &T = h->tab[species];
@@ -1146,6 +1196,7 @@ extern "C" int ab200_get_edge_vars(int km, int nobs, const float *airdens, const
                                    float *pe, float *ze, float *te) {
   if (km < 1 || nobs < 0) { ab200_set_error("getEdgeVars: bad argument"); return AB200_ERR_ARG; }
   if (nobs == 0) return 0;
+  if (!airdens || !delp || !pe || !ze || !te) { ab200_set_error("getEdgeVars: NULL array argument"); return AB200_ERR_ARG; }
   size_t nin = (size_t)km * nobs, nout = (size_t)(km + 1) * nobs;
   float *d = nullptr;
   AB_CUDA_OK(cudaMalloc(&d, 4 * (2 * nin + 3 * nout)));

@@ -523,7 +523,11 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int ngeom, i
                  const double *pmom, const double *he, const double *albedo, const double *sza, const double *raa,
                  const double *vza, const double *flux_factor, double MISSING, double *radiance, double *reflectance,
                  double *Q, double *U, int *rc) {
+  if (!rc) { ab200_set_error("vlidort: rc is NULL"); return AB200_ERR_ARG; }
   *rc = 0;
+  if (km < 1 || nch < 0 || nobs < 0 || nstreams < 1 || nMom < 0 || nPol < 1) { ab200_set_error("vlidort: negative or zero dimension"); return AB200_ERR_ARG; }
+  if ((size_t)nobs * nch > 0 && (!ROT || !depol || !tau || !ssa || !pmom || !he || !albedo || !sza || !raa || !vza || !radiance || !reflectance ||
+                                 (S == 3 && (!Q || !U)))) { ab200_set_error("vlidort: NULL array argument"); return AB200_ERR_ARG; }
   // VLIDORT_Init dimension checks (V283/VLIDORT_Mod.F90:366-374; GEOS-sized maxima of vlidort_pars.f90:136-199)
   if (nstreams > 25) { *rc = 2; return 2; }
   if (km > 72) { *rc = 3; return 3; }
@@ -686,7 +690,16 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
                const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
                const double *he, const double *sza, const double *raa, const double *vza, double MISSING, const SurfArgs &sa,
                double *radiance, double *reflectance, double *Q, double *U, cudaStream_t st, int *rc) {
+  if (!rc) { ab200_set_error("vlidort: rc is NULL"); return AB200_ERR_ARG; }
   *rc = 0;
+  if (km < 1 || nch < 0 || nobs < 0 || nstreams < 1 || nMom < 0 || nPol < 1) { ab200_set_error("vlidort: negative or zero dimension"); return AB200_ERR_ARG; }
+  if ((size_t)nobs * nch > 0) {
+    const bool cx = (sa.kind != SURF_MODIS);
+    if (!ROT || !depol || !tau || !ssa || !pmom || !he || !sza || !raa || !vza || !radiance || !reflectance || (S == 3 && (!Q || !U)) ||
+        (cx && (!sa.u10m || !sa.v10m || !sa.mr)) || (!cx && (!sa.kernel_wt || !sa.param))) {
+      ab200_set_error("vlidort: NULL array argument"); return AB200_ERR_ARG;
+    }
+  }
   if (nstreams > 25) { *rc = 2; return 2; }
   if (km > 72) { *rc = 3; return 3; }
   if (nMom > 1000) { *rc = 5; return 5; }
@@ -764,20 +777,23 @@ extern "C" int ab200_vlidort_vector_lambert(int km, int nch, int nobs, const dou
 extern "C" int ab200_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
                               const double *te, double MISSING, int verbose, double *ROT, double *depol, int *rc) {
   (void)MISSING; (void)verbose;
+  if (!rc) { ab200_set_error("rot_calc: rc is NULL"); return AB200_ERR_ARG; }
   *rc = 0;
+  if (km < 1 || nch < 0 || nobs < 0) { ab200_set_error("rot_calc: negative or zero dimension"); return AB200_ERR_ARG; }
   if (km > 72) { *rc = 3; return 3; }
   const size_t ne = (size_t)(km + 1) * nobs, nr = (size_t)km * nobs * nch;
   if (nr == 0) return 0;
+  if (!channels || !pe || !he || !te || !ROT || !depol) { ab200_set_error("rot_calc: NULL array argument"); return AB200_ERR_ARG; }
   VLContext &C = vl_context();
   std::lock_guard<std::mutex> lock(C.mu);
   AB_CUDA_OK(C.rot.reserve(8 * (3 * ne + nr + 2 * nch) + 4096));
   double *d = C.rot.as<double>();
   double *d_pe = d, *d_he = d + ne, *d_te = d + 2 * ne, *d_ch = d + 3 * ne, *d_dp = d_ch + nch, *d_rot = d_dp + nch;
-  cudaMemcpyAsync(d_pe, pe, 8 * ne, cudaMemcpyHostToDevice, 0); cudaMemcpyAsync(d_he, he, 8 * ne, cudaMemcpyHostToDevice, 0);
-  cudaMemcpyAsync(d_te, te, 8 * ne, cudaMemcpyHostToDevice, 0); cudaMemcpyAsync(d_ch, channels, 8 * nch, cudaMemcpyHostToDevice, 0);
+  AB_CUDA_OK(cudaMemcpyAsync(d_pe, pe, 8 * ne, cudaMemcpyHostToDevice, 0)); AB_CUDA_OK(cudaMemcpyAsync(d_he, he, 8 * ne, cudaMemcpyHostToDevice, 0));
+  AB_CUDA_OK(cudaMemcpyAsync(d_te, te, 8 * ne, cudaMemcpyHostToDevice, 0)); AB_CUDA_OK(cudaMemcpyAsync(d_ch, channels, 8 * nch, cudaMemcpyHostToDevice, 0));
   k_rot_calc<<<(unsigned)((nr + 255) / 256), 256>>>(km, nch, nobs, d_ch, d_pe, d_he, d_te, d_rot, d_dp);
   AB_CUDA_OK(cudaGetLastError());
-  cudaMemcpyAsync(ROT, d_rot, 8 * nr, cudaMemcpyDeviceToHost, 0); cudaMemcpyAsync(depol, d_dp, 8 * nch, cudaMemcpyDeviceToHost, 0);
+  AB_CUDA_OK(cudaMemcpyAsync(ROT, d_rot, 8 * nr, cudaMemcpyDeviceToHost, 0)); AB_CUDA_OK(cudaMemcpyAsync(depol, d_dp, 8 * nch, cudaMemcpyDeviceToHost, 0));
   AB_CUDA_OK(cudaStreamSynchronize(0));
   return 0;
 }

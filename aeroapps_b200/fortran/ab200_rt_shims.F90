@@ -88,7 +88,76 @@ module ab200_c_api
          real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
          integer(c_int), intent(out) :: rc
       end function
+      integer(c_int) function ab200_vlidort_scalar_cx(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, &
+                                                      U10m, V10m, mr, sza, raa, vza, MISSING, verbose, rad, refl, BRDF, rc) bind(C, name="ab200_vlidort_scalar_cx")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), g(*), pmom(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BRDF(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_scalar_gisscx(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, &
+                                                          U10m, V10m, mr, sza, raa, vza, MISSING, verbose, rad, refl, BRDF, rc) bind(C, name="ab200_vlidort_scalar_gisscx")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), g(*), pmom(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BRDF(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_scalar_brdf_modis(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, &
+                                                              pe, he, te, kernel_wt, param, sza, raa, vza, MISSING, verbose, rad, refl, BR, rc) &
+                                                              bind(C, name="ab200_vlidort_scalar_brdf_modis")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), g(*), pmom(*), pe(*), he(*), te(*), kernel_wt(*), param(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      ! multi-geometry forms: angles (nobs,ngeom), outputs (nobs,nch,ngeom)
+      integer(c_int) function ab200_vlidort_vector_lambert_multigeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, &
+                                                                     tau, ssa, pmom, pe, he, te, albedo, sza, raa, vza, flux_factor, MISSING, verbose, &
+                                                                     rad, refl, Q, U, rc) bind(C, name="ab200_vlidort_vector_lambert_multigeom")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), alpha(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), albedo(*), sza(*), raa(*), vza(*), flux_factor(*)
+         real(c_double), intent(out) :: rad(*), refl(*), Q(*), U(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_cx_multigeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, &
+                                                                pe, he, te, U10m, V10m, mr, sza, raa, vza, MISSING, verbose, rad, refl, BR, Q, U, BR_Q, BR_U, rc) &
+                                                                bind(C, name="ab200_vlidort_vector_cx_multigeom")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_brdf_modis_multigeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, nkernel, nparam, &
+                                                                        ROT, depol, tau, ssa, pmom, pe, he, te, kernel_wt, param, sza, raa, vza, MISSING, &
+                                                                        verbose, rad, refl, BR, Q, U, BR_Q, BR_U, rc) &
+                                                                        bind(C, name="ab200_vlidort_vector_brdf_modis_multigeom")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, nkernel, nparam, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), kernel_wt(*), param(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
    end interface
+contains
+   ! the optional switches of the reference's vector wrappers (GV/VLIDORT_LAMBERT.F90:176,350; GV/VLIDORT_BRDF_MODIS.F90:210,417):
+   ! DO_BOA (bottom-of-atmosphere output) and DO_2OS_CORRECTION are outside this library's path -> refuse loudly (rc = -2)
+   logical function ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
+      ab200_unsupported_switch = .false.
+      if (present(DO_2OS_CORRECTION)) ab200_unsupported_switch = ab200_unsupported_switch .or. DO_2OS_CORRECTION
+      if (present(DO_BOA)) ab200_unsupported_switch = ab200_unsupported_switch .or. DO_BOA
+   end function ab200_unsupported_switch
 end module ab200_c_api
 
 module VLIDORT_ROT                      ! replaces geo_vlidort/VLIDORT_ROT.F90:19-86
@@ -107,10 +176,14 @@ contains
    end subroutine VLIDORT_ROT_CALC
 end module VLIDORT_ROT
 
-module VLIDORT_LAMBERT                  ! replaces geo_vlidort/VLIDORT_LAMBERT.F90:34-342 (SingleGeom forms)
+module VLIDORT_LAMBERT                  ! replaces geo_vlidort/VLIDORT_LAMBERT.F90:34-520
    use ab200_c_api
    implicit none
    public :: VLIDORT_Scalar_Lambert, VLIDORT_Vector_Lambert
+   interface VLIDORT_Vector_Lambert      ! VLIDORT_LAMBERT.F90:14-17
+      module procedure VLIDORT_Vector_Lambert_SingleGeom
+      module procedure VLIDORT_Vector_Lambert_MultiGeom
+   end interface
 contains
    subroutine VLIDORT_Scalar_Lambert(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, albedo, &
                                      solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL, reflectance_VL, rc)
@@ -127,8 +200,10 @@ contains
       if (ier /= 0 .and. rc == 0) rc = ier
    end subroutine VLIDORT_Scalar_Lambert
 
-   subroutine VLIDORT_Vector_Lambert(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, albedo, &
-                                     solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL, reflectance_VL, Q, U, rc)
+   subroutine VLIDORT_Vector_Lambert_SingleGeom(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, albedo, &
+                                     solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL, reflectance_VL, Q, U, rc, &
+                                     DO_2OS_CORRECTION, DO_BOA)
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
       integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
       logical, intent(in)  :: plane_parallel
       real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), alpha(km,nobs,nch), tau(km,nch,nobs), ssa(km,nch,nobs)
@@ -137,19 +212,96 @@ contains
       real*8,  intent(out) :: radiance_VL(nobs,nch), reflectance_VL(nobs,nch), Q(nobs,nch), U(nobs,nch)
       integer, intent(out) :: rc
       integer :: ier
+      if (ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)) then
+         rc = -2; return
+      end if
       ier = ab200_vlidort_vector_lambert(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, &
                                          pe, he, te, albedo, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, &
                                          radiance_VL, reflectance_VL, Q, U, rc)
       if (ier /= 0 .and. rc == 0) rc = ier
-   end subroutine VLIDORT_Vector_Lambert
+   end subroutine VLIDORT_Vector_Lambert_SingleGeom
+
+   ! VLIDORT_LAMBERT.F90:346-520.  ngeom is not capped at MAX_USER_OBSGEOMS; albedo(:,:,1) is what the reference uses for every geometry
+   subroutine VLIDORT_Vector_Lambert_MultiGeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, &
+                                     albedo, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL, reflectance_VL, Q, U, rc, &
+                                     DO_2OS_CORRECTION, DO_BOA)
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
+      integer, intent(in)  :: km, nch, nobs, ngeom, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), alpha(km,nobs,nch), tau(km,nch,nobs), ssa(km,nch,nobs)
+      real*8,  intent(in)  :: pmom(km,nch,nobs,nMom,nPol), pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), albedo(nobs,nch,ngeom), flux_factor(nch,nobs)
+      real*8,  intent(in)  :: solar_zenith(nobs,ngeom), relat_azymuth(nobs,ngeom), sensor_zenith(nobs,ngeom), MISSING
+      real*8,  intent(out) :: radiance_VL(nobs,nch,ngeom), reflectance_VL(nobs,nch,ngeom), Q(nobs,nch,ngeom), U(nobs,nch,ngeom)
+      integer, intent(out) :: rc
+      integer :: ier
+      if (ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)) then
+         rc = -2; return
+      end if
+      ! albedo(:,:,1) is contiguous at the start of albedo(nobs,nch,ngeom): passed as is
+      ier = ab200_vlidort_vector_lambert_multigeom(km, nch, nobs, ngeom, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, alpha, tau, ssa, &
+                                                   pmom, pe, he, te, albedo, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, &
+                                                   radiance_VL, reflectance_VL, Q, U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_Lambert_MultiGeom
 end module VLIDORT_LAMBERT
 
 module VLIDORT_BRDF_CX                  ! replaces geo_vlidort/VLIDORT_BRDF_CX.F90:587-762 (note the output order Q,U,BRDF,...)
    use ab200_c_api
    implicit none
-   public :: VLIDORT_Vector_CX, VLIDORT_Vector_GissCX, VLIDORT_Vector_OCICX, VLIDORT_Vector_OCIGissCX
+   public :: VLIDORT_Vector_CX, VLIDORT_Vector_GissCX, VLIDORT_Vector_OCICX, VLIDORT_Vector_OCIGissCX, VLIDORT_Scalar_CX, VLIDORT_Scalar_GissCX
+   interface VLIDORT_Vector_CX           ! VLIDORT_BRDF_CX.F90:27-30
+      module procedure VLIDORT_Vector_CX_SingleGeom
+      module procedure VLIDORT_Vector_CX_MultiGeom
+   end interface
 contains
-   subroutine VLIDORT_Vector_CX(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, &
+   ! VLIDORT_BRDF_CX.F90:420-584 / 1553-1717: scalar forms; BRDF(1,nobs,nch)
+   subroutine VLIDORT_Scalar_CX(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, U10m, V10m, mr, &
+                                solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), g(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BRDF(1,nobs,nch)
+      integer, intent(out) :: rc
+      integer :: ier
+      ier = ab200_vlidort_scalar_cx(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, &
+                                    U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Scalar_CX
+   subroutine VLIDORT_Scalar_GissCX(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, U10m, V10m, mr, &
+                                solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), g(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BRDF(1,nobs,nch)
+      integer, intent(out) :: rc
+      integer :: ier
+      ier = ab200_vlidort_scalar_gisscx(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, &
+                                        U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Scalar_GissCX
+   ! VLIDORT_BRDF_CX.F90:766-947 (note the output order Q, U, BRDF, ... of the Fortran interface)
+   subroutine VLIDORT_Vector_CX_MultiGeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, &
+                                solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, &
+                                Q, U, BRDF, BRDF_Q, BRDF_U, rc)
+      integer, intent(in)  :: km, nch, nobs, ngeom, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch)
+      real*8,  intent(in)  :: solar_zenith(nobs,ngeom), relat_azymuth(nobs,ngeom), sensor_zenith(nobs,ngeom), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch,ngeom), reflectance_VL_SURF(nobs,nch,ngeom), Q(nobs,nch,ngeom), U(nobs,nch,ngeom)
+      real*8,  intent(out) :: BRDF(nobs,nch,ngeom), BRDF_Q(nobs,nch,ngeom), BRDF_U(nobs,nch,ngeom)
+      integer, intent(out) :: rc
+      integer :: ier
+      ier = ab200_vlidort_vector_cx_multigeom(km, nch, nobs, ngeom, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, &
+                                              U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                              radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_CX_MultiGeom
+   subroutine VLIDORT_Vector_CX_SingleGeom(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, &
                                 solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, &
                                 Q, U, BRDF, BRDF_Q, BRDF_U, rc)
       integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
@@ -165,7 +317,7 @@ contains
                                     U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
                                     radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc)
       if (ier /= 0 .and. rc == 0) rc = ier
-   end subroutine VLIDORT_Vector_CX
+   end subroutine VLIDORT_Vector_CX_SingleGeom
    subroutine VLIDORT_Vector_GissCX(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, &
                                 solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, &
                                 Q, U, BRDF, BRDF_Q, BRDF_U, rc)
@@ -222,11 +374,55 @@ end module VLIDORT_BRDF_CX
 module VLIDORT_BRDF_MODIS               ! replaces geo_vlidort/VLIDORT_BRDF_MODIS.F90:206-410
    use ab200_c_api
    implicit none
-   public :: VLIDORT_Vector_LandMODIS
+   public :: VLIDORT_Vector_LandMODIS, VLIDORT_Scalar_LandMODIS
+   interface VLIDORT_Vector_LandMODIS    ! VLIDORT_BRDF_MODIS.F90:15-18
+      module procedure VLIDORT_Vector_LandMODIS_SingleGeom
+      module procedure VLIDORT_Vector_LandMODIS_MultiGeom
+   end interface VLIDORT_Vector_LandMODIS
 contains
-   subroutine VLIDORT_Vector_LandMODIS(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, &
+   ! VLIDORT_BRDF_MODIS.F90:35-202
+   subroutine VLIDORT_Scalar_LandMODIS(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, pe, he, te, &
                                        kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
-                                       radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc)
+                                       radiance_VL_SURF, reflectance_VL_SURF, BR, rc)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), g(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), kernel_wt(3,nch,nobs), param(2,nch,nobs)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BR(nobs,nch)
+      integer, intent(out) :: rc
+      integer :: ier
+      ier = ab200_vlidort_scalar_brdf_modis(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, g, pmom, &
+                                            pe, he, te, kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                            radiance_VL_SURF, reflectance_VL_SURF, BR, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Scalar_LandMODIS
+   ! VLIDORT_BRDF_MODIS.F90:413-...: kernel_wt / param of the first geometry are used (one surface per observation)
+   subroutine VLIDORT_Vector_LandMODIS_MultiGeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, &
+                                       kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                       radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc, DO_2OS_CORRECTION, DO_BOA)
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
+      integer, intent(in)  :: km, nch, nobs, ngeom, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), kernel_wt(3,nch,nobs), param(2,nch,nobs)
+      real*8,  intent(in)  :: solar_zenith(nobs,ngeom), relat_azymuth(nobs,ngeom), sensor_zenith(nobs,ngeom), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch,ngeom), reflectance_VL_SURF(nobs,nch,ngeom), BR(nobs,nch,ngeom), Q(nobs,nch,ngeom), U(nobs,nch,ngeom)
+      real*8,  intent(out) :: BR_Q(nobs,nch,ngeom), BR_U(nobs,nch,ngeom)
+      integer, intent(out) :: rc
+      integer :: ier
+      if (ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)) then
+         rc = -2; return
+      end if
+      ier = ab200_vlidort_vector_brdf_modis_multigeom(km, nch, nobs, ngeom, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, 3, 2, ROT, depol, tau, ssa, &
+                                                      pmom, pe, he, te, kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                                      radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_LandMODIS_MultiGeom
+   subroutine VLIDORT_Vector_LandMODIS_SingleGeom(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, &
+                                       kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                       radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc, DO_2OS_CORRECTION, DO_BOA)
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
       integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
       logical, intent(in)  :: plane_parallel
       real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
@@ -235,9 +431,12 @@ contains
       real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BR(nobs,nch), Q(nobs,nch), U(nobs,nch), BR_Q(nobs,nch), BR_U(nobs,nch)
       integer, intent(out) :: rc
       integer :: ier
+      if (ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)) then
+         rc = -2; return
+      end if
       ier = ab200_vlidort_vector_brdf_modis(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, 3, 2, ROT, depol, tau, ssa, pmom, &
                                             pe, he, te, kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
                                             radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc)
       if (ier /= 0 .and. rc == 0) rc = ier
-   end subroutine VLIDORT_Vector_LandMODIS
+   end subroutine VLIDORT_Vector_LandMODIS_SingleGeom
 end module VLIDORT_BRDF_MODIS

@@ -40,6 +40,15 @@ int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh, int nbin,
                          const double *bext, const double *bsca, const double *bbck, const double *g,
                          const double *refr, const double *refi, const double *pback, const double *pmom,
                          const double *gf, const double *rhop);
+/* The same for a table the caller has already read and interpolated to the handle's channels: the contents of the reference's
+ * type(Chem_MieTable) (Chem_MieTableMod.F90:55-83) after Chem_MieTableRead, float32, in that type's array orders: rh(nrh);
+ * reff,gf,rhop,rhod,vol,area (nrh,nbin); bext,bsca,bbck,g,refr,refi (nrh,nch,nbin); pback (nrh,nch,nbin,nPol);
+ * pmom (nrh,nch,nbin,nMom,nPol) or NULL; rhi(991) (1-based), rha(991).  Used by the Fortran shims of VLIDORT_getAOPscalar/vector
+ * (GV/VLIDORT_MieMod.F90:10,124), which keep the reference's NetCDF reader.  rc 99 when the handle wants moments and pmom is NULL. */
+int ab200_mie_load_table_f32(ab200_mie *h, int species, int nrh, int nbin, int npol, const float *rh, const float *reff,
+                             const float *gf, const float *rhop, const float *rhod, const float *vol, const float *area,
+                             const float *bext, const float *bsca, const float *bbck, const float *g, const float *refr,
+                             const float *refi, const float *pback, const float *pmom, const int *rhi, const float *rha);
 /* registry: tracer name -> (species table, 1-based bin); replaces Chem_Registry + the hard-wired map
  * of Chem_MieMod.F90:343-400 */
 int ab200_mie_register_tracer(ab200_mie *h, const char *name, int species, int bin);

@@ -172,3 +172,27 @@ def test_scalar_handle_with_4_component_tables(built):
     ref = o.getext([550.0], st["vnames"], st["qc"], st["qm"], st["rh"])
     for n, a, b in zip(["ext", "sca", "bsc", "absc_sfc", "absc_toa", "depol"], got[:6], ref[:6]):
         assert (ulp_close(a, b, 1) if n.startswith("absc") else same(a, b)), n
+
+
+def test_interpolated_float32_tables_round_trip(env):
+    """the Fortran boundary (aeroapps_b200/fortran/ab200_mie_shims.F90) hands over the reference's type(Chem_MieTable) members:
+    float32 arrays ALREADY interpolated to the channels by Chem_MieTableRead (CB/Chem_MieTableMod.F90:108-420).  A handle filled
+    through ab200_mie_load_table_f32 from those arrays must give bit-identical AOPs to the handle that read the optics files"""
+    MieObs_, mie, o, tables = env
+    chan = [354e-9, 550e-9, 600e-9]
+    m2 = MieObs_.ChemMie(chan, 40, {})
+    names = ("rh", "reff", "gf", "rhop", "rhod", "vol", "area", "bext", "bsca", "bbck", "g", "refr", "refi", "pback", "pmom", "rhi", "rha")
+    for sp in mt.SPECIES:
+        raw = tables[sp]
+        m2.load_interpolated(sp, raw.nrh, raw.nbin, raw.npol, {k: mie.table(sp, k) for k in names})
+        for k in names:
+            assert np.array_equal(m2.table(sp, k).view(np.uint32), mie.table(sp, k).view(np.uint32)), (sp, k)
+    st = mt.synthetic_state(nobs=21, km=72, seed=5)
+    a = mie.getaopvector([550.0, 354.0], st["vnames"], 0, st["qm"], st["rh"], 40, 6)
+    b = m2.getaopvector([550.0, 354.0], st["vnames"], 0, st["qm"], st["rh"], 40, 6)
+    for x, y in zip(a[:4], b[:4]):
+        assert same(x, y)
+    ref = o.getext([550.0], st["vnames"], st["qc"], st["qm"], st["rh"])
+    got = m2.getext([550.0], st["vnames"], 0, st["qc"], st["qm"], st["rh"])
+    for n, x, y in zip(["ext", "sca", "bsc", "absc_sfc", "absc_toa", "depol"], got[:6], ref[:6]):
+        assert (ulp_close(x, y, 1) if n.startswith("absc") else same(x, y)), n
