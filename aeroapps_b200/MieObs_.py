@@ -180,11 +180,16 @@ def _tables_for(rcfile):
     return _cache[key]
 
 
+last_error = ""
+
+
 def getmiedims(mieTableFile):
     """nCh, nRh, nBin, nMom, nPol, rc  (MieObs_py.F90:7-23 -> Chem_MieTableGetDims)"""
     try:
         raw = mt.read_optics_file(mieTableFile)
-    except Exception:
+    except Exception as e:                                   # the reference returns rc /= 0; keep the reason where a caller can find it
+        global last_error
+        last_error = f"getmiedims({mieTableFile}): {type(e).__name__}: {e}"
         return 0, 0, 0, 0, 0, 1
     return raw.nlam, raw.nrh, raw.nbin, raw.nmom, raw.npol, 0
 

@@ -1,4 +1,4 @@
-// Fused column pipeline: the four calls leo_vlidort / polar_vlidort make per scene
+// Chained column pipeline: the four calls leo_vlidort / polar_vlidort make per scene
 //   MieObs_.getEdgeVars -> VLIDORT_POLAR_.ROT_CALC -> MieObs_.getAOPvector -> VLIDORT_POLAR_.VECTOR_CX
 // (LV/polar_vlidort.py:600-950, LV/py_leo_vlidort/vlidort.py:400-580) behind ONE C-ABI entry.  Only the model state
 // (qm, rh, airdens, delp: ~100 B per voxel) and the geometry cross PCIe; the edge variables, the Rayleigh optical thickness,
@@ -28,7 +28,7 @@ __global__ void k_pmom_f2d(const float *__restrict__ src, double *__restrict__ d
 size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
-extern "C" int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels, const char *vname,
+extern "C" int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch, int nq, const double *channels, const char *vname,
                                         const float *qm, const float *rh, const float *airdens, const float *delp, float ptop,
                                         int nstreams, int plane_parallel, int nMom, int nPol, const double *U10m,
                                         const double *V10m, const double *mr, const double *solar_zenith,
@@ -39,6 +39,8 @@ extern "C" int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch,
   if (!h) { ab200_set_error("pipeline: null Mie handle"); return AB200_ERR_ARG; }
   if (rc) *rc = 0;
   if (km < 1 || nobs < 0 || nch < 1 || nq < 1) { ab200_set_error("pipeline: bad dimensions"); return AB200_ERR_ARG; }
+  if (!channels || !vname || !qm || !rh || !airdens || !delp || !U10m || !V10m || !mr || !solar_zenith || !relat_azymuth || !sensor_zenith ||
+      !radiance_VL_SURF || !reflectance_VL_SURF) { ab200_set_error("pipeline: NULL array argument"); return AB200_ERR_ARG; }
   const size_t npix = (size_t)nobs * nch;
   if (npix == 0) return 0;
   const size_t nvox = (size_t)km * nch * nobs, ncol = (size_t)km * nobs, ne = (size_t)(km + 1) * nobs, nrot = (size_t)km * nobs * nch;
@@ -75,9 +77,11 @@ extern "C" int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch,
   AB_CUDA_OK(cudaMemcpyAsync(F(o_rh), rh, 4 * ncol, cudaMemcpyHostToDevice, st));
   AB_CUDA_OK(cudaMemcpyAsync(F(o_ad), airdens, 4 * ncol, cudaMemcpyHostToDevice, st));
   AB_CUDA_OK(cudaMemcpyAsync(F(o_dp), delp, 4 * ncol, cudaMemcpyHostToDevice, st));
-  std::vector<double> chd(nch);
-  for (int i = 0; i < nch; i++) chd[i] = (double)channels[i];
-  AB_CUDA_OK(cudaMemcpyAsync(D(o_ch), chd.data(), 8 * (size_t)nch, cudaMemcpyHostToDevice, st));
+  // the driver's one wavelength list [nm], real*8: ROT_CALC and VLIDORT see it as it is, the Mie channel match gets the real*4
+  // copy f2py makes for MieObs_ (MieObs_py.F90:232)
+  std::vector<float> chf(nch);
+  for (int i = 0; i < nch; i++) chf[i] = (float)channels[i];
+  AB_CUDA_OK(cudaMemcpyAsync(D(o_ch), channels, 8 * (size_t)nch, cudaMemcpyHostToDevice, st));
   AB_CUDA_OK(cudaMemcpyAsync(D(o_u), U10m, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st));
   AB_CUDA_OK(cudaMemcpyAsync(D(o_v), V10m, 8 * (size_t)nobs, cudaMemcpyHostToDevice, st));
   AB_CUDA_OK(cudaMemcpyAsync(D(o_mr), mr, 8 * (size_t)nch, cudaMemcpyHostToDevice, st));
@@ -93,7 +97,7 @@ extern "C" int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch,
   if (int e = ab200_rot_calc_dev(km, nch, nobs, D(o_ch), D(o_ped), D(o_zed), D(o_ted), D(o_rot), D(o_dep), st)) return e;
   // stage 3: Mie AOPs with the phase-matrix moments (MieObs_py.F90:218-456)
   int rc_ = 0;
-  if (int e = ab200_get_aop_vector_dev(h, km, nobs, nch, nq, channels, vname, F(o_qm), F(o_rh), nMom, nPol, F(o_tau), F(o_ssa),
+  if (int e = ab200_get_aop_vector_dev(h, km, nobs, nch, nq, chf.data(), vname, F(o_qm), F(o_rh), nMom, nPol, F(o_tau), F(o_ssa),
                                        F(o_g), F(o_pm), st, &rc_)) { if (rc) *rc = rc_; return e; }
   if (rc_) { if (rc) *rc = rc_; return rc_; }
   k_f2d<<<296, 256, 0, st>>>(F(o_tau), D(o_taud), nvox);

@@ -259,6 +259,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   size_t chunk = npix;
   if (budget > bvp_work_bytes + (64 << 20)) chunk = std::min<size_t>(npix, (budget - bvp_work_bytes - (64 << 20)) / per_pix);
   else chunk = 1;
+  if (const char *e = getenv("AB200_VL_CHUNK_PIXELS")) { const long c = atol(e); if (c > 0) chunk = std::min<size_t>(chunk, (size_t)c); }   // test hook: force the multi-chunk path
   chunk = std::max<size_t>(1, chunk);
   const size_t total_bytes = chunk * per_pix + chunk * 64 + bvp_work_bytes + (size_t)(NM + 1) * (NM + 1) * N * 3 * 8 + nview + (64 << 20);
   AB_CUDA_OK(C.arena.reserve(total_bytes));

@@ -46,6 +46,13 @@ def read_optics_file(path):
     if path.endswith(".npz"):
         z = np.load(path)
         return RawTable(**{k: z[k] for k in z.files})
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic[:4] == b"\x89HDF":
+        # NetCDF-4 / HDF5 container (nf_open reads both): needs netCDF4 or h5py, neither of which ships in this image
+        return _read_optics_hdf5(path)
+    if magic[:3] != b"CDF":
+        raise ValueError(f"{path}: not a NetCDF classic (CDF-1/2/5) or NetCDF-4/HDF5 optics file (magic {magic[:4]!r})")
     from scipy.io import netcdf_file
     with netcdf_file(path, "r", mmap=False) as nc:
         def var(name, default=None):
@@ -55,6 +62,28 @@ def read_optics_file(path):
         kw = dict(lam=var("lambda"), rh=var("rh"), reff=var("rEff"), bext=var("bext"), bsca=var("bsca"),
                   bbck=var("bbck"), g=var("g"), refr=var("refreal"), refi=var("refimag"), pback=var("pback"),
                   pmom=var("pmom"), gf=var("growth_factor"), rhop=var("rhop"))
+    return RawTable(**kw)
+
+
+def _read_optics_hdf5(path):
+    """NetCDF-4 optics files through netCDF4 or h5py when one of them is importable; a clear error otherwise"""
+    try:
+        import netCDF4
+        ds = netCDF4.Dataset(path)
+        get = lambda n: (np.array(ds.variables[n][:], dtype=np.float64).T if n in ds.variables else None)
+    except ImportError:
+        try:
+            import h5py
+        except ImportError:
+            raise RuntimeError(f"{path} is a NetCDF-4/HDF5 optics file; reading it needs the netCDF4 or h5py package "
+                               "(convert with `nccopy -k classic` or install one of them)") from None
+        ds = h5py.File(path, "r")
+        get = lambda n: (np.array(ds[n][...], dtype=np.float64).T if n in ds else None)
+    try:
+        kw = dict(lam=get("lambda"), rh=get("rh"), reff=get("rEff"), bext=get("bext"), bsca=get("bsca"), bbck=get("bbck"), g=get("g"),
+                  refr=get("refreal"), refi=get("refimag"), pback=get("pback"), pmom=get("pmom"), gf=get("growth_factor"), rhop=get("rhop"))
+    finally:
+        ds.close()
     return RawTable(**kw)
 
 

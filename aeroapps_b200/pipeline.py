@@ -1,4 +1,4 @@
-"""Fused column pipeline: the call sequence of leo_vlidort / polar_vlidort
+"""Chained column pipeline: the call sequence of leo_vlidort / polar_vlidort
     pe, ze, te = MieObs_.getEdgeVars(airdens, delp, ptop)
     ROT, depol = VLIDORT_POLAR_.ROT_CALC(channels, pe, ze, te, ...)
     tau, ssa, g, pmom = MieObs_.getAOPvector(...);  pmom[..., 1] *= -1;  pmom[..., 3] *= -1
@@ -27,7 +27,7 @@ def vector_cx_pipeline(mie, channels, vname, qm, rh, airdens, delp, ptop, nstrea
     mr (nch).  Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc), each (nobs,nch) float64."""
     qm, rh, airdens, delp = _f32(qm), _f32(rh), _f32(airdens), _f32(delp)
     km, nq, nobs = qm.shape
-    ch = np.ascontiguousarray(channels, dtype=np.float32).reshape(-1)
+    ch = _v(channels)
     nch = len(ch)
     vn, nqn = _names(vname)
     assert nqn == nq and rh.shape == (km, nobs) and airdens.shape == (km, nobs) and delp.shape == (km, nobs)
@@ -35,7 +35,7 @@ def vector_cx_pipeline(mie, channels, vname, qm, rh, airdens, delp, ptop, nstrea
     assert len(u) == nobs and len(v) == nobs and len(m) == nch and len(sza) == nobs and len(raa) == nobs and len(vza) == nobs
     outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
     rc = C.c_int(0)
-    check(lib().ab200_pipeline_vector_cx(mie.handle, km, nobs, nch, nq, _p32(ch), vn.ctypes.data_as(C.c_char_p), _p32(qm), _p32(rh),
+    check(lib().ab200_pipeline_vector_cx(mie.handle, km, nobs, nch, nq, _p(ch), vn.ctypes.data_as(C.c_char_p), _p32(qm), _p32(rh),
                                          _p32(airdens), _p32(delp), C.c_float(ptop), int(nstreams), int(bool(plane_parallel)),
                                          int(nmom), int(npol), _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza), C.c_double(MISSING),
                                          int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_pipeline_vector_cx")

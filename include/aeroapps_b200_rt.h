@@ -128,12 +128,12 @@ int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstreams, int pla
 int ab200_rot_calc_dev(int km, int nch, int nobs, const double *channels, const double *pe, const double *he, const double *te,
                        double *ROT, double *depol, void *stream);
 
-/* Fused column pipeline: MieObs_.getEdgeVars -> ROT_CALC -> MieObs_.getAOPvector -> VECTOR_CX, the call
+/* Chained column pipeline (four stages back to back on one stream, not one fused kernel): MieObs_.getEdgeVars -> ROT_CALC -> MieObs_.getAOPvector -> VECTOR_CX, the call
  * sequence of leo_vlidort / polar_vlidort (LV/polar_vlidort.py:600-950, LV/py_leo_vlidort/vlidort.py:400-580), in one call.
- * Host inputs are the model state of the Mie side (qm (km,nq,nobs), rh / airdens / delp (km,nobs) float32, channels [nm]
- * float32, tracer names) and the geometry / wind / refractive index of the RT side (float64); edge variables, Rayleigh
+ * Host inputs are the model state of the Mie side (qm (km,nq,nobs), rh / airdens / delp (km,nobs) float32, tracer names), the
+ * wavelength list channels [nm] float64 (the Mie channel match gets its float32 copy, as f2py makes for MieObs_) and the geometry / wind / refractive index of the RT side (float64); edge variables, Rayleigh
  * optical thickness, tau, ssa and the phase-matrix moments never leave HBM.  Results are bit-identical to the four calls. */
-int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch, int nq, const float *channels, const char *vname,
+int ab200_pipeline_vector_cx(ab200_mie *h, int km, int nobs, int nch, int nq, const double *channels, const char *vname,
                              const float *qm, const float *rh, const float *airdens, const float *delp, float ptop,
                              int nstreams, int plane_parallel, int nMom, int nPol, const double *U10m, const double *V10m,
                              const double *mr, const double *solar_zenith, const double *relat_azymuth,

@@ -243,6 +243,40 @@ def test_legacy_band_elimination_agrees(mods, N, monkeypatch):
     assert rel(I1, I0, I0) < 1e-11 and rel(Q1, Q0, I0) < 1e-11 and rel(U1, U0, I0) < 1e-11
 
 
+@pytest.mark.parametrize("surface", ["cx", "modis", "lambert_mg"])
+def test_multi_chunk_path_is_bit_identical(mods, surface, monkeypatch):
+    """run_vlidort's multi-chunk path (a swath larger than the workspace: shifted state pointers, chunk-local BRDF arrays,
+    per-chunk active lists) forced with AB200_VL_CHUNK_PIXELS = 7 on 2 channels x 13 observations with a MISSING observation: every
+    output and both diagnostics bit-identical to the single-chunk run"""
+    VP, vg = mods
+    nobs, N = 13, 6
+    sc = vg.synthetic_scene(nobs, nch_nm=(470.0, 660.0), nmom=40, seed=17)
+    sc["vza"][4] = 1e15
+    if surface == "cx":
+        call = lambda: VP.vector_cx(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"],
+                                    sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], 1e15, 0)
+    elif surface == "modis":
+        call = lambda: VP.vector_brdf_modis(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"],
+                                            sc["te"], sc["kernel_wt"], sc["param"], sc["sza"], sc["raa"], sc["vza"], 1e15, 0)
+    else:
+        G = 3
+        rng = np.random.default_rng(3)
+        vza = np.asfortranarray(rng.uniform(0.0, 60.0, (nobs, G))); raa = np.asfortranarray(rng.uniform(0.0, 180.0, (nobs, G)))
+        vza[4, 0] = 1e15
+        sza = np.asfortranarray(np.repeat(sc["sza"][:, None], G, axis=1))
+        call = lambda: VP.vector_lambert_multigeom(sc["channels"], N, False, sc["ROT"], sc["depol"], np.zeros_like(sc["ROT"]), sc["tau"], sc["ssa"],
+                                                   sc["pmom"], sc["pe"], sc["he"], sc["te"], sc["albedo"], sza, raa, vza,
+                                                   np.ones((2, nobs), order="F"), 1e15, 0)
+    a = call(); da = VP.last_diag()
+    monkeypatch.setenv("AB200_VL_CHUNK_PIXELS", "7")
+    b = call(); db = VP.last_diag()
+    assert a[-1] == b[-1] == 0
+    for x, y in zip(a[:-1], b[:-1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1])
+    assert (da[1] != 0).any() and (da[1] == 0).any()
+
+
 def test_scalar_brdf_surfaces(mods):
     VP, vg = mods
     nobs, N = 6, 6
