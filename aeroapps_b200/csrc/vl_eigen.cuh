@@ -27,6 +27,9 @@ struct VLSol {                 // per problem q = c*L + k (pixel c, layer k; str
   int *fail;                   // [p] set !=0 when an eigenproblem fails
 };
 
+#ifdef AB_HM_SWEEP_HIST
+static long hm_sweep_hist[16][32]; static int hm_sweep_last; static double hm_off_hist[32];
+#endif
 struct VLQuad {                // quadrature (pixel independent)
   int N;
   double x[32], w[32];
@@ -267,6 +270,9 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
     }
   }
   T.sync();
+#ifdef AB_HM_SWEEP_HIST
+  if (getenv("AB_HM_DUMP") && (k % 12 == 0)) { FILE *f = fopen(getenv("AB_HM_DUMP"), "ab"); int hd[4] = {n, m, k, LDA}; fwrite(hd, 4, 4, f); fwrite(A, 8, (size_t)n * LDA, f); fclose(f); }
+#endif
   // ---- one-sided Jacobi, round-robin ordering, one column pair per lane
   {
     const int np = n + (n & 1), half = np / 2;
@@ -328,8 +334,14 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
       int dummy = 0;
       offmax = T.argmax(offmax, dummy);
       // quadratic convergence: a sweep whose largest pre-rotation |cos(a_p,a_q)| was below 1e-8 leaves ~1e-16 behind
+#ifdef AB_HM_SWEEP_HIST
+      hm_sweep_last = sweep + 1; hm_off_hist[sweep < 31 ? sweep : 31] = offmax;
+#endif
       if (offmax < 1.0e-8) break;
     }
+#ifdef AB_HM_SWEEP_HIST
+    hm_sweep_hist[m < 15 ? m : 15][hm_sweep_last < 31 ? hm_sweep_last : 31]++;
+#endif
   }
   // ---- singular values = eigenvalues k of the layer; y = C u in place in A, x = C^-T u through global memory (XNg)
   bool bad = false;

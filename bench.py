@@ -546,6 +546,50 @@ def time_aop_vector(wl, torch):
             "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "voxels": nvox, "nMom": wl.nmom, "nPol": 6}
 
 
+def time_angles(torch, n=4_000_000):
+    """the geometry calculator of the geo driver (GeoAngles_.satangles) on n points: device-resident rate with its
+    HBM roofline (92 B per point: five int32 + three float64 in, four float64 out), the rate through the host-pointer entry, the CPU
+    restatement on one core, and the largest difference between the two on the sample"""
+    import ctypes as C
+    from aeroapps_b200._lib import lib, check
+    from aeroapps_b200.angles import GeoAngles_
+    rng = np.random.default_rng(20260107)
+    ints = [rng.integers(lo, hi, n).astype(np.int32) for lo, hi in ((2005, 2030), (1, 13), (1, 29), (0, 24), (0, 60))]
+    sec, lat, lon = rng.uniform(0, 60, n), rng.uniform(-70, 70, n), rng.uniform(-160, -40, n)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    di = [torch.from_numpy(a).to(dev) for a in ints]; dd = [torch.from_numpy(a).to(dev) for a in (sec, lat, lon)]
+    lss = torch.full((n,), -100.0, dtype=torch.float64, device=dev); las = torch.zeros(n, dtype=torch.float64, device=dev)
+    outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(4)]
+    pi = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_int)); pd = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_double))
+    stream = torch.cuda.current_stream().cuda_stream
+    run = lambda: check(lib().ab200_satangles_dev(n, *[pi(t) for t in di], *[pd(t) for t in dd], pd(las), pd(lss), C.c_double(0.0),
+                                                  C.c_double(35786.0), 0, *[pd(o) for o in outs], C.c_void_p(stream)), "satangles_dev")
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    bpu = 5 * 4 + 5 * 8 + 4 * 8                                  # the _dev form also reads per-point latss / lonss
+    t0 = time.perf_counter(); got = GeoAngles_.satangles(*ints, sec, lat, lon, -100.0); th = time.perf_counter() - t0
+    from oracle import angles_oracle as ao                       # CPU leg: the checker, timed as cpu_baseline
+    m = 400_000
+    t0 = time.perf_counter(); ref = ao.angles(0, *[a[:m] for a in ints], sec[:m], lat[:m], lon[:m], lonss0=-100.0); tc = time.perf_counter() - t0
+    err = max(float(np.max(np.abs(np.asarray(g)[:m] - r))) for g, r in zip(got, ref))
+    pk = peaks()
+    gbs = n * bpu / (ms * 1e-3) / 1e9
+    return {"metric": "GeoAngles satangles points/sec (view + solar azimuth / zenith per point)", "value": n / (ms * 1e-3), "unit": "points/s",
+            "ms_per_step": ms, "points": n,
+            "roofline": {"bound": "hbm", "kernel": "k_angles", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "bytes_per_unit": bpu, "traffic": None,
+                         "note": "~30 FP64 transcendentals per point: the FP64 pipe, not HBM, is what binds this kernel"},
+            "e2e": {"value": n / th, "unit": "points/s", "h2d_bytes_per_step": n * 44, "d2h_bytes_per_step": n * 32, "host_buffers": "pageable"},
+            "cpu_baseline": {"value": m / tc, "unit": "points/s", "cores": 1, "kind": "port", "sample": f"{m} of {n} points, scalar C restatement"},
+            "parity": {"n": m, "max_abs_deg": err, "bar_deg": 1e-9, "pass": bool(err <= 1e-9)}}
+
+
 def in_library_leg(world, torch):
     """strong scaling INSIDE the library (no torchrun ranks involved): one process, one call of the reference-style host entry
     VLIDORT_Vector_LandMODIS on a FIXED geo_vlidort workload (BASELINE configs[3] shape: 2048 observations x 4 channels), observations
@@ -789,6 +833,8 @@ def main():
                 out.setdefault("extras", {})[name] = x
             del xwl
             gc.collect(); torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            out["extras"]["geo_angles"] = time_angles(torch)
         # in-library multi-GPU: rank 0 alone drives all `world` devices through ONE library call.  The other ranks must leave their
         # GPUs idle meanwhile, so they wait on the host (rendezvous-store key), not inside an NCCL barrier kernel.
         if dist:

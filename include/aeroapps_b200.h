@@ -96,6 +96,7 @@ int ab200_get_edge_vars_dev(int km, int nobs, const float *airdens_dev, const fl
                             float *ze_dev, float *te_dev, void *stream);
 
 #include "aeroapps_b200_rt.h"
+#include "aeroapps_b200_geom.h"
 
 #ifdef __cplusplus
 }

@@ -125,3 +125,8 @@ extern "C" int hm_vlidort(int ngeom, int S, int N, int km, int nch, int nobs, in
   }
   return 0;
 }
+
+#ifdef AB_HM_SWEEP_HIST
+// diagnostic build only (-DAB_HM_SWEEP_HIST): Jacobi sweeps per eigenproblem, by Fourier term
+extern "C" void hm_sweep_histogram(long *out) { for (int m = 0; m < 16; m++) for (int s = 0; s < 32; s++) out[m * 32 + s] = hm_sweep_hist[m][s]; }
+#endif
