@@ -12,6 +12,7 @@
 // solve that is regular, branch-free and whose eigenvectors are exactly orthogonal in the metric the Green's
 // function normalisation (NORM_SAVED) assumes -- also inside degenerate clusters.
 #pragma once
+#include <vector>
 #include "vl_setup.cuh"
 
 namespace vlk {
@@ -33,7 +34,44 @@ static long hm_sweep_hist[16][32]; static int hm_sweep_last; static double hm_of
 struct VLQuad {                // quadrature (pixel independent)
   int N;
   double x[32], w[32];
+  const unsigned short *jsched;  // device: Jacobi pair schedule of the two-warp teams (jacobi_schedule), [jrounds][half]; nullptr = none
+  int jrounds;
 };
+
+// Host: the recursive fixed / moving tournament for n columns (see jacobi_duo_resident).  out[round * half + slot] = a | b << 6 |
+// load_a << 12 | store_a << 13 or 0xFFFF, half = ceil(n / 2) slots per round; returns the number of rounds.
+inline int jacobi_schedule(int n, std::vector<unsigned short> &out) {
+  const int half = (n + (n & 1)) / 2;
+  std::vector<std::vector<int>> ra, rb;                    // [round][slot] -> column or -1
+  auto ensure = [&](size_t r) { while (ra.size() <= r) { ra.emplace_back(half, -1); rb.emplace_back(half, -1); } };
+  struct Job { std::vector<int> cols; int slot0, round0; };
+  std::vector<Job> todo;
+  { Job j; for (int c = 0; c < n; c++) j.cols.push_back(c); j.slot0 = 0; j.round0 = 0; todo.push_back(j); }
+  while (!todo.empty()) {
+    Job j = todo.back(); todo.pop_back();
+    const int sz = (int)j.cols.size();
+    if (sz < 2) continue;
+    const int hf = sz / 2, nm = sz - hf;
+    for (int s = 0; s < nm; s++) {
+      ensure((size_t)j.round0 + s);
+      for (int t = 0; t < hf; t++) { ra[j.round0 + s][j.slot0 + t] = j.cols[t]; rb[j.round0 + s][j.slot0 + t] = j.cols[hf + (t + s) % nm]; }
+    }
+    Job f, m;
+    f.cols.assign(j.cols.begin(), j.cols.begin() + hf); f.slot0 = j.slot0; f.round0 = j.round0 + nm;
+    m.cols.assign(j.cols.begin() + hf, j.cols.end()); m.slot0 = j.slot0 + hf / 2; m.round0 = j.round0 + nm;
+    todo.push_back(f); todo.push_back(m);
+  }
+  const int R = (int)ra.size();
+  out.assign((size_t)R * half, 0xFFFF);
+  for (int r = 0; r < R; r++)
+    for (int t = 0; t < half; t++) {
+      if (ra[r][t] < 0) continue;
+      const bool load = r == 0 || ra[r - 1][t] != ra[r][t];
+      const bool store = r == R - 1 || ra[r + 1][t] != ra[r][t];
+      out[(size_t)r * half + t] = (unsigned short)(ra[r][t] | (rb[r][t] << 6) | (load ? 0x1000 : 0) | (store ? 0x2000 : 0));
+    }
+  return R;
+}
 
 // shared/scratch size in doubles for one problem
 HDFN int eig_lda(int n) { return n | 1; }                                  // odd leading dimension: conflict-free column access
@@ -120,30 +158,127 @@ DEVFN double jacobi_halfpair(double *AB_RESTRICT a, double *AB_RESTRICT b, int r
   }
   return rel;
 }
+// Jacobi rounds of a two-warp team with a RESIDENT column.  The pair schedule (jacobi_schedule below, built on the host) is a
+// recursive "fixed / moving" tournament: the columns are split in halves F and M, slot t keeps F[t] while the columns of M pass by
+// (|M| rounds: every F-M pair), then F and M are scheduled the same way side by side.  Every pair of columns meets exactly once per
+// sweep (n (n-1)/2 rotations in 38 rounds at n = 36 against the 35 of the circle method; the same sweep counts), but the fixed column
+// of a slot stays in the registers of its two lanes for a whole phase: per rotation ONE column is loaded from and stored to shared
+// memory instead of two, which is what binds this kernel (column traffic of the rotations = 3/4 of its shared-memory wavefronts).
+// Entry: a | b << 6 | load_a << 12 | store_a << 13, 0xFFFF = slot idle in this round.
+template <int NRH, class Team>
+DEVFN void jacobi_duo_resident(const Team &T, double *AB_RESTRICT A, int LDA, int n, double *AB_RESTRICT nrm2,
+                               const unsigned short *AB_RESTRICT sch, int nrounds) {
+  const int np = n + (n & 1), half = np / 2;
+  const int ppw = (half + 1) / 2, w = T.rank >> 5, lane = T.rank & 31, h = lane >> 4;
+  const int t = w * ppw + (lane & 15);
+  const bool act = (lane & 15) < ppw && t < half;
+  const int nh = (n + 1) / 2, r0 = h ? nh : 0, nr = h ? n - nh : nh;
+  double ra[NRH], na2 = 0.0;
+#pragma unroll
+  for (int r = 0; r < NRH; r++) ra[r] = 0.0;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    for (int c = T.rank; c < n; c += T.size) {               // exact squared norms at the start of every sweep
+      const double *col = A + c * LDA;
+      double s0 = 0.0, s1 = 0.0;
+      for (int r = 0; r + 1 < n; r += 2) { s0 += col[r] * col[r]; s1 += col[r + 1] * col[r + 1]; }
+      if (n & 1) s0 += col[n - 1] * col[n - 1];
+      nrm2[c] = s0 + s1;
+    }
+    T.sync();
+    double offmax = 0.0;
+    unsigned e = act ? (unsigned)sch[t] : 0xFFFFu;
+    for (int rd = 0; rd < nrounds; rd++) {
+      const unsigned en = (act && rd + 1 < nrounds) ? (unsigned)sch[(rd + 1) * half + t] : 0xFFFFu;     // next round's entry, off the chain
+      const bool run = e != 0xFFFFu;
+      const unsigned rmask = __ballot_sync(0xffffffffu, run);
+      if (run) {
+        const int a = e & 63, b = (e >> 6) & 63;
+        double *pa = A + a * LDA + r0, *pb = A + b * LDA + r0;
+        if (e & 0x1000u) {
+#pragma unroll
+          for (int r = 0; r < NRH; r++) ra[r] = r < nr ? pa[r] : 0.0;
+          na2 = nrm2[a];
+        }
+        double rb[NRH];
+#pragma unroll
+        for (int r = 0; r < NRH; r++) rb[r] = r < nr ? pb[r] : 0.0;
+        double nb2 = nrm2[b];
+        double gap[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < NRH; r++) gap[r & 3] += ra[r] * rb[r];
+        double ga = (gap[0] + gap[1]) + (gap[2] + gap[3]);
+        ga += __shfl_xor_sync(rmask, ga, 16);
+        const double al = na2, be = nb2;
+        // rel = |cos(a,b)| only feeds the convergence test; the rotation is gated by the equivalent product form and its parameters
+        // come from two reciprocal square roots on the dependent chain (the textbook t = g2 / (d + sign(d) sqrt(d^2 + g2^2)),
+        // c = 1 / sqrt(1 + t^2) has a square root, a division and a reciprocal square root in sequence):
+        //   rho^-1 = rsqrt(d^2 + g2^2),  cos 2theta = |d| / rho,  c = cos theta = sqrt((1 + cos 2theta) / 2),  s = sign(d) g2 / (2 rho c)
+        const double ab = al * be;
+        const double rel = fabs(ga) * rsqrt(ab + 1.0e-300);
+        if (rel > offmax) offmax = rel;
+        const bool rot = ga * ga > 1.0e-30 * ab;
+        if (rot) {
+          const double d = be - al, g2 = 2.0 * ga;
+          const double inv = rsqrt(d * d + g2 * g2);
+          const double x = 0.5 + 0.5 * (fabs(d) * inv);
+          const double ic = rsqrt(x);
+          const double c = x * ic, sn = (d >= 0.0 ? 0.5 : -0.5) * (g2 * inv) * ic;
+          const double tt = sn * ic;
+          na2 = al - tt * ga; nb2 = be + tt * ga;
+#pragma unroll
+          for (int r = 0; r < NRH; r++) {
+            const double ua = ra[r], ub = rb[r];
+            ra[r] = c * ua - sn * ub;
+            if (r < nr) pb[r] = sn * ua + c * ub;
+          }
+        }
+        __syncwarp(rmask);                                   // (all running lanes) the partner lane has read the old norm of b
+        if (rot && h == 0) nrm2[b] = nb2;
+        if (e & 0x2000u) {
+#pragma unroll
+          for (int r = 0; r < NRH; r++) if (r < nr) pa[r] = ra[r];
+          if (h == 0) nrm2[a] = na2;
+        }
+      }
+      T.sync();
+      e = en;
+    }
+    int dummy = 0;
+    offmax = T.argmax(offmax, dummy);
+    // quadratic convergence: a sweep whose largest pre-rotation |cos(a_p,a_q)| was below 1e-8 leaves ~1e-16 behind
+    if (offmax < 1.0e-8) break;
+  }
+}
 #endif
 
 // back-transformation of eigenvector column e:  y = C u (in place in the column),  x = C^-T u (returned through xg)
 template <int NR>
-DEVFN void eig_backtransform(const double *AB_RESTRICT B1, int LDB, double *AB_RESTRICT col, double isig, int n, double *AB_RESTRICT xg) {
+DEVFN void eig_backtransform(const double *AB_RESTRICT B1, int LDB, const double *AB_RESTRICT rdiag, double *AB_RESTRICT col, double isig, int n,
+                             double *AB_RESTRICT xg) {
   if (NR > 0) {
     double u[NR > 0 ? NR : 1];
 #pragma unroll
     for (int r = 0; r < NR; r++) u[r] = r < n ? col[r] * isig : 0.0;
+    // y = C u: rows are independent; two partial sums per row halve the dependent chain
 #pragma unroll
     for (int r = 0; r < NR; r++)
       if (r < n) {
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int t = 0; t <= r; t++) s += B1[r * LDB + t] * u[t];
-        col[r] = s;
+        for (int t = 0; t <= r; t += 2) { s0 += B1[r * LDB + t] * u[t]; if (t + 1 <= r) s1 += B1[r * LDB + t + 1] * u[t + 1]; }
+        col[r] = s0 + s1;
       }
+    // x = C^-T u: back substitution, the reciprocal diagonal comes from rdiag (no division on the chain)
 #pragma unroll
     for (int r = NR - 1; r >= 0; r--)
       if (r < n) {
-        double s = u[r];
+        double s0 = u[r], s1 = 0.0;
 #pragma unroll
-        for (int t = r + 1; t < NR; t++) if (t < n) s -= B1[t * LDB + r] * u[t];
-        u[r] = s / B1[r * LDB + r];
+        for (int t = r + 1; t < NR; t += 2) {
+          if (t < n) s0 -= B1[t * LDB + r] * u[t];
+          if (t + 1 < NR && t + 1 < n) s1 -= B1[(t + 1) * LDB + r] * u[t + 1];
+        }
+        u[r] = (s0 + s1) * rdiag[r];
       }
 #pragma unroll
     for (int r = 0; r < NR; r++) if (r < n) xg[r] = u[r];
@@ -157,7 +292,7 @@ DEVFN void eig_backtransform(const double *AB_RESTRICT B1, int LDB, double *AB_R
     for (int r = n - 1; r >= 0; r--) {
       double s = xg[r];
       for (int t = r + 1; t < n; t++) s -= B1[t * LDB + r] * xg[t];
-      xg[r] = s / B1[r * LDB + r];
+      xg[r] = s * rdiag[r];
     }
   }
 }
@@ -184,7 +319,7 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
 
   // ---- generalized spherical functions at the solar cosine (the user cosines follow per view further down)
   if (T.rank == (T.size > 1 ? 1 : 0)) pi_prt(m, NM, sc[0], pi0);
-  for (int r = T.rank; r < n; r += T.size) { const int i = r / S; sr[r] = sqrt(QD.w[i] * QD.x[i]); }
+  for (int r = T.rank; r < n; r += T.size) { const int i = r / S; sr[r] = 1.0 / sqrt(QD.w[i] * QD.x[i]); }      // sr holds 1 / sqrt(w mu)
 
   // ---- lower triangles of the symmetric matrices Q (from Zs) and P (from Zd); item = stream pair i >= j
   for (int idx = T.rank; idx < N * (N + 1) / 2; idx += T.size) {
@@ -227,44 +362,63 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
       }
   }
   T.sync();
-  // ---- Cholesky Q = C C^T and P = Lp Lp^T together, left-looking, in place; item = (matrix, row)
+  // ---- Cholesky Q = C C^T and P = Lp Lp^T together, left-looking, in place; item = (matrix, row).  The columns stay UNSCALED during
+  //      the factorisation (w(r,t) = L(r,t) sqrt(d_t), d_t = the pivot): s = a(r,c) - sum_t w(r,t) w(c,t) / d_t, so a column needs one
+  //      team barrier instead of three and no reciprocal square root on the chain; one parallel pass scales everything at the end
   bool ok = true;
+  double *idq = gup, *idp = gdn;                           // reciprocal pivots of Q and P (both vectors are only written further down)
   for (int c = 0; c < n; c++) {
     const int rem = n - c;
     for (int idx = T.rank; idx < 2 * rem; idx += T.size) {
       const int mat = idx >= rem, r = c + idx - mat * rem;
-      double s;
+      double s0, s1 = 0.0;
       if (!mat) {
         const double *lr = B1 + r * LDB, *lc = B1 + c * LDB;
-        s = lr[c];
-        for (int t = 0; t < c; t++) s -= lr[t] * lc[t];
-        B1[r * LDB + c] = s;
+        s0 = lr[c];
+        int t = 0;
+        for (; t + 1 < c; t += 2) { s0 -= lr[t] * lc[t] * idq[t]; s1 -= lr[t + 1] * lc[t + 1] * idq[t + 1]; }
+        if (t < c) s0 -= lr[t] * lc[t] * idq[t];
+        s0 += s1;
+        B1[r * LDB + c] = s0;
+        if (r == c) idq[c] = 1.0 / s0;
       } else {
-        s = B1[c * LDB + r + 1];
-        for (int t = 0; t < c; t++) s -= B1[t * LDB + r + 1] * B1[t * LDB + c + 1];
-        B1[c * LDB + r + 1] = s;
+        s0 = B1[c * LDB + r + 1];
+        int t = 0;
+        for (; t + 1 < c; t += 2) {
+          s0 -= B1[t * LDB + r + 1] * B1[t * LDB + c + 1] * idp[t]; s1 -= B1[(t + 1) * LDB + r + 1] * B1[(t + 1) * LDB + c + 1] * idp[t + 1];
+        }
+        if (t < c) s0 -= B1[t * LDB + r + 1] * B1[t * LDB + c + 1] * idp[t];
+        s0 += s1;
+        B1[c * LDB + r + 1] = s0;
+        if (r == c) idp[c] = 1.0 / s0;
       }
     }
     T.sync();
     const double dq = B1[c * LDB + c], dp = B1[c * LDB + c + 1];
     if (!(dq > 0.0) || !(dp > 0.0)) { ok = false; break; }
-    const double iq = 1.0 / sqrt(dq), ip = 1.0 / sqrt(dp);
-    T.sync();
-    for (int idx = T.rank; idx < 2 * rem; idx += T.size) {
-      const int mat = idx >= rem, r = c + idx - mat * rem;
-      if (!mat) B1[r * LDB + c] *= iq; else B1[c * LDB + r + 1] *= ip;       // diagonal: d/sqrt(d) = sqrt(d)
-    }
-    T.sync();
   }
   if (!ok) { if (T.rank == 0) Z.fail[p] = 1; return; }
+  // L(r,t) = w(r,t) / sqrt(d_t) (the diagonal becomes sqrt(d_t)): B1(i,j) with j <= i belongs to C (column j), with j > i to Lp (column i)
+  for (int t = T.rank; t < n; t += T.size) { idq[t] = sqrt(idq[t]); idp[t] = sqrt(idp[t]); }
+  T.sync();
+  for (int idx = T.rank; idx < n * LDB; idx += T.size) {
+    const int i = idx / LDB, j = idx - i * LDB;
+    B1[idx] *= (j <= i) ? idq[j] : idp[i];
+  }
+  T.sync();
   // ---- A = C^T Lp  (column-major, A[c*LDA + r])
   {
     int r = T.rank, c = 0;
     while (r >= n) { r -= n; c++; }
     while (c < n) {
-      double s = 0.0;
-      for (int t = (r > c ? r : c); t < n; t++) s += B1[t * LDB + r] * B1[c * LDB + t + 1];
-      A[c * LDA + r] = s;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int t = (r > c ? r : c);
+      for (; t + 3 < n; t += 4) {
+        s0 += B1[t * LDB + r] * B1[c * LDB + t + 1]; s1 += B1[(t + 1) * LDB + r] * B1[c * LDB + t + 2];
+        s2 += B1[(t + 2) * LDB + r] * B1[c * LDB + t + 3]; s3 += B1[(t + 3) * LDB + r] * B1[c * LDB + t + 4];
+      }
+      for (; t < n; t++) s0 += B1[t * LDB + r] * B1[c * LDB + t + 1];
+      A[c * LDA + r] = (s0 + s1) + (s2 + s3);
       r += T.size;
       while (r >= n) { r -= n; c++; }
     }
@@ -273,8 +427,22 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
 #ifdef AB_HM_SWEEP_HIST
   if (getenv("AB_HM_DUMP") && (k % 12 == 0)) { FILE *f = fopen(getenv("AB_HM_DUMP"), "ab"); int hd[4] = {n, m, k, LDA}; fwrite(hd, 4, 4, f); fwrite(A, 8, (size_t)n * LDA, f); fclose(f); }
 #endif
-  // ---- one-sided Jacobi, round-robin ordering, one column pair per lane
-  {
+  // ---- one-sided Jacobi
+  bool jacobi_done = false;
+#if !defined(AB_HOST_MODEL) && !defined(AB200_JACOBI_PAIRS)
+  if constexpr (Team::size == 64) {
+    // two-warp teams: row halves of a pair on two lanes, the slot's fixed column resident in registers (schedule from the host)
+    if (QD.jsched != nullptr) {
+      if (n <= 12) jacobi_duo_resident<6>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      else if (n <= 24) jacobi_duo_resident<12>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      else if (Team::maxhalf <= 18 || n <= 36) jacobi_duo_resident<18>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      else jacobi_duo_resident<(Team::maxhalf > 18 ? Team::maxhalf : 18)>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      jacobi_done = true;
+    }
+  }
+#endif
+  // circle-method ordering, one column pair per lane (sub-warp and one-warp teams, the host model, AB200_JACOBI_PAIRS builds)
+  if (!jacobi_done) {
     const int np = n + (n & 1), half = np / 2;
     double *nrm2 = sig;                                     // squared column norms (sig is only written after the sweeps)
     for (int sweep = 0; sweep < 30; sweep++) {
@@ -345,18 +513,20 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   }
   // ---- singular values = eigenvalues k of the layer; y = C u in place in A, x = C^-T u through global memory (XNg)
   bool bad = false;
+  const double *rdiag = gup;                               // 1 / C(r,r) = 1 / sqrt(pivot), left there by the Cholesky step
   for (int e = T.rank; e < n; e += T.size) {
     double *col = A + e * LDA;
-    double s2 = 0.0;
-    for (int r = 0; r < n; r++) s2 += col[r] * col[r];
-    const double ke = sqrt(s2);
+    double s2a = 0.0, s2b = 0.0;
+    for (int r = 0; r + 1 < n; r += 2) { s2a += col[r] * col[r]; s2b += col[r + 1] * col[r + 1]; }
+    if (n & 1) s2a += col[n - 1] * col[n - 1];
+    const double ke = sqrt(s2a + s2b);
     sig[e] = ke;
     if (!(ke > 0.0)) { bad = true; continue; }
     double *xg = XNg + (size_t)e * n;
-    if (n <= 12) eig_backtransform<12>(B1, LDB, col, 1.0 / ke, n, xg);
-    else if (n <= 24) eig_backtransform<24>(B1, LDB, col, 1.0 / ke, n, xg);
-    else if (n <= 36) eig_backtransform<36>(B1, LDB, col, 1.0 / ke, n, xg);
-    else eig_backtransform<0>(B1, LDB, col, 1.0 / ke, n, xg);
+    if (n <= 12) eig_backtransform<12>(B1, LDB, rdiag, col, 1.0 / ke, n, xg);
+    else if (n <= 24) eig_backtransform<24>(B1, LDB, rdiag, col, 1.0 / ke, n, xg);
+    else if (n <= 36) eig_backtransform<36>(B1, LDB, rdiag, col, 1.0 / ke, n, xg);
+    else eig_backtransform<0>(B1, LDB, rdiag, col, 1.0 / ke, n, xg);
   }
   if (bad) Z.fail[p] = 1;
   T.sync();                                               // C is dead from here on: B1 becomes XNEG [e*LDB + r]
@@ -366,11 +536,12 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
     if (!(ke > 0.0)) continue;
     double *col = A + e * LDA, *xn = B1 + e * LDB;
     const double *xg = XNg + (size_t)e * n;
-    double nrm = 0.0;
-    for (int r = 0; r < n; r++) { const double s = xg[r] / sr[r]; nrm += s * s; }
-    const double inr = 1.0 / sqrt(nrm);
+    double nrm = 0.0, nrm1 = 0.0;
+    for (int r = 0; r + 1 < n; r += 2) { const double s = xg[r] * sr[r], s1 = xg[r + 1] * sr[r + 1]; nrm += s * s; nrm1 += s1 * s1; }
+    if (n & 1) { const double s = xg[n - 1] * sr[n - 1]; nrm += s * s; }
+    const double inr = 1.0 / sqrt(nrm + nrm1), ikr = inr / ke;
     for (int r = 0; r < n; r++) {
-      const double sg = xg[r] / sr[r] * inr, df = col[r] / (sr[r] * ke) * inr;
+      const double sg = xg[r] * sr[r] * inr, df = col[r] * sr[r] * ikr;
       col[r] = 0.5 * (sg + df);            // XPOS(i,o,e)
       xn[r] = 0.5 * (sg - df);             // XNEG(i,o,e)
     }

@@ -284,6 +284,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   VLConv CV; CV.total = A.take<double>(vchunk * 4); CV.state = A.take<int>(vchunk * 4); CV.col_active = A.take<int>(chunk);
   int *listA = A.take<int>(chunk), *listB = A.take<int>(chunk), *counts = A.take<int>(2 * (NM + 4));
   double *d_pq = A.take<double>((size_t)(NM + 1) * N * 3 * (NM + 1));
+  unsigned short *d_jsched = A.take<unsigned short>(4096);          // Jacobi pair schedule of K2's two-warp teams (<= 64 rounds x 32 slots)
   double *work = A.take<double>((size_t)solvers * work_per_solver);
   double *wglob = (!use_add && PB.window) ? A.take<double>((size_t)solvers * PB.window) : nullptr;
   unsigned char *d_skip = A.take<unsigned char>(nview);
@@ -306,6 +307,14 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
         for (int l = m; l <= NM; l++) for (int c = 0; c < 3; c++) h_pq[(size_t)m * (NM + 1) * N * 3 + ((size_t)l * N + i) * 3 + c] = tmp[3 * l + c];
       }
     AB_CUDA_OK(cudaMemcpyAsync(d_pq, h_pq.data(), h_pq.size() * 8, cudaMemcpyHostToDevice, st));
+    std::vector<unsigned short> h_js;
+    if ((PE.kind == 3 || PE.kind == 4) && !getenv("AB200_VL_JACOBI_CIRCLE")) {      // two-warp eigen teams: resident-column pair schedule
+      const int rounds = jacobi_schedule(n, h_js);
+      if (h_js.size() <= 4096) {
+        AB_CUDA_OK(cudaMemcpyAsync(d_jsched, h_js.data(), h_js.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
+        QD.jsched = d_jsched; QD.jrounds = rounds;
+      }
+    }
     AB_CUDA_OK(cudaStreamSynchronize(st));
   }
   // ---- skip mask and the FOCORR_NADIR state quirk (first obs with solar_zenith == 0.0 that is actually run)
