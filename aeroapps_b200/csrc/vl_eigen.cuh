@@ -39,9 +39,13 @@ struct VLQuad {                // quadrature (pixel independent)
 };
 
 // Host: the recursive fixed / moving tournament for n columns (see jacobi_duo_resident).  out[round * half + slot] = a | b << 6 |
-// load_a << 12 | store_a << 13 or 0xFFFF, half = ceil(n / 2) slots per round; returns the number of rounds.
+// load_a << 12 | store_a << 13 or 0xFFFF, half = ceil(n / 2) slots per round, followed by one entry per round: 1 = the round must end
+// with a team barrier (a column crosses from one warp's slots to the other's), 0 = a warp-level barrier is enough.  Slots
+// [0, ppw) belong to warp 0, the rest to warp 1.  The top-level phase (F against M) is split in two halves that keep the moving
+// columns inside one warp (F0 x M0 with F1 x M1, then F0 x M1 with F1 x M0), and every later phase is warp-local by construction, so
+// a sweep needs a handful of team barriers instead of one per round.  Returns the number of rounds.
 inline int jacobi_schedule(int n, std::vector<unsigned short> &out) {
-  const int half = (n + (n & 1)) / 2;
+  const int half = (n + (n & 1)) / 2, ppw = (half + 1) / 2;
   std::vector<std::vector<int>> ra, rb;                    // [round][slot] -> column or -1
   auto ensure = [&](size_t r) { while (ra.size() <= r) { ra.emplace_back(half, -1); rb.emplace_back(half, -1); } };
   struct Job { std::vector<int> cols; int slot0, round0; };
@@ -52,17 +56,40 @@ inline int jacobi_schedule(int n, std::vector<unsigned short> &out) {
     const int sz = (int)j.cols.size();
     if (sz < 2) continue;
     const int hf = sz / 2, nm = sz - hf;
-    for (int s = 0; s < nm; s++) {
-      ensure((size_t)j.round0 + s);
-      for (int t = 0; t < hf; t++) { ra[j.round0 + s][j.slot0 + t] = j.cols[t]; rb[j.round0 + s][j.slot0 + t] = j.cols[hf + (t + s) % nm]; }
+    int used = nm;                                         // rounds of this job's cross phase
+    const int f0 = ppw - j.slot0, f1 = hf - f0;            // fixed columns on warp 0 / warp 1 (when the job spans both)
+    const int m0 = nm / 2, m1 = nm - m0;
+    if (j.slot0 < ppw && f1 > 0 && m0 >= f0 && m0 >= f1) { // (m1 >= m0) warp-local halves
+      for (int ph = 0; ph < 2; ph++) {
+        const int base = ph == 0 ? 0 : m1;                 // phase a takes max(m0, m1) = m1 rounds, phase b the same
+        for (int s = 0; s < m1; s++) {
+          ensure((size_t)j.round0 + base + s);
+          for (int t = 0; t < hf; t++) {
+            const bool w1 = t >= f0;                       // slot on warp 1
+            const bool first = (ph == 0) ? !w1 : w1;       // which half of M this slot meets in this phase: M0 (first) or M1
+            const int off = first ? 0 : m0, len = first ? m0 : m1, tl = w1 ? t - f0 : t;
+            if (s >= len) continue;                        // the shorter half idles in the last round of the phase
+            ra[j.round0 + base + s][j.slot0 + t] = j.cols[t];
+            rb[j.round0 + base + s][j.slot0 + t] = j.cols[hf + off + (tl + s) % len];
+          }
+        }
+      }
+      used = 2 * m1;
+    } else {
+      for (int s = 0; s < nm; s++) {
+        ensure((size_t)j.round0 + s);
+        for (int t = 0; t < hf; t++) { ra[j.round0 + s][j.slot0 + t] = j.cols[t]; rb[j.round0 + s][j.slot0 + t] = j.cols[hf + (t + s) % nm]; }
+      }
     }
     Job f, m;
-    f.cols.assign(j.cols.begin(), j.cols.begin() + hf); f.slot0 = j.slot0; f.round0 = j.round0 + nm;
-    m.cols.assign(j.cols.begin() + hf, j.cols.end()); m.slot0 = j.slot0 + hf / 2; m.round0 = j.round0 + nm;
+    f.cols.assign(j.cols.begin(), j.cols.begin() + hf); f.slot0 = j.slot0; f.round0 = j.round0 + used;
+    m.cols.assign(j.cols.begin() + hf, j.cols.end()); m.slot0 = j.slot0 + hf / 2; m.round0 = j.round0 + used;
+    // keep a whole sub-tournament on one warp when it fits: the moving half starts on warp 1's first slot
+    if (sz == n && hf / 2 <= ppw && nm / 2 <= half - ppw) m.slot0 = ppw;
     todo.push_back(f); todo.push_back(m);
   }
   const int R = (int)ra.size();
-  out.assign((size_t)R * half, 0xFFFF);
+  out.assign((size_t)R * half + R, 0xFFFF);
   for (int r = 0; r < R; r++)
     for (int t = 0; t < half; t++) {
       if (ra[r][t] < 0) continue;
@@ -70,6 +97,27 @@ inline int jacobi_schedule(int n, std::vector<unsigned short> &out) {
       const bool store = r == R - 1 || ra[r + 1][t] != ra[r][t];
       out[(size_t)r * half + t] = (unsigned short)(ra[r][t] | (rb[r][t] << 6) | (load ? 0x1000 : 0) | (store ? 0x2000 : 0));
     }
+  // team barrier after round r iff round r + 1 reads (from shared memory) a column that the OTHER warp has written since the last one
+  std::vector<int> writer(n, -1);                          // warp that stored the column since the last team barrier
+  for (int r = 0; r < R; r++) {
+    for (int t = 0; t < half; t++) {
+      if (ra[r][t] < 0) continue;
+      const int w = t >= ppw;
+      writer[rb[r][t]] = w;
+      if (out[(size_t)r * half + t] & 0x2000) writer[ra[r][t]] = w;
+    }
+    bool need = (r == R - 1);                              // the sweep ends with one (norms are recomputed by the whole team)
+    if (r + 1 < R)
+      for (int t = 0; t < half && !need; t++) {
+        if (ra[r + 1][t] < 0) continue;
+        const int w = t >= ppw;
+        const int cb = rb[r + 1][t], ca = ra[r + 1][t];
+        if (writer[cb] >= 0 && writer[cb] != w) need = true;
+        if ((out[(size_t)(r + 1) * half + t] & 0x1000) && writer[ca] >= 0 && writer[ca] != w) need = true;
+      }
+    out[(size_t)R * half + r] = need ? 1 : 0;
+    if (need) std::fill(writer.begin(), writer.end(), -1);
+  }
   return R;
 }
 
@@ -240,7 +288,7 @@ DEVFN void jacobi_duo_resident(const Team &T, double *AB_RESTRICT A, int LDA, in
           if (h == 0) nrm2[a] = na2;
         }
       }
-      T.sync();
+      if (sch[nrounds * half + rd]) T.sync(); else __syncwarp();   // team barrier only where a column changes warps (host flag)
       e = en;
     }
     int dummy = 0;
