@@ -213,14 +213,18 @@ DEVFN double jacobi_halfpair(double *AB_RESTRICT a, double *AB_RESTRICT b, int r
 // of a slot stays in the registers of its two lanes for a whole phase: per rotation ONE column is loaded from and stored to shared
 // memory instead of two, which is what binds this kernel (column traffic of the rotations = 3/4 of its shared-memory wavefronts).
 // Entry: a | b << 6 | load_a << 12 | store_a << 13, 0xFFFF = slot idle in this round.
-template <int NRH, class Team>
+// LP lanes per pair: 2 (row halves on lanes 16 apart) or 3 (row thirds on neighbouring lanes: 27 busy lanes per warp at n = 36, a
+// third fewer instructions per rotation); NRH >= rows per lane.
+template <int NRH, int LP, class Team>
 DEVFN void jacobi_duo_resident(const Team &T, double *AB_RESTRICT A, int LDA, int n, double *AB_RESTRICT nrm2,
                                const unsigned short *AB_RESTRICT sch, int nrounds) {
   const int np = n + (n & 1), half = np / 2;
-  const int ppw = (half + 1) / 2, w = T.rank >> 5, lane = T.rank & 31, h = lane >> 4;
-  const int t = w * ppw + (lane & 15);
-  const bool act = (lane & 15) < ppw && t < half;
-  const int nh = (n + 1) / 2, r0 = h ? nh : 0, nr = h ? n - nh : nh;
+  const int ppw = (half + 1) / 2, w = T.rank >> 5, lane = T.rank & 31;
+  const int h = LP == 2 ? lane >> 4 : lane % 3, tl = LP == 2 ? (lane & 15) : lane / 3, lbase = lane - h;
+  const int t = w * ppw + tl;
+  const bool act = tl < ppw && t < half;
+  const int nseg = (n + LP - 1) / LP, r0 = h * nseg, nr = (n - r0 < nseg) ? (n - r0 > 0 ? n - r0 : 0) : nseg;
+  (void)lbase;
   double ra[NRH], na2 = 0.0;
 #pragma unroll
   for (int r = 0; r < NRH; r++) ra[r] = 0.0;
@@ -255,7 +259,8 @@ DEVFN void jacobi_duo_resident(const Team &T, double *AB_RESTRICT A, int LDA, in
 #pragma unroll
         for (int r = 0; r < NRH; r++) gap[r & 3] += ra[r] * rb[r];
         double ga = (gap[0] + gap[1]) + (gap[2] + gap[3]);
-        ga += __shfl_xor_sync(rmask, ga, 16);
+        if (LP == 2) ga += __shfl_xor_sync(rmask, ga, 16);
+        else ga = (__shfl_sync(rmask, ga, lbase) + __shfl_sync(rmask, ga, lbase + 1)) + __shfl_sync(rmask, ga, lbase + 2);   // same order on all three lanes
         const double al = na2, be = nb2;
         // rel = |cos(a,b)| only feeds the convergence test; the rotation is gated by the equivalent product form and its parameters
         // come from two reciprocal square roots on the dependent chain (the textbook t = g2 / (d + sign(d) sqrt(d^2 + g2^2)),
@@ -481,10 +486,9 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   if constexpr (Team::size == 64) {
     // two-warp teams: row halves of a pair on two lanes, the slot's fixed column resident in registers (schedule from the host)
     if (QD.jsched != nullptr) {
-      if (n <= 12) jacobi_duo_resident<6>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
-      else if (n <= 24) jacobi_duo_resident<12>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
-      else if (Team::maxhalf <= 18 || n <= 36) jacobi_duo_resident<18>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
-      else jacobi_duo_resident<(Team::maxhalf > 18 ? Team::maxhalf : 18)>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      if (n <= 24) jacobi_duo_resident<8, 3>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      else if (Team::maxhalf <= 18 || n <= 36) jacobi_duo_resident<12, 3>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
+      else jacobi_duo_resident<(Team::maxhalf > 18 ? Team::maxhalf : 18), 2>(T, A, LDA, n, sig, QD.jsched, QD.jrounds);
       jacobi_done = true;
     }
   }
