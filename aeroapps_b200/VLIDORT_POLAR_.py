@@ -211,6 +211,43 @@ def _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs):
     return a[0], a[1], a[2], ngeom
 
 
+def vector_gisscx_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m,
+                        V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Vector_GissCx_Cloud (GV/VLIDORT_BRDF_CX.F90:2276): aerosol + ice + liquid cloud layers over the GISS Cox-Munk ocean.
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI,
+                                                                                              tauL, ssaL, pmomL))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert tauI.shape == tau.shape and tauL.shape == tau.shape and pmomI.shape == pmom.shape and pmomL.shape == pmom.shape
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_gisscx_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp),
+                                                  _p(tau), _p(ssa), _p(pmom), _p(tauI), _p(ssaI), _p(pmomI), _p(tauL), _p(ssaL), _p(pmomL),
+                                                  _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza), C.c_double(MISSING),
+                                                  int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_gisscx_cloud")
+    return (*outs, rc.value)
+
+
+def vector_brdf_modis_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he,
+                            te, kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """f2py VECTOR_BRDF_MODIS_CLOUD (VLIDORT_POLAR_py.F90:43): returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, kernel_wt, param, flux_factor = (
+        _F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, kernel_wt, param, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert tauI.shape == tau.shape and tauL.shape == tau.shape and pmomI.shape == pmom.shape and pmomL.shape == pmom.shape
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_brdf_modis_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                      kernel_wt.shape[0], param.shape[0], _p(ROT), _p(dp), _p(alpha), _p(tau), _p(ssa), _p(pmom),
+                                                      _p(tauI), _p(ssaI), _p(pmomI), _p(tauL), _p(ssaL), _p(pmomL), _p(pe), _p(he), _p(te),
+                                                      _p(kernel_wt), _p(param), _p(sza), _p(raa), _p(vza), _p(flux_factor), C.c_double(MISSING),
+                                                      int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_brdf_modis_cloud")
+    return (*outs, rc.value)
+
+
 def vector_lambert_multigeom(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, albedo,
                              solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
     """returns (radiance, reflectance, Q, U (nobs,nch,ngeom), rc)"""

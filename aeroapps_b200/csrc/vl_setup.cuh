@@ -20,6 +20,10 @@ struct VLIn {                 // device pointers in the reference's Fortran layo
   const double *alpha;        // (km,nobs,nch) or null
   const double *tau, *ssa;    // (km,nch,nobs)
   const double *pmom;         // (km,nch,nobs,nMom,nPol)
+  // cloud variants (VLIDORT_Run_Vector_Cloud, V283/VLIDORT_ScatMod.F90:1865-2220): ice and liquid cloud optical depth and single
+  // scattering albedo (km,nch,nobs) and the P11 moments (km,nch,nobs,nMom) -- the reference mixes in the first element of
+  // pmomI / pmomL only (:2125-2131); all six null for the clear-sky entry points
+  const double *tauI, *ssaI, *pmomI, *tauL, *ssaL, *pmomL;
   const double *ze;           // (km+1,nobs) [m]
   const double *albedo;       // (nobs,nch)   (Lambertian)
   const double *sza;          // (nobs): one sun per observation
@@ -172,6 +176,9 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
   const double albedo = in.lambertian ? in.albedo[j + (size_t)in.nobs * i] : 0.0;
   const double cos_sza = cos(sza * DEG_TO_RAD), ustream = cos(DEG_TO_RAD * vza), usec = 1.0 / ustream;
   const double *pm = in.pmom + (size_t)L * (i + (size_t)in.nch * j);       // + k + stride_m*(m + nMom*pol)
+  const bool cloud = in.tauI != nullptr;
+  const double *pmL = cloud ? in.pmomL + (size_t)L * (i + (size_t)in.nch * j) : nullptr;      // P11 only: + k + stride_m*m
+  const double *pmI = cloud ? in.pmomI + (size_t)L * (i + (size_t)in.nch * j) : nullptr;
   const size_t stride_m = (size_t)L * in.nch * in.nobs;
   const double f32_1em3 = (double)1.0e-3f, w_clamp = (double)0.99999f;
   // Rayleigh Greek constants (VLIDORT_ScatMod.F90:456-485); SQRT(6.) is single precision there
@@ -188,11 +195,15 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
     const double ray = in.ROT[k + (size_t)L * (j + (size_t)in.nobs * i)];
     const double alp = in.alpha ? in.alpha[k + (size_t)L * (j + (size_t)in.nobs * i)] : 0.0;
     const double tau = in.tau[k + (size_t)L * (i + (size_t)in.nch * j)], ssa = in.ssa[k + (size_t)L * (i + (size_t)in.nch * j)];
-    const double tau_ext = alp + ray + tau, tau_scat = ray + ssa * tau;
+    const size_t okc = k + (size_t)L * (i + (size_t)in.nch * j);
+    const double tI = cloud ? in.tauI[okc] : 0.0, wI = cloud ? in.ssaI[okc] : 0.0, tL = cloud ? in.tauL[okc] : 0.0, wL = cloud ? in.ssaL[okc] : 0.0;
+    const double tau_ext = cloud ? alp + ray + tau + tL + tI : alp + ray + tau;
+    const double tau_scat = cloud ? ray + ssa * tau + tL * wL + tI * wI : ray + ssa * tau;
     double w = tau_scat / tau_ext;
     if (w > w_clamp) w = w_clamp;
     din[k] = tau_ext; win[k] = w;
     const double aerswt = ssa * tau / tau_scat, rayswt = ray / tau_scat;
+    const double clLswt = wL * tL / tau_scat, clIswt = wI * tI / tau_scat;
     // input checks (VLIDORT_CHECK_INPUT_OPTICAL); greek(0,k,1) is forced to 1 by the glue
     if (!(tau_ext > 0.0) || !(w <= 1.0 - OMEGA_SMALLNUM) || !(w >= OMEGA_SMALLNUM)) flag[0] = 1.0;   // benign race: any writer sets 1
     // delta-M truncation factor from moment 2N of the mixed input
@@ -201,6 +212,7 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
     if (nm1 <= nMom) {
       const double aer = (nm1 <= nMom - 1) ? pm[k + stride_m * (size_t)(nm1 + (size_t)nMom * 0)] : 0.0;
       g2n = aer * aerswt + (nm1 == 2 ? raysmom2 * rayswt : 0.0);
+      if (cloud && nm1 <= nMom - 1) g2n += pmL[k + stride_m * (size_t)nm1] * clLswt + pmI[k + stride_m * (size_t)nm1] * clIswt;
       if (nm1 == 0) g2n = 1.0;
     }
     const double fdel = g2n / (double)(2 * nm1 + 1), fac2 = 1.0 - fdel;
@@ -221,6 +233,7 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
         }
       }
       double g11 = a1 * aerswt, g12 = a2 * aerswt, g22 = a5 * aerswt, g33 = a3 * aerswt;
+      if (cloud && l <= nMom - 1) g11 += pmL[k + stride_m * (size_t)l] * clLswt + pmI[k + stride_m * (size_t)l] * clIswt;
       if (l == 2) { g11 += raysmom2 * rayswt; if (S > 1) { g12 += gammamom2 * rayswt; g22 += alphamom2 * rayswt; } }
       if (l == 0) g11 = 1.0;                      // greekmat_total_input(0,i,1) = 1.0
       if (g11 == 0.0) nzero_tail++;
@@ -436,15 +449,20 @@ DEVFN void setup_pixel(const Team &T, const VLIn &in, const VLPix &X, int p, dou
       const int k = nn - 1;
       const double ray = in.ROT[k + (size_t)L * (j + (size_t)in.nobs * i)];
       const double tau = in.tau[k + (size_t)L * (i + (size_t)in.nch * j)], ssa = in.ssa[k + (size_t)L * (i + (size_t)in.nch * j)];
-      const double tau_scat = ray + ssa * tau, aerswt = ssa * tau / tau_scat, rayswt = ray / tau_scat;
-      double f1 = 0.0, f2 = 0.0;
+      const size_t okc = k + (size_t)L * (i + (size_t)in.nch * j);
+      const double tI = cloud ? in.tauI[okc] : 0.0, wI = cloud ? in.ssaI[okc] : 0.0, tL = cloud ? in.tauL[okc] : 0.0, wL = cloud ? in.ssaL[okc] : 0.0;
+      const double tau_scat = cloud ? ray + ssa * tau + tL * wL + tI * wI : ray + ssa * tau;
+      const double aerswt = ssa * tau / tau_scat, rayswt = ray / tau_scat;
+      double f1 = 0.0, f2 = 0.0, fL = 0.0, fI = 0.0;
       for (int l = 0; l <= nMom - 1; l++) {
         f1 += gs1[l] * pm[k + stride_m * (size_t)(l + (size_t)nMom * 0)];
         if (S > 1 && !in.scalar_glue) f2 += gs2[l] * pm[k + stride_m * (size_t)(l + (size_t)nMom * 1)];
+        if (cloud && l >= 1) { fL += gs1[l] * pmL[k + stride_m * (size_t)l]; fI += gs1[l] * pmI[k + stride_m * (size_t)l]; }
       }
       // l = 0 term of the mixed input is forced to 1; Rayleigh adds l = 2 (and nothing else for 11/12)
       const double a0 = (nMom >= 1) ? pm[k + stride_m * (size_t)(0)] : 0.0;
       f1 = (f1 - gs1[0] * a0) * aerswt + gs1[0] * 1.0;
+      if (cloud) f1 += fL * (wL * tL / tau_scat) + fI * (wI * tI / tau_scat);
       f2 = f2 * aerswt;
       if (nMom >= 2) { f1 += gs1[2] * raysmom2 * rayswt; if (S > 1) f2 += gs2[2] * gammamom2 * rayswt; }
       const double tms = win[k] / (1.0 - trunc[k] * win[k]);

@@ -121,7 +121,7 @@ __global__ void k_vl_init_active(VLPix X, VLConv CV, VLSol Z, int npix_chunk, in
 }
 
 // Rayleigh optical thickness (VLIDORT_ROT_CALC): one thread per (layer, obs, channel)
-__device__ double f_air_dev(double XX2, double C) {
+__host__ __device__ double f_air_dev(double XX2, double C) {
   const double depol1 = (double)1.034f + (double)3.17e-4f * XX2;
   const double depol2 = (double)1.096f + (double)1.385e-3f * XX2 + (double)1.448e-4f * XX2 * XX2;
   const float s3 = (78.084f + 20.946f) + 0.934f;
@@ -195,6 +195,7 @@ struct RunDesc {
   double MISSING;
   // device inputs (Fortran layouts)
   const double *ROT, *depol, *alpha, *tau, *ssa, *pmom, *he, *albedo, *sza, *raa, *vza, *flux_factor;
+  const double *tauI, *ssaI, *pmomI, *tauL, *ssaL, *pmomL;     // cloud variants (pmomI / pmomL: P11 moments only, (km,nch,nobs,nMom)); null otherwise
   // BRDF (device, per pixel) when !lambertian
   VLSurf surf; const double *exactdb;
   const VLBrdf *brdf;              // non-null: the Fourier components are computed per chunk from the wrappers' surface inputs
@@ -331,6 +332,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   in.planpar = R.planpar; in.lambertian = R.lambertian; in.scalar_glue = R.scalar_glue; in.nadir_from_obs = nadir_from; in.ngeom = G;
   in.MISSING = R.MISSING; in.earth_radius = 6371.0;
   in.ROT = R.ROT; in.depol = R.depol; in.alpha = R.alpha; in.tau = R.tau; in.ssa = R.ssa; in.pmom = R.pmom; in.ze = R.he;
+  in.tauI = R.tauI; in.ssaI = R.ssaI; in.pmomI = R.pmomI; in.tauL = R.tauL; in.ssaL = R.ssaL; in.pmomL = R.pmomL;
   in.albedo = R.albedo; in.sza = R.sza; in.raa = R.raa; in.vza = R.vza; in.flux_factor = R.flux_factor; in.exactdb = R.exactdb;
   in.skip = d_skip;
   const double accuracy = (double)0.0001f;
@@ -574,7 +576,11 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int ngeom, i
 
 
 // ------------------------------------------------------------------------------------------------ BRDF wrappers
-struct SurfArgs { int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; const double *alpha = nullptr, *flux_factor = nullptr; };
+struct SurfArgs {
+  int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; const double *alpha = nullptr, *flux_factor = nullptr;
+  // cloud variants (host pointers, full reference shapes): all six set or all null
+  const double *tauI = nullptr, *ssaI = nullptr, *pmomI = nullptr, *tauL = nullptr, *ssaL = nullptr, *pmomL = nullptr;
+};
 
 // pixel-independent BRDF tables -> device
 int build_brdf_tables(VLContext &C, VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, cudaStream_t st) {
@@ -598,7 +604,7 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   const size_t npix = (size_t)nj * nch, nview = npix * G;
   const bool cx = (sa.kind != SURF_MODIS);
   const size_t n_rot = (size_t)km * nj * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nj;
-  const size_t bytes = 8 * (n_rot * 4 + n_pm + n_he + (3 + 2 * (size_t)G) * nj + 2 * nch + 6 * npix + 7 * nview + 16 * nview) + 16 * nview + 4096 * 32;
+  const size_t bytes = 8 * (n_rot * 4 + n_pm + (sa.tauI ? n_rot * (4 + 2 * (size_t)nMom) : 0) + n_he + (3 + 2 * (size_t)G) * nj + 2 * nch + 6 * npix + 7 * nview + 16 * nview) + 16 * nview + 4096 * 40;
   VLContext &C = vl_context();
   std::lock_guard<std::mutex> lock(C.mu);
   AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * nview + 7 * nview) + 16 * nview + 4096 * 8 : bytes));
@@ -622,6 +628,10 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   R.ROT = put(ROT, km, nch); R.depol = putv(depol, nch); R.tau = put(tau, (size_t)km * nch, 1); R.ssa = put(ssa, (size_t)km * nch, 1);
   R.pmom = put(pmom, (size_t)km * nch, (size_t)nMom * nPol); R.he = put(he, km + 1, 1); R.sza = put(sza, 1, 1); R.raa = put(raa, 1, G); R.vza = put(vza, 1, G);
   R.alpha = sa.alpha ? put(sa.alpha, km, nch) : nullptr; R.flux_factor = sa.flux_factor ? put(sa.flux_factor, nch, 1) : nullptr;
+  if (sa.tauI) {                                           // only the P11 block (first nMom moments) of the cloud phase matrices is used
+    R.tauI = put(sa.tauI, (size_t)km * nch, 1); R.ssaI = put(sa.ssaI, (size_t)km * nch, 1); R.pmomI = put(sa.pmomI, (size_t)km * nch, (size_t)nMom);
+    R.tauL = put(sa.tauL, (size_t)km * nch, 1); R.ssaL = put(sa.ssaL, (size_t)km * nch, 1); R.pmomL = put(sa.pmomL, (size_t)km * nch, (size_t)nMom);
+  }
   const double *d_u = cx ? put(sa.u10m, 1, 1) : nullptr, *d_v = cx ? put(sa.v10m, 1, 1) : nullptr, *d_mr = cx ? putv(sa.mr, nch) : nullptr;
   const double *d_kw = cx ? nullptr : put(sa.kernel_wt, (size_t)3 * nch, 1), *d_pr = cx ? nullptr : put(sa.param, (size_t)2 * nch, 1);
   double *d_exact = put(nullptr, 16, (size_t)nch * G);
@@ -920,6 +930,57 @@ extern "C" int ab200_vlidort_vector_ocigisscx(int km, int nch, int nobs, const d
   (void)channels; (void)pe; (void)te; (void)verbose;
   SurfArgs sa = {SURF_OCIGISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U, alpha, flux_factor};
   return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+// ---- cloud variants: VLIDORT_Run_Vector_Cloud mixes ice and liquid cloud layers into the optical input (P11 moments of pmomI / pmomL only)
+//      and takes the Rayleigh depolarisation from the wavelength, not from the caller's depol (V283/VLIDORT_ScatMod.F90:2031-2032)
+static void cloud_depol(int nch, const double *channels, std::vector<double> &dp) {
+  dp.resize(nch > 0 ? nch : 0);
+  const double C = (double)(360.0f * 1e-6f);
+  for (int i = 0; i < nch; i++) {
+    const double X = channels[i] * (double)1.e-3f, XX = 1.0 / X, fa = f_air_dev(XX * XX, C);
+    dp[i] = 6.0 * (fa - 1.0) / (7.0 * fa + 3.0);
+  }
+}
+static bool cloud_args_ok(int npix, const double *channels, const double *a, const double *b, const double *c, const double *d, const double *e,
+                          const double *f) {
+  if (npix > 0 && (!channels || !a || !b || !c || !d || !e || !f)) { ab200_set_error("cloud variant: NULL cloud array or channels"); return false; }
+  return true;
+}
+extern "C" int ab200_vlidort_vector_gisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                 int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                                 const double *pmom, const double *tauI, const double *ssaI, const double *pmomI,
+                                                 const double *tauL, const double *ssaL, const double *pmomL, const double *pe,
+                                                 const double *he, const double *te, const double *U10m, const double *V10m, const double *mr,
+                                                 const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                                 double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                                 double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)depol; (void)pe; (void)te; (void)verbose;
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_brdf_modis_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                     int nMom, int nPol, int nkernel, int nparam, const double *ROT, const double *depol,
+                                                     const double *alpha, const double *tau, const double *ssa, const double *pmom,
+                                                     const double *tauI, const double *ssaI, const double *pmomI, const double *tauL,
+                                                     const double *ssaL, const double *pmomL, const double *pe, const double *he,
+                                                     const double *te, const double *kernel_wt, const double *param,
+                                                     const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                                     const double *flux_factor, double MISSING, int verbose, double *radiance_VL_SURF,
+                                                     double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U,
+                                                     int *rc) {
+  (void)depol; (void)pe; (void)te; (void)verbose;
+  if (nkernel != 3 || nparam != 2) { ab200_set_error("vector_brdf_modis_cloud: nkernel must be 3 and nparam 2 (GV/VLIDORT_BRDF_MODIS.F90:851-852)"); return AB200_ERR_ARG; }
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("vector_brdf_modis_cloud: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U, alpha, flux_factor};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 extern "C" int ab200_vlidort_scalar_gisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,

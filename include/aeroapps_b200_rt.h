@@ -115,6 +115,31 @@ int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const double *cha
                                     const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
                                     double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
                                     double *BR, int *rc);
+/* ---- cloud variants: the entry points whose reference wrapper calls VLIDORT_Run_Vector_Cloud
+ * (V283/VLIDORT_ScatMod.F90:1865-2220): ice (tauI, ssaI, pmomI) and liquid (tauL, ssaL, pmomL) cloud layers are added to the extinction
+ * and scattering optical depth and their P11 moments to the Greek matrix (only the first element of pmomI / pmomL is used, :2125-2131);
+ * the Rayleigh depolarisation ratio is recomputed from the wavelength (:2031-2032), the depol argument is not used.
+ * tauI, ssaI, tauL, ssaL (km,nch,nobs); pmomI, pmomL (km,nch,nobs,nMom,nPol).
+ * VLIDORT_Vector_GissCx_Cloud (GV/VLIDORT_BRDF_CX.F90:2276-2467) */
+int ab200_vlidort_vector_gisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                      int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                      const double *pmom, const double *tauI, const double *ssaI, const double *pmomI,
+                                      const double *tauL, const double *ssaL, const double *pmomL, const double *pe, const double *he,
+                                      const double *te, const double *U10m, const double *V10m, const double *mr,
+                                      const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                      double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                      double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_LandMODIS_Cloud_SingleGeom (GV/VLIDORT_BRDF_MODIS.F90:825-1053; f2py VECTOR_BRDF_MODIS_CLOUD,
+ * LV/VLIDORT_POLAR_py.F90:43-134): with trace-gas absorption alpha (km,nobs,nch) and solar flux flux_factor (nch,nobs) */
+int ab200_vlidort_vector_brdf_modis_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                          int nPol, int nkernel, int nparam, const double *ROT, const double *depol, const double *alpha,
+                                          const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                          const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                          const double *pmomL, const double *pe, const double *he, const double *te,
+                                          const double *kernel_wt, const double *param, const double *solar_zenith,
+                                          const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                          double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                          double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
 /* ab200_vlidort_vector_cx with every array (inputs and outputs) resident in device memory; stream = cudaStream_t */
 int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
                                 const double *ROT, const double *depol, const double *tau, const double *ssa,

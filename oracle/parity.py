@@ -39,11 +39,14 @@ def oracle_parallel(kind, S, N, planpar, sc, nthreads=None, scalar_glue=False, M
     else:
         ranges = [(int(j), int(j) + 1) for j in obs]
     vg.set_asymtx_tolerance(asymtx_tol)
+    if "tauI" in sc:
+        vg.set_cloud(sc)                                          # cloud variants: mixed into the glue of every run below
     try:
         with ThreadPoolExecutor(nthreads) as ex:
             parts = list(ex.map(lambda ab: _run(kind, S, N, planpar, sc, ab, scalar_glue, MISSING), ranges))
     finally:
         vg.set_asymtx_tolerance(1e-12)
+        vg.set_cloud(None)
     out = {}
     for k in KEYS:
         if k not in parts[0]:

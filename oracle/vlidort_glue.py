@@ -60,6 +60,22 @@ def set_asymtx_tolerance(tol=1e-12):
     vo.lib().orc_set_asymtx_tolerance(C.c_double(tol))
 
 
+_cloud_keep = None
+
+
+def set_cloud(sc=None):
+    """register (sc: dict with tauI, ssaI, pmomI, tauL, ssaL, pmomL, channels) or clear (None) the cloud inputs mixed into the glue of the
+    following oracle runs: VLIDORT_Run_Vector_Cloud (V283/VLIDORT_ScatMod.F90:1865-2220)"""
+    global _cloud_keep
+    if sc is None:
+        _cloud_keep = None
+        vo.lib().orc_set_cloud(None, None, None, None, None, None, None)
+        return
+    keep = [F(sc[k]) for k in ("tauI", "ssaI", "pmomI", "tauL", "ssaL", "pmomL")] + [np.ascontiguousarray(sc["channels"], dtype=np.float64)]
+    _cloud_keep = keep                                            # the oracle holds raw pointers: keep the arrays alive
+    vo.lib().orc_set_cloud(*[_p(a) for a in keep])
+
+
 class _OrcSurface(C.Structure):
     _fields_ = [("kind", C.c_int)] + [(n, C.POINTER(C.c_double)) for n in ("u10m", "v10m", "mr", "kernel_wt", "param", "BR", "BR_Q", "BR_U")]
 

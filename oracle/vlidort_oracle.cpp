@@ -669,6 +669,31 @@ static inline bool is_missing(double x, double MISSING) { return std::fabs(x / M
 static double g_asymtx_tolerance = 1.0e-12;
 extern "C" void orc_set_asymtx_tolerance(double tol) { g_asymtx_tolerance = tol; }
 
+/* Cloud variants (VLIDORT_Run_Vector_Cloud_SingleGeom, V283/VLIDORT_ScatMod.F90:1865-2220).  The arrays registered here are mixed into
+ * the glue of the NEXT orc_vlidort_run* calls until cleared with all-NULL arguments (test infrastructure: set once, then run the
+ * observation ranges in parallel, then clear):  tau_ext += tauL + tauI, tau_scat += tauL ssaL + tauI ssaI (:2095-2097),
+ * greekmat(l,.,1) += pmomL(.,l+1,1) clLswt + pmomI(.,l+1,1) clIswt (:2125-2145: only the first element of the cloud matrices is
+ * used), DEPOL_RATIO = coef_depol(wavelength * 1.E-3) instead of the caller's depol (:2031-2032, coef_depol :249-281). */
+static const double *g_cl_tauI = nullptr, *g_cl_ssaI = nullptr, *g_cl_pmomI = nullptr, *g_cl_tauL = nullptr, *g_cl_ssaL = nullptr,
+                    *g_cl_pmomL = nullptr, *g_cl_channels = nullptr;
+extern "C" void orc_set_cloud(const double *tauI, const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                              const double *pmomL, const double *channels) {
+  g_cl_tauI = tauI; g_cl_ssaI = ssaI; g_cl_pmomI = pmomI; g_cl_tauL = tauL; g_cl_ssaL = ssaL; g_cl_pmomL = pmomL; g_cl_channels = channels;
+}
+static double orc_f_air(double XX2, double C) {               /* F_air, VLIDORT_ScatMod.F90:265-281 (single-precision literals) */
+  const double depol1 = (double)1.034f + (double)3.17e-4f * XX2;
+  const double depol2 = (double)1.096f + (double)1.385e-3f * XX2 + (double)1.448e-4f * XX2 * XX2;
+  const double depol3 = 1.0, depol4 = (double)1.15f;
+  const float den = (78.084f + 20.946f) + 0.934f;             /* the three constants are added in real*4 before C*100.0 promotes the sum */
+  return ((double)78.084f * depol1 + (double)20.946f * depol2 + (double)0.934f * depol3 + C * (double)100.0f * depol4) /
+         ((double)den + C * (double)100.0f);
+}
+static double orc_coef_depol(double X) {                      /* coef_depol, :249-263 */
+  const double XX = 1.0 / X, XX2 = XX * XX;
+  const double C = (double)(360.0f * 1e-6f);
+  return 6.0 * (orc_f_air(XX2, C) - 1.0) / (7.0 * orc_f_air(XX2, C) + 3.0);
+}
+
 extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel,
                     int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
                     const double *tau, const double *ssa, const double *pmom, const double *he,
@@ -731,7 +756,8 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
         }
       }
       if (sza[j] == 0.0) nadir_state = true;
-      const double dep = depol[i];
+      const bool cloud = g_cl_tauI != nullptr && !scalar_glue;
+      const double dep = cloud ? orc_coef_depol(g_cl_channels[i] * (double)1.e-3f) : depol[i];
       const double gammamom2 = -sqrt6f * (1.0 - dep) / (2.0 + dep), alphamom2 = 6.0 * (1.0 - dep) / (2.0 + dep);
       const double raysmom2 = (1.0 - dep) / (2.0 + dep);
       std::fill(greek.begin(), greek.end(), 0.0);
@@ -739,11 +765,16 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
       for (int k = 0; k < L; k++) {
         const double ray = ROT[k + (size_t)L * (j + (size_t)nobs * i)], alp = alpha ? alpha[k + (size_t)L * (j + (size_t)nobs * i)] : 0.0;
         const double t = tau[k + (size_t)L * (i + (size_t)nch * j)], w = ssa[k + (size_t)L * (i + (size_t)nch * j)];
-        const double tau_ext = alp + ray + t, tau_scat = ray + w * t;
+        const size_t okc = k + (size_t)L * (i + (size_t)nch * j);
+        const double tI = cloud ? g_cl_tauI[okc] : 0.0, wI = cloud ? g_cl_ssaI[okc] : 0.0, tL = cloud ? g_cl_tauL[okc] : 0.0,
+                     wL = cloud ? g_cl_ssaL[okc] : 0.0;
+        const double tau_ext = cloud ? alp + ray + t + tL + tI : alp + ray + t;
+        const double tau_scat = cloud ? ray + w * t + tL * wL + tI * wI : ray + w * t;
         double ssa_tot = tau_scat / tau_ext;
         if (ssa_tot > wclamp) ssa_tot = wclamp;
         dtau[k] = tau_ext; omg[k] = ssa_tot;
         const double aerswt = w * t / tau_scat, rayswt = ray / tau_scat;
+        const double clLswt = wL * tL / tau_scat, clIswt = wI * tI / tau_scat;
         auto PM = [&](int l, int pol) { return pmom[k + (size_t)L * (i + (size_t)nch * (j + (size_t)nobs * (l + (size_t)nMom * pol)))]; };
 #define GK_(l, q) greek[((size_t)(l) * L + k) * 16 + (q)]
         if (scalar_glue) {
@@ -760,6 +791,10 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
             if (l == 1) r[15] = 3.0 * (1.0 - 2.0 * dep) / (2.0 + dep);
             if (l == 2) { r[0] = raysmom2; r[1] = gammamom2; r[4] = gammamom2; r[5] = alphamom2; }
             for (int q = 0; q < 16; q++) GK_(l, q) = (l <= 2 ? r[q] * rayswt : 0.0) + a[q] * aerswt;
+            if (cloud && l <= nMom - 1) {
+              const size_t oc = k + (size_t)L * (i + (size_t)nch * (j + (size_t)nobs * (size_t)l));     /* (k,i,j,l+1,1) */
+              GK_(l, 0) += g_cl_pmomL[oc] * clLswt + g_cl_pmomI[oc] * clIswt;
+            }
           }
           GK_(0, 0) = 1.0;
         }

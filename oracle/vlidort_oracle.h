@@ -62,6 +62,9 @@ int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nch, int nobs
                     double *radiance, double *reflectance, double *Q, double *U, int *nfourier, int *status,
                     const orc_surface *sf);
 void orc_set_asymtx_tolerance(double tol);   /* default 1e-12 = the reference glue's value */
+/* cloud inputs of VLIDORT_Run_Vector_Cloud for the following runs; all NULL clears them (see vlidort_oracle.cpp) */
+void orc_set_cloud(const double *tauI, const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                   const double *pmomL, const double *channels);
 /* VLIDORT_ROT_CALC (GV/VLIDORT_ROT.F90:19-86 -> V283/VLIDORT_ScatMod.F90:143-281) */
 void orc_rot_calc(int km, int nch, int nobs, const double *channels, const double *pe, const double *he,
                   const double *te, double *ROT, double *depol);
