@@ -148,6 +148,30 @@ module ab200_c_api
          real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
          integer(c_int), intent(out) :: rc
       end function
+      integer(c_int) function ab200_vlidort_vector_gisscx_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, &
+                                                                tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sza, raa, vza, &
+                                                                MISSING, verbose, rad, refl, BR, Q, U, BR_Q, BR_U, rc) &
+                                                                bind(C, name="ab200_vlidort_vector_gisscx_cloud")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), tauI(*), ssaI(*), pmomI(*), tauL(*), ssaL(*), pmomL(*)
+         real(c_double), intent(in)  :: pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_brdf_modis_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, nkernel, nparam, ROT, depol, &
+                                                                    alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, kernel_wt, param, &
+                                                                    sza, raa, vza, flux_factor, MISSING, verbose, rad, refl, BR, Q, U, BR_Q, BR_U, rc) &
+                                                                    bind(C, name="ab200_vlidort_vector_brdf_modis_cloud")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, nkernel, nparam, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), alpha(*), tau(*), ssa(*), pmom(*), tauI(*), ssaI(*), pmomI(*), tauL(*), ssaL(*), pmomL(*)
+         real(c_double), intent(in)  :: pe(*), he(*), te(*), kernel_wt(*), param(*), sza(*), raa(*), vza(*), flux_factor(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
    end interface
 contains
    ! the optional switches of the reference's vector wrappers (GV/VLIDORT_LAMBERT.F90:176,350; GV/VLIDORT_BRDF_MODIS.F90:210,417):
@@ -369,6 +393,24 @@ contains
                                            radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc)
       if (ier /= 0 .and. rc == 0) rc = ier
    end subroutine VLIDORT_Vector_OCIGissCX
+   subroutine VLIDORT_Vector_GissCx_Cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, &
+                                          tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                          radiance_VL_SURF, reflectance_VL_SURF, Q, U, BRDF, BRDF_Q, BRDF_U, rc)    ! VLIDORT_BRDF_CX.F90:2276-2467
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: tauI(km,nch,nobs), ssaI(km,nch,nobs), pmomI(km,nch,nobs,nMom,nPol), tauL(km,nch,nobs), ssaL(km,nch,nobs)
+      real*8,  intent(in)  :: pmomL(km,nch,nobs,nMom,nPol), pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), Q(nobs,nch), U(nobs,nch)
+      real*8,  intent(out) :: BRDF(nobs,nch), BRDF_Q(nobs,nch), BRDF_U(nobs,nch)
+      integer, intent(out) :: rc
+      integer :: ier
+      ier = ab200_vlidort_vector_gisscx_cloud(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, pmom, &
+                                              tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth, &
+                                              sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_GissCx_Cloud
 end module VLIDORT_BRDF_CX
 
 module VLIDORT_BRDF_MODIS               ! replaces geo_vlidort/VLIDORT_BRDF_MODIS.F90:206-410
@@ -439,4 +481,31 @@ contains
                                             radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc)
       if (ier /= 0 .and. rc == 0) rc = ier
    end subroutine VLIDORT_Vector_LandMODIS_SingleGeom
+   ! VLIDORT_Vector_LandMODIS_Cloud_SingleGeom (VLIDORT_BRDF_MODIS.F90:825-1053): the specific the f2py VECTOR_BRDF_MODIS_CLOUD reaches;
+   ! the optional DO_2OS_CORRECTION / DO_BOA switches are refused like in the clear-sky forms
+   subroutine VLIDORT_Vector_LandMODIS_Cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, &
+                                             tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, kernel_wt, param, solar_zenith, relat_azymuth, &
+                                             sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, &
+                                             BR_U, rc, DO_2OS_CORRECTION, DO_BOA)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), alpha(km,nobs,nch), tau(km,nch,nobs), ssa(km,nch,nobs)
+      real*8,  intent(in)  :: pmom(km,nch,nobs,nMom,nPol), tauI(km,nch,nobs), ssaI(km,nch,nobs), pmomI(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: tauL(km,nch,nobs), ssaL(km,nch,nobs), pmomL(km,nch,nobs,nMom,nPol), pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs)
+      real*8,  intent(in)  :: kernel_wt(3,nch,nobs), param(2,nch,nobs), solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs)
+      real*8,  intent(in)  :: flux_factor(nch,nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BR(nobs,nch), Q(nobs,nch), U(nobs,nch)
+      real*8,  intent(out) :: BR_Q(nobs,nch), BR_U(nobs,nch)
+      integer, intent(out) :: rc
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
+      integer :: ier
+      if (ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)) then
+         rc = -2; return
+      end if
+      ier = ab200_vlidort_vector_brdf_modis_cloud(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, 3, 2, ROT, depol, alpha, &
+                                                  tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, kernel_wt, param, solar_zenith, &
+                                                  relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, &
+                                                  BR, Q, U, BR_Q, BR_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_LandMODIS_Cloud
 end module VLIDORT_BRDF_MODIS
