@@ -26,6 +26,9 @@ struct VLSol {                 // per problem q = c*L + k (pixel c, layer k; str
   double *aterm, *bterm, *gam_m, *gam_p;   // [q][n]
   double *wupper, *wlower;     // [q][2N*S]
   int *fail;                   // [p] set !=0 when an eigenproblem fails
+  // generalized spherical functions P, R, T (l = 0..NM) of the current Fourier component at the user cosines [v][3(NM+1)] and at the solar
+  // cosine [c][3(NM+1)], filled once per Fourier term by k_vl_pi_angles; null: every problem computes its own (host model)
+  const double *piu_g, *pi0_g;
 };
 
 #ifdef AB_HM_SWEEP_HIST
@@ -359,8 +362,9 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   double *B1 = scr, *A = B1 + n * LDB;
   double *sig = A + n * LDA, *sr = sig + n, *dpi = sr + n, *dmi = dpi + n, *gup = dmi + n, *gdn = gup + n;
   double *KK = gdn + n;               // 12n: user-stream operators [(2*ud+pn)*S+o][r]
-  double *piu = KK + 12 * n;          // 3*(NM+1)  user-stream P,R,T
-  double *pi0 = piu + 3 * (NM + 1);   // 3*(NM+1)  solar P,R,T
+  double *piu_s = KK + 12 * n;        // 3*(NM+1)  user-stream P,R,T (when not precomputed)
+  double *pi0_s = piu_s + 3 * (NM + 1);   // 3*(NM+1)  solar P,R,T (when not precomputed)
+  const double *pi0 = Z.pi0_g ? Z.pi0_g + (size_t)p * 3 * (NM + 1) : pi0_s;
   const double *og = og_ptr(X, p);                          // [(l*L + k)*4]
   const int G = X.G;
   const double *sc = X.scal + (size_t)view0(X, p) * 16;     // sun / flux: the same for every view of the pixel
@@ -371,7 +375,7 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   double *XPg = Z.xp + q * n * n, *XNg = Z.xn + q * n * n;
 
   // ---- generalized spherical functions at the solar cosine (the user cosines follow per view further down)
-  if (T.rank == (T.size > 1 ? 1 : 0)) pi_prt(m, NM, sc[0], pi0);
+  if (!Z.pi0_g && T.rank == (T.size > 1 ? 1 : 0)) pi_prt(m, NM, sc[0], pi0_s);
   for (int r = T.rank; r < n; r += T.size) { const int i = r / S; sr[r] = 1.0 / sqrt(QD.w[i] * QD.x[i]); }      // sr holds 1 / sqrt(w mu)
 
   // ---- lower triangles of the symmetric matrices Q (from Zs) and P (from Zd); item = stream pair i >= j
@@ -608,7 +612,9 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   const size_t qv = q * G + g;
   const double *scv = X.scal + ((size_t)view0(X, p) + g) * 16;
   const double usec = scv[2], udel = X.tduserm[pixL(X, view0(X, p) + g) + k];
-  if (T.rank == 0) pi_prt(m, NM, scv[1], piu);
+  // the same for all 72 layers of the pixel-view: precomputed per Fourier term (a serial recurrence with square roots and divisions)
+  const double *piu = Z.piu_g ? Z.piu_g + ((size_t)view0(X, p) + g) * 3 * (NM + 1) : piu_s;
+  if (!Z.piu_g && T.rank == 0) pi_prt(m, NM, scv[1], piu_s);
   for (int e = T.rank; e < n; e += T.size) {
     const double ke = sig[e];
     if (!(ke > 0.0)) continue;

@@ -103,6 +103,24 @@ __global__ void k_vl_finish(VLPix X, VLConv CV, int p0, int nview_chunk, int nch
   if (U) U[o] = S > 1 ? CV.total[(size_t)vl * 4 + 2] : 0.0;
 }
 
+// generalized spherical functions of Fourier component m at the user cosine of every pixel-view and at the solar cosine of every pixel
+// of the chunk (K2 used to recompute them in every one of the 72 layer problems of a pixel, 60 views each in the polar shape)
+__global__ void k_vl_pi_angles(VLPix X, int m, int nview_chunk, double *__restrict__ piu, double *__restrict__ pi0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NM = X.NM, w = 3 * (NM + 1);
+  double loc[3 * 65];
+  if (t < nview_chunk) {
+    for (int i = 0; i < w; i++) loc[i] = 0.0;
+    pi_prt(m, NM, X.scal[(size_t)t * 16 + 1], loc);
+    for (int i = 0; i < w; i++) piu[(size_t)t * w + i] = loc[i];
+  } else if (t < nview_chunk + nview_chunk / X.G) {
+    const int c = t - nview_chunk;
+    for (int i = 0; i < w; i++) loc[i] = 0.0;
+    pi_prt(m, NM, X.scal[(size_t)c * X.G * 16 + 0], loc);
+    for (int i = 0; i < w; i++) pi0[(size_t)c * w + i] = loc[i];
+  }
+}
+
 // one thread per pixel of the chunk: a pixel enters the Fourier loop when any of its views passed the input checks
 __global__ void k_vl_init_active(VLPix X, VLConv CV, VLSol Z, int npix_chunk, int *list, int *count) {
   const int pl = blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +266,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
     brdf_smem = (size_t)brdf_nscr * 8;
     AB_CUDA_OK(cudaFuncSetAttribute((const void *)k_vl_brdf_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brdf_smem));
   }
-  const size_t per_pix = per_pix_state + per_pix_sol + (size_t)G * (4 * 8 + 4 * 4) + 4 * 4 + per_pix_brdf;
+  const size_t per_pix = per_pix_state + per_pix_sol + (size_t)G * (4 * 8 + 4 * 4) + 4 * 4 + per_pix_brdf + (size_t)(G + 1) * 3 * (NM + 1) * 8 + 512;
   double ws_gb = 24.0;
   if (const char *e = getenv("AB200_VL_WORKSPACE_GB")) ws_gb = atof(e);
   size_t freeb = 0, totalb = 0;
@@ -278,6 +296,8 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   Z.uh_dn = A.take<double>(nq * G * n * S); Z.uh_up = A.take<double>(nq * G * n * S); Z.hm1 = A.take<double>(nq * G * n); Z.hm2 = A.take<double>(nq * G * n);
   Z.aterm = A.take<double>(nq * n); Z.bterm = A.take<double>(nq * n); Z.gam_m = A.take<double>(nq * n); Z.gam_p = A.take<double>(nq * n);
   Z.wupper = A.take<double>(nq * 2 * n); Z.wlower = A.take<double>(nq * 2 * n); Z.fail = A.take<int>(chunk);
+  double *d_piu = A.take<double>(vchunk * 3 * (NM + 1)), *d_pi0 = A.take<double>(chunk * 3 * (NM + 1));
+  Z.piu_g = d_piu; Z.pi0_g = d_pi0;
   VLOps O; memset(&O, 0, sizeof O);
   if (use_add) {
     O.rt = A.take<double>(nq * ops_block_doubles(n)); O.spT = A.take<double>(nq * n * n); O.smT = A.take<double>(nq * n * n);
@@ -364,6 +384,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
       const double *pqm = d_pq + (size_t)m * (NM + 1) * N * 3;
       int *cnt = counts + 1 + m;
       cudaEventRecord(ev[0], st);
+      k_vl_pi_angles<<<(nc * G + nc + 127) / 128, 128, 0, st>>>(X, m, nc * G, d_piu, d_pi0);
       vl_eigen_launch(PE, X, Z, QD, pqm, m, cur, nactive, st);
       cudaEventRecord(ev[1], st);
       if (use_add) {

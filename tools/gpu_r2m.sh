@@ -9,3 +9,9 @@ import json
 d = json.load(open("gpurun_out/r2m_bench.json"))
 print("value", d["value"], "e2e", d["e2e"]["value"], "ms", d["ms_per_step"], d["roofline"]["kernel"], d["roofline"]["frac"], d["roofline"]["kernel_ms"])
 PY
+timeout -s KILL 200 python bench.py --workload polar16 --steps 2 --warmup 3 --no-cpu > gpurun_out/r2m_polar.json 2> gpurun_out/r2m_polar.err; echo "polar rc=$?"
+python - <<PY
+import json
+d = json.load(open("gpurun_out/r2m_polar.json"))
+print("polar16 value", d["value"], "ms", d["ms_per_step"], d["roofline"]["kernel_ms"])
+PY
