@@ -6,6 +6,7 @@
 // the most recent call are per host thread.  Nothing is tied to "the device that was current first".
 #include "vl_launch.h"
 #include "vl_brdf.cuh"
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -193,19 +194,45 @@ struct VLContext {
   std::mutex mu;
   DevArena arena;
   DevBuf io, tab, diag, rot;
+  cudaStream_t stream = nullptr;       // non-blocking stream of the host-pointer entry points (copies and kernels of one slab)
+  std::mutex *upload_mu = nullptr;     // one per device: slabs of the same call upload one after the other, at full PCIe bandwidth
+  std::mutex *compute_mu = nullptr;    // one per device: the solves of pipelined slabs run one after the other (each fills the GPU;
+                                       // run concurrently they were 19 % slower in total), only uploads overlap them
 };
 std::mutex g_ctx_mu;
 std::map<int, std::unique_ptr<VLContext>> g_ctx;
+std::map<int, std::unique_ptr<std::mutex>> g_upload_mu, g_compute_mu;
+// A device has several contexts ("slots"): a large host-pointer call is cut into slabs that are pipelined on ONE device -- slab k + 1 is
+// uploaded while slab k computes -- each slab with its own context, stream and host thread (shard_obs).  Slot 0 is the default.
+thread_local int g_ctx_slot = 0;
 VLContext &vl_context() {
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_ctx_mu);
-  auto &p = g_ctx[dev];
-  if (!p) p.reset(new VLContext);
+  auto &p = g_ctx[dev * 16 + g_ctx_slot];
+  if (!p) {
+    p.reset(new VLContext);
+    auto &um = g_upload_mu[dev];
+    if (!um) um.reset(new std::mutex);
+    p->upload_mu = um.get();
+    auto &cm = g_compute_mu[dev];
+    if (!cm) cm.reset(new std::mutex);
+    p->compute_mu = cm.get();
+  }
+  if (!p->stream && cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) p->stream = nullptr;   // falls back to stream 0
   return *p;
 }
 
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+// AB200_TRACE=1: wall-clock marks of the slab phases on stderr (debugging the upload / compute overlap)
+void vl_trace(const char *what, int j0) {
+  static const bool on = getenv("AB200_TRACE") != nullptr;
+  if (!on) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  fprintf(stderr, "[ab200 %9.2f ms] slab j0=%d %s\n", ms, j0, what);
+}
 
 struct RunDesc {
   int S, N, km, nch, nobs, nMom, nPol, planpar, lambertian, scalar_glue;
@@ -446,9 +473,28 @@ int vl_device_count() {
 }
 
 // f(slab j0, slab nj, an earlier slab already ran an observation with solar_zenith == 0) -> error code; one host thread per device
+// slabs per device of one host-pointer call (AB200_PIPELINE_SLABS, default 3; 1 = off): more than one pipelines upload and compute
+int vl_pipeline_slabs() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("AB200_PIPELINE_SLABS"); v = e ? std::max(1, std::min(8, atoi(e))) : 3; }
+  return v;
+}
+// true when p is ordinary (pageable) host memory: not registered with / allocated by CUDA
+bool vl_is_pageable(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 template <class F>
-int shard_obs(int nobs, int nadir_first, F f) {
-  const int nd = std::max(1, std::min(vl_device_count(), nobs));
+int shard_obs(int nobs, int nadir_first, F f, size_t bytes_per_obs = 0, const void *big_input = nullptr) {
+  const int ndev = std::max(1, std::min(vl_device_count(), nobs));
+  // Pipelining pays when a slab's upload is worth hiding: pageable host arrays (10 GB/s staged copies; measured +21 % on the headline
+  // shape) with at least 64 MB of input per slab.  Pinned arrays upload at PCIe speed and three smaller solves cost more in Fourier-loop
+  // tails than the hidden copy saves (measured -3 %), so they keep one slab unless AB200_PIPELINE_SLABS is set explicitly.
+  int V = vl_pipeline_slabs();
+  if (!getenv("AB200_PIPELINE_SLABS") && big_input && !vl_is_pageable(big_input)) V = 1;
+  while (V > 1 && (bytes_per_obs * (size_t)nobs) / ((size_t)ndev * V) < ((size_t)64 << 20)) V--;
+  const int nd = ndev * V;
   if (nd == 1) return f(0, nobs, 0);
   int cur = 0, vis = 1;
   cudaGetDevice(&cur); cudaGetDeviceCount(&vis);
@@ -457,13 +503,16 @@ int shard_obs(int nobs, int nadir_first, F f) {
   std::vector<std::thread> th;
   auto run = [&](int d) {
     const int j0 = (int)((long)nobs * d / nd), j1 = (int)((long)nobs * (d + 1) / nd);
-    if (d > 0 && cudaSetDevice((cur + d) % vis) != cudaSuccess) { rcs[d] = AB200_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+    if (cudaSetDevice((cur + d / V) % vis) != cudaSuccess) { rcs[d] = AB200_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+    g_ctx_slot = d % V;
     rcs[d] = f(j0, j1 - j0, nadir_first < j0 ? 1 : 0);
+    g_ctx_slot = 0;
     if (rcs[d]) errs[d] = ab200_last_error();
   };
   for (int d = 1; d < nd; d++) th.emplace_back(run, d);
   run(0);
   for (auto &t : th) t.join();
+  cudaSetDevice(cur);
   for (int d = 0; d < nd; d++) if (rcs[d]) { ab200_set_error(errs[d]); return rcs[d]; }
   return 0;
 }
@@ -471,6 +520,16 @@ int shard_obs(int nobs, int nadir_first, F f) {
 // H2D of the slab of a Fortran array (inner, nobs, outer) -> compact device array (inner, nj, outer); D2H the other way round
 cudaError_t put_slab(double *d, const double *src, size_t inner, size_t outer, const Slab &sl, cudaStream_t st) {
   if (sl.nj == sl.nobs || outer == 1) return cudaMemcpyAsync(d, src + inner * sl.j0, inner * sl.nj * outer * 8, cudaMemcpyHostToDevice, st);
+  // large rows go as one 1-D copy each: cudaMemcpy2DAsync moved the 786 KB rows of a pmom slab at 11 GB/s from pinned memory (measured)
+  // where 1-D copies run at PCIe speed
+  const size_t row = inner * sl.nj * 8;
+  if (row >= ((size_t)64 << 10)) {
+    for (size_t o = 0; o < outer; o++) {
+      cudaError_t e = cudaMemcpyAsync(d + o * inner * sl.nj, src + inner * sl.j0 + o * inner * sl.nobs, row, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   return cudaMemcpy2DAsync(d, inner * sl.nj * 8, src + inner * sl.j0, inner * sl.nobs * 8, inner * sl.nj * 8, outer, cudaMemcpyHostToDevice, st);
 }
 cudaError_t get_slab(double *dst, const double *d, size_t inner, size_t outer, const Slab &sl, cudaStream_t st) {
@@ -500,15 +559,17 @@ int lambert_slab(int S, int scalar_glue, int km, int nch, const Slab &sl, int G,
   AB_CUDA_OK(C.io.reserve(bytes));
   char *b = C.io.as<char>(); size_t off = 0;
   cudaError_t cpe = cudaSuccess;
+  const cudaStream_t st = C.stream;
+  std::unique_lock<std::mutex> uplock(*C.upload_mu);       // one slab uploads at a time per device (released once the copies are done)
   // device array (inner, nj, outer) <- the slab of the host array (inner, nobs, outer); src == nullptr: space only
   auto put = [&](const double *src, size_t inner, size_t outer) -> double * {
     off = align256(off); double *d = (double *)(b + off); off += inner * nj * outer * 8;
-    if (src) { cudaError_t e = put_slab(d, src, inner, outer, sl, 0); if (e != cudaSuccess) cpe = e; }
+    if (src) { cudaError_t e = put_slab(d, src, inner, outer, sl, st); if (e != cudaSuccess) cpe = e; }
     return d;
   };
   auto putv = [&](const double *src, size_t n) -> double * {          // not indexed by the observation
     off = align256(off); double *d = (double *)(b + off); off += n * 8;
-    cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, 0); if (e != cudaSuccess) cpe = e;
+    cudaError_t e = cudaMemcpyAsync(d, src, n * 8, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) cpe = e;
     return d;
   };
   RunDesc R; memset(&R, 0, sizeof R);
@@ -532,18 +593,22 @@ int lambert_slab(int S, int scalar_glue, int km, int nch, const Slab &sl, int G,
       for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
     }
   }
-  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = 0;
+  R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
   AB_CUDA_OK(cpe);
-  int e = run_vlidort(C, R);
-  if (e) return e;
-  AB_CUDA_OK(get_slab(radiance, R.radiance, 1, (size_t)nch * G, sl, 0));
-  AB_CUDA_OK(get_slab(reflectance, R.reflectance, 1, (size_t)nch * G, sl, 0));
-  if (Q) AB_CUDA_OK(get_slab(Q, R.Q, 1, (size_t)nch * G, sl, 0));
-  if (U) AB_CUDA_OK(get_slab(U, R.U, 1, (size_t)nch * G, sl, 0));
+  AB_CUDA_OK(cudaStreamSynchronize(st));
+  uplock.unlock();
+  {
+    std::lock_guard<std::mutex> clk(*C.compute_mu);
+    if (int e = run_vlidort(C, R)) return e;
+  }
+  AB_CUDA_OK(get_slab(radiance, R.radiance, 1, (size_t)nch * G, sl, st));
+  AB_CUDA_OK(get_slab(reflectance, R.reflectance, 1, (size_t)nch * G, sl, st));
+  if (Q) AB_CUDA_OK(get_slab(Q, R.Q, 1, (size_t)nch * G, sl, st));
+  if (U) AB_CUDA_OK(get_slab(U, R.U, 1, (size_t)nch * G, sl, st));
   const size_t v0 = (size_t)j0 * nch * G;
-  AB_CUDA_OK(cudaMemcpyAsync(nf_out + v0, R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaMemcpyAsync(st_out + v0, R.status, 4 * nview, cudaMemcpyDeviceToHost, 0));
-  AB_CUDA_OK(cudaStreamSynchronize(0));
+  AB_CUDA_OK(cudaMemcpyAsync(nf_out + v0, R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaMemcpyAsync(st_out + v0, R.status, 4 * nview, cudaMemcpyDeviceToHost, st));
+  AB_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -590,7 +655,7 @@ int lambert_host(int S, int scalar_glue, int km, int nch, int nobs, int ngeom, i
   int e = shard_obs(nobs, nadir_first, [&](int j0, int nj, int nadir_already) {
     return lambert_slab(S, scalar_glue, km, nch, Slab{j0, nj, nobs}, G, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom,
                         he, albedo, sza, raa, vza, flux_factor, MISSING, nadir_already, radiance, reflectance, Q, U, nf.data(), stt.data());
-  });
+  }, (size_t)8 * km * nch * (3 + (size_t)nMom * nPol), pmom);
   g_last_nfourier.swap(nf); g_last_status.swap(stt);
   return e;
 }
@@ -631,6 +696,9 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   AB_CUDA_OK(C.io.reserve(dev ? 8 * (16 * nview + 7 * nview) + 16 * nview + 4096 * 8 : bytes));
   char *b = C.io.as<char>(); size_t off = 0;
   cudaError_t cpe = cudaSuccess;
+  if (!dev) st = C.stream;                                 // host-pointer call: the slab's own non-blocking stream
+  std::unique_lock<std::mutex> uplock(*C.upload_mu, std::defer_lock);
+  if (!dev) { vl_trace("wait upload", j0); uplock.lock(); vl_trace("upload begin", j0); }                                 // one slab uploads at a time per device (released once the copies are done)
   auto put = [&](const double *src, size_t inner, size_t outer) -> double * {
     if (dev && src) return const_cast<double *>(src);
     off = align256(off); double *d = (double *)(b + off); off += inner * nj * outer * 8;
@@ -689,6 +757,7 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   VLBrdf B;
   const int NM = std::min(2 * nstreams - 1, nMom);
   AB_CUDA_OK(cpe);
+  if (!dev) { AB_CUDA_OK(cudaStreamSynchronize(st)); uplock.unlock(); vl_trace("upload end", j0); }
   if (int e = build_brdf_tables(C, B, sa.kind, S, scalar_glue, nstreams, NM, nch, nj, st)) return e;
   B.G = G;
   B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
@@ -708,7 +777,13 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   }
   R.exactdb = d_exact; R.brdf = &B;
   R.h_sza = &h_sza; R.h_skip = &skip; R.stream = st;
-  if (int e = run_vlidort(C, R)) return e;
+  vl_trace("wait compute", j0);
+  {
+    std::lock_guard<std::mutex> clk(*C.compute_mu);
+    vl_trace("compute begin", j0);
+    if (int e = run_vlidort(C, R)) return e;
+  }
+  vl_trace("compute end", j0);
   const size_t v0 = (size_t)j0 * nch * G;
   AB_CUDA_OK(cudaMemcpyAsync(nf_out + v0, R.nfourier, 4 * nview, cudaMemcpyDeviceToHost, st));
   AB_CUDA_OK(cudaMemcpyAsync(st_out + v0, R.status, 4 * nview, cudaMemcpyDeviceToHost, st));
@@ -722,6 +797,7 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
     if (sa.BR_U) AB_CUDA_OK(get_slab(sa.BR_U, d_BRU, 1, oo, sl, st));
   }
   AB_CUDA_OK(cudaStreamSynchronize(st));
+  vl_trace("download end", j0);
   return 0;
 }
 
@@ -781,7 +857,7 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
     e = shard_obs(nobs, nadir_first, [&](int j0, int nj, int nadir_already) {
       return brdf_slab(false, S, scalar_glue, km, nch, Slab{j0, nj, nobs}, G, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he,
                        sza, raa, vza, MISSING, sa, nadir_already, radiance, reflectance, Q, U, st, nf.data(), stt.data());
-    });
+    }, (size_t)8 * km * nch * (3 + (size_t)nMom * nPol), pmom);
   }
   g_last_nfourier.swap(nf); g_last_status.swap(stt);
   return e;
@@ -1137,11 +1213,17 @@ extern "C" int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *m
 
 extern "C" int ab200_vlidort_release(void) {
   // frees the workspaces of the device that is current on the calling thread
-  VLContext &C = vl_context();
-  std::lock_guard<std::mutex> lock(C.mu);
-  if (C.arena.base) cudaFree(C.arena.base);
-  C.arena.base = nullptr; C.arena.cap = 0; C.arena.off = 0;
-  C.io.release(); C.tab.release(); C.diag.release(); C.rot.release();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::vector<VLContext *> cs;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); for (auto &kv : g_ctx) if (kv.first / 16 == dev && kv.second) cs.push_back(kv.second.get()); }
+  for (VLContext *Cp : cs) {                               // every pipeline slot of the device
+    VLContext &C = *Cp;
+    std::lock_guard<std::mutex> lock(C.mu);
+    if (C.arena.base) cudaFree(C.arena.base);
+    C.arena.base = nullptr; C.arena.cap = 0; C.arena.off = 0;
+    C.io.release(); C.tab.release(); C.diag.release(); C.rot.release();
+  }
   return 0;
 }
 
