@@ -735,7 +735,8 @@ extern "C" int ab200_mie_create(int nch, const float *channels_m, int nmom, ab20
   h->channels.assign(channels_m, channels_m + nch);
   cudaError_t e = cudaMalloc(&h->d_channels, sizeof(float) * nch);
   if (e != cudaSuccess) { ab200_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); delete h; return AB200_ERR_CUDA; }
-  cudaMemcpy(h->d_channels, channels_m, sizeof(float) * nch, cudaMemcpyHostToDevice);
+  e = cudaMemcpy(h->d_channels, channels_m, sizeof(float) * nch, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { ab200_set_error(std::string("cudaMemcpy: ") + cudaGetErrorString(e)); cudaFree(h->d_channels); delete h; return AB200_ERR_CUDA; }
   // default registry == the variable tables of Chem_MieRegistry.rc + the SU/NI name filter of
   // Chem_MieMod.F90:376-400
   char buf[32];
@@ -806,16 +807,19 @@ extern "C" int ab200_mie_load_table(ab200_mie *h, int species, int nlam, int nrh
   size_t raw_bytes = sizeof(double) * (nlam + nrh + 3 * n2 + 6 * r3 + r3 * npol + (nmom > 0 ? r3 * (long)nmom_file * npol : 0));
   AB_CUDA_OK(h->ws_tmp.reserve(raw_bytes));
   double *d = h->ws_tmp.as<double>();
+  cudaError_t up_err = cudaSuccess;
   auto up = [&](const double *src, long n) -> double * {
     if (!src) return nullptr;
     double *dst = d; d += n;
-    cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice);
+    cudaError_t ce = cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) up_err = ce;
     return dst;
   };
   double *d_lam = up(lambda, nlam), *d_rh = up(rh, nrh), *d_reff = up(reff, n2), *d_gf = up(gf, n2), *d_rhop = up(rhop, n2);
   double *d_bext = up(bext, r3), *d_bsca = up(bsca, r3), *d_bbck = up(bbck, r3), *d_g = up(g, r3);
   double *d_refr = up(refr, r3), *d_refi = up(refi, r3), *d_pback = up(pback, r3 * npol);
   double *d_pmom = nmom > 0 ? up(pmom, r3 * (long)nmom_file * npol) : nullptr;
+  AB_CUDA_OK(up_err);
   float *P = T.pool;
   auto interp = [&](double *src, long off, int nmomd, int nmoms, int np, int take_abs, float fillv) {
     long n = n3 * nmomd * np;
@@ -1201,13 +1205,13 @@ extern "C" int ab200_get_edge_vars(int km, int nobs, const float *airdens, const
   float *d = nullptr;
   AB_CUDA_OK(cudaMalloc(&d, 4 * (2 * nin + 3 * nout)));
   float *d_ad = d, *d_dp = d + nin, *d_pe = d + 2 * nin, *d_ze = d_pe + nout, *d_te = d_ze + nout;
-  cudaMemcpyAsync(d_ad, airdens, 4 * nin, cudaMemcpyHostToDevice, 0);
-  cudaMemcpyAsync(d_dp, delp, 4 * nin, cudaMemcpyHostToDevice, 0);
-  k_edge_vars<<<(nobs + 127) / 128, 128>>>(km, nobs, d_ad, d_dp, ptop, d_pe, d_ze, d_te);
-  cudaMemcpyAsync(pe, d_pe, 4 * nout, cudaMemcpyDeviceToHost, 0);
-  cudaMemcpyAsync(ze, d_ze, 4 * nout, cudaMemcpyDeviceToHost, 0);
-  cudaMemcpyAsync(te, d_te, 4 * nout, cudaMemcpyDeviceToHost, 0);
-  cudaError_t e = cudaStreamSynchronize(0);
+  cudaError_t e = cudaMemcpyAsync(d_ad, airdens, 4 * nin, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_dp, delp, 4 * nin, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) { k_edge_vars<<<(nobs + 127) / 128, 128>>>(km, nobs, d_ad, d_dp, ptop, d_pe, d_ze, d_te); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pe, d_pe, 4 * nout, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ze, d_ze, 4 * nout, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(te, d_te, 4 * nout, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   cudaFree(d);
   if (e != cudaSuccess) { ab200_set_error(cudaGetErrorString(e)); return AB200_ERR_CUDA; }
   return 0;
