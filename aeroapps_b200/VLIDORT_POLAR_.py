@@ -248,6 +248,36 @@ def vector_brdf_modis_cloud(channels, nstreams, plane_parallel, ROT, depol, alph
     return (*outs, rc.value)
 
 
+def scalar_gisscx_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te,
+                        U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Scalar_GissCX_Cloud (VLIDORT_BRDF_CX.F90:1898): returns (radiance, reflectance, BRDF (nobs,nch), rc)."""
+    arrs = [_F(x) for x in (ROT, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te)]
+    km, nch, nobs, nMom, nPol = _dims(arrs[1], arrs[4])
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(3)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_gisscx_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(arrs[0]), _p(dp),
+                                                  *[_p(a) for a in arrs[1:]], _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza), C.c_double(MISSING),
+                                                  int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_scalar_gisscx_cloud")
+    return (*outs, rc.value)
+
+
+def scalar_brdf_modis_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL,
+                            pe, he, te, kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """VLIDORT_Scalar_LandMODIS_Cloud (VLIDORT_BRDF_MODIS.F90:625): returns (radiance, reflectance, BR (nobs,nch), rc)."""
+    arrs = [_F(x) for x in (ROT, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, kernel_wt, param)]
+    km, nch, nobs, nMom, nPol = _dims(arrs[2], arrs[5])
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    ff = _F(flux_factor)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(3)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_brdf_modis_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(arrs[0]),
+                                                      _p(dp), *[_p(a) for a in arrs[1:]], _p(sza), _p(raa), _p(vza), _p(ff), C.c_double(MISSING),
+                                                      int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_scalar_brdf_modis_cloud")
+    return (*outs, rc.value)
+
+
 def vector_lambert_multigeom(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, pe, he, te, albedo,
                              solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
     """returns (radiance, reflectance, Q, U (nobs,nch,ngeom), rc)"""

@@ -170,7 +170,7 @@ DEVFN double vl_fast_rcp(double x) {
 // with the row number in the low 6 bits, one warp-wide integer max), no row swaps, no row scaling: piv[c] = pivot row of step c,
 // stepof[r] = its inverse; the physical column c holds, after step c, the column of the inverse that belongs to row piv[c] (the
 // unit column it replaces is implicit before).  E(stepof[r], piv[j]) = a(r, j) / pivot(stepof[r]).
-// The pivot row's threads rewrite their mirror entries with unchanged values in their own step (benign).
+// The pivot row's threads leave their mirror entries alone in their own step (the row is being read by all; racecheck-clean).
 // N_, CG_ > 0: compile-time n and column-group count (n = 36 with 128 threads: 3 groups of 12 columns).
 // Scratch: Mw (n x ldm doubles), dinv_s (n), column buffer (2n); ints piv (n), stepof (n).
 HDFN int inv_ldm(int n) { return n | 1; }
@@ -221,7 +221,7 @@ DEVFN bool cta_inverse(int n_, const double *A, int lda, double *E, int lde, dou
         if (N_ > 0 || cg + CG * jj < n) {
           const double v = a[jj] - f * pr[CG * jj];            // (for column c the loaded pivot-row value is not used)
           a[jj] = (CG * jj == dc) ? vc : v;
-          mrow[CG * jj] = a[jj];
+          if (!isp) mrow[CG * jj] = a[jj];                     // (the pivot row is being read by everybody and is never a pivot row again)
           if (CG * jj == dc + 1) cn[r] = a[jj];                // column c + 1 for the next step
         }
       }

@@ -1080,6 +1080,40 @@ extern "C" int ab200_vlidort_vector_brdf_modis_cloud(int km, int nch, int nobs, 
   return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
+extern "C" int ab200_vlidort_scalar_gisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                 int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                                 const double *g, const double *pmom, const double *tauI, const double *ssaI, const double *gI,
+                                                 const double *pmomI, const double *tauL, const double *ssaL, const double *gL,
+                                                 const double *pmomL, const double *pe, const double *he, const double *te, const double *U10m,
+                                                 const double *V10m, const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                                 const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                                 double *reflectance_VL_SURF, double *BRDF, int *rc) {
+  (void)depol; (void)g; (void)gI; (void)gL; (void)pe; (void)te; (void)verbose;
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_GISSCX, U10m, V10m, mr, nullptr, nullptr, BRDF, nullptr, nullptr};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
+}
+extern "C" int ab200_vlidort_scalar_brdf_modis_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                     int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                                     const double *tau, const double *ssa, const double *g, const double *pmom,
+                                                     const double *tauI, const double *ssaI, const double *gI, const double *pmomI,
+                                                     const double *tauL, const double *ssaL, const double *gL, const double *pmomL,
+                                                     const double *pe, const double *he, const double *te, const double *kernel_wt,
+                                                     const double *param, const double *solar_zenith, const double *relat_azymuth,
+                                                     const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                                     double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, int *rc) {
+  (void)depol; (void)g; (void)gI; (void)gL; (void)pe; (void)te; (void)verbose;
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("scalar_brdf_modis_cloud: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, nullptr, nullptr, alpha, flux_factor};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
+}
 extern "C" int ab200_vlidort_scalar_gisscx(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
                                            int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
                                            const double *ssa, const double *g, const double *pmom, const double *pe,

@@ -140,6 +140,26 @@ int ab200_vlidort_vector_brdf_modis_cloud(int km, int nch, int nobs, const doubl
                                           const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
                                           double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
                                           double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+/* scalar forms: VLIDORT_Scalar_GissCX_Cloud (GV/VLIDORT_BRDF_CX.F90:1898-2083), VLIDORT_Scalar_LandMODIS_Cloud
+ * (GV/VLIDORT_BRDF_MODIS.F90:625-823) -> VLIDORT_Run_Scalar_Cloud (V283/VLIDORT_ScatMod.F90:2596-2891).  g, gI, gL (km,nch,nobs) are part of
+ * the reference signatures and, as there, do not enter the result */
+int ab200_vlidort_scalar_gisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                      int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                      const double *g, const double *pmom, const double *tauI, const double *ssaI, const double *gI,
+                                      const double *pmomI, const double *tauL, const double *ssaL, const double *gL, const double *pmomL,
+                                      const double *pe, const double *he, const double *te, const double *U10m, const double *V10m,
+                                      const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                      const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                      double *reflectance_VL_SURF, double *BRDF, int *rc);
+int ab200_vlidort_scalar_brdf_modis_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                          int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                          const double *ssa, const double *g, const double *pmom, const double *tauI, const double *ssaI,
+                                          const double *gI, const double *pmomI, const double *tauL, const double *ssaL, const double *gL,
+                                          const double *pmomL, const double *pe, const double *he, const double *te,
+                                          const double *kernel_wt, const double *param, const double *solar_zenith,
+                                          const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                          double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                          int *rc);
 /* ab200_vlidort_vector_cx with every array (inputs and outputs) resident in device memory; stream = cudaStream_t */
 int ab200_vlidort_vector_cx_dev(int km, int nch, int nobs, int nstreams, int plane_parallel, int nMom, int nPol,
                                 const double *ROT, const double *depol, const double *tau, const double *ssa,

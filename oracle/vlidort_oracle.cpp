@@ -756,7 +756,7 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
         }
       }
       if (sza[j] == 0.0) nadir_state = true;
-      const bool cloud = g_cl_tauI != nullptr && !scalar_glue;
+      const bool cloud = g_cl_tauI != nullptr;
       const double dep = cloud ? orc_coef_depol(g_cl_channels[i] * (double)1.e-3f) : depol[i];
       const double gammamom2 = -sqrt6f * (1.0 - dep) / (2.0 + dep), alphamom2 = 6.0 * (1.0 - dep) / (2.0 + dep);
       const double raysmom2 = (1.0 - dep) / (2.0 + dep);
@@ -782,6 +782,11 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
           if (nMom >= 1) GK_(1, 0) = (1 <= nMom - 1 ? PM(1, 0) : 0.0) * aerswt;
           if (nMom >= 2) GK_(2, 0) = raysmom2 * rayswt + (2 <= nMom - 1 ? PM(2, 0) : 0.0) * aerswt;
           for (int l = 3; l <= nMom; l++) GK_(l, 0) = (l <= nMom - 1 ? PM(l, 0) : 0.0) * aerswt;
+          if (cloud)                                           /* VLIDORT_Run_Scalar_Cloud, :2596-2891: P11 of the cloud matrices, l >= 1 */
+            for (int l = 1; l <= nMom - 1; l++) {
+              const size_t oc = k + (size_t)L * (i + (size_t)nch * (j + (size_t)nobs * (size_t)l));
+              GK_(l, 0) += g_cl_pmomL[oc] * clLswt + g_cl_pmomI[oc] * clIswt;
+            }
         } else {
           for (int l = 0; l <= nMom; l++) {
             double a[16]; for (int q = 0; q < 16; q++) a[q] = 0.0;

@@ -88,3 +88,32 @@ def test_vector_brdf_modis_cloud(mods):
     print("parity modis_cloud", rep)
     assert rep["n"] + rep["n_special"] == 2 * nobs and rep["n"] >= 10 and rep["pass"], rep
     assert (I[3] == M).all()
+
+
+def test_scalar_cloud_variants(mods):
+    """VLIDORT_Scalar_GissCX_Cloud / VLIDORT_Scalar_LandMODIS_Cloud -> VLIDORT_Run_Scalar_Cloud (V283/VLIDORT_ScatMod.F90:2596): nstokes 1,
+    P11 of aerosol and cloud matrices, the g / gI / gL arguments do not enter"""
+    VP, vg, parity = mods
+    nobs, N = 9, 8
+    sc = _cloud_scene(vg, nobs, (550.0,), 64, 503)
+    z = np.zeros_like(sc["tau"])
+    cl = (sc["tauI"], sc["ssaI"], z, sc["pmomI"], sc["tauL"], sc["ssaL"], z + 0.3, sc["pmomL"])
+    I, R, BR, rc = VP.scalar_gisscx_cloud(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["g"], sc["pmom"], *cl, sc["pe"],
+                                          sc["he"], sc["te"], sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], M, 0)
+    assert rc == 0
+    nf, st = VP.last_diag()
+    assert (st == 0).all()
+    flat = dict(sc); del flat["alpha"], flat["flux"]
+    rep = parity.parity_report("gisscx", 1, N, False, flat, dict(radiance=I, reflectance=R, Q=None, U=None, nfourier=nf.reshape(nobs, 1)),
+                               scalar_glue=True, tol_conv=5e-9)
+    print("parity scalar gisscx_cloud", rep)
+    assert rep["n"] == nobs and rep["pass"], str(rep)
+    I, R, BR, rc = VP.scalar_brdf_modis_cloud(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["alpha"], sc["tau"], sc["ssa"], sc["g"], sc["pmom"],
+                                              *cl, sc["pe"], sc["he"], sc["te"], sc["kernel_wt"], sc["param"], sc["sza"], sc["raa"], sc["vza"],
+                                              sc["flux"], M, 0)
+    assert rc == 0
+    nf, st = VP.last_diag()
+    rep = parity.parity_report("modis", 1, N, False, sc, dict(radiance=I, reflectance=R, Q=None, U=None, nfourier=nf.reshape(nobs, 1)),
+                               scalar_glue=True, tol_conv=5e-9)
+    print("parity scalar modis_cloud", rep)
+    assert rep["n"] + rep["n_special"] == nobs and rep["n"] >= 5 and rep["pass"], str(rep)
