@@ -122,7 +122,7 @@ int vl_add_plan(AddPlan &P, int S, int N, int L, int nsm) {
   while (P.threads < 1024 && (n + P.threads / n - 1) / (P.threads / n) > 13) P.threads += 128;
   P.ops_pw = (ops_smem_doubles(n, false) + (size_t)n + 2) & ~(size_t)1;
   P.add_pw = (add_smem_doubles(n, false) + (size_t)n + 2) & ~(size_t)1;
-  P.ops_smem = P.warp ? P.ops_pw * 8 * P.wpc : ops_smem_doubles(n, true) * 8 + (size_t)n * 8 + 16;
+  P.ops_smem = P.warp ? P.ops_pw * 8 * P.wpc : ops_smem_doubles(n, true) * 8 + (size_t)n * 16 + 16;      // + 4n ints (pivots of the inverse pair)
   P.add_smem = P.warp ? P.add_pw * 8 * P.wpc : add_smem_doubles(n, true) * 8 + (size_t)n * 8 + 16;
   if (P.ops_smem > 227 * 1024 || P.add_smem > 227 * 1024 || P.threads > 512) {
     ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory interaction-principle solver");

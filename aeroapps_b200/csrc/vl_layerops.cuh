@@ -28,7 +28,8 @@ struct VLOps {                   // per problem q = p*L + k
 HDFN size_t ops_block_doubles(int n) { return 2 * (size_t)n * mat_ld(n) + 2 * n; }
 
 // team scratch in doubles: Am (later E), Bm, Gp (later R), Tb: n x ld each (ld = mat_ld(n)); 4 boundary vectors; inverse work; ints: 2n
-HDFN size_t ops_smem_doubles(int n, bool cta) { return 4 * (size_t)n * mat_ld(n) + 4 * n + inv_work_doubles(n, cta); }
+// (CTA teams: + 3n + 2 for the small arrays of the second inverse of the pair; ints: 4n)
+HDFN size_t ops_smem_doubles(int n, bool cta) { return 4 * (size_t)n * mat_ld(n) + 4 * n + inv_work_doubles(n, cta) + (cta ? 3 * (size_t)n + 2 : 0); }
 
 template <int S, class Team>
 DEVFN void layer_ops_problem(const Team &T, const VLPix &X, const VLSol &Z, const VLOps &O, int p, int k, double *scr, int *piv) {
@@ -43,6 +44,52 @@ DEVFN void layer_ops_problem(const Team &T, const VLPix &X, const VLSol &Z, cons
     const double sg = ((r % S) > 1) ? -1.0 : 1.0;              // u = D * upwelling
     wdt[r] = WU[r]; wut[r] = sg * WU[n + r]; wdb[r] = WL[r]; wub[r] = sg * WL[n + r];
   }
+#ifndef AB_HOST_MODEL
+  if constexpr (Team::is_cta) {
+    // CTA teams: S+ and S- are inverted together (one barrier per pivot column for both).  Slots: Am <- P + M t, Bm <- P - M t, the second
+    // mirror in Gp..Tb; then Gp <- (M + P t), Tb <- Gp S+ (= G+); Gp <- (M - P t), R -> Tb, Tm -> Am.
+    if (2 * (size_t)n * ld >= (size_t)n * inv_ldm(n)) {
+      double *sm1 = wk + inv_work_doubles(n, true);
+      for (int idx = T.rank; idx < n * n; idx += T.size) {
+        const int e = idx / n, r = idx % n;
+        const double P = XP[idx], Mt = XN[idx] * td[e];
+        Am[(size_t)r * ld + e] = P + Mt; Bm[(size_t)r * ld + e] = P - Mt;
+      }
+      T.sync();
+      if (!team_inverse_pair(T, n, Am, Bm, ld, wk, Gp, sm1, piv)) { if (T.rank == 0) Z.fail[p] = 1; return; }
+      double *SP = O.spT + q * n * n, *SM = O.smT + q * n * n;
+      for (int idx = T.rank; idx < n * n; idx += T.size) {
+        const int r = idx / n, e = idx % n;
+        SP[idx] = Am[(size_t)e * ld + r]; SM[idx] = Bm[(size_t)e * ld + r];
+        Gp[(size_t)e * ld + r] = XN[idx] + XP[idx] * td[r];            // global [r][e] read as (eigen r, stream e): Gp(stream, eigen) = M + P t
+      }
+      T.sync();
+      team_mm(T, n, n, n, Gp, ld, Am, ld, [&](int r, int c, double acc) { Tb[(size_t)r * ld + c] = acc; });          // G+
+      T.sync();
+      for (int idx = T.rank; idx < n * n; idx += T.size) { const int e = idx / n, r = idx % n; Gp[(size_t)r * ld + e] = XN[idx] - XP[idx] * td[e]; }
+      T.sync();
+      team_mm(T, n, n, n, Gp, ld, Bm, ld, [&](int r, int c, double acc) {                                           // G-
+        const double gp = Tb[(size_t)r * ld + c];
+        Tb[(size_t)r * ld + c] = 0.5 * (gp + acc);                     // R
+        Am[(size_t)r * ld + c] = 0.5 * (gp - acc);                     // Tm (S+ is dead: its product is done and it is in HBM)
+      });
+      T.sync();
+      double *Rg = O.rt + q * ops_block_doubles(n), *Tg = Rg + (size_t)n * ld, *sg = Tg + (size_t)n * ld;
+      for (int idx = T.rank; idx < n * ld; idx += T.size) {
+        const bool pad = (idx % ld) >= n;
+        Rg[idx] = pad ? 0.0 : Tb[idx]; Tg[idx] = pad ? 0.0 : Am[idx];
+      }
+      for (int r = T.rank; r < n; r += T.size) {
+        const double *Rr = Tb + (size_t)r * ld, *Tr = Am + (size_t)r * ld;
+        double su = wut[r], sd = wdb[r];
+        for (int c = 0; c < n; c++) { su -= Rr[c] * wdt[c] + Tr[c] * wub[c]; sd -= Tr[c] * wdt[c] + Rr[c] * wub[c]; }
+        sg[r] = su; sg[n + r] = sd;
+      }
+      T.sync();
+      return;
+    }
+  }
+#endif
   for (int sgn = 0; sgn < 2; sgn++) {
     const double s = sgn ? -1.0 : 1.0;
     for (int idx = T.rank; idx < n * n; idx += T.size) {

@@ -239,6 +239,83 @@ DEVFN bool cta_inverse(int n_, const double *A, int lda, double *E, int lde, dou
   return ok;
 }
 
+// Two independent n x n inverses in lock step (in place: A0 <- A0^-1, A1 <- A1^-1): the same algorithm as cta_inverse with both
+// matrices advancing through ONE barrier per pivot column -- the step is a latency chain (barrier, pivot search, reciprocal, pivot-row
+// loads), and two chains in flight per thread halve what K2b pays for its S+ and S- (measured in DESIGN.md section 4).
+// wk0 / wk1: one inverse work area each (mirror n x ldm, dinv n, column buffer 2n; the mirrors may live anywhere), piv0 / piv1: 2n ints each.
+template <int NJ, int N_, int CG_>
+DEVFN bool cta_inverse2(int n_, double *A0, double *A1, int lda, double *Mw0, double *sm0, double *Mw1, double *sm1, int *piv0, int *piv1) {
+  const int n = N_ > 0 ? N_ : n_, CG = CG_ > 0 ? CG_ : (int)blockDim.x / n, ldm = inv_ldm(n);
+  const int rank = threadIdx.x, lane = threadIdx.x & 31;
+  const bool active = rank < n * CG;
+  const int r = active ? rank % n : 0, cg = active ? rank / n : 0;
+  double *dinv0 = sm0, *colb0 = sm0 + n, *dinv1 = sm1, *colb1 = sm1 + n;
+  int *stepof0 = piv0 + n, *stepof1 = piv1 + n;
+  double a0[NJ], a1[NJ];
+  double *mrow0 = Mw0 + (size_t)r * ldm + cg, *mrow1 = Mw1 + (size_t)r * ldm + cg;
+#pragma unroll
+  for (int jj = 0; jj < NJ; jj++) {
+    const int j = cg + CG * jj;
+    const bool in = active && j < n;
+    a0[jj] = in ? A0[(size_t)r * lda + j] : 0.0; a1[jj] = in ? A1[(size_t)r * lda + j] : 0.0;
+    if (in) { mrow0[CG * jj] = a0[jj]; mrow1[CG * jj] = a1[jj]; }
+  }
+  if (active && cg == 0) { colb0[r] = a0[0]; colb1[r] = a1[0]; }
+  unsigned u00 = 0u, u01 = 0u, u10 = 0u, u11 = 0u;             // rows that have been pivots, per matrix (n <= 64)
+  bool ok = true;
+  for (int c = 0; c < n; c++) {
+    __syncthreads();
+    const double *cs0 = colb0 + (c & 1) * n, *cs1 = colb1 + (c & 1) * n;
+    double *cn0 = colb0 + ((c + 1) & 1) * n, *cn1 = colb1 + ((c + 1) & 1) * n;
+    unsigned k0 = 0u, k1 = 0u;
+    if (lane < n) {
+      if (!((u00 >> lane) & 1u)) k0 = (__float_as_uint(fabsf((float)cs0[lane])) & ~63u) | (unsigned)lane;
+      if (!((u10 >> lane) & 1u)) k1 = (__float_as_uint(fabsf((float)cs1[lane])) & ~63u) | (unsigned)lane;
+    }
+    if (lane + 32 < n) {
+      if (!((u01 >> lane) & 1u)) { const unsigned t = (__float_as_uint(fabsf((float)cs0[lane + 32])) & ~63u) | (unsigned)(lane + 32); k0 = t > k0 ? t : k0; }
+      if (!((u11 >> lane) & 1u)) { const unsigned t = (__float_as_uint(fabsf((float)cs1[lane + 32])) & ~63u) | (unsigned)(lane + 32); k1 = t > k1 ? t : k1; }
+    }
+    k0 = __reduce_max_sync(0xffffffffu, k0); k1 = __reduce_max_sync(0xffffffffu, k1);
+    if ((k0 >> 6) == 0u || (k1 >> 6) == 0u) { ok = false; break; }
+    const int p0 = (int)(k0 & 63u), p1 = (int)(k1 & 63u);
+    if (p0 < 32) u00 |= 1u << p0; else u01 |= 1u << (p0 - 32);
+    if (p1 < 32) u10 |= 1u << p1; else u11 |= 1u << (p1 - 32);
+    if (rank == 0) { piv0[c] = p0; stepof0[p0] = c; piv1[c] = p1; stepof1[p1] = c; }
+    const double ip0 = vl_fast_rcp(cs0[p0]), ip1 = vl_fast_rcp(cs1[p1]);
+    if (active) {
+      const bool is0 = (r == p0), is1 = (r == p1);
+      const double f0 = is0 ? 0.0 : cs0[r] * ip0, f1 = is1 ? 0.0 : cs1[r] * ip1;
+      const double vc0 = is0 ? 1.0 : -f0, vc1 = is1 ? 1.0 : -f1;
+      const double *pr0 = Mw0 + (size_t)p0 * ldm + cg, *pr1 = Mw1 + (size_t)p1 * ldm + cg;
+      const int dc = c - cg;
+#pragma unroll
+      for (int jj = 0; jj < NJ; jj++) {
+        if (N_ > 0 || cg + CG * jj < n) {
+          const double v0 = a0[jj] - f0 * pr0[CG * jj], v1 = a1[jj] - f1 * pr1[CG * jj];
+          a0[jj] = (CG * jj == dc) ? vc0 : v0; a1[jj] = (CG * jj == dc) ? vc1 : v1;
+          if (!is0) mrow0[CG * jj] = a0[jj];
+          if (!is1) mrow1[CG * jj] = a1[jj];
+          if (CG * jj == dc + 1) { cn0[r] = a0[jj]; cn1[r] = a1[jj]; }
+        }
+      }
+      if (dc >= 0 && dc % CG == 0) { if (is0) dinv0[c] = ip0; if (is1) dinv1[c] = ip1; }
+    }
+  }
+  __syncthreads();
+  if (ok && active) {
+    const int cr0 = stepof0[r], cr1 = stepof1[r];
+    const double d0 = dinv0[cr0], d1 = dinv1[cr1];
+#pragma unroll
+    for (int jj = 0; jj < NJ; jj++) {
+      const int j = cg + CG * jj;
+      if (j < n) { A0[(size_t)cr0 * lda + piv0[j]] = a0[jj] * d0; A1[(size_t)cr1 * lda + piv1[j]] = a1[jj] * d1; }
+    }
+  }
+  __syncthreads();
+  return ok;
+}
+
 // C = A B for a CTA out of shared memory with 16-byte loads: A (M x K, lda even), B (K x N, ldb even), both 16-byte aligned; every
 // item owns a TM x 2 register tile, two k per step.  epi2(r, c, v0, v1) receives the finished pair (r, c), (r, c + 1) (c even; the
 // second value belongs to column c + 1, which the caller ignores when c + 1 == N).
@@ -294,6 +371,20 @@ DEVFN bool team_inverse(const Team &T, int n, double *A, double *E, int ld, doub
 #endif
   return team_inverse_generic(T, n, A, ld, E, ld, wk, piv);
 }
+
+// CTA teams: A0 <- A0^-1 and A1 <- A1^-1 together (cta_inverse2).  Mw1: n x inv_ldm(n) doubles for the second mirror, sm1: 3n doubles,
+// piv: 4n ints; wk as for team_inverse.
+#ifndef AB_HOST_MODEL
+template <class Team>
+DEVFN bool team_inverse_pair(const Team &T, int n, double *A0, double *A1, int ld, double *wk, double *Mw1, double *sm1, int *piv) {
+  const int CG = T.size / n, nj = (n + CG - 1) / CG;
+  double *Mw0 = wk, *sm0 = wk + (size_t)n * inv_ldm(n);
+  if (n == 36 && CG == 3) return cta_inverse2<12, 36, 3>(n, A0, A1, ld, Mw0, sm0, Mw1, sm1, piv, piv + 2 * n);
+  if (nj <= 6) return cta_inverse2<6, 0, 0>(n, A0, A1, ld, Mw0, sm0, Mw1, sm1, piv, piv + 2 * n);
+  if (nj <= 10) return cta_inverse2<10, 0, 0>(n, A0, A1, ld, Mw0, sm0, Mw1, sm1, piv, piv + 2 * n);
+  return cta_inverse2<13, 0, 0>(n, A0, A1, ld, Mw0, sm0, Mw1, sm1, piv, piv + 2 * n);
+}
+#endif
 
 // C(r, c) = sum_k A(r, k) B(k, c) handed to epi(r, c, value); A, B in team scratch with the leading dimension mat_ld(n)
 template <class Team, class Epi>
