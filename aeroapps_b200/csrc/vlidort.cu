@@ -6,6 +6,7 @@
 // the most recent call are per host thread.  Nothing is tied to "the device that was current first".
 #include "vl_launch.h"
 #include "vl_brdf.cuh"
+#include <atomic>
 #include <chrono>
 #include <algorithm>
 #include <cmath>
@@ -473,11 +474,12 @@ int vl_device_count() {
 }
 
 // f(slab j0, slab nj, an earlier slab already ran an observation with solar_zenith == 0) -> error code; one host thread per device
-// slabs per device of one host-pointer call (AB200_PIPELINE_SLABS, default 3; 1 = off): more than one pipelines upload and compute
+// slabs per device of one host-pointer call (AB200_PIPELINE_SLABS, default 1 = off): more than one pipelines upload and compute.
+// Off by default since the partial pmom upload (put_pmom): with a third of the bytes to move, the Fourier-loop tails of several smaller
+// solves cost more than the hidden copy saves (headline shape, pageable arrays: 4929 pixels/s with 1 slab, 4678 with 2, 4749 with 3).
 int vl_pipeline_slabs() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("AB200_PIPELINE_SLABS"); v = e ? std::max(1, std::min(8, atoi(e))) : 3; }
-  return v;
+  const char *e = getenv("AB200_PIPELINE_SLABS");          // read per call (tests toggle it)
+  return e ? std::max(1, std::min(8, atoi(e))) : 1;
 }
 // true when p is ordinary (pageable) host memory: not registered with / allocated by CUDA
 bool vl_is_pageable(const void *p) {
@@ -488,11 +490,9 @@ bool vl_is_pageable(const void *p) {
 template <class F>
 int shard_obs(int nobs, int nadir_first, F f, size_t bytes_per_obs = 0, const void *big_input = nullptr) {
   const int ndev = std::max(1, std::min(vl_device_count(), nobs));
-  // Pipelining pays when a slab's upload is worth hiding: pageable host arrays (10 GB/s staged copies; measured +21 % on the headline
-  // shape) with at least 64 MB of input per slab.  Pinned arrays upload at PCIe speed and three smaller solves cost more in Fourier-loop
-  // tails than the hidden copy saves (measured -3 %), so they keep one slab unless AB200_PIPELINE_SLABS is set explicitly.
+  // pipelined slabs (opt-in): only when a slab carries at least 64 MB of input
   int V = vl_pipeline_slabs();
-  if (!getenv("AB200_PIPELINE_SLABS") && big_input && !vl_is_pageable(big_input)) V = 1;
+  (void)big_input;
   while (V > 1 && (bytes_per_obs * (size_t)nobs) / ((size_t)ndev * V) < ((size_t)64 << 20)) V--;
   const int nd = ndev * V;
   if (nd == 1) return f(0, nobs, 0);
@@ -518,7 +518,9 @@ int shard_obs(int nobs, int nadir_first, F f, size_t bytes_per_obs = 0, const vo
 }
 
 // H2D of the slab of a Fortran array (inner, nobs, outer) -> compact device array (inner, nj, outer); D2H the other way round
+std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};      // bytes the host-pointer entry points moved over PCIe (ab200_vlidort_io_bytes)
 cudaError_t put_slab(double *d, const double *src, size_t inner, size_t outer, const Slab &sl, cudaStream_t st) {
+  g_h2d_bytes += inner * sl.nj * outer * 8;
   if (sl.nj == sl.nobs || outer == 1) return cudaMemcpyAsync(d, src + inner * sl.j0, inner * sl.nj * outer * 8, cudaMemcpyHostToDevice, st);
   // large rows go as one 1-D copy each: cudaMemcpy2DAsync moved the 786 KB rows of a pmom slab at 11 GB/s from pinned memory (measured)
   // where 1-D copies run at PCIe speed
@@ -533,6 +535,7 @@ cudaError_t put_slab(double *d, const double *src, size_t inner, size_t outer, c
   return cudaMemcpy2DAsync(d, inner * sl.nj * 8, src + inner * sl.j0, inner * sl.nobs * 8, inner * sl.nj * 8, outer, cudaMemcpyHostToDevice, st);
 }
 cudaError_t get_slab(double *dst, const double *d, size_t inner, size_t outer, const Slab &sl, cudaStream_t st) {
+  g_d2h_bytes += inner * sl.nj * outer * 8;
   if (sl.nj == sl.nobs || outer == 1) return cudaMemcpyAsync(dst + inner * sl.j0, d, inner * sl.nj * outer * 8, cudaMemcpyDeviceToHost, st);
   return cudaMemcpy2DAsync(dst + inner * sl.j0, inner * sl.nobs * 8, d, inner * sl.nj * 8, inner * sl.nj * 8, outer, cudaMemcpyDeviceToHost, st);
 }
@@ -545,6 +548,24 @@ bool same_sun(const double *sza, int nobs, int ngeom) {
 
 // one observation slab of a Lambertian call on the device that is current on this thread.  nf_out / st_out: the caller's diagnostics
 // arrays (all views of the call)
+// Upload of pmom (km,nch,nobs,nMom,nPol): the device image keeps the caller's layout, but only what K1 reads is copied -- P11 and (vector
+// runs) P12 with all nMom moments (the single-scatter sums run over every moment), P33 and P22 with the first 2 nstreams moments (the
+// discrete-ordinate part stops at moment 2 nstreams - 1), P34 and P44 not at all.  At nMom = 300, nPol = 6 that is 35 % of the array,
+// which is 99 % of what a Stage-B call uploads.
+cudaError_t put_pmom(double *d, const double *src, int km, int nch, int nMom, int nPol, int nstreams, bool vector, const Slab &sl, cudaStream_t st) {
+  const size_t inner = (size_t)km * nch;
+  const int nrt = std::min(std::min(2 * nstreams - 1, nMom) + 1, nMom);
+  for (int pol = 0; pol < nPol; pol++) {
+    int cnt = 0;
+    if (pol == 0) cnt = nMom;
+    else if (vector) cnt = pol == 1 ? nMom : ((pol == 2 || pol == 4) ? nrt : 0);
+    if (!cnt) continue;
+    cudaError_t e = put_slab(d + (size_t)pol * nMom * inner * sl.nj, src + (size_t)pol * nMom * inner * sl.nobs, inner, cnt, sl, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 int lambert_slab(int S, int scalar_glue, int km, int nch, const Slab &sl, int G, int nstreams, int plane_parallel, int nMom, int nPol,
                  const double *ROT, const double *depol, const double *alpha, const double *tau, const double *ssa,
                  const double *pmom, const double *he, const double *albedo, const double *sza, const double *raa,
@@ -577,7 +598,10 @@ int lambert_slab(int S, int scalar_glue, int km, int nch, const Slab &sl, int G,
   R.lambertian = 1; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G; R.nadir_already = nadir_already;
   R.ROT = put(ROT, km, nch); R.depol = putv(depol, nch); R.alpha = alpha ? put(alpha, km, nch) : nullptr;
   R.tau = put(tau, (size_t)km * nch, 1); R.ssa = put(ssa, (size_t)km * nch, 1);
-  R.pmom = put(pmom, (size_t)km * nch, (size_t)nMom * nPol); R.he = put(he, km + 1, 1); R.albedo = put(albedo, 1, nch); R.sza = put(sza, 1, 1);
+  { double *dpm = put(nullptr, (size_t)km * nch, (size_t)nMom * nPol);
+    cudaError_t e = put_pmom(dpm, pmom, km, nch, nMom, nPol, nstreams, S > 1 && !scalar_glue, sl, st); if (e != cudaSuccess) cpe = e;
+    R.pmom = dpm; }
+  R.he = put(he, km + 1, 1); R.albedo = put(albedo, 1, nch); R.sza = put(sza, 1, 1);
   R.raa = put(raa, 1, G); R.vza = put(vza, 1, G);
   R.flux_factor = flux_factor ? put(flux_factor, nch, 1) : nullptr;
   R.radiance = put(nullptr, 1, (size_t)nch * G); R.reflectance = put(nullptr, 1, (size_t)nch * G); R.Q = put(nullptr, 1, (size_t)nch * G); R.U = put(nullptr, 1, (size_t)nch * G);
@@ -715,7 +739,13 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   R.S = S; R.N = nstreams; R.km = km; R.nch = nch; R.nobs = nj; R.nMom = nMom; R.nPol = nPol; R.planpar = plane_parallel;
   R.lambertian = 0; R.scalar_glue = scalar_glue; R.MISSING = MISSING; R.ngeom = G; R.nadir_already = nadir_already;
   R.ROT = put(ROT, km, nch); R.depol = putv(depol, nch); R.tau = put(tau, (size_t)km * nch, 1); R.ssa = put(ssa, (size_t)km * nch, 1);
-  R.pmom = put(pmom, (size_t)km * nch, (size_t)nMom * nPol); R.he = put(he, km + 1, 1); R.sza = put(sza, 1, 1); R.raa = put(raa, 1, G); R.vza = put(vza, 1, G);
+  if (dev) R.pmom = pmom;
+  else {
+    double *dpm = put(nullptr, (size_t)km * nch, (size_t)nMom * nPol);
+    cudaError_t e = put_pmom(dpm, pmom, km, nch, nMom, nPol, nstreams, S > 1 && !scalar_glue, sl, st); if (e != cudaSuccess) cpe = e;
+    R.pmom = dpm;
+  }
+  R.he = put(he, km + 1, 1); R.sza = put(sza, 1, 1); R.raa = put(raa, 1, G); R.vza = put(vza, 1, G);
   R.alpha = sa.alpha ? put(sa.alpha, km, nch) : nullptr; R.flux_factor = sa.flux_factor ? put(sa.flux_factor, nch, 1) : nullptr;
   if (sa.tauI) {                                           // only the P11 block (first nMom moments) of the cloud phase matrices is used
     R.tauI = put(sa.tauI, (size_t)km * nch, 1); R.ssaI = put(sa.ssaI, (size_t)km * nch, 1); R.pmomI = put(sa.pmomI, (size_t)km * nch, (size_t)nMom);
@@ -1227,6 +1257,12 @@ extern "C" int ab200_vlidort_vector_brdf_modis_multigeom(int km, int nch, int no
 // number of devices the host-pointer Stage-B entries spread their observations over (one contiguous slab and one host thread per
 // device, starting with the device that is current on the calling thread).  n <= 0: every visible device.  Default: AB200_DEVICES, or 1
 // (rank-per-GPU mains such as geo_vlidort.x keep one device per process).  Returns the number that will be used.
+extern "C" int ab200_vlidort_io_bytes(double *h2d_bytes, double *d2h_bytes, int reset) {
+  if (h2d_bytes) *h2d_bytes = (double)g_h2d_bytes.load();
+  if (d2h_bytes) *d2h_bytes = (double)g_d2h_bytes.load();
+  if (reset) { g_h2d_bytes = 0; g_d2h_bytes = 0; }
+  return 0;
+}
 extern "C" int ab200_set_devices(int n) {
   { static std::mutex mu; std::lock_guard<std::mutex> lk(mu); g_devices_req = n <= 0 ? 0 : n; }
   return vl_device_count();

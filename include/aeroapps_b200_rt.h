@@ -225,6 +225,9 @@ int ab200_vlidort_stats(double *ms_setup, double *ms_eigen, double *ms_bvp, long
  * of the results straight into the caller's arrays.  n <= 0: every visible device; default AB200_DEVICES, else 1 (rank-per-GPU
  * mains keep one device per process).  Returns the number of devices that will be used. */
 int ab200_set_devices(int n);
+/* bytes the host-pointer Stage-B entry points have copied host -> device and device -> host since the last reset (slab arrays; of pmom only
+ * the elements and moments the solve reads are uploaded: P11, P12 fully, P33 and P22 up to moment 2 nstreams - 1) */
+int ab200_vlidort_io_bytes(double *h2d_bytes, double *d2h_bytes, int reset);
 /* self-test of the CTA linear algebra of the boundary-value kernels (tests/test_linalg_gpu.py): E = A^-1 (register-resident
  * Gauss-Jordan with partial pivoting) and P = A E (16-byte-load product) for one n x n row-major matrix, one CTA of `threads`
  * threads.  Returns 0, or 1 when the matrix is singular to working precision. */

@@ -277,6 +277,30 @@ def test_multi_chunk_path_is_bit_identical(mods, surface, monkeypatch):
     assert (da[1] != 0).any() and (da[1] == 0).any()
 
 
+def test_pipelined_slabs_are_bit_identical(mods, monkeypatch):
+    """a large host-pointer call with pageable arrays is cut into slabs that are uploaded and solved in a pipeline on one device
+    (AB200_PIPELINE_SLABS = 2, 3; a slab must carry >= 64 MB): every output and the diagnostics must equal the one-slab call bit for
+    bit, including a MISSING observation, the FOCORR_NADIR state quirk (an observation with solar_zenith == 0 in the middle) and a slab
+    boundary that is not a multiple of anything"""
+    VP, vg = mods
+    nobs, N = 301, 4
+    sc = vg.synthetic_scene(nobs, nmom=300, seed=23)
+    sc["sza"][150] = 0.0; sc["vza"][7] = 1e15
+    call = lambda: VP.vector_cx(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"],
+                                sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], 1e15, 0)
+    monkeypatch.setenv("AB200_PIPELINE_SLABS", "1")
+    a = call(); da = VP.last_diag()
+    monkeypatch.setenv("AB200_PIPELINE_SLABS", "3")
+    b = call(); db = VP.last_diag()
+    monkeypatch.setenv("AB200_PIPELINE_SLABS", "2")
+    c = call(); dc = VP.last_diag()
+    assert a[-1] == b[-1] == c[-1] == 0
+    for x, y, z in zip(a[:-1], b[:-1], c[:-1]):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    assert np.array_equal(da[0], db[0]) and np.array_equal(da[1], db[1]) and np.array_equal(da[0], dc[0])
+    assert a[0][7, 0] == 1e15 and (da[1] != 0).sum() == 1
+
+
 def test_scalar_brdf_surfaces(mods):
     VP, vg = mods
     nobs, N = 6, 6
