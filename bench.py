@@ -145,6 +145,21 @@ class AopScalarWorkload:
             p(self.h_out[2]), C.byref(rc)), "aop_scalar")
         assert rc.value == 0
 
+    def step_pageable(self):
+        """the same call with ordinary (pageable) numpy arrays: what the f2py module's caller has"""
+        C = self.C
+        if not hasattr(self, "p_qm"):
+            st = self.state
+            self.p_qm = np.ascontiguousarray(st["qm"].T).copy(); self.p_rh = np.ascontiguousarray(st["rh"].T).copy()
+            self.p_out = [np.empty(self.units_per_step, np.float32) for _ in range(3)]
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        rc = C.c_int(0)
+        self.check(self.lib.ab200_get_aop_scalar(
+            self.mie.handle, self.km, self.nobs, self.nch, self.nq, self.channels.ctypes.data_as(C.POINTER(C.c_float)),
+            self.vn.ctypes.data_as(C.c_char_p), 0, p(self.p_qm), p(self.p_rh), p(self.p_out[0]), p(self.p_out[1]),
+            p(self.p_out[2]), C.byref(rc)), "aop_scalar")
+        assert rc.value == 0
+
     # ---- CPU arm (oracle = restatement of the reference Fortran; test infrastructure used as checker/baseline)
     def setup_cpu(self, sample_cols):
         from oracle import mie_oracle as orc
