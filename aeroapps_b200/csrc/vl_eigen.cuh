@@ -29,6 +29,9 @@ struct VLSol {                 // per problem q = c*L + k (pixel c, layer k; str
   // generalized spherical functions P, R, T (l = 0..NM) of the current Fourier component at the user cosines [v][3(NM+1)] and at the solar
   // cosine [c][3(NM+1)], filled once per Fourier term by k_vl_pi_angles; null: every problem computes its own (host model)
   const double *piu_g, *pi0_g;
+  // multi-geometry calls: per-problem workspace [q][(NM+1)][n][3] for the view-independent moment sums of the user-stream solutions
+  // (z_l(e), see eigen_problem); null: every view builds its operator matrices (single-geometry calls, host model without it)
+  double *zws;
 };
 
 #ifdef AB_HM_SWEEP_HIST
@@ -607,6 +610,71 @@ DEVFN void eigen_problem(const Team &T, const VLPix &X, const VLSol &Z, const VL
   }
   T.sync();
   for (int idx = T.rank; idx < n * n; idx += T.size) { XPg[idx] = A[(idx / n) * LDA + (idx % n)]; XNg[idx] = B1[(idx / n) * LDB + (idx % n)]; }
+  // ---- multi-geometry calls: user-stream solutions through per-eigenvector moment sums (the reference's HELP_QFUNC formulation,
+  //      VM/vlidort_solutions.f90:1167-1508).  With H(l,j) = a_j [[P,0,0],[0,R,T],[0,T,R]](l, mu_j), H' = diag(1,1,-1) H and B_l the Greek
+  //      block of the layer, z_l(e) = B_l sum_j [H(l,j) X+(j,e) + (-1)^(l-m) H'(l,j) X-(j,e)] does not depend on the viewing direction;
+  //      a view then costs ~10 flops per (l, e) instead of building its 12 n operator matrix and multiplying it with X+, X-.
+  if (G > 1 && Z.zws != nullptr) {
+    double *zw = Z.zws + q * (size_t)(NM + 1) * n * 3;
+    const int nl = NM + 1 - m;
+    for (int idx = T.rank; idx < nl * n; idx += T.size) {
+      const int l = m + idx / n, e = idx % n;
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+      if (layscat && sig[e] > 0.0) {
+        const double ps = ((l - m) & 1) ? -1.0 : 1.0;
+        const double *xp_ = A + e * LDA, *xn_ = B1 + e * LDB;
+        for (int j = 0; j < N; j++) {
+          const double a5 = 0.5 * QD.w[j];
+          const double *pj_ = pq + ((size_t)l * N + j) * 3;
+          if (S == 1) { w0 += a5 * pj_[0] * (xp_[j] + ps * xn_[j]); }
+          else {
+            const double Pj = a5 * pj_[0], Rj = a5 * pj_[1], Tj = a5 * pj_[2];
+            const double x0 = xp_[S * j], x1 = xp_[S * j + 1], x2 = xp_[S * j + 2], y0 = xn_[S * j], y1 = xn_[S * j + 1], y2 = xn_[S * j + 2];
+            w0 += Pj * (x0 + ps * y0);
+            w1 += Rj * (x1 + ps * y1) + Tj * (x2 + ps * y2);
+            w2 += Tj * (x1 - ps * y1) + Rj * (x2 - ps * y2);
+          }
+        }
+      }
+      const double *o4 = og + ((size_t)l * L + k) * 4;
+      double *z = zw + ((size_t)(l - m) * n + e) * 3;
+      if (S == 1) { z[0] = o4[0] * w0; z[1] = 0.0; z[2] = 0.0; }
+      else { z[0] = o4[0] * w0 + o4[1] * w1; z[1] = o4[1] * w0 + o4[2] * w1; z[2] = o4[3] * w2; }
+    }
+    T.sync();
+    for (int e = T.rank; e < n; e += T.size) {
+      const double ke = sig[e];
+      const double hlp = ke * deltau, tde = hlp > MAX_TAU_PATH ? 0.0 : exp(-hlp);
+      for (int g = 0; g < G; g++) {
+        const size_t qv = q * G + g;
+        const size_t v = (size_t)view0(X, p) + g;
+        if (ke > 0.0) {
+          const double *scv = X.scal + v * 16;
+          const double usec = scv[2], udel = X.tduserm[pixL(X, v) + k];
+          const double rho_p = usec + ke, rho_m = usec - ke;
+          const bool hs = fabs(rho_m) < TAYLOR_SMALL;
+          Z.hm1[qv * n + e] = hs ? taylor_series_1(rho_m, deltau, udel, usec) : usec * (tde - udel) / rho_m;
+          Z.hm2[qv * n + e] = usec * (1.0 - tde * udel) / rho_p;
+        }
+        const double *piu = Z.piu_g ? Z.piu_g + v * 3 * (NM + 1) : nullptr;
+        double dn[3] = {0.0, 0.0, 0.0}, up[3] = {0.0, 0.0, 0.0};
+        if (piu != nullptr)
+          for (int l = m; l <= NM; l++) {
+            const double ps = ((l - m) & 1) ? -1.0 : 1.0;
+            const double *z = zw + ((size_t)(l - m) * n + e) * 3, *pu = piu + 3 * l;
+            const double Pu = pu[0], Ru = pu[1], Tu = pu[2], z0 = z[0], z1 = z[1], z2 = z[2];
+            dn[0] += ps * Pu * z0; up[0] += Pu * z0;
+            if (S > 1) {
+              dn[1] += ps * (Ru * z1 - Tu * z2); dn[2] += ps * (Ru * z2 - Tu * z1);
+              up[1] += Ru * z1 + Tu * z2;        up[2] += -(Tu * z1 + Ru * z2);
+            }
+          }
+#pragma unroll
+        for (int o = 0; o < S; o++) { Z.uh_dn[(qv * n + e) * S + o] = dn[o]; Z.uh_up[(qv * n + e) * S + o] = up[o]; }
+      }
+    }
+    T.sync();
+  } else
   // ---- per view geometry: whole-layer multipliers and user-stream solutions
   for (int g = 0; g < G; g++) {
   const size_t qv = q * G + g;

@@ -294,7 +294,8 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
     brdf_smem = (size_t)brdf_nscr * 8;
     AB_CUDA_OK(cudaFuncSetAttribute((const void *)k_vl_brdf_fourier, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brdf_smem));
   }
-  const size_t per_pix = per_pix_state + per_pix_sol + (size_t)G * (4 * 8 + 4 * 4) + 4 * 4 + per_pix_brdf + (size_t)(G + 1) * 3 * (NM + 1) * 8 + 512;
+  const size_t per_pix = per_pix_state + per_pix_sol + (size_t)G * (4 * 8 + 4 * 4) + 4 * 4 + per_pix_brdf + (size_t)(G + 1) * 3 * (NM + 1) * 8 + 512 +
+                         (G > 1 ? (size_t)L * (NM + 1) * n * 3 * 8 + 256 : 0);
   double ws_gb = 24.0;
   if (const char *e = getenv("AB200_VL_WORKSPACE_GB")) ws_gb = atof(e);
   size_t freeb = 0, totalb = 0;
@@ -326,6 +327,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
   Z.wupper = A.take<double>(nq * 2 * n); Z.wlower = A.take<double>(nq * 2 * n); Z.fail = A.take<int>(chunk);
   double *d_piu = A.take<double>(vchunk * 3 * (NM + 1)), *d_pi0 = A.take<double>(chunk * 3 * (NM + 1));
   Z.piu_g = d_piu; Z.pi0_g = d_pi0;
+  Z.zws = G > 1 ? A.take<double>(nq * (size_t)(NM + 1) * n * 3) : nullptr;       // multi-geometry: view-independent moment sums per problem
   VLOps O; memset(&O, 0, sizeof O);
   if (use_add) {
     O.rt = A.take<double>(nq * ops_block_doubles(n)); O.spT = A.take<double>(nq * n * n); O.smT = A.take<double>(nq * n * n);

@@ -57,7 +57,7 @@ extern "C" int hm_vlidort(int ngeom, int S, int N, int km, int nch, int nobs, in
   VLQuad QD; QD.N = N;
   if (N == 1) { QD.x[0] = std::sqrt(1.0 / 3.0); QD.w[0] = 1.0; } else gauss01(N, QD.x, QD.w);
   // one pixel at a time to keep the workspace small
-  VLSol Z; Z.n = n; Z.S = S; Z.N = N; Z.piu_g = nullptr; Z.pi0_g = nullptr;
+  VLSol Z; Z.n = n; Z.S = S; Z.N = N; Z.piu_g = nullptr; Z.pi0_g = nullptr; Z.zws = nullptr;
   std::vector<double> keig((size_t)L * n), tde(keig), xp((size_t)L * n * n), xn(xp), uhd((size_t)L * G * n * S), uhu(uhd), hm1((size_t)L * G * n), hm2(hm1), at(keig), bt(keig), gm(keig), gp(keig), wu((size_t)L * 2 * n), wl(wu);
   std::vector<int> fail(npix, 0), colact(npix, 0);
   std::vector<double> total((size_t)nview * 4, 0.0); std::vector<int> cstate((size_t)nview * 4, 0);
