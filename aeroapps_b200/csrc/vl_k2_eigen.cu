@@ -31,9 +31,10 @@ __global__ void __launch_bounds__(256) k_vl_eigen_sub(VLPix X, VLSol Z, VLQuad Q
   eigen_problem<S>(T, X, Z, QD, pq, m, p, k, smem_d + (size_t)slot * scr_doubles);
 }
 
-// two warps per (pixel, layer) problem (DuoTeam): same shared memory per problem, twice the warps per SM
+// two warps per (pixel, layer) problem (DuoTeam): same shared memory per problem, twice the warps per SM.  The 24-row instantiation
+// (36 < n <= 48) runs two problems per CTA (shared memory), so it may use up to 255 registers: no spills of the 48 column values per lane
 template <int S, int MAXHALF = 18>
-__global__ void __launch_bounds__(256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
+__global__ void __launch_bounds__(MAXHALF > 18 ? 128 : 256, 2) k_vl_eigen_duo(VLPix X, VLSol Z, VLQuad QD, const double *__restrict__ pq, int m,
                                                         const int *__restrict__ active, int nactive, int scr_doubles) {
   extern __shared__ double smem_d[];
   const int duo = threadIdx.x >> 6, ppc = blockDim.x >> 6;
@@ -78,7 +79,9 @@ int vl_eigen_plan(EigenPlan &P, int S, int N, int NM) {
     P.kind = subw == 8 ? 1 : 2; P.threads = 32 * sub_warps; P.probs_per_cta = sub_warps * subs;
     P.smem = (size_t)P.probs_per_cta * P.scr_d * 8;
   } else if (duo) {
-    P.kind = n > 36 ? 4 : 3; P.threads = 64 * wpc; P.probs_per_cta = wpc; P.smem = (size_t)wpc * (P.scr_d + 4) * 8;
+    P.kind = n > 36 ? 4 : 3;
+    if (P.kind == 4) wpc = std::min(wpc, 2);             // the 24-row kernel is compiled for at most 128 threads per CTA (255 registers)
+    P.threads = 64 * wpc; P.probs_per_cta = wpc; P.smem = (size_t)wpc * (P.scr_d + 4) * 8;
   } else {
     P.kind = 0; P.threads = 32 * wpc; P.probs_per_cta = wpc; P.smem = (size_t)wpc * P.scr_d * 8;
   }
