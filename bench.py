@@ -588,7 +588,10 @@ def time_angles(torch, n=4_000_000):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     bpu = 5 * 4 + 5 * 8 + 4 * 8                                  # the _dev form also reads per-point latss / lonss
-    t0 = time.perf_counter(); got = GeoAngles_.satangles(*ints, sec, lat, lon, -100.0); th = time.perf_counter() - t0
+    GeoAngles_.satangles(*[a[:1000] for a in ints], sec[:1000], lat[:1000], lon[:1000], -100.0)       # warm-up of the host-pointer entry
+    th = 1e30
+    for _ in range(2):                                            # best of two: one call is 50 ms, allocator noise is of that order
+        t0 = time.perf_counter(); got = GeoAngles_.satangles(*ints, sec, lat, lon, -100.0); th = min(th, time.perf_counter() - t0)
     from oracle import angles_oracle as ao                       # CPU leg: the checker, timed as cpu_baseline
     m = 400_000
     t0 = time.perf_counter(); ref = ao.angles(0, *[a[:m] for a in ints], sec[:m], lat[:m], lon[:m], lonss0=-100.0); tc = time.perf_counter() - t0
