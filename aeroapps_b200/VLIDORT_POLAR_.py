@@ -211,6 +211,44 @@ def _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs):
     return a[0], a[1], a[2], ngeom
 
 
+def _opt(a):
+    return None if a is None else _p(_F(a))
+
+
+def vector_lambert_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te,
+                         albedo, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """f2py VECTOR_LAMBERT_CLOUD (VLIDORT_POLAR_py.F90:371).  The reference wrapper calls the clear-sky runner: the cloud arrays do not
+    enter its result (GV/VLIDORT_LAMBERT.F90:843), nor this one (they may be None).  Returns (radiance, reflectance, Q, U, rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor = (_F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(4)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_lambert_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp),
+                                                   _p(alpha), _p(tau), _p(ssa), _p(pmom), _opt(tauI), _opt(ssaI), _opt(pmomI), _opt(tauL),
+                                                   _opt(ssaL), _opt(pmomL), _p(pe), _p(he), _p(te), _p(albedo), _p(sza), _p(raa), _p(vza),
+                                                   _p(flux_factor), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_lambert_cloud")
+    return outs[0], outs[1], outs[2], outs[3], rc.value
+
+
+def vector_cx_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m,
+                    mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_CX_CLOUD (VLIDORT_POLAR_py.F90:746); cloud arrays ignored as in the reference (GV/VLIDORT_BRDF_CX.F90:1118).
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_cx_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp), _p(tau),
+                                              _p(ssa), _p(pmom), _opt(tauI), _opt(ssaI), _opt(pmomI), _opt(tauL), _opt(ssaL), _opt(pmomL), _p(pe),
+                                              _p(he), _p(te), _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                              *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_cx_cloud")
+    return (*outs, rc.value)
+
+
 def vector_gisscx_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m,
                         V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
     """VLIDORT_Vector_GissCx_Cloud (GV/VLIDORT_BRDF_CX.F90:2276): aerosol + ice + liquid cloud layers over the GISS Cox-Munk ocean.

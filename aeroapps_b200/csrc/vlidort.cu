@@ -1112,6 +1112,35 @@ extern "C" int ab200_vlidort_vector_brdf_modis_cloud(int km, int nch, int nobs, 
   return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
+// VLIDORT_Vector_Lambert_Cloud_SingleGeom and VLIDORT_Vector_CX_Cloud_SingleGeom take the cloud arrays, point SCAT at them and then call the
+// CLEAR-SKY runner VLIDORT_Run_Vector (GV/VLIDORT_LAMBERT.F90:843, GV/VLIDORT_BRDF_CX.F90:1118; the header comment there says "Place
+// holder"): the cloud arrays do not enter the reference's result, and they do not enter here.
+extern "C" int ab200_vlidort_vector_lambert_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                  int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                                  const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                                  const double *pmomI, const double *tauL, const double *ssaL, const double *pmomL,
+                                                  const double *pe, const double *he, const double *te, const double *albedo,
+                                                  const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                                  const double *flux_factor, double MISSING, int verbose, double *radiance_VL,
+                                                  double *reflectance_VL, double *Q, double *U, int *rc) {
+  (void)tauI; (void)ssaI; (void)pmomI; (void)tauL; (void)ssaL; (void)pmomL;
+  return ab200_vlidort_vector_lambert(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, pe, he, te,
+                                      albedo, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL,
+                                      reflectance_VL, Q, U, rc);
+}
+extern "C" int ab200_vlidort_vector_cx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                             int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                             const double *pmom, const double *tauI, const double *ssaI, const double *pmomI,
+                                             const double *tauL, const double *ssaL, const double *pmomL, const double *pe, const double *he,
+                                             const double *te, const double *U10m, const double *V10m, const double *mr,
+                                             const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                             double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                             double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)tauI; (void)ssaI; (void)pmomI; (void)tauL; (void)ssaL; (void)pmomL;
+  return ab200_vlidort_vector_cx(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m,
+                                 mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q,
+                                 U, BR_Q, BR_U, rc);
+}
 extern "C" int ab200_vlidort_scalar_gisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
                                                  int nPol, const double *ROT, const double *depol, const double *tau, const double *ssa,
                                                  const double *g, const double *pmom, const double *tauI, const double *ssaI, const double *gI,

@@ -140,6 +140,24 @@ int ab200_vlidort_vector_brdf_modis_cloud(int km, int nch, int nobs, const doubl
                                           const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
                                           double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
                                           double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_Lambert_Cloud_SingleGeom (GV/VLIDORT_LAMBERT.F90:688-879; f2py VECTOR_LAMBERT_CLOUD, LV/VLIDORT_POLAR_py.F90:371) and
+ * VLIDORT_Vector_CX_Cloud_SingleGeom (GV/VLIDORT_BRDF_CX.F90:951-1144; f2py VECTOR_CX_CLOUD, :746).  Both reference wrappers accept the
+ * cloud arrays and then call the clear-sky runner VLIDORT_Run_Vector (VLIDORT_LAMBERT.F90:843, VLIDORT_BRDF_CX.F90:1118): the cloud
+ * arrays do not enter the result there, nor here (they may be NULL). */
+int ab200_vlidort_vector_lambert_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                       int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                       const double *ssa, const double *pmom, const double *tauI, const double *ssaI, const double *pmomI,
+                                       const double *tauL, const double *ssaL, const double *pmomL, const double *pe, const double *he,
+                                       const double *te, const double *albedo, const double *solar_zenith, const double *relat_azymuth,
+                                       const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                       double *radiance_VL, double *reflectance_VL, double *Q, double *U, int *rc);
+int ab200_vlidort_vector_cx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom, int nPol,
+                                  const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
+                                  const double *tauI, const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                  const double *pmomL, const double *pe, const double *he, const double *te, const double *U10m,
+                                  const double *V10m, const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                  const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                  double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
 /* scalar forms: VLIDORT_Scalar_GissCX_Cloud (GV/VLIDORT_BRDF_CX.F90:1898-2083), VLIDORT_Scalar_LandMODIS_Cloud
  * (GV/VLIDORT_BRDF_MODIS.F90:625-823) -> VLIDORT_Run_Scalar_Cloud (V283/VLIDORT_ScatMod.F90:2596-2891).  g, gI, gL (km,nch,nobs) are part of
  * the reference signatures and, as there, do not enter the result */

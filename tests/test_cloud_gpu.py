@@ -117,3 +117,23 @@ def test_scalar_cloud_variants(mods):
                                scalar_glue=True, tol_conv=5e-9)
     print("parity scalar modis_cloud", rep)
     assert rep["n"] + rep["n_special"] == nobs and rep["n"] >= 5 and rep["pass"], str(rep)
+
+
+def test_lambert_and_cx_cloud_wrappers_ignore_the_clouds_like_the_reference(mods):
+    """VLIDORT_Vector_Lambert_Cloud / VLIDORT_Vector_CX_Cloud (f2py VECTOR_LAMBERT_CLOUD, VECTOR_CX_CLOUD) accept the cloud arrays and then
+    call the clear-sky runner (GV/VLIDORT_LAMBERT.F90:843, GV/VLIDORT_BRDF_CX.F90:1118): the drop-in must equal the clear-sky entry bit for
+    bit whatever the cloud arrays hold"""
+    VP, vg, _ = mods
+    nobs, N = 7, 6
+    sc = _cloud_scene(vg, nobs, (550.0,), 40, 504)
+    cl = [sc[k] for k in ("tauI", "ssaI", "pmomI", "tauL", "ssaL", "pmomL")]
+    a = VP.vector_lambert_cloud(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["alpha"], sc["tau"], sc["ssa"], sc["pmom"], *cl, sc["pe"], sc["he"],
+                                sc["te"], sc["albedo"], sc["sza"], sc["raa"], sc["vza"], sc["flux"], M, 0)
+    b = VP.vector_lambert(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["alpha"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"],
+                          sc["albedo"], sc["sza"], sc["raa"], sc["vza"], sc["flux"], M, 0)
+    assert a[-1] == b[-1] == 0 and all(np.array_equal(x, y) for x, y in zip(a[:-1], b[:-1]))
+    a = VP.vector_cx_cloud(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], *([None] * 6), sc["pe"], sc["he"],
+                           sc["te"], sc["u10m"], sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], M, 0)
+    b = VP.vector_cx(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"], sc["u10m"],
+                     sc["v10m"], sc["mr"], sc["sza"], sc["raa"], sc["vza"], M, 0)
+    assert a[-1] == b[-1] == 0 and all(np.array_equal(x, y) for x, y in zip(a[:-1], b[:-1]))
