@@ -483,12 +483,6 @@ int vl_pipeline_slabs() {
   const char *e = getenv("AB200_PIPELINE_SLABS");          // read per call (tests toggle it)
   return e ? std::max(1, std::min(8, atoi(e))) : 1;
 }
-// true when p is ordinary (pageable) host memory: not registered with / allocated by CUDA
-bool vl_is_pageable(const void *p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
-  return a.type == cudaMemoryTypeUnregistered;
-}
 template <class F>
 int shard_obs(int nobs, int nadir_first, F f, size_t bytes_per_obs = 0, const void *big_input = nullptr) {
   const int ndev = std::max(1, std::min(vl_device_count(), nobs));
