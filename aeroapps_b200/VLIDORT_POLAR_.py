@@ -150,6 +150,22 @@ def vector_brdf_modis(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, 
     return (*outs, rc.value)
 
 
+def vector_bpdf(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, BPDFparam, solar_zenith, relat_azymuth,
+                sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_BPDF (VLIDORT_POLAR_py.F90:295): BPDFparam (3,nch,nobs) = refractive index, NDVI, scaling factor.
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te, bp = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, BPDFparam))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert bp.shape == (3, nch, nobs), "BPDFparam must be (3,nch,nobs)"
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_bpdf(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, 3, _p(ROT), _p(dp), _p(tau),
+                                          _p(ssa), _p(pmom), _p(pe), _p(he), _p(te), _p(bp), _p(sza), _p(raa), _p(vza), C.c_double(MISSING),
+                                          int(verbose), *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_bpdf")
+    return (*outs, rc.value)
+
+
 def scalar_cx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
               relat_azymuth, sensor_zenith, MISSING, verbose):
     """VLIDORT_Scalar_CX (VLIDORT_BRDF_CX.F90:420): returns (radiance, reflectance, BRDF (1,nobs,nch), rc)."""

@@ -19,9 +19,12 @@ constexpr int BRDF_NSCAL = 24;       // SCALING_NSTREAMS: white-sky-albedo quadr
 constexpr int BRDF_MAXNB = 100;      // azimuth quadrature streams (MAXSTREAMS_BRDF)
 
 // OCI variants (V283/VLIDORT_SurfaceMod.F90:82-538): same kernels, slope variance sigma2 = 0.00534 W instead of 0.003 + 0.00512 W
-enum { SURF_LAMBERT = 0, SURF_CX = 2, SURF_GISSCX = 3, SURF_MODIS = 4, SURF_OCICX = 5, SURF_OCIGISSCX = 6 };
+enum { SURF_LAMBERT = 0, SURF_CX = 2, SURF_GISSCX = 3, SURF_MODIS = 4, SURF_OCICX = 5, SURF_OCIGISSCX = 6, SURF_BPDF = 7 };
 HDFN bool surf_is_giss(int kind) { return kind == SURF_GISSCX || kind == SURF_OCIGISSCX; }
 HDFN bool surf_is_oci(int kind) { return kind == SURF_OCICX || kind == SURF_OCIGISSCX; }
+HDFN bool surf_is_land(int kind) { return kind == SURF_MODIS || kind == SURF_BPDF; }      // NSTREAMS_BRDF = 50, BR < 0 -> -500, no wind inputs
+HDFN bool surf_is_vec(int kind) { return surf_is_giss(kind) || kind == SURF_BPDF; }        // kernel with a full Mueller block (index >= 10)
+HDFN bool brdf_vec_which(int which) { return which == 10 || which == 14; }
 
 struct VLBrdf {
   int kind, N, NM, NB, nq, half_range, nch, nobs, bns;   // bns: BRDF nstokes (1 or 3)
@@ -29,7 +32,7 @@ struct VLBrdf {
   const double *sza;                        // (nobs)
   const double *vza, *raa;                  // (nobs,G)
   const double *u10m, *v10m, *mr;           // (nobs) (nobs) (nch)      Cox-Munk family
-  const double *kernel_wt, *param;          // (3,nch,nobs) (2,nch,nobs) MODIS RTLS
+  const double *kernel_wt, *param;          // (3,nch,nobs) (2,nch,nobs) MODIS RTLS; param (3,nch,nobs) = BPDFparam for SURF_BPDF
   const double *xb, *ab, *cxb, *sxb;        // [NB] azimuth quadrature (angles, weights, cos, sin)
   const double *caz, *saz;                  // [NM+1][NB]  weight*cos(m x), weight*sin(m x)
   const double *sx, *ss, *ssw;              // [24] scaling quadrature: cosines, sines, cosine*weight
@@ -48,10 +51,10 @@ struct VLBrdf {
 inline void brdf_host_tables(VLBrdf &B, int kind, int S, int scalar_glue, int N, int NM, int nch, int nobs, std::vector<double> &h) {
   memset(&B, 0, sizeof B);
   B.kind = kind; B.N = N; B.NM = NM; B.nch = nch; B.nobs = nobs;
-  B.half_range = !surf_is_giss(kind);
-  const int nsb = (kind == SURF_MODIS) ? 50 : 100;                        // NSTREAMS_BRDF of the surface glue
+  B.half_range = !surf_is_vec(kind);
+  const int nsb = surf_is_land(kind) ? 50 : 100;                        // NSTREAMS_BRDF of the surface glue
   B.NB = B.half_range ? nsb / 2 : nsb;
-  B.bns = (surf_is_giss(kind) && !scalar_glue && S == 3) ? 3 : 1;
+  B.bns = (surf_is_vec(kind) && !scalar_glue && S == 3) ? 3 : 1;
   B.nq = (B.bns == 3) ? 16 : 1;
   const int NB = B.NB;
   h.assign((size_t)4 * NB + (size_t)2 * (NM + 1) * NB + 3 * BRDF_NSCAL, 0.0);
@@ -178,6 +181,55 @@ HDFN void brdf_giss_kernel(const double *pars, double XI, double SXI, double XJ,
   for (int t = 0; t < 9; t++) K[t] *= shadow;
 }
 
+// BPDF-NDVI (Maignan et al. 2009; BPDFNDVI_VFUNCTION, VB/vbrdf_sup_kernels.f90:3017-3198, with FRESNEL_VECTOR :3560-3702): Fresnel
+// reflection matrix of a facet of refractive index pars[0], scaled by C exp(-NDVI) exp(-tan(gamma)) / (4 (mu_i + mu_r));
+// pars = (refractive index, NDVI, C).  3x3 block K[3*o1+o2] like the GISS kernel.
+HDFN void brdf_bpdf_kernel(const double *pars, double XI, double SXI, double XJ, double SXJ, double cphi, double sphi, double *K) {
+  double xi = XI, xj = XJ;
+  if (fabs(xi - 1.0) < 1e-9) xi = 0.999999999999;
+  if (fabs(xj - 1.0) < 1e-9) xj = 0.999999999999;
+  double Z = xi * xj - SXI * SXJ * cphi;
+  if (Z > 1.0) Z = 1.0;
+  const double Z1 = acos(Z), Z2 = cos(Z1 * 0.5);
+  double NDVI = pars[1];
+  if (NDVI > 1.0 || NDVI < -1.0) NDVI = 0.0;
+  const double Fp0 = 0.25 * exp(-NDVI) / (xi + xj);
+  const double cgamma = Z2, sgamma = sqrt(1.0 - cgamma * cgamma), atten = exp(-sgamma / cgamma);
+  double HF = pars[2] * Fp0 * atten;
+  // FRESNEL_VECTOR (CN1 = 1, CN2 = pars[0]; incident azimuth 0)
+  const double VI1 = SXI, VI3 = -xi;
+  const double VR1 = SXJ * cphi, VR2 = SXJ * sphi, VR3 = xj;
+  const double U1 = VI1 - VR1, U2 = -VR2, U3 = VI3 - VR3;
+  const double FACT1 = U1 * U1 + U2 * U2 + U3 * U3, FACTOR = sqrt(1.0 / FACT1);
+  const double CN2 = pars[0];
+  const double XI1 = FACTOR * (U1 * VI1 + U3 * VI3);
+  const double CXI2 = sqrt(1.0 - (1.0 - XI1 * XI1) / (CN2 * CN2));
+  double C1 = XI1, C2 = CN2 * CXI2; const double CRPER = (C1 - C2) / (C1 + C2);
+  C1 = CN2 * XI1; C2 = CXI2; const double CRPAR = (C1 - C2) / (C1 + C2);
+  const double TI1 = -xi, TI3 = -SXI;
+  const double TR1 = xj * cphi, TR3 = -SXJ;
+  const double PR1 = -sphi;
+  const double PIKR = VR2, PRKI = PR1 * VI1;
+  const double TIKR = TI1 * VR1 + TI3 * VR3, TRKI = TR1 * VI1 + TR3 * VI3;
+  const double E1 = PIKR * PRKI, E2 = TIKR * TRKI, E3 = TIKR * PRKI, E4 = PIKR * TRKI;
+  double CF11 = E1 * CRPER + E2 * CRPAR, CF12 = -E3 * CRPER + E4 * CRPAR, CF21 = -E4 * CRPER + E3 * CRPAR, CF22 = E2 * CRPER + E1 * CRPAR;
+  const double VP1 = -VI3 * VR2, VP2 = VI3 * VR1 - VI1 * VR3, VP3 = VI1 * VR2;
+  double DMOD = VP1 * VP1 + VP2 * VP2 + VP3 * VP3; DMOD = DMOD * DMOD;
+  if (DMOD == 0.0) { CF11 = CRPAR; CF22 = CRPER; DMOD = 1.0; }
+  HF = HF / DMOD;
+  const double AF11 = CF11 * CF11, AF12 = CF12 * CF12, AF21 = CF21 * CF21, AF22 = CF22 * CF22, AF = 0.5 * HF;
+  K[0] = (AF11 + AF12 + AF21 + AF22) * AF; K[1] = (AF11 - AF12 + AF21 - AF22) * AF;
+  K[3] = (AF11 - AF22 + AF12 - AF21) * AF; K[4] = (AF11 - AF12 - AF21 + AF22) * AF;
+  const double CTTTP = CF11 * CF12, CTTPT = CF11 * CF21, CTTPP = CF11 * CF22, CTPPT = CF12 * CF21, CTPPP = CF12 * CF22, CPTPP = CF21 * CF22;
+  K[2] = -(CTTTP + CPTPP) * HF; K[5] = -(CTTTP - CPTPP) * HF; K[6] = -(CTTPT + CTPPP) * HF;
+  K[7] = -(CTTPT - CTPPP) * HF; K[8] = (CTTPP + CTPPT) * HF;
+}
+// kernels with a Mueller block (which = 10 GISS Cox-Munk, 14 BPDF-NDVI)
+HDFN void brdf_vec_kernel(int which, const double *pars, double XI, double SXI, double XJ, double SXJ, double cphi, double sphi, double *K) {
+  if (which == 10) brdf_giss_kernel(pars, XI, SXI, XJ, SXJ, cphi, sphi, K);
+  else brdf_bpdf_kernel(pars, XI, SXI, XJ, SXJ, cphi, sphi, K);
+}
+
 struct SurfPars { int nk, which[3], lam[3]; double fac[3], pars[3][3]; };
 
 // surface parameters of pixel (obs j, channel i) as the glue sets them
@@ -188,6 +240,12 @@ HDFN void surf_params(const VLBrdf &B, int j, int i, SurfPars &P) {
     P.nk = 3; P.which[0] = 1; P.which[1] = 3; P.which[2] = 4; P.lam[0] = 1;
     P.fac[0] = kw[0]; P.fac[1] = kw[2]; P.fac[2] = kw[1];                       // (fiso, fvol, fgeo)
     P.pars[2][0] = pr[0]; P.pars[2][1] = pr[1];
+    return;
+  }
+  if (B.kind == SURF_BPDF) {                                                   // VLIDORT_BPDF, V283/VLIDORT_SurfaceMod.F90:2279-2480
+    const double *pr = B.param + 3 * (i + (size_t)B.nch * j);
+    P.nk = 1; P.which[0] = 14; P.fac[0] = 1.0;
+    P.pars[0][0] = pr[0]; P.pars[0][1] = pr[1]; P.pars[0][2] = pr[2];
     return;
   }
   double W = sqrt(B.u10m[j] * B.u10m[j] + B.v10m[j] * B.v10m[j]);
@@ -215,8 +273,8 @@ HDFN void brdf_exact_pixel(const VLBrdf &B, int p) {
   double ex[16];
   for (int q = 0; q < 16; q++) ex[q] = 0.0;
   for (int k = 0; k < P.nk; k++) {
-    if (P.which[k] == 10) {
-      double K[9]; brdf_giss_kernel(P.pars[k], mu0, smu0, muv, smuv, cphi, sphi, K);
+    if (brdf_vec_which(P.which[k])) {
+      double K[9]; brdf_vec_kernel(P.which[k], P.pars[k], mu0, smu0, muv, smuv, cphi, sphi, K);
       if (B.bns == 1) ex[0] += P.fac[k] * K[0];
       else for (int t = 0; t < 9; t++) ex[brdf_q16(t)] += P.fac[k] * K[t];
     } else ex[0] += P.fac[k] * brdf_scalar_kernel(P.which[k], P.pars[k], mu0, smu0, muv, smuv, cphi, sphi);
@@ -253,7 +311,7 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
       for (int idx = T.rank; idx < tot; idx += T.size) {
         const int b = idx % NB, ij = idx / NB, jj = ij % BRDF_NSCAL, ii = ij / BRDF_NSCAL;
         double v;
-        if (P.which[k] == 10) { double K[9]; brdf_giss_kernel(P.pars[k], B.sx[jj], B.ss[jj], B.sx[ii], B.ss[ii], B.cxb[b], B.sxb[b], K); v = K[0]; }
+        if (brdf_vec_which(P.which[k])) { double K[9]; brdf_vec_kernel(P.which[k], P.pars[k], B.sx[jj], B.ss[jj], B.sx[ii], B.ss[ii], B.cxb[b], B.sxb[b], K); v = K[0]; }
         else v = brdf_scalar_kernel(P.which[k], P.pars[k], B.sx[jj], B.ss[jj], B.sx[ii], B.ss[ii], B.cxb[b], B.sxb[b]);
         part += v * B.ab[b] * B.ssw[jj] * B.ssw[ii];
       }
@@ -293,8 +351,8 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
           const double muv = cos(B.vza[j + (size_t)B.nobs * g] * DEG_TO_RAD);
           XI = B.qx[jc]; SXI = B.qs[jc]; XJ = muv; SXJ = sqrt(1.0 - muv * muv);
         }
-        if (P.which[k] == 10) {
-          double K[9]; brdf_giss_kernel(P.pars[k], XI, SXI, XJ, SXJ, B.cxb[b], B.sxb[b], K);
+        if (brdf_vec_which(P.which[k])) {
+          double K[9]; brdf_vec_kernel(P.which[k], P.pars[k], XI, SXI, XJ, SXJ, B.cxb[b], B.sxb[b], K);
           if (nqs == 1) vals[(size_t)el * NB + b] = K[0];
           else for (int t = 0; t < 9; t++) vals[((size_t)el * 9 + t) * NB + b] = K[t];
         } else vals[(size_t)el * NB + b] = brdf_scalar_kernel(P.which[k], P.pars[k], XI, SXI, XJ, SXJ, B.cxb[b], B.sxb[b]);

@@ -52,14 +52,14 @@ __global__ void k_vl_brdf_exact(VLBrdf B, int npix, const unsigned char *__restr
   if (skip[p]) { for (int q = 0; q < 16; q++) B.exactdb[(size_t)p * 16 + q] = 0.0; BR[o] = 0.0; if (BR_Q) { BR_Q[o] = 0.0; BR_U[o] = 0.0; } return; }
   brdf_exact_pixel(B, p);
   double br = B.exactdb[(size_t)p * 16];
-  const bool neg = (B.kind == SURF_MODIS && br < 0);
+  const bool neg = (surf_is_land(B.kind) && br < 0);
   if (neg) br = -500.0;
   BR[o] = br;
   // BRDF_Q / BRDF_U: elements (1,2) and (1,3) of the exact direct-bounce BRDF for the GISS and the OCI wrappers
   // (BS_DBOUNCE_BRDFUNC(2,1,1,1), (3,1,1,1): VLIDORT_BRDF_CX.F90:199-201,388-389,1865-1866), 0 for Vector_CX (:733-734) and
   // LandMODIS (VLIDORT_BRDF_MODIS.F90:365-366)
   if (BR_Q) {
-    const bool pol = surf_is_giss(B.kind) || B.kind == SURF_OCICX;
+    const bool pol = surf_is_giss(B.kind) || B.kind == SURF_OCICX || B.kind == SURF_BPDF;
     BR_Q[o] = neg ? -500.0 : (pol ? B.exactdb[(size_t)p * 16 + 1] : 0.0);
     BR_U[o] = neg ? -500.0 : (pol ? B.exactdb[(size_t)p * 16 + 2] : 0.0);
   }
@@ -708,7 +708,7 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
               int nadir_already, double *radiance, double *reflectance, double *Q, double *U, cudaStream_t st, int *nf_out, int *st_out) {
   const int nj = sl.nj, nobs = sl.nobs, j0 = sl.j0;
   const size_t npix = (size_t)nj * nch, nview = npix * G;
-  const bool cx = (sa.kind != SURF_MODIS);
+  const bool cx = !surf_is_land(sa.kind);
   const size_t n_rot = (size_t)km * nj * nch, n_pm = n_rot * nMom * nPol, n_he = (size_t)(km + 1) * nj;
   const size_t bytes = 8 * (n_rot * 4 + n_pm + (sa.tauI ? n_rot * (4 + 2 * (size_t)nMom) : 0) + n_he + (3 + 2 * (size_t)G) * nj + 2 * nch + 6 * npix + 7 * nview + 16 * nview) + 16 * nview + 4096 * 40;
   VLContext &C = vl_context();
@@ -748,7 +748,8 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
     R.tauL = put(sa.tauL, (size_t)km * nch, 1); R.ssaL = put(sa.ssaL, (size_t)km * nch, 1); R.pmomL = put(sa.pmomL, (size_t)km * nch, (size_t)nMom);
   }
   const double *d_u = cx ? put(sa.u10m, 1, 1) : nullptr, *d_v = cx ? put(sa.v10m, 1, 1) : nullptr, *d_mr = cx ? putv(sa.mr, nch) : nullptr;
-  const double *d_kw = cx ? nullptr : put(sa.kernel_wt, (size_t)3 * nch, 1), *d_pr = cx ? nullptr : put(sa.param, (size_t)2 * nch, 1);
+  const double *d_kw = sa.kind == SURF_MODIS ? put(sa.kernel_wt, (size_t)3 * nch, 1) : nullptr;
+  const double *d_pr = cx ? nullptr : put(sa.param, (size_t)(sa.kind == SURF_BPDF ? 3 : 2) * nch, 1);
   double *d_exact = put(nullptr, 16, (size_t)nch * G);
   double *d_BR, *d_BRQ, *d_BRU;
   const size_t oo = (size_t)nch * G;
@@ -792,7 +793,7 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   k_vl_brdf_exact<<<(unsigned)((nview + 127) / 128), 128, 0, st>>>(B, (int)nview, d_skip0, d_BR, d_BRQ, d_BRU);
   AB_CUDA_OK(cudaGetLastError());
   { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.n_launches += 1; }
-  if (sa.kind == SURF_MODIS) {                         // BR < 0 -> every output -500, pixel-view not run
+  if (surf_is_land(sa.kind)) {                         // BR < 0 -> every output -500, pixel-view not run
     std::vector<double> h_br(nview);
     AB_CUDA_OK(cudaMemcpyAsync(h_br.data(), d_BR, 8 * nview, cudaMemcpyDeviceToHost, st));
     AB_CUDA_OK(cudaStreamSynchronize(st));
@@ -837,9 +838,9 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   *rc = 0;
   if (km < 1 || nch < 0 || nobs < 0 || nstreams < 1 || nMom < 0 || nPol < 1) { ab200_set_error("vlidort: negative or zero dimension"); return AB200_ERR_ARG; }
   if ((size_t)nobs * nch > 0) {
-    const bool cx = (sa.kind != SURF_MODIS);
+    const bool cx = !surf_is_land(sa.kind);
     if (!ROT || !depol || !tau || !ssa || !pmom || !he || !sza || !raa || !vza || !radiance || !reflectance || (S == 3 && (!Q || !U)) ||
-        (cx && (!sa.u10m || !sa.v10m || !sa.mr)) || (!cx && (!sa.kernel_wt || !sa.param))) {
+        (cx && (!sa.u10m || !sa.v10m || !sa.mr)) || (!cx && (!sa.param || (sa.kind == SURF_MODIS && !sa.kernel_wt)))) {
       ab200_set_error("vlidort: NULL array argument"); return AB200_ERR_ARG;
     }
   }
@@ -873,7 +874,7 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
     e = brdf_slab(true, S, scalar_glue, km, nch, Slab{0, nobs, nobs}, G, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, sza,
                   raa, vza, MISSING, sa, 0, radiance, reflectance, Q, U, st, nf.data(), stt.data());
   } else {
-    const bool cx = (sa.kind != SURF_MODIS);
+    const bool cx = !surf_is_land(sa.kind);
     int nadir_first = nobs;       // first observation with solar_zenith == 0.0 that is actually run (FOCORR_NADIR state quirk)
     for (int j = 0; j < nobs && nadir_first == nobs; j++) {
       if (sza[j] != 0.0 || is_missing_h(sza[j], MISSING) || is_missing_h(vza[j], MISSING) || is_missing_h(raa[j], MISSING)) continue;
@@ -1203,6 +1204,19 @@ extern "C" int ab200_vlidort_vector_brdf_modis(int km, int nch, int nobs, const 
   (void)channels; (void)pe; (void)te; (void)verbose;
   if (nkernel != 3 || nparam != 2) { ab200_set_error("vector_brdf_modis: nkernel must be 3 and nparam 2 (GV/VLIDORT_BRDF_MODIS.F90:224-225)"); return AB200_ERR_ARG; }
   SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+// VLIDORT_Vector_BPDF (GV/VLIDORT_BRDF_MODIS_BPDF.F90:459-643; f2py VECTOR_BPDF, LV/VLIDORT_POLAR_py.F90:295): one BPDF-NDVI kernel
+extern "C" int ab200_vlidort_vector_bpdf(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                         int nPol, int nparam, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                         const double *pmom, const double *pe, const double *he, const double *te, const double *BPDFparam,
+                                         const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                                         int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                         double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (nparam != 3) { ab200_set_error("vector_bpdf: nparam must be 3 (GV/VLIDORT_BRDF_MODIS_BPDF.F90:472)"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_BPDF, nullptr, nullptr, nullptr, nullptr, BPDFparam, BR, BR_Q, BR_U};
   return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }

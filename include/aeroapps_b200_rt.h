@@ -107,6 +107,15 @@ int ab200_vlidort_vector_brdf_modis(int km, int nch, int nobs, const double *cha
                                     const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
                                     double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
                                     double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_BPDF (GV/VLIDORT_BRDF_MODIS_BPDF.F90:459-643; f2py VECTOR_BPDF, LV/VLIDORT_POLAR_py.F90:295-368): polarised land surface,
+ * one BPDF-NDVI kernel (VLIDORT_BPDF, V283/VLIDORT_SurfaceMod.F90:2279; kernel index 14, 50 azimuth streams).  BPDFparam (nparam = 3,nch,nobs) =
+ * refractive index, NDVI, scaling factor C.  BR_Q, BR_U = elements (1,2), (1,3) of the exact direct-bounce BRDF; BR < 0 -> all outputs -500. */
+int ab200_vlidort_vector_bpdf(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom, int nPol,
+                              int nparam, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                              const double *pmom, const double *pe, const double *he, const double *te, const double *BPDFparam,
+                              const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                              int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                              double *BR_Q, double *BR_U, int *rc);
 /* VLIDORT_Scalar_LandMODIS (VLIDORT_BRDF_MODIS.F90:35-202) */
 int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
                                     int nMom, int nPol, const double *ROT, const double *depol, const double *tau,

@@ -84,6 +84,52 @@ void kernel_eval(int which, const double *pars, double xinc, double sxinc, doubl
     K[0] *= 1.0 / (1.0 + shadowi + shadowr);
     return;
   }
+  if (which == 14) {                                                  /* BPDFNDVI_VFUNCTION (VB/vbrdf_sup_kernels.f90:3017-3198) */
+    double xi = XI, xj = XJ;
+    const double CN1 = 1.0, CN2 = pars[0];
+    if (std::fabs(xi - 1.0) < 1e-9) xi = 0.999999999999;
+    if (std::fabs(xj - 1.0) < 1e-9) xj = 0.999999999999;
+    double Z = xi * xj - SXI * SXJ * cphi; if (Z > 1.0) Z = 1.0;
+    double Z1 = std::acos(Z), Z2 = std::cos(Z1 * 0.5);
+    double NDVI = pars[1];
+    if (NDVI > 1.0 || NDVI < -1.0) NDVI = 0.0;
+    double DEXPNDVI = std::exp(-NDVI);
+    double Fp0 = 0.25 * DEXPNDVI / (xi + xj);
+    double cgamma = Z2, sgamma = std::sqrt(1.0 - cgamma * cgamma), atten = std::exp(-sgamma / cgamma);
+    double C = pars[2];
+    double HFUNCTION = C * Fp0 * atten;
+    /* FRESNEL_VECTOR (:3560-3702) */
+    const double ckphi_inc = 1.0, skphi_inc = 0.0, ckphi_ref = cphi, skphi_ref = sphi;
+    double VI1 = SXI * ckphi_inc, VI2 = SXI * skphi_inc, VI3 = -xi;
+    double VR1 = SXJ * ckphi_ref, VR2 = SXJ * skphi_ref, VR3 = xj;
+    double U1 = VI1 - VR1, U2 = VI2 - VR2, U3 = VI3 - VR3;
+    double FACT1 = U1 * U1 + U2 * U2 + U3 * U3, FACTOR = std::sqrt(1.0 / FACT1);
+    double XI1 = FACTOR * (U1 * VI1 + U2 * VI2 + U3 * VI3);
+    double CXI2 = 1.0 - (1.0 - XI1 * XI1) * CN1 * CN1 / (CN2 * CN2); CXI2 = std::sqrt(CXI2);
+    double C1 = CN1 * XI1, C2 = CN2 * CXI2, CRPER = (C1 - C2) / (C1 + C2);
+    C1 = CN2 * XI1; C2 = CN1 * CXI2; double CRPAR = (C1 - C2) / (C1 + C2);
+    double TI1 = -xi * ckphi_inc, TI2 = -xi * skphi_inc, TI3 = -SXI;
+    double TR1 = xj * ckphi_ref, TR2 = xj * skphi_ref, TR3 = -SXJ;
+    double PI1 = -skphi_inc, PII2 = ckphi_inc, PI3 = 0.0, PR1 = -skphi_ref, PR2 = ckphi_ref, PR3 = 0.0;
+    double PIKR = PI1 * VR1 + PII2 * VR2 + PI3 * VR3, PRKI = PR1 * VI1 + PR2 * VI2 + PR3 * VI3;
+    double TIKR = TI1 * VR1 + TI2 * VR2 + TI3 * VR3, TRKI = TR1 * VI1 + TR2 * VI2 + TR3 * VI3;
+    double E1 = PIKR * PRKI, E2 = TIKR * TRKI, E3 = TIKR * PRKI, E4 = PIKR * TRKI;
+    double CF11 = E1 * CRPER + E2 * CRPAR, CF12 = -E3 * CRPER + E4 * CRPAR, CF21 = -E4 * CRPER + E3 * CRPAR, CF22 = E2 * CRPER + E1 * CRPAR;
+    double VP1 = VI2 * VR3 - VI3 * VR2, VP2 = VI3 * VR1 - VI1 * VR3, VP3 = VI1 * VR2 - VI2 * VR1;
+    double DMOD = VP1 * VP1 + VP2 * VP2 + VP3 * VP3; DMOD = DMOD * DMOD;
+    if (DMOD == 0.0) { CF11 = CRPAR; CF22 = CRPER; DMOD = 1.0; }
+    HFUNCTION = HFUNCTION / DMOD;
+    double AF11 = std::fabs(CF11), AF12 = std::fabs(CF12), AF21 = std::fabs(CF21), AF22 = std::fabs(CF22);
+    AF11 = AF11 * AF11; AF12 = AF12 * AF12; AF21 = AF21 * AF21; AF22 = AF22 * AF22;
+    double F = 0.5 * HFUNCTION;
+    K[0] = (AF11 + AF12 + AF21 + AF22) * F; K[1] = (AF11 - AF12 + AF21 - AF22) * F;
+    K[4] = (AF11 - AF22 + AF12 - AF21) * F; K[5] = (AF11 - AF12 - AF21 + AF22) * F;
+    double CTTTP = CF11 * CF12, CTTPT = CF11 * CF21, CTTPP = CF11 * CF22, CTPPT = CF12 * CF21, CTPPP = CF12 * CF22, CPTPP = CF21 * CF22;
+    F = HFUNCTION;
+    K[2] = -(CTTTP + CPTPP) * F; K[6] = -(CTTTP - CPTPP) * F; K[8] = -(CTTPT + CTPPP) * F;
+    K[9] = -(CTTPT - CTPPP) * F; K[10] = (CTTPP + CTPPT) * F; K[15] = (CTTPP - CTPPT) * F;
+    return;
+  }
   if (which == 10) {                                                  /* GISSCOXMUNK_VFUNCTION */
     const double CRITEXP = 88.0;
     double xi = XI, xj = XJ;

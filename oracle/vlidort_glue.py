@@ -80,7 +80,7 @@ class _OrcSurface(C.Structure):
     _fields_ = [("kind", C.c_int)] + [(n, C.POINTER(C.c_double)) for n in ("u10m", "v10m", "mr", "kernel_wt", "param", "BR", "BR_Q", "BR_U")]
 
 
-SURFACE_KINDS = {"cx": 2, "gisscx": 3, "modis": 4, "ocicx": 5, "ocigisscx": 6}
+SURFACE_KINDS = {"cx": 2, "gisscx": 3, "modis": 4, "ocicx": 5, "ocigisscx": 6, "bpdf": 7}
 
 
 def vlidort_run_surface(kind, nstokes, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, he, sza, raa, vza, u10m=None,
