@@ -166,6 +166,40 @@ def vector_bpdf(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, 
     return (*outs, rc.value)
 
 
+def vector_brdf_modis_bpdf(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, kernel_wt, RTLSparam, BPDFparam,
+                           solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_BRDF_MODIS_BPDF (VLIDORT_POLAR_py.F90:214): kernel_wt (3,nch,nobs), RTLSparam (2,nch,nobs), BPDFparam (3,nch,nobs).
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te, kw, rp, bp = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, kernel_wt, RTLSparam, BPDFparam))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert kw.shape == (3, nch, nobs) and rp.shape == (2, nch, nobs) and bp.shape == (3, nch, nobs)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_brdf_modis_bpdf(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, 3, 2, 3, _p(ROT),
+                                                     _p(dp), _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te), _p(kw), _p(rp), _p(bp), _p(sza),
+                                                     _p(raa), _p(vza), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_brdf_modis_bpdf")
+    return (*outs, rc.value)
+
+
+def vector_lambert_bpdf(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, albedo, BPDFparam, solar_zenith,
+                        relat_azymuth, sensor_zenith, MISSING, verbose):
+    """f2py VECTOR_LAMBERT_BPDF (VLIDORT_POLAR_py.F90:528): albedo (nobs,nch), BPDFparam (3,nch,nobs).
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te, alb, bp = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, albedo, BPDFparam))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert alb.shape == (nobs, nch) and bp.shape == (3, nch, nobs)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_lambert_bpdf(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, 3, _p(ROT), _p(dp),
+                                                  _p(tau), _p(ssa), _p(pmom), _p(pe), _p(he), _p(te), _p(alb), _p(bp), _p(sza), _p(raa), _p(vza),
+                                                  C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_lambert_bpdf")
+    return (*outs, rc.value)
+
+
 def scalar_cx(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, pe, he, te, U10m, V10m, mr, solar_zenith,
               relat_azymuth, sensor_zenith, MISSING, verbose):
     """VLIDORT_Scalar_CX (VLIDORT_BRDF_CX.F90:420): returns (radiance, reflectance, BRDF (1,nobs,nch), rc)."""

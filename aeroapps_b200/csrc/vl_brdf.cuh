@@ -19,11 +19,14 @@ constexpr int BRDF_NSCAL = 24;       // SCALING_NSTREAMS: white-sky-albedo quadr
 constexpr int BRDF_MAXNB = 100;      // azimuth quadrature streams (MAXSTREAMS_BRDF)
 
 // OCI variants (V283/VLIDORT_SurfaceMod.F90:82-538): same kernels, slope variance sigma2 = 0.00534 W instead of 0.003 + 0.00512 W
-enum { SURF_LAMBERT = 0, SURF_CX = 2, SURF_GISSCX = 3, SURF_MODIS = 4, SURF_OCICX = 5, SURF_OCIGISSCX = 6, SURF_BPDF = 7 };
+enum { SURF_LAMBERT = 0, SURF_CX = 2, SURF_GISSCX = 3, SURF_MODIS = 4, SURF_OCICX = 5, SURF_OCIGISSCX = 6, SURF_BPDF = 7,
+       SURF_MODIS_BPDF = 8, SURF_LAMBERT_BPDF = 9 };
 HDFN bool surf_is_giss(int kind) { return kind == SURF_GISSCX || kind == SURF_OCIGISSCX; }
 HDFN bool surf_is_oci(int kind) { return kind == SURF_OCICX || kind == SURF_OCIGISSCX; }
-HDFN bool surf_is_land(int kind) { return kind == SURF_MODIS || kind == SURF_BPDF; }      // NSTREAMS_BRDF = 50, BR < 0 -> -500, no wind inputs
-HDFN bool surf_is_vec(int kind) { return surf_is_giss(kind) || kind == SURF_BPDF; }        // kernel with a full Mueller block (index >= 10)
+HDFN bool surf_has_bpdf(int kind) { return kind == SURF_BPDF || kind == SURF_MODIS_BPDF || kind == SURF_LAMBERT_BPDF; }
+HDFN bool surf_has_rtls(int kind) { return kind == SURF_MODIS || kind == SURF_MODIS_BPDF; }
+HDFN bool surf_is_land(int kind) { return kind == SURF_MODIS || surf_has_bpdf(kind); }      // NSTREAMS_BRDF = 50, BR < 0 -> -500, no wind inputs
+HDFN bool surf_is_vec(int kind) { return surf_is_giss(kind) || surf_has_bpdf(kind); }        // kernel with a full Mueller block (index >= 10)
 HDFN bool brdf_vec_which(int which) { return which == 10 || which == 14; }
 
 struct VLBrdf {
@@ -33,6 +36,7 @@ struct VLBrdf {
   const double *vza, *raa;                  // (nobs,G)
   const double *u10m, *v10m, *mr;           // (nobs) (nobs) (nch)      Cox-Munk family
   const double *kernel_wt, *param;          // (3,nch,nobs) (2,nch,nobs) MODIS RTLS; param (3,nch,nobs) = BPDFparam for SURF_BPDF
+  const double *bpdf, *albedo;              // SURF_MODIS_BPDF / SURF_LAMBERT_BPDF: BPDFparam (3,nch,nobs); SURF_LAMBERT_BPDF: albedo (nobs,nch)
   const double *xb, *ab, *cxb, *sxb;        // [NB] azimuth quadrature (angles, weights, cos, sin)
   const double *caz, *saz;                  // [NM+1][NB]  weight*cos(m x), weight*sin(m x)
   const double *sx, *ss, *ssw;              // [24] scaling quadrature: cosines, sines, cosine*weight
@@ -230,11 +234,25 @@ HDFN void brdf_vec_kernel(int which, const double *pars, double XI, double SXI, 
   else brdf_bpdf_kernel(pars, XI, SXI, XJ, SXJ, cphi, sphi, K);
 }
 
-struct SurfPars { int nk, which[3], lam[3]; double fac[3], pars[3][3]; };
+struct SurfPars { int nk, which[4], lam[4]; double fac[4], pars[4][3]; };
 
 // surface parameters of pixel (obs j, channel i) as the glue sets them
 HDFN void surf_params(const VLBrdf &B, int j, int i, SurfPars &P) {
-  for (int k = 0; k < 3; k++) { P.lam[k] = 0; P.fac[k] = 0.0; P.which[k] = 0; for (int t = 0; t < 3; t++) P.pars[k][t] = 0.0; }
+  for (int k = 0; k < 4; k++) { P.lam[k] = 0; P.fac[k] = 0.0; P.which[k] = 0; for (int t = 0; t < 3; t++) P.pars[k][t] = 0.0; }
+  if (B.kind == SURF_LAMBERT_BPDF) {                                           // VLIDORT_LAMBERTIAN_BPDF, V283/VLIDORT_SurfaceMod.F90:2065-2275
+    const double *bp = B.bpdf + 3 * (i + (size_t)B.nch * j);
+    P.nk = 2; P.which[0] = 1; P.lam[0] = 1; P.fac[0] = B.albedo[j + (size_t)B.nobs * i];
+    P.which[1] = 14; P.fac[1] = 1.0; P.pars[1][0] = bp[0]; P.pars[1][1] = bp[1]; P.pars[1][2] = bp[2];
+    return;
+  }
+  if (B.kind == SURF_MODIS_BPDF) {                                             // VLIDORT_LANDMODIS_BPDF, :1826-2060: RTLS + BPDF-NDVI
+    const double *kw = B.kernel_wt + 3 * (i + (size_t)B.nch * j), *pr = B.param + 2 * (i + (size_t)B.nch * j), *bp = B.bpdf + 3 * (i + (size_t)B.nch * j);
+    P.nk = 4; P.which[0] = 1; P.which[1] = 3; P.which[2] = 4; P.which[3] = 14; P.lam[0] = 1;
+    P.fac[0] = kw[0]; P.fac[1] = kw[2]; P.fac[2] = kw[1]; P.fac[3] = 1.0;
+    P.pars[2][0] = pr[0]; P.pars[2][1] = pr[1];
+    P.pars[3][0] = bp[0]; P.pars[3][1] = bp[1]; P.pars[3][2] = bp[2];
+    return;
+  }
   if (B.kind == SURF_MODIS) {
     const double *kw = B.kernel_wt + 3 * (i + (size_t)B.nch * j), *pr = B.param + 2 * (i + (size_t)B.nch * j);
     P.nk = 3; P.which[0] = 1; P.which[1] = 3; P.which[2] = 4; P.lam[0] = 1;
@@ -338,6 +356,7 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
       T.sync();
       continue;
     }
+    const int kq = brdf_vec_which(P.which[k]) ? nqs : 1;       // Mueller elements this kernel fills: a scalar kernel only has (1,1)
     for (int e0 = 0; e0 < NE; e0 += EB) {
       const int ne = (NE - e0 < EB) ? NE - e0 : EB;
       // kernel values on the azimuth quadrature
@@ -353,16 +372,16 @@ DEVFN void brdf_pixel(const Team &T, const VLBrdf &B, int p, int pc, double *scr
         }
         if (brdf_vec_which(P.which[k])) {
           double K[9]; brdf_vec_kernel(P.which[k], P.pars[k], XI, SXI, XJ, SXJ, B.cxb[b], B.sxb[b], K);
-          if (nqs == 1) vals[(size_t)el * NB + b] = K[0];
+          if (kq == 1) vals[(size_t)el * NB + b] = K[0];
           else for (int t = 0; t < 9; t++) vals[((size_t)el * 9 + t) * NB + b] = K[t];
         } else vals[(size_t)el * NB + b] = brdf_scalar_kernel(P.which[k], P.pars[k], XI, SXI, XJ, SXJ, B.cxb[b], B.sxb[b]);
       }
       T.sync();
       // projection on the Fourier components
-      const int ncombo = ne * nqs * (NM + 1);
+      const int ncombo = ne * kq * (NM + 1);
       for (int idx = T.rank; idx < ncombo; idx += T.size) {
-        const int el = idx % ne, r = idx / ne, t = r % nqs, m = r / nqs, e = e0 + el;
-        const double *v = vals + ((size_t)el * nqs + t) * NB;
+        const int el = idx % ne, r = idx / ne, t = r % kq, m = r / kq, e = e0 + el;
+        const double *v = vals + ((size_t)el * kq + t) * NB;
         const int cs = brdf_cossin(t);
         const double *tab = (cs == 1 ? B.caz : B.saz) + (size_t)m * NB;
         double s = 0.0;

@@ -59,7 +59,7 @@ __global__ void k_vl_brdf_exact(VLBrdf B, int npix, const unsigned char *__restr
   // (BS_DBOUNCE_BRDFUNC(2,1,1,1), (3,1,1,1): VLIDORT_BRDF_CX.F90:199-201,388-389,1865-1866), 0 for Vector_CX (:733-734) and
   // LandMODIS (VLIDORT_BRDF_MODIS.F90:365-366)
   if (BR_Q) {
-    const bool pol = surf_is_giss(B.kind) || B.kind == SURF_OCICX || B.kind == SURF_BPDF;
+    const bool pol = surf_is_giss(B.kind) || B.kind == SURF_OCICX || surf_has_bpdf(B.kind);
     BR_Q[o] = neg ? -500.0 : (pol ? B.exactdb[(size_t)p * 16 + 1] : 0.0);
     BR_U[o] = neg ? -500.0 : (pol ? B.exactdb[(size_t)p * 16 + 2] : 0.0);
   }
@@ -686,6 +686,7 @@ struct SurfArgs {
   int kind; const double *u10m, *v10m, *mr, *kernel_wt, *param; double *BR, *BR_Q, *BR_U; const double *alpha = nullptr, *flux_factor = nullptr;
   // cloud variants (host pointers, full reference shapes): all six set or all null
   const double *tauI = nullptr, *ssaI = nullptr, *pmomI = nullptr, *tauL = nullptr, *ssaL = nullptr, *pmomL = nullptr;
+  const double *bpdf = nullptr, *albedo = nullptr;        // SURF_MODIS_BPDF / SURF_LAMBERT_BPDF: BPDFparam (3,nch,nobs); SURF_LAMBERT_BPDF: albedo (nobs,nch)
 };
 
 // pixel-independent BRDF tables -> device
@@ -748,8 +749,10 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
     R.tauL = put(sa.tauL, (size_t)km * nch, 1); R.ssaL = put(sa.ssaL, (size_t)km * nch, 1); R.pmomL = put(sa.pmomL, (size_t)km * nch, (size_t)nMom);
   }
   const double *d_u = cx ? put(sa.u10m, 1, 1) : nullptr, *d_v = cx ? put(sa.v10m, 1, 1) : nullptr, *d_mr = cx ? putv(sa.mr, nch) : nullptr;
-  const double *d_kw = sa.kind == SURF_MODIS ? put(sa.kernel_wt, (size_t)3 * nch, 1) : nullptr;
-  const double *d_pr = cx ? nullptr : put(sa.param, (size_t)(sa.kind == SURF_BPDF ? 3 : 2) * nch, 1);
+  const double *d_kw = surf_has_rtls(sa.kind) ? put(sa.kernel_wt, (size_t)3 * nch, 1) : nullptr;
+  const double *d_pr = (surf_has_rtls(sa.kind) || sa.kind == SURF_BPDF) ? put(sa.param, (size_t)(sa.kind == SURF_BPDF ? 3 : 2) * nch, 1) : nullptr;
+  const double *d_bp = (sa.kind == SURF_MODIS_BPDF || sa.kind == SURF_LAMBERT_BPDF) ? put(sa.bpdf, (size_t)3 * nch, 1) : nullptr;
+  const double *d_alb = sa.kind == SURF_LAMBERT_BPDF ? put(sa.albedo, 1, nch) : nullptr;
   double *d_exact = put(nullptr, 16, (size_t)nch * G);
   double *d_BR, *d_BRQ, *d_BRU;
   const size_t oo = (size_t)nch * G;
@@ -776,7 +779,8 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
     const bool ma = is_missing_h(h_sza[j], MISSING) || is_missing_h(h_vza[j], MISSING) || is_missing_h(h_raa[j], MISSING);
     const bool mw = cx && (is_missing_h(h_u[j], MISSING) || is_missing_h(h_v[j], MISSING));
     for (int i = 0; i < nch; i++) {
-      const unsigned char sk = (ma || mw || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
+      const bool malb = sa.kind == SURF_LAMBERT_BPDF && !dev && is_missing_h(sa.albedo[(size_t)(j0 + j) + (size_t)nobs * i], MISSING);   // GV/VLIDORT_LAMBERT_BPDF.F90:128-134
+      const unsigned char sk = (ma || mw || malb || (cx && is_missing_h(h_mr[i], MISSING))) ? 1 : 0;
       for (int g = 0; g < G; g++) skip[((size_t)j * nch + i) * G + g] = sk;
     }
   }
@@ -787,7 +791,7 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   if (!dev) { AB_CUDA_OK(cudaStreamSynchronize(st)); uplock.unlock(); vl_trace("upload end", j0); }
   if (int e = build_brdf_tables(C, B, sa.kind, S, scalar_glue, nstreams, NM, nch, nj, st)) return e;
   B.G = G;
-  B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr;
+  B.sza = R.sza; B.vza = R.vza; B.raa = R.raa; B.u10m = d_u; B.v10m = d_v; B.mr = d_mr; B.kernel_wt = d_kw; B.param = d_pr; B.bpdf = d_bp; B.albedo = d_alb;
   B.exactdb = d_exact;
   off = align256(off); B.wsa_fail = (int *)(b + off); off += 4 * npix;
   k_vl_brdf_exact<<<(unsigned)((nview + 127) / 128), 128, 0, st>>>(B, (int)nview, d_skip0, d_BR, d_BRQ, d_BRU);
@@ -840,7 +844,8 @@ int brdf_front(bool dev, int S, int scalar_glue, int km, int nch, int nobs, int 
   if ((size_t)nobs * nch > 0) {
     const bool cx = !surf_is_land(sa.kind);
     if (!ROT || !depol || !tau || !ssa || !pmom || !he || !sza || !raa || !vza || !radiance || !reflectance || (S == 3 && (!Q || !U)) ||
-        (cx && (!sa.u10m || !sa.v10m || !sa.mr)) || (!cx && (!sa.param || (sa.kind == SURF_MODIS && !sa.kernel_wt)))) {
+        (cx && (!sa.u10m || !sa.v10m || !sa.mr)) || (surf_has_rtls(sa.kind) && (!sa.param || !sa.kernel_wt)) || (sa.kind == SURF_BPDF && !sa.param) ||
+        ((sa.kind == SURF_MODIS_BPDF || sa.kind == SURF_LAMBERT_BPDF) && !sa.bpdf) || (sa.kind == SURF_LAMBERT_BPDF && !sa.albedo)) {
       ab200_set_error("vlidort: NULL array argument"); return AB200_ERR_ARG;
     }
   }
@@ -1217,6 +1222,36 @@ extern "C" int ab200_vlidort_vector_bpdf(int km, int nch, int nobs, const double
   (void)channels; (void)pe; (void)te; (void)verbose;
   if (nparam != 3) { ab200_set_error("vector_bpdf: nparam must be 3 (GV/VLIDORT_BRDF_MODIS_BPDF.F90:472)"); return AB200_ERR_ARG; }
   SurfArgs sa = {SURF_BPDF, nullptr, nullptr, nullptr, nullptr, BPDFparam, BR, BR_Q, BR_U};
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+// VLIDORT_Vector_LandMODIS_BPDF (GV/VLIDORT_BRDF_MODIS_BPDF.F90:23-230; f2py VECTOR_BRDF_MODIS_BPDF): RTLS kernels + BPDF-NDVI
+extern "C" int ab200_vlidort_vector_brdf_modis_bpdf(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                    int nPol, int nkernel, int nparam, int nparam_bpdf, const double *ROT, const double *depol,
+                                                    const double *tau, const double *ssa, const double *pmom, const double *pe, const double *he,
+                                                    const double *te, const double *kernel_wt, const double *RTLSparam, const double *BPDFparam,
+                                                    const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                                    double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                                    double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (nkernel != 3 || nparam != 2 || nparam_bpdf != 3) { ab200_set_error("vector_brdf_modis_bpdf: nkernel, nparam, nparam_bpdf must be 3, 2, 3 (GV/VLIDORT_BRDF_MODIS_BPDF.F90:37-39)"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_MODIS_BPDF, nullptr, nullptr, nullptr, kernel_wt, RTLSparam, BR, BR_Q, BR_U};
+  sa.bpdf = BPDFparam;
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+// VLIDORT_Vector_Lambert_BPDF (GV/VLIDORT_LAMBERT_BPDF.F90:23-223; f2py VECTOR_LAMBERT_BPDF): Lambertian albedo + BPDF-NDVI
+extern "C" int ab200_vlidort_vector_lambert_bpdf(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                 int nPol, int nparam, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                                 const double *pmom, const double *pe, const double *he, const double *te, const double *albedo,
+                                                 const double *BPDFparam, const double *solar_zenith, const double *relat_azymuth,
+                                                 const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                                 double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U,
+                                                 int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose;
+  if (nparam != 3) { ab200_set_error("vector_lambert_bpdf: nparam must be 3 (GV/VLIDORT_LAMBERT_BPDF.F90:39)"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_LAMBERT_BPDF, nullptr, nullptr, nullptr, nullptr, nullptr, BR, BR_Q, BR_U};
+  sa.bpdf = BPDFparam; sa.albedo = albedo;
   return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }

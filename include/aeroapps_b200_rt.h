@@ -116,6 +116,25 @@ int ab200_vlidort_vector_bpdf(int km, int nch, int nobs, const double *channels,
                               const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith, double MISSING,
                               int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
                               double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_LandMODIS_BPDF (GV/VLIDORT_BRDF_MODIS_BPDF.F90:23-230; f2py VECTOR_BRDF_MODIS_BPDF, LV/VLIDORT_POLAR_py.F90:214-292): the MODIS
+ * RTLS kernels (kernel_wt (3,nch,nobs), RTLSparam (2,nch,nobs)) plus the BPDF-NDVI kernel (BPDFparam (3,nch,nobs)); VLIDORT_LANDMODIS_BPDF,
+ * V283/VLIDORT_SurfaceMod.F90:1826-2060 */
+int ab200_vlidort_vector_brdf_modis_bpdf(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                         int nPol, int nkernel, int nparam, int nparam_bpdf, const double *ROT, const double *depol,
+                                         const double *tau, const double *ssa, const double *pmom, const double *pe, const double *he,
+                                         const double *te, const double *kernel_wt, const double *RTLSparam, const double *BPDFparam,
+                                         const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                         double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR,
+                                         double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_Lambert_BPDF (GV/VLIDORT_LAMBERT_BPDF.F90:23-223; f2py VECTOR_LAMBERT_BPDF, LV/VLIDORT_POLAR_py.F90:528-603): Lambertian
+ * albedo (nobs,nch) plus the BPDF-NDVI kernel; VLIDORT_LAMBERTIAN_BPDF, V283/VLIDORT_SurfaceMod.F90:2065-2275.  A MISSING albedo makes
+ * the pixel MISSING. */
+int ab200_vlidort_vector_lambert_bpdf(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                      int nPol, int nparam, const double *ROT, const double *depol, const double *tau, const double *ssa,
+                                      const double *pmom, const double *pe, const double *he, const double *te, const double *albedo,
+                                      const double *BPDFparam, const double *solar_zenith, const double *relat_azymuth,
+                                      const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                      double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
 /* VLIDORT_Scalar_LandMODIS (VLIDORT_BRDF_MODIS.F90:35-202) */
 int ab200_vlidort_scalar_brdf_modis(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
                                     int nMom, int nPol, const double *ROT, const double *depol, const double *tau,

@@ -25,7 +25,7 @@ def _run(kind, S, N, planpar, sc, obs_range, scalar_glue, MISSING):
     return vg.vlidort_run_surface(kind, S, N, planpar, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["he"], sc["sza"],
                                   sc["raa"], sc["vza"], sc.get("u10m"), sc.get("v10m"), sc.get("mr"), sc.get("kernel_wt"), sc.get("param"),
                                   MISSING=MISSING, scalar_glue=scalar_glue, obs_range=obs_range, alpha=sc.get("alpha"),
-                                  flux_factor=sc.get("flux"))
+                                  flux_factor=sc.get("flux"), bpdf=sc.get("bpdf"), albedo=sc.get("albedo"))
 
 
 def oracle_parallel(kind, S, N, planpar, sc, nthreads=None, scalar_glue=False, MISSING=1e15, obs=None, asymtx_tol=1e-12):

@@ -77,15 +77,15 @@ def set_cloud(sc=None):
 
 
 class _OrcSurface(C.Structure):
-    _fields_ = [("kind", C.c_int)] + [(n, C.POINTER(C.c_double)) for n in ("u10m", "v10m", "mr", "kernel_wt", "param", "BR", "BR_Q", "BR_U")]
+    _fields_ = [("kind", C.c_int)] + [(n, C.POINTER(C.c_double)) for n in ("u10m", "v10m", "mr", "kernel_wt", "param", "BR", "BR_Q", "BR_U", "bpdf")]
 
 
-SURFACE_KINDS = {"cx": 2, "gisscx": 3, "modis": 4, "ocicx": 5, "ocigisscx": 6, "bpdf": 7}
+SURFACE_KINDS = {"cx": 2, "gisscx": 3, "modis": 4, "ocicx": 5, "ocigisscx": 6, "bpdf": 7, "modis_bpdf": 8, "lambert_bpdf": 9}
 
 
 def vlidort_run_surface(kind, nstokes, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, he, sza, raa, vza, u10m=None,
                         v10m=None, mr=None, kernel_wt=None, param=None, MISSING=1e15, scalar_glue=False, obs_range=None,
-                        alpha=None, flux_factor=None):
+                        alpha=None, flux_factor=None, bpdf=None, albedo=None):
     """BRDF wrappers (VLIDORT_Vector_CX / _GissCX / _LandMODIS and their scalar forms): dict(radiance, reflectance, Q, U,
     BR, BR_Q, BR_U (nobs,nch), nfourier, status)."""
     ROT, tau, ssa, pmom, he = F(ROT), F(tau), F(ssa), F(pmom), F(he)
@@ -99,10 +99,12 @@ def vlidort_run_surface(kind, nstokes, nstreams, plane_parallel, ROT, depol, tau
     keep += [F(kernel_wt) if kernel_wt is not None else None, F(param) if param is not None else None]
     alpha = F(alpha) if alpha is not None else None
     flux_factor = F(flux_factor) if flux_factor is not None else None
-    sf = _OrcSurface(SURFACE_KINDS[kind], *[_p(k) for k in keep], _p(out["BR"]), _p(out["BR_Q"]), _p(out["BR_U"]))
+    bpdf = F(bpdf) if bpdf is not None else None
+    albedo = F(albedo) if (albedo is not None and kind == "lambert_bpdf") else None
+    sf = _OrcSurface(SURFACE_KINDS[kind], *[_p(k) for k in keep], _p(out["BR"]), _p(out["BR_Q"]), _p(out["BR_U"]), _p(bpdf))
     o0, o1 = obs_range if obs_range else (0, nobs)
     vo.lib().orc_vlidort_run_surf(int(nstokes), int(scalar_glue), km, nch, nobs, int(nstreams), int(plane_parallel), nMom, nPol,
-                                  _p(ROT), _p(depol), _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(he), None, _p(sza), _p(raa), _p(vza),
+                                  _p(ROT), _p(depol), _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(he), _p(albedo), _p(sza), _p(raa), _p(vza),
                                   _p(flux_factor), C.c_double(MISSING), 0, None, None, None, None, None, None, int(o0), int(o1),
                                   _p(out["radiance"]), _p(out["reflectance"]), _p(out["Q"]), _p(out["U"]),
                                   nf.ctypes.data_as(C.POINTER(C.c_int)), st.ctypes.data_as(C.POINTER(C.c_int)), C.byref(sf))

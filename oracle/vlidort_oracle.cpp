@@ -723,10 +723,21 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
       if (sf) {
         /* surface set-up of the BRDF wrappers: GV/VLIDORT_BRDF_CX.F90:587-762 (Cox-Munk), :1720-1894 (GISS Cox-Munk),
          * GV/VLIDORT_BRDF_MODIS.F90:206-410 (RTLS); kernels/parameters from V283/VLIDORT_SurfaceMod.F90:586-1042,1376-1596 */
-        int which[3], lam[3] = {0, 0, 0}, nk = 1, nsb = 100; double fac[3] = {1.0, 0.0, 0.0}, pars[12] = {0};
+        int which[4], lam[4] = {0, 0, 0, 0}, nk = 1, nsb = 100; double fac[4] = {1.0, 0.0, 0.0, 0.0}, pars[16] = {0};
         /* kinds 5, 6: the OCI variants of 2, 3 (V283/VLIDORT_SurfaceMod.F90:82-538: sigma2 = 0.00534 * W10m) */
         const bool giss = (sf->kind == 3 || sf->kind == 6), oci = (sf->kind == 5 || sf->kind == 6);
-        if (sf->kind == 7) {                                             /* VLIDORT_BPDF (V283/VLIDORT_SurfaceMod.F90:2279-2480): one BPDF-NDVI kernel */
+        if (sf->kind == 9) {                                             /* VLIDORT_LAMBERTIAN_BPDF (:2065-2275): Lambertian albedo + BPDF-NDVI */
+          if (is_missing(albedo[j + (size_t)nobs * i], MISSING)) { set_missing(); continue; }       /* GV/VLIDORT_LAMBERT_BPDF.F90:128-134 */
+          const double *bp = sf->bpdf + 3 * (i + (size_t)nch * j);
+          nk = 2; nsb = 50; which[0] = 1; lam[0] = 1; fac[0] = albedo[j + (size_t)nobs * i];
+          which[1] = 14; fac[1] = 1.0; pars[4] = bp[0]; pars[5] = bp[1]; pars[6] = bp[2];
+        } else if (sf->kind == 8) {                                      /* VLIDORT_LANDMODIS_BPDF (:1826-2060): RTLS kernels + BPDF-NDVI */
+          const double *kw = sf->kernel_wt + 3 * (i + (size_t)nch * j), *pr = sf->param + 2 * (i + (size_t)nch * j), *bp = sf->bpdf + 3 * (i + (size_t)nch * j);
+          nk = 4; nsb = 50; which[0] = 1; which[1] = 3; which[2] = 4; which[3] = 14; lam[0] = 1;
+          fac[0] = kw[0]; fac[1] = kw[2]; fac[2] = kw[1]; fac[3] = 1.0;
+          pars[8] = pr[0]; pars[9] = pr[1];
+          pars[12] = bp[0]; pars[13] = bp[1]; pars[14] = bp[2];
+        } else if (sf->kind == 7) {                                      /* VLIDORT_BPDF (V283/VLIDORT_SurfaceMod.F90:2279-2480): one BPDF-NDVI kernel */
           const double *pr = sf->param + 3 * (i + (size_t)nch * j);
           nk = 1; nsb = 50; which[0] = 14; fac[0] = 1.0;
           pars[0] = pr[0]; pars[1] = pr[1]; pars[2] = pr[2];
@@ -743,16 +754,16 @@ extern "C" int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nc
           fac[0] = kw[0]; fac[1] = kw[2]; fac[2] = kw[1];             /* (fiso, fvol, fgeo) <- kernel_wt (fiso, fgeo, fvol) */
           pars[8] = pr[0]; pars[9] = pr[1];
         }
-        const int bns = ((giss || sf->kind == 7) && !scalar_glue) ? 3 : 1;   /* only the GISS and BPDF kernels have polarised elements */
+        const int bns = ((giss || sf->kind >= 7) && !scalar_glue) ? 3 : 1;   /* only the GISS and BPDF kernels have polarised elements */
         orc_vbrdf(bns, N, nk, which, fac, pars, lam, nsb, 1, sza[j], vza[j], raa[j], sb_f.data(), sb_f0.data(), sb_uf.data(),
                   sb_uf0.data(), sb_ex.data(), nullptr);
         if (sf->BR) sf->BR[o] = sb_ex[0];
         /* BRDF_Q, BRDF_U = BS_DBOUNCE_BRDFUNC(2,1,1,1), (3,1,1,1) in Vector_GissCX / OCIGissCX / OCICX
          * (GV/VLIDORT_BRDF_CX.F90:199-201,388-389,1865-1866); 0 in Vector_CX (:733-734) and LandMODIS */
-        const bool polout = giss || sf->kind == 5 || sf->kind == 7;
+        const bool polout = giss || sf->kind == 5 || sf->kind >= 7;
         if (sf->BR_Q) sf->BR_Q[o] = polout ? sb_ex[1] : 0.0;
         if (sf->BR_U) sf->BR_U[o] = polout ? sb_ex[2] : 0.0;
-        if ((sf->kind == 4 || sf->kind == 7) && sb_ex[0] < 0) {
+        if ((sf->kind == 4 || sf->kind >= 7) && sb_ex[0] < 0) {
           radiance[o] = reflectance[o] = -500.0; if (Q) Q[o] = -500.0; if (U) U[o] = -500.0;
           if (sf->BR) sf->BR[o] = -500.0; if (sf->BR_Q) sf->BR_Q[o] = -500.0; if (sf->BR_U) sf->BR_U[o] = -500.0;
           if (status) status[p] = 98; if (nfourier) nfourier[p] = 0;

@@ -51,6 +51,7 @@ typedef struct {
   int kind;
   const double *u10m, *v10m, *mr, *kernel_wt, *param;
   double *BR, *BR_Q, *BR_U;
+  const double *bpdf;            /* kinds 8, 9: BPDFparam (3,nch,nobs) (kind 7 passes it as param) */
 } orc_surface;
 int orc_vlidort_run_surf(int nstokes, int scalar_glue, int km, int nch, int nobs, int nstreams, int plane_parallel,
                     int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
