@@ -172,6 +172,38 @@ module ab200_c_api
          real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
          integer(c_int), intent(out) :: rc
       end function
+      integer(c_int) function ab200_vlidort_vector_bpdf(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, nparam, ROT, depol, tau, ssa, pmom, &
+                                                        pe, he, te, BPDFparam, sza, raa, vza, MISSING, verbose, rad, refl, BR, Q, U, BR_Q, BR_U, rc) &
+                                                        bind(C, name="ab200_vlidort_vector_bpdf")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, nparam, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), BPDFparam(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_brdf_modis_bpdf(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, nkernel, nparam, nparam_bpdf, &
+                                                                   ROT, depol, tau, ssa, pmom, pe, he, te, kernel_wt, RTLSparam, BPDFparam, sza, raa, vza, &
+                                                                   MISSING, verbose, rad, refl, BR, Q, U, BR_Q, BR_U, rc) &
+                                                                   bind(C, name="ab200_vlidort_vector_brdf_modis_bpdf")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, nkernel, nparam, nparam_bpdf, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), kernel_wt(*), RTLSparam(*), BPDFparam(*)
+         real(c_double), intent(in)  :: sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_lambert_bpdf(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, nparam, ROT, depol, tau, ssa, &
+                                                                pmom, pe, he, te, albedo, BPDFparam, sza, raa, vza, MISSING, verbose, rad, refl, BR, Q, U, &
+                                                                BR_Q, BR_U, rc) bind(C, name="ab200_vlidort_vector_lambert_bpdf")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, nparam, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), albedo(*), BPDFparam(*), sza(*), raa(*), vza(*)
+         real(c_double), intent(out) :: rad(*), refl(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
+         integer(c_int), intent(out) :: rc
+      end function
    end interface
 contains
    ! the optional switches of the reference's vector wrappers (GV/VLIDORT_LAMBERT.F90:176,350; GV/VLIDORT_BRDF_MODIS.F90:210,417):
@@ -509,3 +541,77 @@ contains
       if (ier /= 0 .and. rc == 0) rc = ier
    end subroutine VLIDORT_Vector_LandMODIS_Cloud
 end module VLIDORT_BRDF_MODIS
+
+module VLIDORT_BRDF_MODIS_BPDF             ! replaces geo_vlidort/VLIDORT_BRDF_MODIS_BPDF.F90:23-230,459-643 (the _BPDF_Cloud form is not provided)
+   use ab200_c_api
+   implicit none
+contains
+   subroutine VLIDORT_Vector_LandMODIS_BPDF(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, &
+                                            kernel_wt, RTLSparam, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+                                            radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc, DO_BOA)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), kernel_wt(3,nch,nobs), RTLSparam(2,nch,nobs), BPDFparam(3,nch,nobs)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BR(nobs,nch), Q(nobs,nch), U(nobs,nch)
+      real*8,  intent(out) :: BR_Q(nobs,nch), BR_U(nobs,nch)
+      integer, intent(out) :: rc
+      logical, optional, intent(in) :: DO_BOA
+      integer :: ier
+      if (ab200_unsupported_switch(DO_BOA = DO_BOA)) then
+         rc = -2; return
+      end if
+      ier = ab200_vlidort_vector_brdf_modis_bpdf(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, 3, 2, 3, ROT, depol, tau, ssa, &
+                                                 pmom, pe, he, te, kernel_wt, RTLSparam, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, &
+                                                 verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_LandMODIS_BPDF
+   subroutine VLIDORT_Vector_BPDF(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, BPDFparam, &
+                                  solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, &
+                                  BR_Q, BR_U, rc, DO_BOA)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), BPDFparam(3,nch,nobs)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BR(nobs,nch), Q(nobs,nch), U(nobs,nch)
+      real*8,  intent(out) :: BR_Q(nobs,nch), BR_U(nobs,nch)
+      integer, intent(out) :: rc
+      logical, optional, intent(in) :: DO_BOA
+      integer :: ier
+      if (ab200_unsupported_switch(DO_BOA = DO_BOA)) then
+         rc = -2; return
+      end if
+      ier = ab200_vlidort_vector_bpdf(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, 3, ROT, depol, tau, ssa, pmom, pe, he, te, &
+                                      BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, &
+                                      BR, Q, U, BR_Q, BR_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_BPDF
+end module VLIDORT_BRDF_MODIS_BPDF
+
+module VLIDORT_LAMBERT_BPDF                ! replaces geo_vlidort/VLIDORT_LAMBERT_BPDF.F90:23-223 (the _BPDF_Cloud form is not provided)
+   use ab200_c_api
+   implicit none
+contains
+   subroutine VLIDORT_Vector_Lambert_BPDF(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, albedo, &
+                                          BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL, reflectance_VL, BR, Q, U, &
+                                          BR_Q, BR_U, rc, DO_2OS_CORRECTION, DO_BOA)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol)
+      real*8,  intent(in)  :: pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), albedo(nobs,nch), BPDFparam(3,nch,nobs)
+      real*8,  intent(in)  :: solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL(nobs,nch), reflectance_VL(nobs,nch), BR(nobs,nch), Q(nobs,nch), U(nobs,nch), BR_Q(nobs,nch), BR_U(nobs,nch)
+      integer, intent(out) :: rc
+      logical, optional, intent(in) :: DO_2OS_CORRECTION, DO_BOA
+      integer :: ier
+      if (ab200_unsupported_switch(DO_2OS_CORRECTION, DO_BOA)) then
+         rc = -2; return
+      end if
+      ier = ab200_vlidort_vector_lambert_bpdf(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, 3, ROT, depol, tau, ssa, pmom, &
+                                              pe, he, te, albedo, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL, &
+                                              reflectance_VL, BR, Q, U, BR_Q, BR_U, rc)
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_Lambert_BPDF
+end module VLIDORT_LAMBERT_BPDF
