@@ -429,7 +429,7 @@ int run_vlidort(VLContext &C, const RunDesc &R) {
       }
       cudaEventRecord(ev[2], st);
       AB_CUDA_OK(cudaGetLastError());
-      stats.n_eigen_problems += nprob; stats.n_bvp_problems += nactive; stats.n_launches += 2;
+      stats.n_eigen_problems += nprob; stats.n_bvp_problems += nactive; stats.n_launches += 3;      // k_vl_pi_angles, K2, K3 (K2b counted above)
       {  // algorithmic flops of SURVEY.md 8(d): eigen part (2+25+2) n^3 + 4 S^3 N^2 (2N-m); BVP part (14/3)(2n)^3 + 12 (2n)^2
         const double n3 = (double)n * n * n;
         stats.flops_eigen += (double)nprob * (29.0 * n3 + 4.0 * S * S * S * (double)N * N * (2 * N - m));
