@@ -416,6 +416,156 @@ def vector_brdf_modis_multigeom(channels, nstreams, plane_parallel, ROT, depol, 
     return (*outs, rc.value)
 
 
+# ---- the remaining cloud forms of the reference's Fortran modules (no f2py wrapper exists for them; Fortran callers reach them through
+#      the generic interfaces of fortran/ab200_rt_shims.F90).  Python names follow the f2py naming pattern of their siblings.
+def scalar_lambert_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL,
+                         pe, he, te, albedo, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """VLIDORT_Scalar_Lambert_Cloud (GV/VLIDORT_LAMBERT.F90:524): clear-sky scalar runner with alpha and flux_factor; the cloud arrays do not
+    enter (they may be None).  Returns (radiance, reflectance, rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor = (_F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, albedo, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(2)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_lambert_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp),
+                                                   _p(alpha), _p(tau), _p(ssa), _opt(g), _p(pmom), _opt(tauI), _opt(ssaI), _opt(gI), _opt(pmomI),
+                                                   _opt(tauL), _opt(ssaL), _opt(gL), _opt(pmomL), _p(pe), _p(he), _p(te), _p(albedo), _p(sza),
+                                                   _p(raa), _p(vza), _p(flux_factor), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs],
+                                                   C.byref(rc)), "ab200_vlidort_scalar_lambert_cloud")
+    return (*outs, rc.value)
+
+
+def vector_lambert_cloud_multigeom(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL,
+                                   pe, he, te, albedo, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Vector_Lambert_Cloud_MultiGeom (GV/VLIDORT_LAMBERT.F90:881): clear-sky multi-geometry runner with alpha, unit solar flux.
+    Returns (radiance, reflectance, Q, U (nobs,nch,ngeom), rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, albedo = (_F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, albedo))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    sza, raa, vza, ngeom = _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs)
+    ch, dp = _v(channels), _v(depol)
+    outs = [np.zeros((nobs, nch, ngeom), order="F") for _ in range(4)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_lambert_cloud_multigeom(km, nch, nobs, ngeom, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                             _p(ROT), _p(dp), _p(alpha), _p(tau), _p(ssa), _p(pmom), _opt(tauI), _opt(ssaI),
+                                                             _opt(pmomI), _opt(tauL), _opt(ssaL), _opt(pmomL), _p(pe), _p(he), _p(te), _p(albedo),
+                                                             _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                                             *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_lambert_cloud_multigeom")
+    return (*outs, rc.value)
+
+
+def vector_cx_cloud_multigeom(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te,
+                              U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Vector_CX_Cloud_MultiGeom (GV/VLIDORT_BRDF_CX.F90:1147): clear-sky runner, cloud arrays ignored as in the reference.
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U (nobs,nch,ngeom), rc)."""
+    ROT, tau, ssa, pmom, pe, he, te = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    sza, raa, vza, ngeom = _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs)
+    ch, dp, u, v, m = _v(channels), _v(depol), _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch, ngeom), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_cx_cloud_multigeom(km, nch, nobs, ngeom, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                        _p(ROT), _p(dp), _p(tau), _p(ssa), _p(pmom), _opt(tauI), _opt(ssaI), _opt(pmomI),
+                                                        _opt(tauL), _opt(ssaL), _opt(pmomL), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sza),
+                                                        _p(raa), _p(vza), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs],
+                                                        C.byref(rc)), "ab200_vlidort_vector_cx_cloud_multigeom")
+    return (*outs, rc.value)
+
+
+def vector_brdf_modis_cloud_multigeom(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL,
+                                      pmomL, pe, he, te, kernel_wt, param, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING,
+                                      verbose):
+    """VLIDORT_Vector_LandMODIS_Cloud_MultiGeom (GV/VLIDORT_BRDF_MODIS.F90:1055): cloud runner for all geometries of an observation.
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U (nobs,nch,ngeom), rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, kernel_wt, param, flux_factor = (
+        _F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, kernel_wt, param, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert tauI.shape == tau.shape and tauL.shape == tau.shape and pmomI.shape == pmom.shape and pmomL.shape == pmom.shape
+    sza, raa, vza, ngeom = _geom(solar_zenith, relat_azymuth, sensor_zenith, nobs)
+    ch, dp = _v(channels), _v(depol)
+    outs = [np.zeros((nobs, nch, ngeom), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_brdf_modis_cloud_multigeom(km, nch, nobs, ngeom, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                                kernel_wt.shape[0], param.shape[0], _p(ROT), _p(dp), _p(alpha), _p(tau), _p(ssa),
+                                                                _p(pmom), _p(tauI), _p(ssaI), _p(pmomI), _p(tauL), _p(ssaL), _p(pmomL), _p(pe),
+                                                                _p(he), _p(te), _p(kernel_wt), _p(param), _p(sza), _p(raa), _p(vza),
+                                                                _p(flux_factor), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs],
+                                                                C.byref(rc)), "ab200_vlidort_vector_brdf_modis_cloud_multigeom")
+    return (*outs, rc.value)
+
+
+def vector_ocigisscx_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te,
+                           U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """VLIDORT_Vector_OCIGissCX_Cloud (GV/VLIDORT_BRDF_CX.F90:2468): OCI GISS Cox-Munk ocean, trace gases, solar flux, aerosol + ice + liquid
+    cloud layers.  Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, flux_factor = (
+        _F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert tauI.shape == tau.shape and tauL.shape == tau.shape and pmomI.shape == pmom.shape and pmomL.shape == pmom.shape
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_ocigisscx_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp),
+                                                     _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(tauI), _p(ssaI), _p(pmomI), _p(tauL), _p(ssaL),
+                                                     _p(pmomL), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza),
+                                                     _p(flux_factor), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_vector_ocigisscx_cloud")
+    return (*outs, rc.value)
+
+
+def scalar_ocigisscx_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL,
+                           pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose):
+    """VLIDORT_Scalar_OCIGissCX_Cloud (GV/VLIDORT_BRDF_CX.F90:2084): returns (radiance, reflectance, BRDF (nobs,nch), rc)."""
+    arrs = [_F(x) for x in (ROT, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te)]
+    km, nch, nobs, nMom, nPol = _dims(arrs[2], arrs[5])
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m, ff = _v(U10m), _v(V10m), _v(mr), _F(flux_factor)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(3)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_ocigisscx_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(arrs[0]),
+                                                     _p(dp), *[_p(a) for a in arrs[1:]], _p(u), _p(v), _p(m), _p(sza), _p(raa), _p(vza), _p(ff),
+                                                     C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc)),
+          "ab200_vlidort_scalar_ocigisscx_cloud")
+    return (*outs, rc.value)
+
+
+def vector_brdf_modis_bpdf_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe,
+                                 he, te, kernel_wt, RTLSparam, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING,
+                                 verbose):
+    """VLIDORT_Vector_LandMODIS_BPDF_Cloud (GV/VLIDORT_BRDF_MODIS_BPDF.F90:232): "place holder" in the reference -- clear-sky runner with alpha
+    and flux_factor, the cloud arrays do not enter (they may be None).  Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, kernel_wt, RTLSparam, BPDFparam, flux_factor = (
+        _F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, kernel_wt, RTLSparam, BPDFparam, flux_factor))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_brdf_modis_bpdf_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                           kernel_wt.shape[0], RTLSparam.shape[0], BPDFparam.shape[0], _p(ROT), _p(dp), _p(alpha),
+                                                           _p(tau), _p(ssa), _p(pmom), _opt(tauI), _opt(ssaI), _opt(pmomI), _opt(tauL), _opt(ssaL),
+                                                           _opt(pmomL), _p(pe), _p(he), _p(te), _p(kernel_wt), _p(RTLSparam), _p(BPDFparam),
+                                                           _p(sza), _p(raa), _p(vza), _p(flux_factor), C.c_double(MISSING), int(verbose),
+                                                           *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_brdf_modis_bpdf_cloud")
+    return (*outs, rc.value)
+
+
+def vector_lambert_bpdf_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te,
+                              albedo, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Vector_Lambert_BPDF_Cloud (GV/VLIDORT_LAMBERT_BPDF.F90:228): clear-sky runner, cloud arrays ignored as in the reference.
+    Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc)."""
+    ROT, tau, ssa, pmom, pe, he, te, albedo, BPDFparam = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, albedo, BPDFparam))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_lambert_bpdf_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol,
+                                                        BPDFparam.shape[0], _p(ROT), _p(dp), _p(tau), _p(ssa), _p(pmom), _opt(tauI), _opt(ssaI),
+                                                        _opt(pmomI), _opt(tauL), _opt(ssaL), _opt(pmomL), _p(pe), _p(he), _p(te), _p(albedo),
+                                                        _p(BPDFparam), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                                        *[_p(o) for o in outs], C.byref(rc)), "ab200_vlidort_vector_lambert_bpdf_cloud")
+    return (*outs, rc.value)
+
+
 def last_diag():
     """(nfourier, status) per pixel p = j*nch + i (per pixel-view (j*nch + i)*ngeom + g for the multi-geometry forms) of this
     thread's most recent VLIDORT call -- diagnostics, not in the reference."""

@@ -1328,6 +1328,152 @@ extern "C" int ab200_vlidort_vector_brdf_modis_multigeom(int km, int nch, int no
                     relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
 }
 
+// ---- the remaining cloud forms of the reference modules; none of them has an f2py wrapper, Fortran callers reach
+//      them through the generic interfaces (fortran/ab200_rt_shims.F90).
+// VLIDORT_Scalar_Lambert_Cloud (GV/VLIDORT_LAMBERT.F90:524-686): takes the cloud arrays and calls the CLEAR-SKY scalar runner (:663), but
+// unlike VLIDORT_Scalar_Lambert it associates alpha and sets the solar flux (:640,:650) -- both enter VLIDORT_Run_Scalar
+// (V283/VLIDORT_ScatMod.F90:1152-1163,1233-1242)
+extern "C" int ab200_vlidort_scalar_lambert_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                  int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                                  const double *ssa, const double *g, const double *pmom, const double *tauI,
+                                                  const double *ssaI, const double *gI, const double *pmomI, const double *tauL,
+                                                  const double *ssaL, const double *gL, const double *pmomL, const double *pe,
+                                                  const double *he, const double *te, const double *albedo, const double *solar_zenith,
+                                                  const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                                  double MISSING, int verbose, double *radiance_VL, double *reflectance_VL, int *rc) {
+  (void)channels; (void)g; (void)pe; (void)te; (void)verbose;
+  (void)tauI; (void)ssaI; (void)gI; (void)pmomI; (void)tauL; (void)ssaL; (void)gL; (void)pmomL;
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("scalar_lambert_cloud: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  return lambert_host(1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, he, albedo,
+                      solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, radiance_VL, reflectance_VL, nullptr, nullptr, rc);
+}
+// VLIDORT_Vector_Lambert_Cloud_MultiGeom (GV/VLIDORT_LAMBERT.F90:881-1075): clear-sky multi-geometry runner (:1036) with alpha (:1025); no
+// flux_factor argument (the flux stays 1).  VLIDORT_Vector_CX_Cloud_MultiGeom (GV/VLIDORT_BRDF_CX.F90:1147-1348): clear-sky runner (:1320).
+extern "C" int ab200_vlidort_vector_lambert_cloud_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                            int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                                            const double *alpha, const double *tau, const double *ssa, const double *pmom,
+                                                            const double *tauI, const double *ssaI, const double *pmomI, const double *tauL,
+                                                            const double *ssaL, const double *pmomL, const double *pe, const double *he,
+                                                            const double *te, const double *albedo, const double *solar_zenith,
+                                                            const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                                                            int verbose, double *radiance_VL, double *reflectance_VL, double *Q, double *U,
+                                                            int *rc) {
+  (void)tauI; (void)ssaI; (void)pmomI; (void)tauL; (void)ssaL; (void)pmomL;
+  return ab200_vlidort_vector_lambert_multigeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa,
+                                                pmom, pe, he, te, albedo, solar_zenith, relat_azymuth, sensor_zenith, nullptr, MISSING, verbose,
+                                                radiance_VL, reflectance_VL, Q, U, rc);
+}
+extern "C" int ab200_vlidort_vector_cx_cloud_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                       int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                                       const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                                       const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                                       const double *pmomL, const double *pe, const double *he, const double *te,
+                                                       const double *U10m, const double *V10m, const double *mr, const double *solar_zenith,
+                                                       const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                                       double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                                       double *BR_Q, double *BR_U, int *rc) {
+  (void)tauI; (void)ssaI; (void)pmomI; (void)tauL; (void)ssaL; (void)pmomL;
+  return ab200_vlidort_vector_cx_multigeom(km, nch, nobs, ngeom, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he,
+                                           te, U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF,
+                                           reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc);
+}
+// VLIDORT_Vector_LandMODIS_Cloud_MultiGeom (GV/VLIDORT_BRDF_MODIS.F90:1055-1268): the cloud runner (:1258) for all geometries of an observation
+extern "C" int ab200_vlidort_vector_brdf_modis_cloud_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                               int plane_parallel, int nMom, int nPol, int nkernel, int nparam,
+                                                               const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                                               const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                                               const double *pmomI, const double *tauL, const double *ssaL,
+                                                               const double *pmomL, const double *pe, const double *he, const double *te,
+                                                               const double *kernel_wt, const double *param, const double *solar_zenith,
+                                                               const double *relat_azymuth, const double *sensor_zenith,
+                                                               const double *flux_factor, double MISSING, int verbose,
+                                                               double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                                               double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)depol; (void)pe; (void)te; (void)verbose;
+  if (ngeom < 1) { ab200_set_error("multigeom: ngeom must be >= 1"); return AB200_ERR_ARG; }
+  if (nkernel != 3 || nparam != 2) { ab200_set_error("vector_brdf_modis_cloud: nkernel must be 3 and nparam 2 (GV/VLIDORT_BRDF_MODIS.F90:1069-1070)"); return AB200_ERR_ARG; }
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("vector_brdf_modis_cloud_multigeom: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_MODIS, nullptr, nullptr, nullptr, kernel_wt, param, BR, BR_Q, BR_U, alpha, flux_factor};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 3, 0, km, nch, nobs, ngeom, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+// VLIDORT_Vector_OCIGissCX_Cloud (GV/VLIDORT_BRDF_CX.F90:2468-2668) and VLIDORT_Scalar_OCIGissCX_Cloud (:2084-2273): the OCI flavour of the GISS
+// Cox-Munk set-up (VLIDORT_OCIGissCoxMunk) with trace-gas absorption, solar flux and the cloud runners (:2642, :2251)
+extern "C" int ab200_vlidort_vector_ocigisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                    int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                                    const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                                    const double *pmomI, const double *tauL, const double *ssaL, const double *pmomL,
+                                                    const double *pe, const double *he, const double *te, const double *U10m,
+                                                    const double *V10m, const double *mr, const double *solar_zenith,
+                                                    const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                                    double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                                    double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)depol; (void)pe; (void)te; (void)verbose;
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("vector_ocigisscx_cloud: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_OCIGISSCX, U10m, V10m, mr, nullptr, nullptr, BR, BR_Q, BR_U, alpha, flux_factor};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_scalar_ocigisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                                    int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                                    const double *ssa, const double *g, const double *pmom, const double *tauI,
+                                                    const double *ssaI, const double *gI, const double *pmomI, const double *tauL,
+                                                    const double *ssaL, const double *gL, const double *pmomL, const double *pe,
+                                                    const double *he, const double *te, const double *U10m, const double *V10m,
+                                                    const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                                    const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                                    double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc) {
+  (void)depol; (void)g; (void)gI; (void)gL; (void)pe; (void)te; (void)verbose;
+  if (!cloud_args_ok(nch * nobs, channels, tauI, ssaI, pmomI, tauL, ssaL, pmomL)) return AB200_ERR_ARG;
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("scalar_ocigisscx_cloud: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  std::vector<double> dp; cloud_depol(nch, channels, dp);
+  SurfArgs sa = {SURF_OCIGISSCX, U10m, V10m, mr, nullptr, nullptr, BRDF, nullptr, nullptr, alpha, flux_factor};
+  sa.tauI = tauI; sa.ssaI = ssaI; sa.pmomI = pmomI; sa.tauL = tauL; sa.ssaL = ssaL; sa.pmomL = pmomL;
+  return brdf_front(false, 1, 1, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, dp.data(), tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, nullptr, nullptr, 0, rc);
+}
+// VLIDORT_Vector_LandMODIS_BPDF_Cloud (GV/VLIDORT_BRDF_MODIS_BPDF.F90:232-455): "place holder" -- takes the cloud arrays, never points SCAT at
+// them and calls the clear-sky runner (:427); differs from VLIDORT_Vector_LandMODIS_BPDF by alpha (:390) and the solar flux (:355).
+// VLIDORT_Vector_Lambert_BPDF_Cloud (GV/VLIDORT_LAMBERT_BPDF.F90:228-440): clear-sky runner (:409), no alpha, no flux.
+extern "C" int ab200_vlidort_vector_brdf_modis_bpdf_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                          int nMom, int nPol, int nkernel, int nparam, int nparam_bpdf, const double *ROT,
+                                                          const double *depol, const double *alpha, const double *tau, const double *ssa,
+                                                          const double *pmom, const double *tauI, const double *ssaI, const double *pmomI,
+                                                          const double *tauL, const double *ssaL, const double *pmomL, const double *pe,
+                                                          const double *he, const double *te, const double *kernel_wt, const double *RTLSparam,
+                                                          const double *BPDFparam, const double *solar_zenith, const double *relat_azymuth,
+                                                          const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                                          double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                                          double *U, double *BR_Q, double *BR_U, int *rc) {
+  (void)channels; (void)pe; (void)te; (void)verbose; (void)tauI; (void)ssaI; (void)pmomI; (void)tauL; (void)ssaL; (void)pmomL;
+  if (nkernel != 3 || nparam != 2 || nparam_bpdf != 3) { ab200_set_error("vector_brdf_modis_bpdf_cloud: nkernel, nparam, nparam_bpdf must be 3, 2, 3 (GV/VLIDORT_BRDF_MODIS_BPDF.F90:245-247)"); return AB200_ERR_ARG; }
+  if (nch * nobs > 0 && (!alpha || !flux_factor)) { ab200_set_error("vector_brdf_modis_bpdf_cloud: NULL alpha or flux_factor"); return AB200_ERR_ARG; }
+  SurfArgs sa = {SURF_MODIS_BPDF, nullptr, nullptr, nullptr, kernel_wt, RTLSparam, BR, BR_Q, BR_U, alpha, flux_factor};
+  sa.bpdf = BPDFparam;
+  return brdf_front(false, 3, 0, km, nch, nobs, 1, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, he, solar_zenith,
+                    relat_azymuth, sensor_zenith, MISSING, sa, radiance_VL_SURF, reflectance_VL_SURF, Q, U, 0, rc);
+}
+extern "C" int ab200_vlidort_vector_lambert_bpdf_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                       int nMom, int nPol, int nparam, const double *ROT, const double *depol,
+                                                       const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                                       const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                                       const double *pmomL, const double *pe, const double *he, const double *te,
+                                                       const double *albedo, const double *BPDFparam, const double *solar_zenith,
+                                                       const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                                       double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                                       double *BR_Q, double *BR_U, int *rc) {
+  (void)tauI; (void)ssaI; (void)pmomI; (void)tauL; (void)ssaL; (void)pmomL;
+  return ab200_vlidort_vector_lambert_bpdf(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, nparam, ROT, depol, tau, ssa, pmom, pe, he,
+                                           te, albedo, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF,
+                                           reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc);
+}
+
 // number of devices the host-pointer Stage-B entries spread their observations over (one contiguous slab and one host thread per
 // device, starting with the device that is current on the calling thread).  n <= 0: every visible device.  Default: AB200_DEVICES, or 1
 // (rank-per-GPU mains such as geo_vlidort.x keep one device per process).  Returns the number that will be used.

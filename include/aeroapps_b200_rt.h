@@ -259,6 +259,92 @@ int ab200_vlidort_vector_brdf_modis_multigeom(int km, int nch, int nobs, int nge
                                               const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
                                               double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q,
                                               double *BR_U, int *rc);
+/* ---- the remaining cloud forms of the reference modules (Fortran module procedures without an f2py wrapper).
+ * VLIDORT_Scalar_Lambert_Cloud (GV/VLIDORT_LAMBERT.F90:524-686): clear-sky scalar runner (:663) with alpha (km,nobs,nch) and flux_factor
+ * (nch,nobs); the cloud arrays and g, gI, gL do not enter (they may be NULL) */
+int ab200_vlidort_scalar_lambert_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                       int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                       const double *ssa, const double *g, const double *pmom, const double *tauI,
+                                       const double *ssaI, const double *gI, const double *pmomI, const double *tauL,
+                                       const double *ssaL, const double *gL, const double *pmomL, const double *pe,
+                                       const double *he, const double *te, const double *albedo, const double *solar_zenith,
+                                       const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                       double MISSING, int verbose, double *radiance_VL, double *reflectance_VL, int *rc);
+/* VLIDORT_Vector_Lambert_Cloud_MultiGeom (GV/VLIDORT_LAMBERT.F90:881-1075) and VLIDORT_Vector_CX_Cloud_MultiGeom (GV/VLIDORT_BRDF_CX.F90:
+ * 1147-1348): multi-geometry forms that take the cloud arrays and call the clear-sky runner (:1036, :1320); shapes as for the
+ * _multigeom entries above, albedo (nobs,nch) = the reference's albedo(:,:,1) */
+int ab200_vlidort_vector_lambert_cloud_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                 int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                                 const double *alpha, const double *tau, const double *ssa, const double *pmom,
+                                                 const double *tauI, const double *ssaI, const double *pmomI, const double *tauL,
+                                                 const double *ssaL, const double *pmomL, const double *pe, const double *he,
+                                                 const double *te, const double *albedo, const double *solar_zenith,
+                                                 const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                                                 int verbose, double *radiance_VL, double *reflectance_VL, double *Q, double *U,
+                                                 int *rc);
+int ab200_vlidort_vector_cx_cloud_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                            int plane_parallel, int nMom, int nPol, const double *ROT, const double *depol,
+                                            const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                            const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                            const double *pmomL, const double *pe, const double *he, const double *te,
+                                            const double *U10m, const double *V10m, const double *mr, const double *solar_zenith,
+                                            const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                            double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                            double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_LandMODIS_Cloud_MultiGeom (GV/VLIDORT_BRDF_MODIS.F90:1055-1268): cloud runner, all geometries of an observation */
+int ab200_vlidort_vector_brdf_modis_cloud_multigeom(int km, int nch, int nobs, int ngeom, const double *channels, int nstreams,
+                                                    int plane_parallel, int nMom, int nPol, int nkernel, int nparam,
+                                                    const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                                    const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                                    const double *pmomI, const double *tauL, const double *ssaL,
+                                                    const double *pmomL, const double *pe, const double *he, const double *te,
+                                                    const double *kernel_wt, const double *param, const double *solar_zenith,
+                                                    const double *relat_azymuth, const double *sensor_zenith,
+                                                    const double *flux_factor, double MISSING, int verbose,
+                                                    double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                                    double *U, double *BR_Q, double *BR_U, int *rc);
+/* VLIDORT_Vector_OCIGissCX_Cloud (GV/VLIDORT_BRDF_CX.F90:2468-2668) and VLIDORT_Scalar_OCIGissCX_Cloud (:2084-2273): OCI GISS Cox-Munk
+ * set-up, trace-gas absorption, solar flux, cloud runners */
+int ab200_vlidort_vector_ocigisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                         int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                         const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                         const double *pmomI, const double *tauL, const double *ssaL, const double *pmomL,
+                                         const double *pe, const double *he, const double *te, const double *U10m,
+                                         const double *V10m, const double *mr, const double *solar_zenith,
+                                         const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                         double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                         double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc);
+int ab200_vlidort_scalar_ocigisscx_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom,
+                                         int nPol, const double *ROT, const double *depol, const double *alpha, const double *tau,
+                                         const double *ssa, const double *g, const double *pmom, const double *tauI,
+                                         const double *ssaI, const double *gI, const double *pmomI, const double *tauL,
+                                         const double *ssaL, const double *gL, const double *pmomL, const double *pe,
+                                         const double *he, const double *te, const double *U10m, const double *V10m,
+                                         const double *mr, const double *solar_zenith, const double *relat_azymuth,
+                                         const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                         double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc);
+/* VLIDORT_Vector_LandMODIS_BPDF_Cloud (GV/VLIDORT_BRDF_MODIS_BPDF.F90:232-455) and VLIDORT_Vector_Lambert_BPDF_Cloud
+ * (GV/VLIDORT_LAMBERT_BPDF.F90:228-440): "place holder" wrappers that call the clear-sky runner (:427, :409); the first differs from
+ * VLIDORT_Vector_LandMODIS_BPDF by alpha and flux_factor; the cloud arrays do not enter (they may be NULL) */
+int ab200_vlidort_vector_brdf_modis_bpdf_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                               int nMom, int nPol, int nkernel, int nparam, int nparam_bpdf, const double *ROT,
+                                               const double *depol, const double *alpha, const double *tau, const double *ssa,
+                                               const double *pmom, const double *tauI, const double *ssaI, const double *pmomI,
+                                               const double *tauL, const double *ssaL, const double *pmomL, const double *pe,
+                                               const double *he, const double *te, const double *kernel_wt, const double *RTLSparam,
+                                               const double *BPDFparam, const double *solar_zenith, const double *relat_azymuth,
+                                               const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                               double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q,
+                                               double *U, double *BR_Q, double *BR_U, int *rc);
+int ab200_vlidort_vector_lambert_bpdf_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                            int nMom, int nPol, int nparam, const double *ROT, const double *depol,
+                                            const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                            const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                            const double *pmomL, const double *pe, const double *he, const double *te,
+                                            const double *albedo, const double *BPDFparam, const double *solar_zenith,
+                                            const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
+                                            double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                            double *BR_Q, double *BR_U, int *rc);
 
 /* diagnostics of the calling thread's most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i (per pixel-view
  * (j*nch + i)*ngeom + g for the multi-geometry forms); returns their number */
