@@ -769,7 +769,8 @@ int brdf_slab(bool dev, int S, int scalar_glue, int km, int nch, const Slab &sl,
   std::vector<double> h_sza(nj), h_vza(nj), h_raa(nj), h_u, h_v, h_mr;
   auto fetch = [&](std::vector<double> &hv, const double *src, size_t n, size_t o) {
     hv.resize(n);
-    if (dev) cudaMemcpyAsync(hv.data(), src, 8 * n, cudaMemcpyDeviceToHost, st); else std::copy(src + o, src + o + n, hv.begin());
+    if (dev) { cudaError_t e = cudaMemcpyAsync(hv.data(), src, 8 * n, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) cpe = e; }
+    else std::copy(src + o, src + o + n, hv.begin());
   };
   fetch(h_sza, sza, nj, j0); fetch(h_vza, vza, nj, j0); fetch(h_raa, raa, nj, j0);
   if (cx) { fetch(h_u, sa.u10m, nj, j0); fetch(h_v, sa.v10m, nj, j0); fetch(h_mr, sa.mr, nch, 0); }
