@@ -566,6 +566,109 @@ def vector_lambert_bpdf_cloud(channels, nstreams, plane_parallel, ROT, depol, ta
     return (*outs, rc.value)
 
 
+def vector_ocigisscx_nobm_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he,
+                                te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith, flux_factor,
+                                MISSING, verbose):
+    """f2py VECTOR_OCIGissCX_NOBM_Cloud (VLIDORT_POLAR_py.F90:1055): OCI GISS Cox-Munk ocean + clouds + NOBM water-leaving radiance
+    sleave (nch,nobs).  Returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc, ADJUSTED_SLEAVE).  With sleave_adjust False VLIDORT 2.8.3
+    drops the water-leaving term (its transmittance factor stays zero, see include/aeroapps_b200_rt.h) and so does this entry;
+    sleave_adjust True (the transmittance iteration) is refused with a RuntimeError."""
+    ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, flux_factor, sleave = (
+        _F(x) for x in (ROT, alpha, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, flux_factor, sleave))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert tauI.shape == tau.shape and tauL.shape == tau.shape and pmomI.shape == pmom.shape and pmomL.shape == pmom.shape
+    assert sleave.shape == (nch, nobs), "sleave must be (nch,nobs)"
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    adj = np.zeros((nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_ocigisscx_nobm_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT),
+                                                          _p(dp), _p(alpha), _p(tau), _p(ssa), _p(pmom), _p(tauI), _p(ssaI), _p(pmomI), _p(tauL),
+                                                          _p(ssaL), _p(pmomL), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sleave),
+                                                          int(bool(sleave_iso)), int(bool(sleave_adjust)), _p(sza), _p(raa), _p(vza),
+                                                          _p(flux_factor), C.c_double(MISSING), int(verbose), *[_p(o) for o in outs], C.byref(rc),
+                                                          _p(adj)), "ab200_vlidort_vector_ocigisscx_nobm_cloud")
+    return (*outs, rc.value, adj)
+
+
+def vector_gisscx_nobm_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m,
+                             V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Vector_GissCX_NOBM_Cloud (GV/VLIDORT_BRDF_CX.F90:3102): returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc,
+    ADJUSTED_SLEAVE); sleave_adjust as for vector_ocigisscx_nobm_cloud."""
+    ROT, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, sleave = (
+        _F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, tauI, ssaI, pmomI, tauL, ssaL, pmomL, sleave))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert sleave.shape == (nch, nobs), "sleave must be (nch,nobs)"
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    adj = np.zeros((nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_gisscx_nobm_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp),
+                                                       _p(tau), _p(ssa), _p(pmom), _p(tauI), _p(ssaI), _p(pmomI), _p(tauL), _p(ssaL), _p(pmomL),
+                                                       _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sleave), int(bool(sleave_iso)),
+                                                       int(bool(sleave_adjust)), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                                       *[_p(o) for o in outs], C.byref(rc), _p(adj)), "ab200_vlidort_vector_gisscx_nobm_cloud")
+    return (*outs, rc.value, adj)
+
+
+def vector_cx_nobm(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust,
+                   solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Vector_CX_NOBM (GV/VLIDORT_BRDF_CX.F90:1351): returns (radiance, reflectance, BR, Q, U, BR_Q, BR_U, rc, ADJUSTED_SLEAVE)."""
+    ROT, tau, ssa, pmom, pe, he, te, sleave = (_F(x) for x in (ROT, tau, ssa, pmom, pe, he, te, sleave))
+    km, nch, nobs, nMom, nPol = _dims(tau, pmom)
+    assert sleave.shape == (nch, nobs), "sleave must be (nch,nobs)"
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m = _v(U10m), _v(V10m), _v(mr)
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(7)]
+    adj = np.zeros((nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_vector_cx_nobm(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(ROT), _p(dp), _p(tau),
+                                             _p(ssa), _p(pmom), _p(pe), _p(he), _p(te), _p(u), _p(v), _p(m), _p(sleave), int(bool(sleave_iso)),
+                                             int(bool(sleave_adjust)), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                             *[_p(o) for o in outs], C.byref(rc), _p(adj)), "ab200_vlidort_vector_cx_nobm")
+    return (*outs, rc.value, adj)
+
+
+def scalar_gisscx_nobm_cloud(channels, nstreams, plane_parallel, ROT, depol, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he,
+                             te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose):
+    """VLIDORT_Scalar_GissCX_NOBM_Cloud (GV/VLIDORT_BRDF_CX.F90:2671): returns (radiance, reflectance, BRDF, rc, ADJUSTED_SLEAVE)."""
+    arrs = [_F(x) for x in (ROT, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te)]
+    km, nch, nobs, nMom, nPol = _dims(arrs[1], arrs[4])
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m, sl = _v(U10m), _v(V10m), _v(mr), _F(sleave)
+    assert sl.shape == (nch, nobs), "sleave must be (nch,nobs)"
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(3)]
+    adj = np.zeros((nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_gisscx_nobm_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(arrs[0]),
+                                                       _p(dp), *[_p(a) for a in arrs[1:]], _p(u), _p(v), _p(m), _p(sl), int(bool(sleave_iso)),
+                                                       int(bool(sleave_adjust)), _p(sza), _p(raa), _p(vza), C.c_double(MISSING), int(verbose),
+                                                       *[_p(o) for o in outs], C.byref(rc), _p(adj)), "ab200_vlidort_scalar_gisscx_nobm_cloud")
+    return (*outs, rc.value, adj)
+
+
+def scalar_ocigisscx_nobm_cloud(channels, nstreams, plane_parallel, ROT, depol, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL,
+                                pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith,
+                                flux_factor, MISSING, verbose):
+    """VLIDORT_Scalar_OCIGissCX_NOBM_Cloud (GV/VLIDORT_BRDF_CX.F90:2883): returns (radiance, reflectance, BRDF, rc, ADJUSTED_SLEAVE)."""
+    arrs = [_F(x) for x in (ROT, alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te)]
+    km, nch, nobs, nMom, nPol = _dims(arrs[2], arrs[5])
+    ch, dp, sza, raa, vza = _v(channels), _v(depol), _v(solar_zenith), _v(relat_azymuth), _v(sensor_zenith)
+    u, v, m, sl, ff = _v(U10m), _v(V10m), _v(mr), _F(sleave), _F(flux_factor)
+    assert sl.shape == (nch, nobs), "sleave must be (nch,nobs)"
+    outs = [np.zeros((nobs, nch), order="F") for _ in range(3)]
+    adj = np.zeros((nobs, nch), order="F")
+    rc = C.c_int(0)
+    check(lib().ab200_vlidort_scalar_ocigisscx_nobm_cloud(km, nch, nobs, _p(ch), int(nstreams), int(bool(plane_parallel)), nMom, nPol, _p(arrs[0]),
+                                                          _p(dp), *[_p(a) for a in arrs[1:]], _p(u), _p(v), _p(m), _p(sl), int(bool(sleave_iso)),
+                                                          int(bool(sleave_adjust)), _p(sza), _p(raa), _p(vza), _p(ff), C.c_double(MISSING),
+                                                          int(verbose), *[_p(o) for o in outs], C.byref(rc), _p(adj)),
+          "ab200_vlidort_scalar_ocigisscx_nobm_cloud")
+    return (*outs, rc.value, adj)
+
+
 def last_diag():
     """(nfourier, status) per pixel p = j*nch + i (per pixel-view (j*nch + i)*ngeom + g for the multi-geometry forms) of this
     thread's most recent VLIDORT call -- diagnostics, not in the reference."""

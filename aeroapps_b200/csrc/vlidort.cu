@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -1473,6 +1474,117 @@ extern "C" int ab200_vlidort_vector_lambert_bpdf_cloud(int km, int nch, int nobs
   return ab200_vlidort_vector_lambert_bpdf(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, nparam, ROT, depol, tau, ssa, pmom, pe, he,
                                            te, albedo, BPDFparam, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF,
                                            reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc);
+}
+
+// ---- NOBM water-leaving forms (GV/VLIDORT_BRDF_CX.F90:1351,2671,2883,3102,3320; f2py VECTOR_OCIGissCX_NOBM_Cloud, LV/VLIDORT_POLAR_py.F90:1055).
+// The wrappers hand the sun-normalised water-leaving radiance sleave(nch,nobs) to VLIDORT as SLTERM_ISOTROPIC (sleave_iso) or
+// SLTERM_USERANGLES and switch DO_SURFACE_LEAVING + DO_WATER_LEAVING on; DO_EXTERNAL_WLEAVE is never set (V283/VLIDORT_ScatMod.F90:388-405,
+// VM/vlidort_inputs.f90:416).  What VLIDORT 2.8.3 does with that depends on sleave_adjust:
+//  * sleave_adjust = false (DO_TF_ITERATION off): the water-leaving term is scaled by TRANS_ATMOS_FINAL everywhere -- in the first-order
+//    term (VM/vlidort_masters_V2p8p3.f90:2493-2499) and in the boundary-value column (VM/vlidort_bvproblem.f90:1500-1513: not included for
+//    Fourier 0; for m > 0 it is SLTERM_F_0, which AeroApps never fills) -- and without the iteration or the external flag
+//    TRANS_ATMOS_FINAL stays at the zero it is reset to (:1563-1571).  The reference's result is the result WITHOUT water-leaving, and
+//    ADJUSTED_SLEAVE is 0 (GV/VLIDORT_BRDF_CX.F90:3524-3531).  That is what these entries return: the sibling entry, bit for bit.
+//  * sleave_adjust = true (the transmittance iteration BVP_ADJUSTED_BACKSUB, VM/vlidort_bvproblem.f90:2487-2910) is not part of this
+//    library: refused with AB200_ERR_ARG and rc = -2 instead of a silently different answer.
+static int nobm_gate(const char *who, int npix, const double *sleave, int sleave_adjust, int *rc) {
+  if (!rc) { ab200_set_error("vlidort: rc is NULL"); return AB200_ERR_ARG; }
+  *rc = 0;
+  if (npix > 0 && !sleave) { ab200_set_error((std::string(who) + ": NULL sleave").c_str()); return AB200_ERR_ARG; }
+  if (sleave_adjust) {
+    *rc = -2;
+    ab200_set_error((std::string(who) + ": sleave_adjust (VLIDORT's water-leaving transmittance iteration) is not supported").c_str());
+    return AB200_ERR_ARG;
+  }
+  return 0;
+}
+static void nobm_zero(double *ADJUSTED_SLEAVE, int nobs, int nch) {
+  if (ADJUSTED_SLEAVE) std::fill(ADJUSTED_SLEAVE, ADJUSTED_SLEAVE + (size_t)(nobs > 0 ? nobs : 0) * (nch > 0 ? nch : 0), 0.0);
+}
+extern "C" int ab200_vlidort_vector_cx_nobm(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom, int nPol,
+                                            const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
+                                            const double *pe, const double *he, const double *te, const double *U10m, const double *V10m,
+                                            const double *mr, const double *sleave, int sleave_iso, int sleave_adjust,
+                                            const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                                            int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                            double *BR_Q, double *BR_U, int *rc, double *ADJUSTED_SLEAVE) {
+  (void)sleave_iso;
+  if (int e = nobm_gate("vector_cx_nobm", nch * nobs, sleave, sleave_adjust, rc)) return e;
+  nobm_zero(ADJUSTED_SLEAVE, nobs, nch);
+  return ab200_vlidort_vector_cx(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, V10m,
+                                 mr, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q,
+                                 U, BR_Q, BR_U, rc);
+}
+extern "C" int ab200_vlidort_vector_gisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                      int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                                      const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                                      const double *pmomI, const double *tauL, const double *ssaL, const double *pmomL,
+                                                      const double *pe, const double *he, const double *te, const double *U10m,
+                                                      const double *V10m, const double *mr, const double *sleave, int sleave_iso,
+                                                      int sleave_adjust, const double *solar_zenith, const double *relat_azymuth,
+                                                      const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                                      double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U,
+                                                      int *rc, double *ADJUSTED_SLEAVE) {
+  (void)sleave_iso;
+  if (int e = nobm_gate("vector_gisscx_nobm_cloud", nch * nobs, sleave, sleave_adjust, rc)) return e;
+  nobm_zero(ADJUSTED_SLEAVE, nobs, nch);
+  return ab200_vlidort_vector_gisscx_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, tauI, ssaI,
+                                           pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth, sensor_zenith,
+                                           MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q, BR_U, rc);
+}
+extern "C" int ab200_vlidort_vector_ocigisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                         int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                                         const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                                         const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                                         const double *pmomL, const double *pe, const double *he, const double *te,
+                                                         const double *U10m, const double *V10m, const double *mr, const double *sleave,
+                                                         int sleave_iso, int sleave_adjust, const double *solar_zenith,
+                                                         const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                                         double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                                         double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc,
+                                                         double *ADJUSTED_SLEAVE) {
+  (void)sleave_iso;
+  if (int e = nobm_gate("vector_ocigisscx_nobm_cloud", nch * nobs, sleave, sleave_adjust, rc)) return e;
+  nobm_zero(ADJUSTED_SLEAVE, nobs, nch);
+  return ab200_vlidort_vector_ocigisscx_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, tauI,
+                                              ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth,
+                                              sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BR, Q, U, BR_Q,
+                                              BR_U, rc);
+}
+extern "C" int ab200_vlidort_scalar_gisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                      int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                                      const double *ssa, const double *g, const double *pmom, const double *tauI,
+                                                      const double *ssaI, const double *gI, const double *pmomI, const double *tauL,
+                                                      const double *ssaL, const double *gL, const double *pmomL, const double *pe,
+                                                      const double *he, const double *te, const double *U10m, const double *V10m,
+                                                      const double *mr, const double *sleave, int sleave_iso, int sleave_adjust,
+                                                      const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                                      double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                                      double *BRDF, int *rc, double *ADJUSTED_SLEAVE) {
+  (void)sleave_iso;
+  if (int e = nobm_gate("scalar_gisscx_nobm_cloud", nch * nobs, sleave, sleave_adjust, rc)) return e;
+  nobm_zero(ADJUSTED_SLEAVE, nobs, nch);
+  return ab200_vlidort_scalar_gisscx_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, tauI, ssaI,
+                                           gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth,
+                                           sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc);
+}
+extern "C" int ab200_vlidort_scalar_ocigisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                                         int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                                         const double *tau, const double *ssa, const double *g, const double *pmom,
+                                                         const double *tauI, const double *ssaI, const double *gI, const double *pmomI,
+                                                         const double *tauL, const double *ssaL, const double *gL, const double *pmomL,
+                                                         const double *pe, const double *he, const double *te, const double *U10m,
+                                                         const double *V10m, const double *mr, const double *sleave, int sleave_iso,
+                                                         int sleave_adjust, const double *solar_zenith, const double *relat_azymuth,
+                                                         const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                                         double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc,
+                                                         double *ADJUSTED_SLEAVE) {
+  (void)sleave_iso;
+  if (int e = nobm_gate("scalar_ocigisscx_nobm_cloud", nch * nobs, sleave, sleave_adjust, rc)) return e;
+  nobm_zero(ADJUSTED_SLEAVE, nobs, nch);
+  return ab200_vlidort_scalar_ocigisscx_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, g, pmom,
+                                              tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, solar_zenith, relat_azymuth,
+                                              sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc);
 }
 
 // number of devices the host-pointer Stage-B entries spread their observations over (one contiguous slab and one host thread per

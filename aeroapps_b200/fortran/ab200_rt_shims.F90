@@ -352,6 +352,71 @@ module ab200_c_api
          real(c_double), intent(out) :: radiance_VL(*), reflectance_VL(*), BR(*), Q(*), U(*), BR_Q(*), BR_U(*)
          integer(c_int), intent(out) :: rc
       end function
+      ! ---- NOBM water-leaving forms
+      integer(c_int) function ab200_vlidort_vector_cx_nobm(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, &
+            pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, &
+            radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc, ADJUSTED_SLEAVE) &
+            bind(C, name="ab200_vlidort_vector_cx_nobm")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, sleave_iso, sleave_adjust, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), &
+            sleave(*), solar_zenith(*), relat_azymuth(*), sensor_zenith(*)
+         real(c_double), intent(out) :: radiance_VL_SURF(*), reflectance_VL_SURF(*), BRDF(*), Q(*), U(*), BRDF_Q(*), BRDF_U(*), ADJUSTED_SLEAVE(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_scalar_gisscx_nobm_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, &
+            ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, &
+            relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc, ADJUSTED_SLEAVE) &
+            bind(C, name="ab200_vlidort_scalar_gisscx_nobm_cloud")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, sleave_iso, sleave_adjust, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), g(*), pmom(*), tauI(*), ssaI(*), gI(*), pmomI(*), tauL(*), &
+            ssaL(*), gL(*), pmomL(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sleave(*), solar_zenith(*), relat_azymuth(*), sensor_zenith(*)
+         real(c_double), intent(out) :: radiance_VL_SURF(*), reflectance_VL_SURF(*), BRDF(*), ADJUSTED_SLEAVE(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_scalar_ocigisscx_nobm_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, &
+            alpha, tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, &
+            solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc, &
+            ADJUSTED_SLEAVE) &
+            bind(C, name="ab200_vlidort_scalar_ocigisscx_nobm_cloud")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, sleave_iso, sleave_adjust, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), alpha(*), tau(*), ssa(*), g(*), pmom(*), tauI(*), ssaI(*), gI(*), pmomI(*), &
+            tauL(*), ssaL(*), gL(*), pmomL(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sleave(*), solar_zenith(*), relat_azymuth(*), &
+            sensor_zenith(*), flux_factor(*)
+         real(c_double), intent(out) :: radiance_VL_SURF(*), reflectance_VL_SURF(*), BRDF(*), ADJUSTED_SLEAVE(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_gisscx_nobm_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, &
+            ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, &
+            relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc, ADJUSTED_SLEAVE) &
+            bind(C, name="ab200_vlidort_vector_gisscx_nobm_cloud")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, sleave_iso, sleave_adjust, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), tau(*), ssa(*), pmom(*), tauI(*), ssaI(*), pmomI(*), tauL(*), ssaL(*), &
+            pmomL(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sleave(*), solar_zenith(*), relat_azymuth(*), sensor_zenith(*)
+         real(c_double), intent(out) :: radiance_VL_SURF(*), reflectance_VL_SURF(*), BRDF(*), Q(*), U(*), BRDF_Q(*), BRDF_U(*), ADJUSTED_SLEAVE(*)
+         integer(c_int), intent(out) :: rc
+      end function
+      integer(c_int) function ab200_vlidort_vector_ocigisscx_nobm_cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, &
+            alpha, tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, &
+            relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc, &
+            ADJUSTED_SLEAVE) &
+            bind(C, name="ab200_vlidort_vector_ocigisscx_nobm_cloud")
+         import :: c_int, c_double
+         integer(c_int), value :: km, nch, nobs, nstreams, plane_parallel, nMom, nPol, sleave_iso, sleave_adjust, verbose
+         real(c_double), value :: MISSING
+         real(c_double), intent(in)  :: channels(*), ROT(*), depol(*), alpha(*), tau(*), ssa(*), pmom(*), tauI(*), ssaI(*), pmomI(*), tauL(*), &
+            ssaL(*), pmomL(*), pe(*), he(*), te(*), U10m(*), V10m(*), mr(*), sleave(*), solar_zenith(*), relat_azymuth(*), sensor_zenith(*), &
+            flux_factor(*)
+         real(c_double), intent(out) :: radiance_VL_SURF(*), reflectance_VL_SURF(*), BRDF(*), Q(*), U(*), BRDF_Q(*), BRDF_U(*), ADJUSTED_SLEAVE(*)
+         integer(c_int), intent(out) :: rc
+      end function
    end interface
 contains
    ! the optional switches of the reference's vector wrappers (GV/VLIDORT_LAMBERT.F90:176,350; GV/VLIDORT_BRDF_MODIS.F90:210,417):
@@ -519,6 +584,8 @@ module VLIDORT_BRDF_CX                  ! replaces geo_vlidort/VLIDORT_BRDF_CX.F
    use ab200_c_api
    implicit none
    public :: VLIDORT_Vector_CX, VLIDORT_Vector_GissCX, VLIDORT_Vector_OCICX, VLIDORT_Vector_OCIGissCX, VLIDORT_Scalar_CX, VLIDORT_Scalar_GissCX
+   public :: VLIDORT_Vector_CX_NOBM, VLIDORT_Scalar_GissCX_NOBM_Cloud, VLIDORT_Scalar_OCIGissCX_NOBM_Cloud, VLIDORT_Vector_GissCX_NOBM_Cloud, &
+             VLIDORT_Vector_OCIGissCx_NOBM_Cloud
    public :: VLIDORT_Vector_CX_Cloud, VLIDORT_Vector_GissCx_Cloud, VLIDORT_Vector_OCIGissCX_Cloud, VLIDORT_Scalar_GissCX_Cloud, VLIDORT_Scalar_OCIGissCX_Cloud
    interface VLIDORT_Vector_CX_Cloud     ! VLIDORT_BRDF_CX.F90:33-36
       module procedure VLIDORT_Vector_CX_Cloud_SingleGeom
@@ -755,6 +822,121 @@ contains
             verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc)
       if (ier /= 0 .and. rc == 0) rc = ier
    end subroutine VLIDORT_Scalar_GissCX_Cloud
+   ! VLIDORT_BRDF_CX.F90:1351-1550.  sleave_adjust = .true. (VLIDORT's transmittance iteration) is refused: rc = -2
+   subroutine VLIDORT_Vector_CX_NOBM(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, pe, he, te, U10m, &
+            V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, &
+            reflectance_VL_SURF, Q, U, BRDF, BRDF_Q, BRDF_U, rc, ADJUSTED_SLEAVE)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel, sleave_iso, sleave_adjust
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol), &
+            pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch), sleave(nch,nobs), solar_zenith(nobs), relat_azymuth(nobs), &
+            sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), Q(nobs,nch), U(nobs,nch), BRDF(nobs,nch), BRDF_Q(nobs,nch), &
+            BRDF_U(nobs,nch)
+      integer, intent(out) :: rc
+      real*8,  optional, intent(out) :: ADJUSTED_SLEAVE(nobs,nch)
+      real*8, allocatable :: adj(:,:)
+      integer :: ier
+      allocate(adj(nobs,nch))
+      ier = ab200_vlidort_vector_cx_nobm(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, pmom, pe, &
+            he, te, U10m, V10m, mr, sleave, merge(1, 0, sleave_iso), merge(1, 0, sleave_adjust), solar_zenith, relat_azymuth, sensor_zenith, MISSING, &
+            verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc, adj)
+      if (present(ADJUSTED_SLEAVE)) ADJUSTED_SLEAVE = adj
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_CX_NOBM
+   ! VLIDORT_BRDF_CX.F90:2671-2880.  sleave_adjust = .true. (VLIDORT's transmittance iteration) is refused: rc = -2
+   subroutine VLIDORT_Scalar_GissCX_NOBM_Cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, g, pmom, tauI, &
+            ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, &
+            sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc, ADJUSTED_SLEAVE)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel, sleave_iso, sleave_adjust
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), g(km,nch,nobs), &
+            pmom(km,nch,nobs,nMom,nPol), tauI(km,nch,nobs), ssaI(km,nch,nobs), gI(km,nch,nobs), pmomI(km,nch,nobs,nMom,nPol), tauL(km,nch,nobs), &
+            ssaL(km,nch,nobs), gL(km,nch,nobs), pmomL(km,nch,nobs,nMom,nPol), pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), &
+            mr(nch), sleave(nch,nobs), solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BRDF(nobs,nch)
+      integer, intent(out) :: rc
+      real*8,  optional, intent(out) :: ADJUSTED_SLEAVE(nobs,nch)
+      real*8, allocatable :: adj(:,:)
+      integer :: ier
+      allocate(adj(nobs,nch))
+      ier = ab200_vlidort_scalar_gisscx_nobm_cloud(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, &
+            g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, sleave, merge(1, 0, sleave_iso), &
+            merge(1, 0, sleave_adjust), solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, &
+            rc, adj)
+      if (present(ADJUSTED_SLEAVE)) ADJUSTED_SLEAVE = adj
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Scalar_GissCX_NOBM_Cloud
+   ! VLIDORT_BRDF_CX.F90:2883-3099.  sleave_adjust = .true. (VLIDORT's transmittance iteration) is refused: rc = -2
+   subroutine VLIDORT_Scalar_OCIGissCX_NOBM_Cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, g, &
+            pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, &
+            relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, rc, ADJUSTED_SLEAVE)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel, sleave_iso, sleave_adjust
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), alpha(km,nobs,nch), tau(km,nch,nobs), ssa(km,nch,nobs), g(km,nch,nobs), &
+            pmom(km,nch,nobs,nMom,nPol), tauI(km,nch,nobs), ssaI(km,nch,nobs), gI(km,nch,nobs), pmomI(km,nch,nobs,nMom,nPol), tauL(km,nch,nobs), &
+            ssaL(km,nch,nobs), gL(km,nch,nobs), pmomL(km,nch,nobs,nMom,nPol), pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), &
+            mr(nch), sleave(nch,nobs), solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), flux_factor(nch,nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), BRDF(nobs,nch)
+      integer, intent(out) :: rc
+      real*8,  optional, intent(out) :: ADJUSTED_SLEAVE(nobs,nch)
+      real*8, allocatable :: adj(:,:)
+      integer :: ier
+      allocate(adj(nobs,nch))
+      ier = ab200_vlidort_scalar_ocigisscx_nobm_cloud(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, alpha, &
+            tau, ssa, g, pmom, tauI, ssaI, gI, pmomI, tauL, ssaL, gL, pmomL, pe, he, te, U10m, V10m, mr, sleave, merge(1, 0, sleave_iso), &
+            merge(1, 0, sleave_adjust), solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, &
+            reflectance_VL_SURF, BRDF, rc, adj)
+      if (present(ADJUSTED_SLEAVE)) ADJUSTED_SLEAVE = adj
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Scalar_OCIGissCX_NOBM_Cloud
+   ! VLIDORT_BRDF_CX.F90:3102-3317.  sleave_adjust = .true. (VLIDORT's transmittance iteration) is refused: rc = -2
+   subroutine VLIDORT_Vector_GissCX_NOBM_Cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, tau, ssa, pmom, tauI, ssaI, &
+            pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, sensor_zenith, &
+            MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, Q, U, BRDF, BRDF_Q, BRDF_U, rc, ADJUSTED_SLEAVE)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel, sleave_iso, sleave_adjust
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), tau(km,nch,nobs), ssa(km,nch,nobs), pmom(km,nch,nobs,nMom,nPol), &
+            tauI(km,nch,nobs), ssaI(km,nch,nobs), pmomI(km,nch,nobs,nMom,nPol), tauL(km,nch,nobs), ssaL(km,nch,nobs), pmomL(km,nch,nobs,nMom,nPol), &
+            pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch), sleave(nch,nobs), solar_zenith(nobs), relat_azymuth(nobs), &
+            sensor_zenith(nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), Q(nobs,nch), U(nobs,nch), BRDF(nobs,nch), BRDF_Q(nobs,nch), &
+            BRDF_U(nobs,nch)
+      integer, intent(out) :: rc
+      real*8,  optional, intent(out) :: ADJUSTED_SLEAVE(nobs,nch)
+      real*8, allocatable :: adj(:,:)
+      integer :: ier
+      allocate(adj(nobs,nch))
+      ier = ab200_vlidort_vector_gisscx_nobm_cloud(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, tau, ssa, &
+            pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sleave, merge(1, 0, sleave_iso), merge(1, 0, sleave_adjust), &
+            solar_zenith, relat_azymuth, sensor_zenith, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc, adj)
+      if (present(ADJUSTED_SLEAVE)) ADJUSTED_SLEAVE = adj
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_GissCX_NOBM_Cloud
+   ! VLIDORT_BRDF_CX.F90:3320-3538 (f2py VECTOR_OCIGissCX_NOBM_Cloud).  sleave_adjust = .true. (VLIDORT's transmittance iteration) is refused: rc = -2
+   subroutine VLIDORT_Vector_OCIGissCx_NOBM_Cloud(km, nch, nobs, channels, nstreams, plane_parallel, nMom, nPol, ROT, depol, alpha, tau, ssa, pmom, &
+            tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sleave, sleave_iso, sleave_adjust, solar_zenith, relat_azymuth, &
+            sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, reflectance_VL_SURF, Q, U, BRDF, BRDF_Q, BRDF_U, rc, ADJUSTED_SLEAVE)
+      integer, intent(in)  :: km, nch, nobs, nstreams, nMom, nPol, verbose
+      logical, intent(in)  :: plane_parallel, sleave_iso, sleave_adjust
+      real*8,  intent(in)  :: channels(nch), ROT(km,nobs,nch), depol(nch), alpha(km,nobs,nch), tau(km,nch,nobs), ssa(km,nch,nobs), &
+            pmom(km,nch,nobs,nMom,nPol), tauI(km,nch,nobs), ssaI(km,nch,nobs), pmomI(km,nch,nobs,nMom,nPol), tauL(km,nch,nobs), ssaL(km,nch,nobs), &
+            pmomL(km,nch,nobs,nMom,nPol), pe(km+1,nobs), he(km+1,nobs), te(km+1,nobs), U10m(nobs), V10m(nobs), mr(nch), sleave(nch,nobs), &
+            solar_zenith(nobs), relat_azymuth(nobs), sensor_zenith(nobs), flux_factor(nch,nobs), MISSING
+      real*8,  intent(out) :: radiance_VL_SURF(nobs,nch), reflectance_VL_SURF(nobs,nch), Q(nobs,nch), U(nobs,nch), BRDF(nobs,nch), BRDF_Q(nobs,nch), &
+            BRDF_U(nobs,nch)
+      integer, intent(out) :: rc
+      real*8,  optional, intent(out) :: ADJUSTED_SLEAVE(nobs,nch)
+      real*8, allocatable :: adj(:,:)
+      integer :: ier
+      allocate(adj(nobs,nch))
+      ier = ab200_vlidort_vector_ocigisscx_nobm_cloud(km, nch, nobs, channels, nstreams, merge(1, 0, plane_parallel), nMom, nPol, ROT, depol, alpha, &
+            tau, ssa, pmom, tauI, ssaI, pmomI, tauL, ssaL, pmomL, pe, he, te, U10m, V10m, mr, sleave, merge(1, 0, sleave_iso), &
+            merge(1, 0, sleave_adjust), solar_zenith, relat_azymuth, sensor_zenith, flux_factor, MISSING, verbose, radiance_VL_SURF, &
+            reflectance_VL_SURF, BRDF, Q, U, BRDF_Q, BRDF_U, rc, adj)
+      if (present(ADJUSTED_SLEAVE)) ADJUSTED_SLEAVE = adj
+      if (ier /= 0 .and. rc == 0) rc = ier
+   end subroutine VLIDORT_Vector_OCIGissCx_NOBM_Cloud
 end module VLIDORT_BRDF_CX
 
 module VLIDORT_BRDF_MODIS               ! replaces geo_vlidort/VLIDORT_BRDF_MODIS.F90:206-410

@@ -345,6 +345,63 @@ int ab200_vlidort_vector_lambert_bpdf_cloud(int km, int nch, int nobs, const dou
                                             const double *relat_azymuth, const double *sensor_zenith, double MISSING, int verbose,
                                             double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
                                             double *BR_Q, double *BR_U, int *rc);
+/* ---- NOBM water-leaving forms: VLIDORT_Vector_CX_NOBM, VLIDORT_Scalar_GissCX_NOBM_Cloud, VLIDORT_Scalar_OCIGissCX_NOBM_Cloud,
+ * VLIDORT_Vector_GissCX_NOBM_Cloud, VLIDORT_Vector_OCIGissCx_NOBM_Cloud (GV/VLIDORT_BRDF_CX.F90:1351,2671,2883,3102,3320; the last one is
+ * f2py VECTOR_OCIGissCX_NOBM_Cloud, LV/VLIDORT_POLAR_py.F90:1055).  sleave (nch,nobs) = sun-normalised water-leaving radiance;
+ * sleave_iso / sleave_adjust = the reference's logicals; ADJUSTED_SLEAVE (nobs,nch) may be NULL (optional in the reference).
+ * sleave_adjust = 0: VLIDORT 2.8.3 scales every water-leaving term by TRANS_ATMOS_FINAL, which stays 0 without the transmittance
+ *   iteration or DO_EXTERNAL_WLEAVE (VM/vlidort_bvproblem.f90:1500-1513,1563-1571; VM/vlidort_masters_V2p8p3.f90:2493-2499) -- the reference's
+ *   answer is the one without water-leaving and ADJUSTED_SLEAVE = 0; these entries return exactly that (the sibling entry's result).
+ * sleave_adjust = 1 (BVP_ADJUSTED_BACKSUB, VM/vlidort_bvproblem.f90:2487-2910) is NOT supported: AB200_ERR_ARG, rc = -2. */
+int ab200_vlidort_vector_cx_nobm(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel, int nMom, int nPol,
+                                 const double *ROT, const double *depol, const double *tau, const double *ssa, const double *pmom,
+                                 const double *pe, const double *he, const double *te, const double *U10m, const double *V10m,
+                                 const double *mr, const double *sleave, int sleave_iso, int sleave_adjust,
+                                 const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith, double MISSING,
+                                 int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BR, double *Q, double *U,
+                                 double *BR_Q, double *BR_U, int *rc, double *ADJUSTED_SLEAVE);
+int ab200_vlidort_vector_gisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                           int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                           const double *ssa, const double *pmom, const double *tauI, const double *ssaI,
+                                           const double *pmomI, const double *tauL, const double *ssaL, const double *pmomL,
+                                           const double *pe, const double *he, const double *te, const double *U10m,
+                                           const double *V10m, const double *mr, const double *sleave, int sleave_iso,
+                                           int sleave_adjust, const double *solar_zenith, const double *relat_azymuth,
+                                           const double *sensor_zenith, double MISSING, int verbose, double *radiance_VL_SURF,
+                                           double *reflectance_VL_SURF, double *BR, double *Q, double *U, double *BR_Q, double *BR_U,
+                                           int *rc, double *ADJUSTED_SLEAVE);
+int ab200_vlidort_vector_ocigisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                              int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                              const double *tau, const double *ssa, const double *pmom, const double *tauI,
+                                              const double *ssaI, const double *pmomI, const double *tauL, const double *ssaL,
+                                              const double *pmomL, const double *pe, const double *he, const double *te,
+                                              const double *U10m, const double *V10m, const double *mr, const double *sleave,
+                                              int sleave_iso, int sleave_adjust, const double *solar_zenith,
+                                              const double *relat_azymuth, const double *sensor_zenith, const double *flux_factor,
+                                              double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                              double *BR, double *Q, double *U, double *BR_Q, double *BR_U, int *rc,
+                                              double *ADJUSTED_SLEAVE);
+int ab200_vlidort_scalar_gisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                           int nMom, int nPol, const double *ROT, const double *depol, const double *tau,
+                                           const double *ssa, const double *g, const double *pmom, const double *tauI,
+                                           const double *ssaI, const double *gI, const double *pmomI, const double *tauL,
+                                           const double *ssaL, const double *gL, const double *pmomL, const double *pe,
+                                           const double *he, const double *te, const double *U10m, const double *V10m,
+                                           const double *mr, const double *sleave, int sleave_iso, int sleave_adjust,
+                                           const double *solar_zenith, const double *relat_azymuth, const double *sensor_zenith,
+                                           double MISSING, int verbose, double *radiance_VL_SURF, double *reflectance_VL_SURF,
+                                           double *BRDF, int *rc, double *ADJUSTED_SLEAVE);
+int ab200_vlidort_scalar_ocigisscx_nobm_cloud(int km, int nch, int nobs, const double *channels, int nstreams, int plane_parallel,
+                                              int nMom, int nPol, const double *ROT, const double *depol, const double *alpha,
+                                              const double *tau, const double *ssa, const double *g, const double *pmom,
+                                              const double *tauI, const double *ssaI, const double *gI, const double *pmomI,
+                                              const double *tauL, const double *ssaL, const double *gL, const double *pmomL,
+                                              const double *pe, const double *he, const double *te, const double *U10m,
+                                              const double *V10m, const double *mr, const double *sleave, int sleave_iso,
+                                              int sleave_adjust, const double *solar_zenith, const double *relat_azymuth,
+                                              const double *sensor_zenith, const double *flux_factor, double MISSING, int verbose,
+                                              double *radiance_VL_SURF, double *reflectance_VL_SURF, double *BRDF, int *rc,
+                                              double *ADJUSTED_SLEAVE);
 
 /* diagnostics of the calling thread's most recent VLIDORT call: Fourier count and status per pixel p = j*nch + i (per pixel-view
  * (j*nch + i)*ngeom + g for the multi-geometry forms); returns their number */

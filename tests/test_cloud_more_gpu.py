@@ -183,3 +183,45 @@ def test_clear_sky_placeholders_equal_their_clear_sky_entries(mods):
     b = VP.vector_brdf_modis_bpdf(sc["channels"], N, False, sc["ROT"], sc["depol"], sc["tau"], sc["ssa"], sc["pmom"], sc["pe"], sc["he"], sc["te"],
                                   sc["kernel_wt"], sc["param"], bp, sc["sza"], sc["raa"], sc["vza"], M, 0)
     assert same(a, b)
+
+
+def test_nobm_forms_without_adjustment_equal_their_siblings(mods):
+    """NOBM water-leaving forms (GV/VLIDORT_BRDF_CX.F90:1351,2671,2883,3102,3320; f2py VECTOR_OCIGissCX_NOBM_Cloud).  With sleave_adjust False
+    VLIDORT 2.8.3 multiplies every water-leaving term by TRANS_ATMOS_FINAL, which stays at the zero it is reset to unless the transmittance
+    iteration or DO_EXTERNAL_WLEAVE is on (VM/vlidort_bvproblem.f90:1500-1513,1563-1571; VM/vlidort_masters_V2p8p3.f90:2493-2499; AeroApps sets
+    neither, V283/VLIDORT_ScatMod.F90:388-405): the reference's answer is the one without water-leaving, ADJUSTED_SLEAVE = 0.  The entries must
+    therefore equal their siblings (which the tests above pin to the oracle) bit for bit, whatever sleave / sleave_iso are, and must refuse
+    sleave_adjust True instead of returning an unadjusted answer"""
+    VP, vg, parity = mods
+    nobs, N = 6, 6
+    sc = _cloud_scene(vg, nobs, (440.0, 865.0), 40, 608)
+    sc["v10m"][1] = M
+    cl = [sc[k] for k in CL]
+    scl = (sc["tauI"], sc["ssaI"], sc["g"], sc["pmomI"], sc["tauL"], sc["ssaL"], sc["g"], sc["pmomL"])
+    sleave = np.asfortranarray(np.random.default_rng(609).uniform(0.0, 0.02, (2, nobs)))
+    geo = (sc["sza"], sc["raa"], sc["vza"])
+    atm = (sc["channels"], N, False, sc["ROT"], sc["depol"])
+    lev = (sc["pe"], sc["he"], sc["te"], sc["u10m"], sc["v10m"], sc["mr"])
+    same = lambda a, b: a[-1] == b[-1] == 0 and all(np.array_equal(x, y) for x, y in zip(a[:-1], b[:-1]))
+    for iso in (True, False):
+        a = VP.vector_ocigisscx_nobm_cloud(*atm, sc["alpha"], sc["tau"], sc["ssa"], sc["pmom"], *cl, *lev, sleave, iso, False, *geo, sc["flux"], M, 0)
+        b = VP.vector_ocigisscx_cloud(*atm, sc["alpha"], sc["tau"], sc["ssa"], sc["pmom"], *cl, *lev, *geo, sc["flux"], M, 0)
+        assert len(a) == 9 and same(a[:8], b) and a[8].shape == (nobs, 2) and (a[8] == 0).all()
+        assert (a[0][1] == M).all() and (a[0][0] != M).all() and (a[0][0] > 0).all()
+        a = VP.vector_gisscx_nobm_cloud(*atm, sc["tau"], sc["ssa"], sc["pmom"], *cl, *lev, sleave, iso, False, *geo, M, 0)
+        b = VP.vector_gisscx_cloud(*atm, sc["tau"], sc["ssa"], sc["pmom"], *cl, *lev, *geo, M, 0)
+        assert same(a[:8], b) and (a[8] == 0).all()
+        a = VP.vector_cx_nobm(*atm, sc["tau"], sc["ssa"], sc["pmom"], *lev, sleave, iso, False, *geo, M, 0)
+        b = VP.vector_cx(*atm, sc["tau"], sc["ssa"], sc["pmom"], *lev, *geo, M, 0)
+        assert same(a[:8], b) and (a[8] == 0).all()
+        a = VP.scalar_gisscx_nobm_cloud(*atm, sc["tau"], sc["ssa"], sc["g"], sc["pmom"], *scl, *lev, sleave, iso, False, *geo, M, 0)
+        b = VP.scalar_gisscx_cloud(*atm, sc["tau"], sc["ssa"], sc["g"], sc["pmom"], *scl, *lev, *geo, M, 0)
+        assert same(a[:4], b) and (a[4] == 0).all()
+        a = VP.scalar_ocigisscx_nobm_cloud(*atm, sc["alpha"], sc["tau"], sc["ssa"], sc["g"], sc["pmom"], *scl, *lev, sleave, iso, False, *geo, sc["flux"],
+                                           M, 0)
+        b = VP.scalar_ocigisscx_cloud(*atm, sc["alpha"], sc["tau"], sc["ssa"], sc["g"], sc["pmom"], *scl, *lev, *geo, sc["flux"], M, 0)
+        assert same(a[:4], b) and (a[4] == 0).all()
+    with pytest.raises(RuntimeError, match="sleave_adjust"):
+        VP.vector_ocigisscx_nobm_cloud(*atm, sc["alpha"], sc["tau"], sc["ssa"], sc["pmom"], *cl, *lev, sleave, True, True, *geo, sc["flux"], M, 0)
+    with pytest.raises(RuntimeError, match="sleave_adjust"):
+        VP.vector_cx_nobm(*atm, sc["tau"], sc["ssa"], sc["pmom"], *lev, sleave, True, True, *geo, M, 0)
