@@ -638,8 +638,8 @@ def cpu_arm(wl, cores, passes=1, warmup=0):
     the workload's bounded sample; returns (units/s, sample description)"""
     native = False
     try:
-        from oracle import vlidort_oracle as vo
-        native = vo.use_native(True) if hasattr(wl, "kind") else False
+        from oracle import vlidort_oracle as vo, mie_oracle as mo
+        native = vo.use_native(True) if hasattr(wl, "kind") else mo.use_native(True)
     except Exception:
         native = False
     try:
@@ -651,7 +651,7 @@ def cpu_arm(wl, cores, passes=1, warmup=0):
             units += u; secs += dt
     finally:
         if native:
-            vo.use_native(False)
+            vo.use_native(False); mo.use_native(False)
     what = wl.unit.split("/")[0]
     return units / secs, secs, (f"{units // max(passes, 1)} of {wl.units_per_step} {what} of the same step, {passes} pass(es), {cores} threads "
                                 f"(oracle/: C/C++ restatement of the reference Fortran, "

@@ -29,14 +29,40 @@ class _Raw(C.Structure):
 
 
 _lib = None
+_native = None
+_use_native = False
 
 
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
+def use_native(on=True):
+    """bench.py's CPU arms: time a -O3 -march=native build of mie_oracle.c (still -ffp-contract=off: the float32 operation order is the
+    algorithm), built on first use on the host that runs it into oracle/_native/.  The portable -O2 build stays the checker of the parity
+    tests.  Objects (OracleMie) must be created while the build they are to run with is active.  Returns True when the native build is on."""
+    global _native, _use_native
+    if on and _native is None:
+        from .vlidort_oracle import _cpu_tag
+        d = os.path.join(_HERE, "_native")
+        so = os.path.join(d, f"libmie_oracle_{_cpu_tag()}.so")
+        try:
+            if not os.path.exists(so):
+                os.makedirs(d, exist_ok=True)
+                subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", so,
+                                       os.path.join(_HERE, "mie_oracle.c"), "-lm"])
+            _native = C.CDLL(so)
+            _native.orc_mie_table_read.restype = C.POINTER(_Table)
+        except Exception:
+            _native = False
+    _use_native = bool(on and _native)
+    return _use_native
+
+
 def lib():
     global _lib
+    if _use_native:
+        return _native
     if _lib is None:
         if not os.path.exists(_SO):
             build()
