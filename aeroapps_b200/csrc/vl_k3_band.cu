@@ -118,7 +118,11 @@ int vl_band_plan(BandPlan &P, int S, int N, int L, int nsm) {
     P.per_sm = std::max(1, std::min(P.per_sm, 16));
     P.grid_max = nsm * P.per_sm * P.wpc;
   } else {
-    if (P.smem > 227 * 1024) { ab200_set_error("vlidort: nstokes*nstreams too large for the shared-memory BVP window"); return AB200_ERR_ARG; }
+    if (P.smem > 227 * 1024) {
+      ab200_set_error("vlidort: nstokes*nstreams too large (> 64: vector calls take up to 21 streams, scalar calls the reference's 25): the "
+                      "boundary-value working set of a pixel does not fit the shared memory of an SM");
+      return AB200_ERR_ARG;
+    }
     auto kb = (const void *)band_kernel(S, P.var);
     AB_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
     AB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&P.per_sm, kb, 384, P.smem));
