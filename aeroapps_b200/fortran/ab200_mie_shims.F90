@@ -2,12 +2,14 @@
 !   VLIDORT_getAOPscalar / VLIDORT_getAOPvector   replace the bodies in Components/rtms/geo_vlidort/VLIDORT_MieMod.F90:10,124
 !   getAOPscalar / getAOPvector / getExt / getInt / getEdgeVars   replace the bodies in GMAO_Shared/Chem_Base/MieObs_py.F90:27-770
 ! Names, argument lists and intents are the reference's, so geo_vlidort.F90, leo_vlidort_cloud.F90 and the f2py module MieObs_
-! compile and link untouched.  The NetCDF optics-file reader and the rc parser stay the reference's (Chem_MieCreate): the shim takes the
+! compile and link untouched. The NetCDF optics-file reader and the rc parser stay the reference's (Chem_MieCreate): the shim
+!  takes the
 ! type(Chem_Mie) it returns, uploads the interpolated float32 tables once per (rcfile, channels, nMom) through
 ! ab200_mie_load_table_f32 and keeps the GPU handle in a small cache, so a caller that creates the tables per call (MieObs_py does)
 ! pays the upload once.  Link with -L<repo>/aeroapps_b200 -laeroapps_b200 -lcudart.
 ! NOT compiled in this repository's CI: neither the build image nor the GPU box has a Fortran compiler (DESIGN.md section 2);
-! the C entry points underneath are exercised with the same Fortran-ordered buffers by tests/cabi/test_cabi.c and tests/test_mie_gpu.py.
+! the C entry points underneath are exercised with the same Fortran-ordered buffers by tests/cabi/test_cabi.c and
+!  tests/test_mie_gpu.py.
 module ab200_mie_c_api
    use iso_c_binding
    implicit none
@@ -22,7 +24,8 @@ module ab200_mie_c_api
          import :: c_int, c_ptr
          type(c_ptr), value :: h
       end function
-      integer(c_int) function ab200_mie_load_table_f32(h, species, nrh, nbin, npol, rh, reff, gf, rhop, rhod, vol, area, bext, bsca, bbck, g, &
+      integer(c_int) function ab200_mie_load_table_f32(h, species, nrh, nbin, npol, rh, reff, gf, rhop, rhod, vol, area, bext, &
+            bsca, bbck, g, &
                                                        refr, refi, pback, pmom, rhi, rha) bind(C, name="ab200_mie_load_table_f32")
          import :: c_int, c_ptr
          type(c_ptr), value :: h
@@ -39,7 +42,8 @@ module ab200_mie_c_api
          real(c_float), intent(out) :: tau(*), ssa(*), g(*)
          integer(c_int), intent(out) :: rc
       end function
-      integer(c_int) function ab200_get_aop_vector(h, km, nobs, nch, nq, channels, vname, verbose, qm, rh, nmom, npol, tau, ssa, g, pmom, rc) &
+      integer(c_int) function ab200_get_aop_vector(h, km, nobs, nch, nq, channels, vname, verbose, qm, rh, nmom, npol, tau, ssa, &
+            g, pmom, rc) &
                                                    bind(C, name="ab200_get_aop_vector")
          import :: c_int, c_float, c_ptr, c_char
          type(c_ptr), value :: h
@@ -49,7 +53,8 @@ module ab200_mie_c_api
          real(c_float), intent(out) :: tau(*), ssa(*), g(*), pmom(*)
          integer(c_int), intent(out) :: rc
       end function
-      integer(c_int) function ab200_get_ext(h, km, nobs, nch, nq, channels, vname, verbose, qc, qm, rh, ext, sca, bsc, absc_sfc, absc_toa, depol, rc) &
+      integer(c_int) function ab200_get_ext(h, km, nobs, nch, nq, channels, vname, verbose, qc, qm, rh, ext, sca, bsc, absc_sfc, &
+            absc_toa, depol, rc) &
                                             bind(C, name="ab200_get_ext")
          import :: c_int, c_float, c_ptr, c_char
          type(c_ptr), value :: h
@@ -59,7 +64,8 @@ module ab200_mie_c_api
          real(c_float), intent(out) :: ext(*), sca(*), bsc(*), absc_sfc(*), absc_toa(*), depol(*)
          integer(c_int), intent(out) :: rc
       end function
-      integer(c_int) function ab200_get_int(h, km, nobs, nch, nq, channels, vname, verbose, qc, qm, rh, vol, area, refr, refi, reff, rc) &
+      integer(c_int) function ab200_get_int(h, km, nobs, nch, nq, channels, vname, verbose, qc, qm, rh, vol, area, refr, refi, &
+            reff, rc) &
                                             bind(C, name="ab200_get_int")
          import :: c_int, c_float, c_ptr, c_char
          type(c_ptr), value :: h
@@ -121,7 +127,8 @@ contains
       if (associated(t%refr)) p_refr = c_loc(t%refr(1,1,1))
       if (associated(t%refi)) p_refi = c_loc(t%refi(1,1,1))
       rc = ab200_mie_load_table_f32(h, species, t%nrh, t%nbin, npol, c_loc(t%rh(1)), c_loc(t%reff(1,1)), p_gf, p_rhop, p_rhod, &
-                                    c_loc(t%vol(1,1)), c_loc(t%area(1,1)), c_loc(t%bext(1,1,1)), c_loc(t%bsca(1,1,1)), c_loc(t%bbck(1,1,1)), &
+                                    c_loc(t%vol(1,1)), c_loc(t%area(1,1)), c_loc(t%bext(1,1,1)), c_loc(t%bsca(1,1,1)), &
+                                          c_loc(t%bbck(1,1,1)), &
                                     c_loc(t%g(1,1,1)), p_refr, p_refi, p_pback, p_pmom, c_loc(t%rhi(1)), c_loc(t%rha(1)))
    end subroutine
 
@@ -286,7 +293,8 @@ subroutine getExt(km, nobs, nch, nq, rcfile, channels, vname, verbose, qc, qm, r
    real,    intent(in)  :: channels(nch)
    character, intent(in) :: vname(nq,16)
    real,    intent(in)  :: qc(km,nq,nobs), qm(km,nq,nobs), rh(km,nobs)
-   real,    intent(out) :: ext(km,nch,nobs), sca(km,nch,nobs), bsc(km,nch,nobs), absc_SFC(km,nch,nobs), absc_TOA(km,nch,nobs), depol(km,nch,nobs)
+   real,    intent(out) :: ext(km,nch,nobs), sca(km,nch,nobs), bsc(km,nch,nobs), absc_SFC(km,nch,nobs), absc_TOA(km,nch,nobs), &
+         depol(km,nch,nobs)
    integer, intent(out) :: rc
    type(c_ptr) :: h
    integer :: st
